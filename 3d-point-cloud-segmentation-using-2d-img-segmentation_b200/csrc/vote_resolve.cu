@@ -1,0 +1,198 @@
+// Level-V vote (uv2pt + mask -> votes), mask nearest-resize, and kernel (3) label resolve.
+//   VotingSegmentation.vote     Fusion3DSeg/segUtils/voting.py:75-104
+//   VotingSegmentation.segment  Fusion3DSeg/segUtils/voting.py:106-137
+//   cv2.resize(INTER_NEAREST)   call site voting.py:93
+#include "f3d_common.cuh"
+#include "f3d_host.h"
+
+// ---- level V ----------------------------------------------------------------------------------------------------
+// numpy's buffered `votes[idx, cls] += 1` (voting.py:98) counts each distinct (point, class) pair of a frame ONCE.
+// A vote cell is (frame_tag << 16 | count): a pixel adds 1 only if the cell's tag is not the current frame's tag.
+// Pixels of one warp that carry the same (point, class) key are first aggregated with __match_any_sync so a
+// single lane issues the CAS (adjacent pixels usually map to the same fused point).
+__global__ void __launch_bounds__(256) vote_uv2pt_kernel(const int32_t* __restrict__ uv2pt, const uint8_t* __restrict__ mask,
+                                                         int64_t npix, uint32_t tag, uint32_t* __restrict__ votes, int64_t N,
+                                                         int C1) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // warp-uniform trip count so that __match_any_sync sees the whole warp
+    const int64_t iters = (npix + stride - 1) / stride;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = start + it * stride;
+        long long key = -1;
+        if (i < npix) {
+            const int pt = __ldg(uv2pt + i);
+            const int cls = __ldg(mask + i);
+            if (pt >= 0 && pt < N && cls < C1) key = (long long)pt * C1 + cls;   // valid = uv2pt != -1 (voting.py:95)
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const bool leader = (__ffs(peers) - 1) == (int)(threadIdx.x & 31);
+        if (key >= 0 && leader) {
+            uint32_t* cell = votes + key;
+            uint32_t old = *cell;
+            while ((old >> 16) != tag) {
+                const uint32_t assumed = old;
+                old = atomicCAS(cell, assumed, (tag << 16) | ((assumed & 0xffffu) + 1u));
+                if (old == assumed) break;
+            }
+        }
+    }
+}
+
+__global__ void vote_finalize_kernel(uint32_t* __restrict__ v, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] &= 0xffffu;
+}
+
+// ---- cv2.resize(..., INTER_NEAREST): sx = min(floor(dx * (1 / (dst_w / src_w))), src_w - 1), float64 ---------------
+__global__ void resize_nearest_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh, int dw,
+                                      double ifx, double ify) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int img = blockIdx.z;
+    if (x >= dw) return;
+    int sx = (int)floor(xmul((double)x, ifx));
+    int sy = (int)floor(xmul((double)y, ify));
+    sx = min(sx, sw - 1);
+    sy = min(sy, sh - 1);
+    dst[((size_t)img * dh + y) * dw + x] = __ldg(src + ((size_t)img * sh + sy) * sw + sx);
+}
+
+// ---- kernel (3): label resolve --------------------------------------------------------------------------------------------
+#define RES_MAX_FILTER 256
+struct ResolveParams {
+    int nfilter;                       // 0 = all columns
+    int32_t filter[RES_MAX_FILTER];    // column ids in caller order
+    int32_t remap[RES_MAX_FILTER + 1]; // composed sequential remap (voting.py:133-135) for arg-max index i
+    int32_t unclassified;              // value for "unclassified" after the same remap
+    double threshold;
+};
+
+// One warp per point row: lanes stride over the C1 int32 counters (coalesced 128 B segments), a shuffle reduction
+// gives the row total and the first maximum among the filter columns, lane 0 applies the float64 tests of
+// voting.py:126-131.  HBM-bound: 4*C1 bytes read + 8 bytes written per point.
+template <bool FILTERED>
+__global__ void __launch_bounds__(256) resolve_kernel(const int32_t* __restrict__ votes, int64_t N, int C1,
+                                                      const ResolveParams rp, int64_t* __restrict__ labels) {
+    __shared__ int32_t s_fpos[RES_MAX_FILTER];   // column -> first position in the filter list, or INT_MAX
+    const int lane = threadIdx.x & 31;
+    if (FILTERED) {
+        for (int c = threadIdx.x; c < C1 && c < RES_MAX_FILTER; c += blockDim.x) {
+            int pos = 0x7fffffff;
+            for (int k = rp.nfilter - 1; k >= 0; --k)
+                if (rp.filter[k] == c) pos = k;
+            s_fpos[c] = pos;
+        }
+        __syncthreads();
+    }
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < N; row += warps_total) {
+        const int32_t* __restrict__ r = votes + row * C1;
+        long long total = 0;
+        int best = -1;               // maximum vote among considered columns
+        int bpos = 0x7fffffff;       // its position (first maximum wins: smallest position among equal values)
+        for (int c = lane; c < C1; c += 32) {
+            const int v = __ldg(r + c);
+            total += v;
+            const int pos = FILTERED ? s_fpos[c] : c;
+            if (pos != 0x7fffffff && (v > best || (v == best && pos < bpos))) {
+                best = v;
+                bpos = pos;
+            }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            total += __shfl_xor_sync(0xffffffffu, total, s);
+            const int ob = __shfl_xor_sync(0xffffffffu, best, s);
+            const int op = __shfl_xor_sync(0xffffffffu, bpos, s);
+            if (ob > best || (ob == best && op < bpos)) {
+                best = ob;
+                bpos = op;
+            }
+        }
+        if (lane == 0) {
+            int32_t out;
+            bool unc = (total <= 0) || (best <= 0);                         // voting.py:126,131
+            if (!unc) {
+                const double prob = xdiv((double)best, (double)total);       // voting.py:128
+                unc = prob < rp.threshold;                                   // voting.py:129-130
+            }
+            if (unc) out = rp.unclassified;
+            else out = FILTERED ? rp.remap[bpos] : bpos;
+            labels[row] = (int64_t)out;
+        }
+    }
+}
+
+// ---- C ABI ---------------------------------------------------------------------------------------------------------------
+static unsigned grid_for(int64_t n, int block, int max_blocks) {
+    int64_t b = (n + block - 1) / block;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (unsigned)b;
+}
+
+extern "C" int f3d_vote_uv2pt(const int32_t* uv2pt, const uint8_t* mask, int32_t nframes, int64_t npix, int32_t first_tag,
+                              uint32_t* votes_packed, int64_t N, int32_t C1, void* stream) {
+    if (!uv2pt || !mask || !votes_packed || nframes < 0 || npix < 0 || N < 0 || C1 <= 0)
+        return f3d_fail(F3D_ERR_ARG, "f3d_vote_uv2pt: bad argument");
+    if (first_tag < 1 || (int64_t)first_tag + nframes - 1 > 65535)
+        return f3d_fail(F3D_ERR_ARG, "f3d_vote_uv2pt: frame tags must stay within 1..65535");
+    if (npix == 0 || N == 0) return F3D_OK;
+    // frames are serialised by stream order: a cell's tag identifies the frame that last voted for it
+    const unsigned grid = grid_for(npix, 256, 148 * 8);
+    for (int f = 0; f < nframes; ++f) {
+        vote_uv2pt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(uv2pt + (size_t)f * npix, mask + (size_t)f * npix, npix,
+                                                                  (uint32_t)(first_tag + f), votes_packed, N, C1);
+    }
+    return f3d_check_launch("f3d_vote_uv2pt");
+}
+
+extern "C" int f3d_vote_finalize(uint32_t* votes_packed, int64_t ncells, void* stream) {
+    if (!votes_packed || ncells < 0) return f3d_fail(F3D_ERR_ARG, "f3d_vote_finalize: bad argument");
+    if (ncells == 0) return F3D_OK;
+    vote_finalize_kernel<<<grid_for(ncells, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(votes_packed, ncells);
+    return f3d_check_launch("f3d_vote_finalize");
+}
+
+extern "C" int f3d_resize_nearest_u8(const uint8_t* src, int32_t nimg, int32_t src_h, int32_t src_w, uint8_t* dst,
+                                     int32_t dst_h, int32_t dst_w, void* stream) {
+    if (!src || !dst || nimg <= 0 || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || nimg > 65535 || dst_h > 65535)
+        return f3d_fail(F3D_ERR_ARG, "f3d_resize_nearest_u8: bad argument");
+    // OpenCV: inv_scale = dsize / ssize (double), ifx = 1 / inv_scale
+    volatile double isx = (double)dst_w / (double)src_w, isy = (double)dst_h / (double)src_h;
+    const double ifx = 1.0 / isx, ify = 1.0 / isy;
+    dim3 grid((unsigned)((dst_w + 255) / 256), (unsigned)dst_h, (unsigned)nimg);
+    resize_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_h, src_w, dst, dst_h, dst_w, ifx, ify);
+    return f3d_check_launch("f3d_resize_nearest_u8");
+}
+
+extern "C" int f3d_resolve_labels(const int32_t* votes, int64_t N, int32_t C1, double threshold, const int32_t* h_filter,
+                                  int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream) {
+    if (!votes || !labels || N < 0 || C1 <= 0 || nfilter < 0 || (nfilter > 0 && !h_filter))
+        return f3d_fail(F3D_ERR_ARG, "f3d_resolve_labels: bad argument");
+    if (nfilter > RES_MAX_FILTER || (nfilter > 0 && C1 > RES_MAX_FILTER))
+        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_resolve_labels: more than 256 filter classes / columns");
+    if (N == 0) return F3D_OK;
+    ResolveParams rp;
+    rp.nfilter = nfilter;
+    rp.threshold = threshold;
+    rp.unclassified = nclasses_id;
+    for (int k = 0; k < nfilter; ++k) {
+        if (h_filter[k] < 0 || h_filter[k] >= C1) return f3d_fail(F3D_ERR_ARG, "f3d_resolve_labels: filter class out of range");
+        rp.filter[k] = h_filter[k];
+    }
+    // compose the sequential remap `for i, cls in enumerate(filter): pc[pc == i] = cls` (voting.py:133-135),
+    // including its aliasing, for every start value an arg-max index or the unclassified id can take
+    for (int start = 0; start <= nfilter; ++start) {
+        int v = start < nfilter ? start : nclasses_id;
+        for (int i = 0; i < nfilter; ++i)
+            if (v == i) v = h_filter[i];
+        if (start < nfilter) rp.remap[start] = v;
+        else rp.unclassified = v;
+    }
+    const unsigned grid = grid_for(N * 32, 256, 148 * 8);
+    if (nfilter > 0) resolve_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(votes, N, C1, rp, labels);
+    else resolve_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(votes, N, C1, rp, labels);
+    return f3d_check_launch("f3d_resolve_labels");
+}

@@ -1,0 +1,223 @@
+"""PyTorch host plumbing over the libf3d C ABI: device buffers, streams and argument marshalling only -- all
+arithmetic of the label-fusion path runs in the CUDA kernels of csrc/.  Every function takes / returns torch CUDA
+tensors; the reference-shaped numpy API lives in the `Fusion3DSeg/` and `get3DSeg.py` mirrors next to this file.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DEPTH_F32_M, DEPTH_U16_MM, NSTATS, STAT_NAMES, F3dError, check, host_f64, load, ptr, require_cuda, stream_ptr
+
+
+def as_cuda(a, dtype=None) -> torch.Tensor:
+    dev = require_cuda()
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=dev, dtype=dtype) if (a.device != dev or (dtype is not None and a.dtype != dtype)) else a
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(dev)
+    return t.contiguous()
+
+
+def pack_points(points) -> torch.Tensor:
+    """[N,3] (numpy / torch, any float dtype) -> float32 [N,4] device tensor (x, y, z, 0), the float4 stream the
+    fused kernel reads.  The kernels' contract is float32 coordinates (exactly widened to fp64 in the exact path)."""
+    p = as_cuda(points)
+    if p.ndim != 2 or p.shape[1] not in (3, 4):
+        raise ValueError("points must be [N,3]")
+    if p.shape[1] == 4 and p.dtype == torch.float32:
+        return p
+    out = torch.zeros((p.shape[0], 4), dtype=torch.float32, device=p.device)
+    out[:, :3] = p[:, :3].to(torch.float32)
+    return out
+
+
+def points_are_float32(points) -> bool:
+    a = np.asarray(points)
+    return a.dtype == np.float32 or bool(np.array_equal(a, a.astype(np.float32).astype(a.dtype)))
+
+
+class FrameTable:
+    """Device table of per-frame pose / frustum / projection records (f3d_frames_setup).
+    Mirrors the state `Fusion.__init__` derives from `parse_rts` (Fusion3DSeg/fusion.py:94-103)."""
+
+    def __init__(self, K, width, height, wxyz, translations, max_depth):
+        load()
+        dev = require_cuda()
+        self.K = host_f64(K, 9)
+        self.W, self.H = int(width), int(height)
+        self.max_depth = float(max_depth)
+        q = torch.as_tensor(np.ascontiguousarray(np.asarray(wxyz, dtype=np.float64).reshape(-1, 4))).to(dev)
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(translations, dtype=np.float64).reshape(-1, 3))).to(dev)
+        if len(q) != len(t):
+            raise ValueError("wxyz and translations must have the same number of frames")
+        self.F = int(len(t))
+        nbytes = int(load().f3d_frame_table_bytes(max(self.F, 1)))
+        self.table = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if self.F:
+            check(load().f3d_frames_setup(ptr(self.K), self.W, self.H, ptr(q), ptr(t), self.F, self.max_depth,
+                                          ptr(self.table), stream_ptr()), "f3d_frames_setup")
+
+    def export(self):
+        dev = self.table.device
+        eyes = torch.empty((self.F, 3), dtype=torch.float64, device=dev)
+        look = torch.empty((self.F, 3), dtype=torch.float64, device=dev)
+        nrm = torch.empty((self.F, 4, 3), dtype=torch.float64, device=dev)
+        check(load().f3d_frames_export(ptr(self.table), self.F, ptr(eyes), ptr(look), ptr(nrm), stream_ptr()),
+              "f3d_frames_export")
+        return eyes, look, nrm
+
+
+def _depth_fmt(depth: torch.Tensor) -> int:
+    if depth.dtype == torch.uint16:
+        return DEPTH_U16_MM
+    if depth.dtype == torch.float32:
+        return DEPTH_F32_M
+    raise TypeError("depth must be uint16 (millimetres) or float32 (metres)")
+
+
+def new_stats() -> torch.Tensor:
+    return torch.zeros(NSTATS, dtype=torch.int64, device=require_cuda())
+
+
+def stats_dict(stats: torch.Tensor) -> dict:
+    v = stats.cpu().tolist()
+    return {n: int(v[i]) for i, n in enumerate(STAT_NAMES)}
+
+
+def fuse_project_vote(points4, table: FrameTable, depth, mask, nclasses1, radius=0.05, zmin=0.1, zmax=4.0, votes=None,
+                      accumulate=False, stats=None, audit=False, frame_begin=0, frame_end=None):
+    """Kernel (1).  depth / mask: [F', H, W] device tensors covering frames [frame_begin, frame_end)."""
+    frame_end = table.F if frame_end is None else frame_end
+    N = points4.shape[0]
+    if votes is None:
+        votes = torch.empty((N, nclasses1), dtype=torch.int32, device=points4.device)
+        accumulate = False
+    nf = frame_end - frame_begin
+    if nf > 0 and (depth.shape[0] != nf or mask.shape[0] != nf or tuple(depth.shape[1:]) != (table.H, table.W)
+                   or tuple(mask.shape[1:]) != (table.H, table.W)):
+        raise ValueError("depth / mask must be [frame_end-frame_begin, H, W]")
+    check(load().f3d_fuse_project_vote(
+        ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth) if nf else None,
+        _depth_fmt(depth) if nf else 0, ptr(mask) if nf else None, table.H, table.W, ptr(table.K), float(radius),
+        float(zmin), float(zmax), ptr(votes), int(nclasses1), int(bool(accumulate)), ptr(stats), int(bool(audit)),
+        stream_ptr()), "f3d_fuse_project_vote")
+    return votes
+
+
+def fuse_uv2pt(points4, table: FrameTable, depth, radius=0.05, zmin=0.1, zmax=4.0, stats=None, audit=False,
+               frame_begin=0, frame_end=None):
+    frame_end = table.F if frame_end is None else frame_end
+    nf = frame_end - frame_begin
+    uv2pt = torch.full((nf, table.H * table.W), -1, dtype=torch.int32, device=points4.device)
+    if nf:
+        check(load().f3d_fuse_uv2pt(ptr(points4), points4.shape[0], ptr(table.table), frame_begin, frame_end, ptr(depth),
+                                    _depth_fmt(depth), table.H, table.W, ptr(table.K), float(radius), float(zmin),
+                                    float(zmax), ptr(uv2pt), ptr(stats), int(bool(audit)), stream_ptr()), "f3d_fuse_uv2pt")
+    return uv2pt
+
+
+def zbuffer_splat(points4, table: FrameTable, border=0, stats=None, audit=False, frame_begin=0, frame_end=None,
+                  zbuf=None, out=None):
+    """Kernel (2): uint16-millimetre depth images [F', H, W] of the cloud seen from frames [frame_begin, frame_end)."""
+    frame_end = table.F if frame_end is None else frame_end
+    nf = frame_end - frame_begin
+    dev = points4.device
+    if zbuf is None:
+        zbuf = torch.empty((nf, table.H * table.W), dtype=torch.int32, device=dev)
+    if out is None:
+        out = torch.empty((nf, table.H, table.W), dtype=torch.uint16, device=dev)
+    if nf:
+        check(load().f3d_zbuffer_splat(ptr(points4), points4.shape[0], ptr(table.table), frame_begin, frame_end, table.H,
+                                       table.W, ptr(table.K), ptr(zbuf), ptr(out), int(border), ptr(stats),
+                                       int(bool(audit)), stream_ptr()), "f3d_zbuffer_splat")
+    return out
+
+
+def vote_uv2pt(votes_packed, uv2pt, mask, first_tag):
+    """Level V: uv2pt [F, HW] int32, mask [F, HW] uint8 (already at depth resolution), votes_packed [N, C1] int32."""
+    F, npix = uv2pt.shape
+    N, C1 = votes_packed.shape
+    check(load().f3d_vote_uv2pt(ptr(uv2pt), ptr(mask), F, npix, int(first_tag), ptr(votes_packed), N, C1, stream_ptr()),
+          "f3d_vote_uv2pt")
+    return votes_packed
+
+
+def vote_finalize(votes_packed):
+    check(load().f3d_vote_finalize(ptr(votes_packed), votes_packed.numel(), stream_ptr()), "f3d_vote_finalize")
+    return votes_packed
+
+
+def resize_nearest(masks, height, width):
+    """[n, sh, sw] uint8 -> [n, height, width] with OpenCV's INTER_NEAREST index rule."""
+    n, sh, sw = masks.shape
+    out = torch.empty((n, height, width), dtype=torch.uint8, device=masks.device)
+    check(load().f3d_resize_nearest_u8(ptr(masks), n, sh, sw, ptr(out), height, width, stream_ptr()),
+          "f3d_resize_nearest_u8")
+    return out
+
+
+def resolve_labels(votes, nclasses_id, threshold=0.5, filter_classes=None, out=None):
+    """Kernel (3): votes [N, C1] int32 -> int64 [N]."""
+    N, C1 = votes.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.int64, device=votes.device)
+    filt = None if filter_classes is None else np.ascontiguousarray(np.asarray(filter_classes, dtype=np.int32))
+    if filt is not None and filt.size == 0:
+        raise ValueError("filter_classes must not be empty")
+    check(load().f3d_resolve_labels(ptr(votes), N, C1, float(threshold), ptr(filt), 0 if filt is None else int(filt.size),
+                                    int(nclasses_id), ptr(out), stream_ptr()), "f3d_resolve_labels")
+    return out
+
+
+def project_pixels(points64, K, quat, translation):
+    p = as_cuda(points64, torch.float64)
+    N = p.shape[0]
+    uv = torch.empty((2, N), dtype=torch.int32, device=p.device)
+    check(load().f3d_project_pixels(ptr(p), N, ptr(host_f64(K, 9)), ptr(host_f64(quat, 4)), ptr(host_f64(translation, 3)),
+                                    ptr(uv), stream_ptr()), "f3d_project_pixels")
+    return uv
+
+
+def frustum_mask(points64, plane_points, normals):
+    p = as_cuda(points64, torch.float64)
+    N = p.shape[0]
+    pp, nn = host_f64(plane_points), host_f64(normals)
+    if pp.size != nn.size or pp.size % 3:
+        raise ValueError("plane_points / normals must both be [M,3]")
+    out = torch.empty(N, dtype=torch.uint8, device=p.device)
+    check(load().f3d_frustum_mask(ptr(p), N, ptr(pp), ptr(nn), pp.size // 3, ptr(out), stream_ptr()), "f3d_frustum_mask")
+    return out
+
+
+def box_pairs_aabb(lo, hi, group, cap=None):
+    """All i<j pairs of equal group whose closed AABBs overlap.  -> int32 [E,2] (unordered)."""
+    lo, hi = as_cuda(lo, torch.float64), as_cuda(hi, torch.float64)
+    group = as_cuda(group, torch.int32)
+    B = lo.shape[0]
+    cap = max(1024, 8 * B) if cap is None else cap
+    while True:
+        edges = torch.empty((cap, 2), dtype=torch.int32, device=lo.device)
+        count = torch.zeros(1, dtype=torch.int64, device=lo.device)
+        check(load().f3d_box_pairs_aabb(ptr(lo), ptr(hi), ptr(group), B, ptr(edges), cap, ptr(count), stream_ptr()),
+              "f3d_box_pairs_aabb")
+        n = int(count.item())
+        if n <= cap:
+            return edges[:n]
+        cap = n
+
+
+def union_find(nboxes, edges):
+    labels = torch.empty(nboxes, dtype=torch.int32, device=require_cuda())
+    E = 0 if edges is None else int(edges.shape[0])
+    check(load().f3d_union_find(int(nboxes), ptr(edges) if E else None, E, ptr(labels), stream_ptr()), "f3d_union_find")
+    return labels
+
+
+def obb_contains(points64, boxes15):
+    p = as_cuda(points64, torch.float64)
+    b = as_cuda(boxes15, torch.float64).reshape(-1, 15)
+    out = torch.empty((b.shape[0], p.shape[0]), dtype=torch.uint8, device=p.device)
+    check(load().f3d_obb_contains(ptr(p), p.shape[0], ptr(b), b.shape[0], ptr(out), stream_ptr()), "f3d_obb_contains")
+    return out

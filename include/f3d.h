@@ -1,0 +1,155 @@
+/*
+ * libf3d -- C ABI of the B200-native multi-view 2D->3D label-fusion path.
+ *
+ * The reference (raviraj988/3D-POINT-CLOUD-SEGMENTATION-USING-2D-IMG-SEGMENTATION) is pure Python and has no
+ * FFI; this header is the boundary a maintainer would bind with ctypes.  Each entry point
+ * cites the reference statement(s) it replaces (paths relative to the reference repository).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer borrowed from the caller (e.g. a torch tensor) unless its name starts
+ *    with `h_` (host).  The library never allocates, frees or retains caller memory and keeps no global
+ *    mutable state, so calls on different streams / devices may run concurrently.
+ *  - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued on it, nothing synchronises.
+ *  - return value: 0 = OK, < 0 = error; `f3d_last_error()` gives a thread-local message.
+ *  - there is no CPU fallback: without a CUDA device every compute call returns F3D_ERR_CUDA.
+ */
+#ifndef F3D_H_
+#define F3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F3D_OK 0
+#define F3D_ERR_ARG (-1)
+#define F3D_ERR_CUDA (-2)
+#define F3D_ERR_UNSUPPORTED (-3)
+
+/* depth image formats (per-frame [H,W] images, frames contiguous) */
+#define F3D_DEPTH_U16_MM 0 /* uint16 millimetres, RTAB export convention (RTAB_utils/ios_rtab.py:97-113,185) */
+#define F3D_DEPTH_F32_M 1  /* float32 metres (extension: the /1000 step of ios_rtab.py:185 is skipped)      */
+
+/* indices into the uint64 statistics block written by f3d_fuse_* (F3D_NSTATS entries, accumulated) */
+#define F3D_STAT_CANDIDATES 0 /* point-views that survived the conservative tile x frustum cull            */
+#define F3D_STAT_EXACT 1      /* point-views re-evaluated in fp64 (inside an fp32 uncertainty band)        */
+#define F3D_STAT_DIVERGED 2   /* of those, fp32 best guess != fp64 outcome (logged fp32-vs-fp64 divergence) */
+#define F3D_STAT_NEAR_EDGE 3  /* in-bounds point-views whose fp64 u or v is within 1e-4 px of an integer   */
+#define F3D_STAT_SEEN 4       /* point-views that passed visibility (votes cast / depth samples written)   */
+#define F3D_STAT_AUDIT_BAD 5  /* audit mode only: fp32 path certified an outcome that fp64 contradicts     */
+#define F3D_NSTATS 8
+
+const char* f3d_last_error(void);
+int f3d_version(void);
+
+/* ---- frame table -------------------------------------------------------------------------------------- */
+
+/* Bytes of packed per-frame data the caller must provide per frame to f3d_frames_setup. */
+int64_t f3d_frame_table_bytes(int32_t nframes);
+
+/* Builds the per-frame table on the device: fp64 pose / inverse pose / frustum planes in the reference's
+ * operation order (Fusion._get_frustum_data, Fusion3DSeg/fusion.py:119-132; camera_utils.py:60-171; planes
+ * fusion.py:254-258) plus fp32 projection tiles for the fast path.
+ *   h_K9      host, row-major 3x3 intrinsic (upper triangular)        camera_utils.py:14
+ *   wxyz      [F,4] float64 (w,x,y,z), NOT normalised                 fusion.py:71-72
+ *   trans     [F,3] float64
+ *   max_depth far-plane distance along the look-at ray                fusion.py:256 */
+int f3d_frames_setup(const double* h_K9, int32_t W, int32_t H, const double* wxyz, const double* trans,
+                     int32_t nframes, double max_depth, void* frame_table, void* stream);
+
+/* Copies the fp64 frustum data out of a frame table for inspection / parity tests:
+ * eyes [F,3], lookats [F,3], face_normals [F,4,3] (device float64). */
+int f3d_frames_export(const void* frame_table, int32_t nframes, double* eyes, double* lookats,
+                      double* face_normals, void* stream);
+
+/* ---- kernel (1): fused project + z-test + mask gather + vote (level P) ---------------------------------- */
+
+/* Replaces, for a FIXED cloud, the per-frame body of Fusion.fuse (fusion.py:248-298: point_inside_polyhedra
+ * -> points2pixel -> single-pixel criterion) composed with VotingSegmentation.vote (segUtils/voting.py:89-98).
+ *   points   [N] float4 (x,y,z,unused) -- float32 values are the contract (widened exactly to fp64)
+ *   depth    [F,H,W] uint16 mm or float32 m (depth_fmt); mask [F,H,W] uint8 class ids < C1
+ *   radius   criterion distance (fusion.py:225, strict <); zmin/zmax valid range (fusion.py:62-63: > / <=)
+ *   votes    [N,C1] int32, row-major like the reference's votes[npts, nclasses+1] (voting.py:34).
+ *            accumulate = 0: every cell is overwritten (no memset needed); 1: added to.
+ *   labels   optional [N] int64: if non-NULL the label resolve of f3d_resolve_labels is fused into the
+ *            epilogue (only meaningful when this call sees all frames, i.e. accumulate = 0)
+ *   stats    optional uint64[F3D_NSTATS], accumulated with atomics (caller zeroes)
+ *   flags    bit 0: audit mode (fp64 for every candidate, counts F3D_STAT_AUDIT_BAD) */
+int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                          int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
+                          int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
+                          int32_t* votes, int32_t C1, int32_t accumulate, uint64_t* stats, int32_t flags,
+                          void* stream);
+
+/* Same traversal, but writes the reference's exchange format instead of votes: uv2pt [F,H*W] int32,
+ * value = highest cloud-point index seen through the pixel, -1 = none (fusion.py:253,297,322).  The caller
+ * fills uv2pt with -1 first. */
+int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                   int32_t frame_end, const void* depth, int32_t depth_fmt, int32_t H, int32_t W,
+                   const double* h_K9, double radius, double zmin, double zmax, int32_t* uv2pt,
+                   uint64_t* stats, int32_t flags, void* stream);
+
+/* ---- kernel (2): z-buffer splat ----------------------------------------------------------------------------- */
+
+/* Depth images of the cloud itself: per pixel min over in-frustum points of camera z (the row points2pixel
+ * discards, camera_utils.py:23-24), quantised floor(z*1000+0.5) clamped to [1,65535].
+ *   zbuf   scratch [F,H*W] uint32 (the call initialises it);  depth_out [F,H,W] uint16, 0 = hole;
+ *   border: pixels closer than `border` to the image edge are zeroed (ios_rtab.py:105-109). */
+int f3d_zbuffer_splat(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                      int32_t frame_end, int32_t H, int32_t W, const double* h_K9, uint32_t* zbuf,
+                      uint16_t* depth_out, int32_t border, uint64_t* stats, int32_t flags, void* stream);
+
+/* ---- level V: uv2pt + mask vote --------------------------------------------------------------------------------- */
+
+/* VotingSegmentation.vote for a batch of frames (segUtils/voting.py:89-98): votes[uv2pt[i], mask[i]] += 1 with
+ * numpy's per-frame collapse of duplicate (point, class) pairs.  `votes_packed` [N,C1] uint32 holds
+ * (frame_tag << 16 | count) while accumulating; frame tags first_tag .. first_tag+F-1 must stay in 1..65535
+ * and increase across calls.  Call f3d_vote_finalize to strip the tags. */
+int f3d_vote_uv2pt(const int32_t* uv2pt, const uint8_t* mask, int32_t nframes, int64_t npix, int32_t first_tag,
+                   uint32_t* votes_packed, int64_t N, int32_t C1, void* stream);
+int f3d_vote_finalize(uint32_t* votes_packed, int64_t ncells, void* stream);
+
+/* cv2.resize(mask, (w, h), INTER_NEAREST) (voting.py:93) for a batch of uint8 images. */
+int f3d_resize_nearest_u8(const uint8_t* src, int32_t nimg, int32_t src_h, int32_t src_w, uint8_t* dst,
+                          int32_t dst_h, int32_t dst_w, void* stream);
+
+/* ---- kernel (3): label resolve ------------------------------------------------------------------------------------ */
+
+/* VotingSegmentation.segment (segUtils/voting.py:106-137): total over all C1 columns, first arg-max over the
+ * filter columns (in the given order; NULL/0 = all columns), max/total < threshold (float64) or max == 0 or
+ * total == 0 -> nclasses_id, then the sequential index->class remap with its aliasing.
+ *   h_filter host int32[nfilter];  labels [N] int64. */
+int f3d_resolve_labels(const int32_t* votes, int64_t N, int32_t C1, double threshold, const int32_t* h_filter,
+                       int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream);
+
+/* ---- single-call projection / cull operators (a-1, a-4) ----------------------------------------------------------- */
+
+/* points2pixel (Fusion3DSeg/camera_utils.py:9-26): uv [2,N] int32, evaluated in fp64. points [N,3] float64. */
+int f3d_project_pixels(const double* points, int64_t N, const double* h_K9, const double* h_wxyz,
+                       const double* h_t, int32_t* uv, void* stream);
+
+/* point_inside_polyhedra (Fusion3DSeg/intersections.py:146-164): inside [N] uint8. */
+int f3d_frustum_mask(const double* points, int64_t N, const double* h_plane_points, const double* h_normals,
+                     int32_t nplanes, uint8_t* inside, void* stream);
+
+/* ---- kernel (4): instance-box merge -------------------------------------------------------------------------------- */
+
+/* Closed-interval AABB overlap of check_intersection (merge_intersecting_bb.py:49-53) over all pairs i<j
+ * with equal group id.  edges [cap,2] int32, *count = number found (may exceed cap: then re-run larger). */
+int f3d_box_pairs_aabb(const double* lo, const double* hi, const int32_t* group, int32_t B, int32_t* edges,
+                       int64_t cap, unsigned long long* count, void* stream);
+
+/* Union-find closure: labels[i] = smallest box index of i's connected component. */
+int f3d_union_find(int32_t B, const int32_t* edges, int64_t E, int32_t* labels, void* stream);
+
+/* Open3D OrientedBoundingBox.get_point_indices_within_bounding_box rule (merge_intersecting_bb.py:76,87):
+ * inside [nboxes, N] uint8 for boxes [nboxes,15] float64 = centre[3], R[9] (row major, columns = axes),
+ * extent[3] (device). */
+int f3d_obb_contains(const double* points, int64_t N, const double* boxes15, int32_t nboxes,
+                     uint8_t* inside, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F3D_H_ */

@@ -1,0 +1,284 @@
+"""GPU parity tests: the CUDA path (called through the C ABI) against the golden vectors produced by the unmodified
+reference and against the numpy oracle on seeded scenes.  Integer outcomes must be bit-exact."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG_NAME, load_golden, small_scene
+from oracle import f3d_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# frame table, projection, cull (a-1, a-3, a-4)
+# ---------------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tag", ["640", "1920", "3840"])
+def test_frame_table_matches_oracle_bitwise(engine, tag):
+    g = load_golden(f"g1_{tag}")
+    W, H = int(g["W"]), int(g["H"])
+    tab = engine.FrameTable(g["K"], W, H, g["wxyz"], g["t"], 4.0)
+    eyes, look, nrm = [x.cpu().numpy() for x in tab.export()]
+    oe, ol, on = orc.frustum_data(g["K"], W, H, g["wxyz"], g["t"])
+    assert np.array_equal(eyes, oe) and np.array_equal(look, ol) and np.array_equal(nrm, on)
+    # and the reference's own numbers up to its BLAS rounding
+    np.testing.assert_allclose(nrm, g["face_normals"], rtol=0, atol=4e-16)
+
+
+@pytest.mark.parametrize("tag", ["640", "1920", "3840"])
+def test_points2pixel_and_cull_golden(engine, tag):
+    cam = importlib.import_module(PKG_NAME + ".Fusion3DSeg.camera_utils")
+    isec = importlib.import_module(PKG_NAME + ".Fusion3DSeg.intersections")
+    g = load_golden(f"g1_{tag}")
+    p = g["points"].astype(np.float64)
+    K, W, H = g["K"], int(g["W"]), int(g["H"])
+    for j in range(len(g["t"])):
+        uv = cam.points2pixel(p, K, g["wxyz"][j], g["t"][j])
+        assert uv.dtype == np.int32 and uv.shape == (2, len(p))
+        with np.errstate(all="ignore"):
+            ouv = orc.points2pixel(p, K, g["wxyz"][j], g["t"][j])
+        assert np.array_equal(uv, ouv)                              # everywhere, including behind the camera
+        _, _, h2 = orc.project_homogeneous(p, K, g["wxyz"][j], g["t"][j])
+        front = h2 > 1e-3
+        assert np.array_equal(uv[:, front], g["uv"][j][:, front])   # the reference's output
+        pp, pn = orc.frame_planes(g["eyes"][j], g["lookats"][j], g["face_normals"][j], 4.0)
+        inside = isec.point_inside_polyhedra(p, pp, pn)
+        assert inside.dtype == bool and np.array_equal(inside, g["inside"][j])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# kernel (1) fused project + z-test + gather + vote, uv2pt writer
+# ---------------------------------------------------------------------------------------------------------------------
+
+def run_fused(engine, s, depth=None, radius=0.05, zmin=0.1, zmax=None, audit=False, chunks=None, nclasses1=134):
+    zmax = s["zmax"] if zmax is None else zmax
+    tab = engine.FrameTable(s["K"], s["W"], s["H"], s["wxyz"], s["t"], zmax)
+    p4 = engine.pack_points(s["points"])
+    d = dev(s["depths"] if depth is None else depth)
+    m = dev(s["masks"])
+    stats = engine.new_stats()
+    F = len(s["t"])
+    if chunks is None:
+        votes = engine.fuse_project_vote(p4, tab, d, m, nclasses1, radius, zmin, zmax, stats=stats, audit=audit)
+    else:
+        votes = None
+        for (a, b) in chunks:
+            votes = engine.fuse_project_vote(p4, tab, d[a:b], m[a:b], nclasses1, radius, zmin, zmax, votes=votes,
+                                             accumulate=votes is not None, stats=stats, audit=audit, frame_begin=a,
+                                             frame_end=b)
+    torch.cuda.synchronize()
+    return votes.cpu().numpy(), engine.stats_dict(stats), tab, p4
+
+
+def test_level_p_golden(engine):
+    g = load_golden("g2_levelp")
+    s = dict(points=g["points"], K=g["K"], W=int(g["W"]), H=int(g["H"]), wxyz=g["wxyz"], t=g["t"], depths=g["depths"],
+             masks=g["masks"], zmax=float(g["zmax"]))
+    votes, st, tab, p4 = run_fused(engine, s)
+    assert votes.dtype == np.int32 and np.array_equal(votes, g["votes"])
+    assert st["seen"] == int(g["votes"].sum()) and st["audit_bad"] == 0
+    votes_a, st_a, _, _ = run_fused(engine, s, audit=True)
+    assert np.array_equal(votes_a, g["votes"]) and st_a["audit_bad"] == 0
+    uv2pt = engine.fuse_uv2pt(p4, tab, dev(g["depths"]), 0.05, 0.1, 4.0).cpu().numpy()
+    assert np.array_equal(uv2pt, g["uv2pt"])
+    lab = engine.resolve_labels(dev(votes), 133, 0.5, [86, 114, 115]).cpu().numpy()
+    assert lab.dtype == np.int64 and np.array_equal(lab, g["seg_default"])
+    assert np.array_equal(engine.resolve_labels(dev(votes), 133, 0.5, None).cpu().numpy(), g["seg_all"])
+
+
+@pytest.mark.parametrize("W,H,N,F,seed", [(160, 120, 30000, 6, 7), (640, 480, 50001, 5, 11), (1920, 1440, 40000, 4, 13),
+                                          (3840, 2160, 40000, 3, 17), (64, 48, 255, 3, 19), (64, 48, 1, 2, 23)])
+def test_level_p_vs_oracle(engine, scenes, W, H, N, F, seed):
+    s = small_scene(scenes, orc, npoints=N, nframes=F, width=W, height=H, seed=seed, border=2, block=16)
+    ost = {}
+    ov = orc.fuse_project_vote(s["points"], s["K"], W, H, s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0, 0.05, 0.1,
+                               s["zmax"], s["zmax"], stats=ost)
+    votes, st, _, _ = run_fused(engine, s)
+    assert np.array_equal(votes, ov)
+    assert st["near_edge"] == ost.get("near_edge_1e-4", 0)          # boundary points are counted exactly
+    assert st["seen"] == int(ov.sum())
+    votes_a, st_a, _, _ = run_fused(engine, s, audit=True)
+    assert np.array_equal(votes_a, ov) and st_a["audit_bad"] == 0   # fp32 never certifies a wrong outcome
+    if N > 1000:
+        assert ov.sum() > 0 and st["exact"] < 0.2 * max(st["candidates"], 1)
+
+
+def test_level_p_float32_depth_and_thresholds(engine, scenes):
+    s = small_scene(scenes, orc, npoints=30000, nframes=5, width=320, height=240, seed=29, border=0)
+    dm = (s["depths"].astype(np.float32) * np.float32(0.001)).astype(np.float32)
+    for radius, zmin, zmax in [(0.05, 0.1, 4.0), (0.004, 0.5, 2.5), (0.3, 0.0, 3.0)]:
+        ov = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], dm, s["masks"], 134, 1, radius,
+                                   zmin, zmax, 4.0)
+        tab = engine.FrameTable(s["K"], s["W"], s["H"], s["wxyz"], s["t"], 4.0)
+        votes = engine.fuse_project_vote(engine.pack_points(s["points"]), tab, dev(dm), dev(s["masks"]), 134, radius, zmin,
+                                         zmax).cpu().numpy()
+        assert np.array_equal(votes, ov)
+        ov16 = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0,
+                                     radius, zmin, zmax, 4.0)
+        v16 = engine.fuse_project_vote(engine.pack_points(s["points"]), tab, dev(s["depths"]), dev(s["masks"]), 134, radius,
+                                       zmin, zmax).cpu().numpy()
+        assert np.array_equal(v16, ov16)
+
+
+def test_level_p_chunked_accumulate_and_empty(engine, scenes):
+    s = small_scene(scenes, orc, npoints=20000, nframes=7, width=160, height=120, seed=31)
+    full, _, tab, p4 = run_fused(engine, s)
+    a, _, _, _ = run_fused(engine, s, chunks=[(0, 3), (3, 7)])
+    b, _, _, _ = run_fused(engine, s, chunks=[(4, 7), (0, 2), (2, 4)])      # votes commute over frames
+    assert np.array_equal(full, a) and np.array_equal(full, b)
+    # zero frames: vote tensor is overwritten with zeros (no memset needed by the caller)
+    z = torch.full((len(s["points"]), 134), 7, dtype=torch.int32, device="cuda")
+    engine.fuse_project_vote(p4, tab, dev(s["depths"][:0]), dev(s["masks"][:0]), 134, votes=z, accumulate=False,
+                             frame_begin=0, frame_end=0)
+    assert int(z.abs().sum()) == 0
+    # all-zero depth (no valid pixel) -> no votes
+    v0 = engine.fuse_project_vote(p4, tab, dev(np.zeros_like(s["depths"])), dev(s["masks"]), 134).cpu().numpy()
+    assert v0.sum() == 0
+
+
+def test_unsorted_cloud_same_votes(engine, scenes):
+    s = small_scene(scenes, orc, npoints=20000, nframes=4, width=160, height=120, seed=37)
+    base, _, _, _ = run_fused(engine, s)
+    perm = np.random.default_rng(0).permutation(len(s["points"]))
+    s2 = dict(s, points=np.ascontiguousarray(s["points"][perm]))
+    shuf, _, _, _ = run_fused(engine, s2)
+    assert np.array_equal(shuf, base[perm])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# kernel (2) z-buffer splat
+# ---------------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("W,H,N,F,seed", [(160, 120, 30000, 5, 41), (1920, 1440, 30000, 2, 43), (96, 64, 60000, 3, 47)])
+def test_zbuffer_splat_vs_oracle(engine, scenes, W, H, N, F, seed):
+    s = small_scene(scenes, orc, npoints=N, nframes=F, width=W, height=H, seed=seed, border=3)
+    tab = engine.FrameTable(s["K"], W, H, s["wxyz"], s["t"], s["zmax"])
+    st = engine.new_stats()
+    d = engine.zbuffer_splat(engine.pack_points(s["points"]), tab, border=3, stats=st).cpu().numpy()
+    assert d.dtype == np.uint16 and np.array_equal(d, s["depths"])
+    d_a = engine.zbuffer_splat(engine.pack_points(s["points"]), tab, border=3, stats=st, audit=True).cpu().numpy()
+    assert np.array_equal(d_a, s["depths"]) and engine.stats_dict(st)["audit_bad"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# level V vote + resize, kernel (3) resolve
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_level_v_golden_through_reference_class(engine, tmp_path):
+    import cv2
+    voting = importlib.import_module(PKG_NAME + ".Fusion3DSeg.segUtils.voting")
+    g = load_golden("g3_levelv")
+    H, W = int(g["H"]), int(g["W"])
+    (tmp_path / "masks").mkdir()
+    (tmp_path / "uv2pt").mkdir()
+    for f in range(len(g["uv2pt"])):
+        np.save(tmp_path / "uv2pt" / f"{f + 1}.npy", g["uv2pt"][f])
+        cv2.imwrite(str(tmp_path / "masks" / f"{f + 1}.png"), g["masks_big"][f])
+    voter = voting.VotingSegmentation(int(g["npts"]), (H, W), tmp_path / "masks", tmp_path / "uv2pt", 133)
+    assert voter.nframes == len(g["uv2pt"]) and voter.votes.shape == (int(g["npts"]), 134)
+    v = voter.vote(resize=True, filename=tmp_path / "seg" / "votes.npy")
+    assert v.dtype == np.float64 and np.array_equal(v, g["votes"].astype(np.float64))
+    assert np.array_equal(np.load(tmp_path / "seg" / "votes.npy"), v)
+    cases = {"seg_default": (0.5, [86, 114, 115]), "seg_all": (0.5, None), "seg_t075": (0.75, None),
+             "seg_alias": (0.3, [1, 0, 5]), "seg_t0": (0.0, [3, 2, 1, 0])}
+    for k, (thr, fc) in cases.items():
+        out = voter.segment(thr, fc)
+        assert out.dtype == np.int64 and np.array_equal(out, g[k]), k
+    # votes= argument, votes_file constructor (nclasses quirk: 134 when loaded, voting.py:40)
+    assert np.array_equal(voter.segment(0.5, None, votes=v), g["seg_all"])
+    v2 = voting.VotingSegmentation(None, None, None, None, None, votes_file=tmp_path / "seg" / "votes.npy")
+    assert v2.nclasses == 134
+    ref_quirk = orc.segment(g["votes"], 134, 0.75, None)
+    assert np.array_equal(v2.segment(0.75, None), ref_quirk)
+    # second vote() call accumulates like the reference (votes double)
+    voter.vote(resize=True)
+    assert np.array_equal(voter.votes, 2.0 * g["votes"])
+    voter.zero()
+    assert voter.votes.sum() == 0
+
+
+def test_resize_nearest_golden(engine):
+    g = load_golden("g4_resize")
+    for k in range(4):
+        d = g[f"dst{k}"]
+        out = engine.resize_nearest(dev(g[f"src{k}"][None]), d.shape[0], d.shape[1]).cpu().numpy()[0]
+        assert np.array_equal(out, d)
+
+
+def test_level_v_dedup_random(engine):
+    rng = np.random.default_rng(5)
+    N, C1, F, npix = 5000, 134, 9, 40000
+    uv = rng.integers(-1, 600, (F, npix)).astype(np.int32)            # heavy duplication: 600 points, 40k pixels
+    uv[rng.random((F, npix)) < 0.3] = -1
+    mask = rng.integers(0, 6, (F, npix)).astype(np.uint8)
+    ov = np.zeros((N, C1), np.int64)
+    for f in range(F):
+        orc.vote_uv2pt(ov, uv[f], mask[f])
+    packed = torch.zeros((N, C1), dtype=torch.int32, device="cuda")
+    engine.vote_uv2pt(packed, dev(uv), dev(mask), 1)
+    engine.vote_finalize(packed)
+    assert np.array_equal(packed.cpu().numpy(), ov)
+    assert ov.max() == F
+
+
+def test_resolve_random_vs_oracle(engine):
+    rng = np.random.default_rng(9)
+    N, C1 = 20011, 134
+    votes = np.zeros((N, C1), np.int32)
+    nz = rng.random((N, C1)) < 0.03
+    votes[nz] = rng.integers(1, 6, nz.sum())
+    votes[:500] = 0                                                   # unvoted points
+    votes[500:700, 133] = 9                                           # mostly "unclassified" votes
+    votes[700:900, [3, 7]] = 4                                        # exact ties -> first maximum
+    dv = dev(votes)
+    for thr in (0.0, 0.5, 0.75, 1.0):
+        for fc in (None, [86, 114, 115], [1, 0], [7, 3], [5, 5, 2], list(range(133, -1, -1)), [133]):
+            for ncls in (133, 134, 2):
+                ref = orc.segment(votes, ncls, thr, fc)
+                out = engine.resolve_labels(dv, ncls, thr, fc).cpu().numpy()
+                assert np.array_equal(out, ref), (thr, fc, ncls)
+    # a narrow vote matrix and a single row
+    small = rng.integers(0, 3, (7, 5)).astype(np.int32)
+    assert np.array_equal(engine.resolve_labels(dev(small), 4, 0.4, None).cpu().numpy(), orc.segment(small, 4, 0.4, None))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# kernel (4) box pairs + union-find
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_box_merge_vs_oracle(engine, scenes):
+    lo, hi, group, _ = scenes.make_boxes(4000, seed=3, extent=(40.0, 40.0, 6.0), ngroups=4)
+    lo[10], hi[10] = lo[11].copy(), lo[11].copy() + 0.0               # degenerate box touching a corner (closed test)
+    group[10] = group[11]
+    oe = orc.box_pairs_aabb(lo, hi, group)
+    assert len(oe) > 500
+    e = engine.box_pairs_aabb(lo, hi, group, cap=16)                   # forces the grow-and-retry path
+    es = np.unique(e.cpu().numpy().astype(np.int64), axis=0)
+    assert len(es) == len(e) and np.array_equal(es, oe)
+    lab = engine.union_find(len(lo), e).cpu().numpy()
+    assert np.array_equal(lab, orc.union_find_labels(len(lo), oe))
+    assert np.array_equal(engine.union_find(5, None).cpu().numpy(), np.arange(5))
+
+
+def test_obb_contains_vs_oracle(engine):
+    rng = np.random.default_rng(2)
+    pts = rng.normal(0, 1.0, (20000, 3))
+    boxes = []
+    for _ in range(5):
+        A = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        boxes.append(np.concatenate([rng.normal(0, 0.3, 3), A.reshape(-1), rng.uniform(0.5, 2.0, 3)]))
+    boxes = np.stack(boxes)
+    out = engine.obb_contains(pts, boxes).cpu().numpy().astype(bool)
+    for b in range(5):
+        ref = orc.obb_contains(boxes[b, :3], boxes[b, 3:12].reshape(3, 3), boxes[b, 12:], pts)
+        assert np.array_equal(out[b], ref)

@@ -367,9 +367,10 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P)
         int j = tid / P.C1, c = tid - j * P.C1;
         const int dj = FUSE_BLOCK / P.C1, dc = FUSE_BLOCK - dj * P.C1;
         for (int e = tid; e < total; e += FUSE_BLOCK) {
-            int v = hist[c * HS + j];
-            if (P.accumulate) v += out[e];
-            out[e] = v;
+            const int v = hist[c * HS + j];
+            // accumulate mode touches only the (sparse) non-zero cells; overwrite mode writes every cell once
+            if (!P.accumulate) out[e] = v;
+            else if (v) out[e] += v;
             j += dj;
             c += dc;
             if (c >= P.C1) {

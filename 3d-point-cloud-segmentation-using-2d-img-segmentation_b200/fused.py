@@ -82,3 +82,57 @@ def fuse_labels(points, K, width, height, wxyz, translations, depths, masks, poi
     if return_votes:
         return fl.votes_numpy(), labels
     return labels
+
+
+def _pin(a):
+    """numpy / torch host array -> pinned torch tensor (no copy if already pinned)."""
+    t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(a))
+    return t if t.is_pinned() else t.pin_memory()
+
+
+def vote_stream(fl: FusedLabeler, host_depths, host_masks, chunk_frames=64, frame_begin=0):
+    """Streaming ingest: frames live in (ideally pinned) HOST memory and are copied to the device in chunks on a
+    copy stream while the previous chunk is being fused on the compute stream (two staging buffers).  This is
+    the end-to-end path bench.py times: host->device copies are inside the call."""
+    F = int(host_depths.shape[0])
+    dev = fl.points4.device
+    compute = torch.cuda.current_stream()
+    copy = torch.cuda.Stream(device=dev)
+    hd = host_depths if isinstance(host_depths, torch.Tensor) else torch.as_tensor(host_depths)
+    hm = host_masks if isinstance(host_masks, torch.Tensor) else torch.as_tensor(host_masks)
+    nb = 2
+    cf = max(1, min(chunk_frames, F))
+    dbuf = [torch.empty((cf,) + tuple(hd.shape[1:]), dtype=hd.dtype, device=dev) for _ in range(nb)]
+    mbuf = [torch.empty((cf,) + tuple(hm.shape[1:]), dtype=torch.uint8, device=dev) for _ in range(nb)]
+    ready = [torch.cuda.Event() for _ in range(nb)]
+    free = [torch.cuda.Event() for _ in range(nb)]
+    for e in free:
+        e.record(compute)
+    k = 0
+    for a in range(0, F, cf):
+        b = min(a + cf, F)
+        s = k % nb
+        with torch.cuda.stream(copy):
+            copy.wait_event(free[s])
+            dbuf[s][: b - a].copy_(hd[a:b], non_blocking=True)
+            mbuf[s][: b - a].copy_(hm[a:b], non_blocking=True)
+            ready[s].record(copy)
+        compute.wait_event(ready[s])
+        fl.vote(dbuf[s][: b - a], mbuf[s][: b - a], frame_begin=frame_begin + a, frame_end=frame_begin + b)
+        free[s].record(compute)
+        k += 1
+    return fl.votes
+
+
+def fuse_labels_from_host(points, K, width, height, wxyz, translations, host_depths, host_masks,
+                          point_range=(0.1, 4.0), radius=0.05, nclasses=133, threshold=0.5, filter_classes=None,
+                          chunk_frames=64):
+    """Public end-to-end call: everything starts in host memory, labels (int64 [N]) come back to host memory.
+    Votes stay on the device (fetch them with `FusedLabeler.votes_numpy()` when needed)."""
+    fl = FusedLabeler(points, K, width, height, wxyz, translations, point_range, radius, nclasses)
+    vote_stream(fl, host_depths, host_masks, chunk_frames)
+    labels = fl.segment(threshold, filter_classes)
+    out = torch.empty(labels.shape, dtype=labels.dtype, pin_memory=True)
+    out.copy_(labels, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out.numpy(), fl

@@ -1,22 +1,29 @@
-// Kernel (1) fused project + z-test + mask gather + vote, kernel (2) z-buffer splat and the uv2pt writer.
+// Kernel (1) fused project + z-test + mask gather + vote (+ optional fused label resolve), kernel (2) z-buffer splat
+// and the uv2pt writer.
 //
 // Replaces, for a fixed cloud, the per-frame body of Fusion.fuse (Fusion3DSeg/fusion.py:248-298:
 // point_inside_polyhedra intersections.py:146-164 -> points2pixel camera_utils.py:9-26 -> single-pixel
-// `criterion` fusion.py:223-228) composed with VotingSegmentation.vote (segUtils/voting.py:89-98).
+// `criterion` fusion.py:223-228) composed with VotingSegmentation.vote (segUtils/voting.py:89-98) and, when asked,
+// VotingSegmentation.segment (segUtils/voting.py:106-137).
 //
 // Design (point-stationary, B200):
 //   * one CTA owns a tile of BLOCK consecutive points (float4, coalesced 16 B/thread); a thread keeps its point
 //     in registers for the whole launch, so the cloud is streamed from HBM exactly once;
 //   * the tile's axis-aligned box is tested conservatively against every frame's five frustum planes (fp32 with
 //     an explicit rounding margin); surviving frame ids are compacted into shared memory.  With a spatially
-//     sorted cloud this skips ~90 % of the nominal point-views without changing any result;
-//   * candidate frames' 128-byte fp32 projection tiles are staged into shared memory in batches and broadcast;
+//     sorted cloud this skips ~97 % of the nominal point-views without changing any result;
+//   * candidate frames' 128-byte fp32 projection tiles are staged into shared memory with TMA bulk copies
+//     (cp.async.bulk + mbarrier, double buffered) and broadcast to the threads;
+//   * candidates are processed NB at a time: all NB projections first, then all NB depth + mask gathers are
+//     issued together (memory-level parallelism: one DRAM round trip per NB candidates instead of 2 per candidate),
+//     then the distance tests and histogram updates;
 //   * per point-view the fp32 path carries a rigorous rounding bound; any decision (frustum, pixel floor, depth
 //     distance) that falls inside its bound is re-evaluated by `exact_eval` in fp64 in the reference's operation
 //     order, so every integer outcome is bit-exact against the numpy path.  Both the population of that band
 //     and every fp32-vs-fp64 divergence inside it are counted;
-//   * votes are accumulated in a per-CTA shared-memory histogram (uint16 [C1][BLOCK], conflict-free: a thread
-//     owns its point's column) and written to HBM exactly once, coalesced -- no global atomics, no memset.
+//   * votes are accumulated in a per-CTA shared-memory histogram (uint16 [BLOCK][RS], a thread owns its point's
+//     row; RS/2 odd => conflict-free) and written to HBM exactly once with 16-byte stores -- no global atomics,
+//     no memset.  The label resolve can run straight from that histogram.
 #include "f3d_common.cuh"
 #include "f3d_host.h"
 
@@ -25,9 +32,18 @@
 #define MODE_UV2PT 2
 
 #define FUSE_BLOCK 256
-#define FUSE_FCHUNK 1024  // frames culled per pass (candidate list capacity)
-#define FUSE_STAGE 16     // FrameFast tiles staged per batch (2 KB)
-#define HIST_PAD 2
+#define FUSE_FCHUNK 512   // frames culled per pass (candidate list capacity)
+#define FUSE_STAGE 16     // FrameFast tiles per staging buffer (2 KB); two buffers
+#define FUSE_NB 8         // candidates whose gathers are in flight together
+#define RES_MAXC 256
+
+struct FuseResolve {
+    int enabled, nfilter;
+    int32_t unclassified;
+    double threshold;
+    int16_t fpos[RES_MAXC];        // column -> first position in the filter list (or column itself), -1 = not considered
+    int32_t remap[RES_MAXC];       // arg-max position -> label (sequential remap of voting.py:133-135 composed)
+};
 
 struct FuseParams {
     const float4* points;
@@ -39,14 +55,14 @@ struct FuseParams {
     int H, W;
     double K[9];
     float cx, cy, inv_fx, inv_fy;
-    float dunit;            // depth sample -> metres (0.001 for uint16 mm, 1 for float32 m)
     float radius;
     double radius_d, zmin, zmax;
     uint32_t d_lo, d_hi;    // uint16 depth: valid <=> d_lo <= d <= d_hi   (fusion.py:62-63 on d/1000)
     int32_t* votes;
-    int C1, accumulate;
+    int C1, RS, accumulate;
     int32_t* uv2pt;
     uint32_t* zbuf;
+    int64_t* labels;
     unsigned long long* stats;
     int audit;
 };
@@ -113,16 +129,172 @@ __device__ __forceinline__ uint32_t quantise_mm(double z) {
     return (uint32_t)q;
 }
 
+// ---- mbarrier / TMA bulk-copy helpers (cp.async.bulk: SASS UBLKCP) -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// classification of one point-view by the fp32 path
+//   st: 0 = certainly not seen, 1 = pixel certified (depth test pending), 2 = unsure -> fp64
+struct Cls {
+    int st, g_in;
+    uint32_t puv;   // fu | fv << 16 when st != 0
+    float z;
+};
+
+__device__ __forceinline__ Cls classify(const float4* __restrict__ s, const float4 pt, const float fW, const float fH) {
+    Cls c;
+    c.st = 0;
+    c.g_in = 0;
+    c.puv = 0;
+    c.z = 0.f;
+    const float4 A0 = s[0], A1 = s[1];
+    const float d0 = (pt.x - A0.x) - A1.x;
+    const float d1 = (pt.y - A0.y) - A1.y;
+    const float d2 = (pt.z - A0.z) - A1.z;
+    const float S = fabsf(d0) + fabsf(d1) + fabsf(d2) + 1.0e-9f;
+    const float4 Mz = s[4];
+    const float z = fmaf(Mz.x, d0, fmaf(Mz.y, d1, Mz.z * d2));
+    const float ez = 8.0f * F3D_U24 * Mz.w * S;
+    c.z = z;
+    if (z < -16.0f * ez) return c;
+    if (z <= 16.0f * ez) {
+        c.st = 2;
+        return c;
+    }
+    const float4 Mu = s[2], Mv = s[3];
+    const float a = fmaf(Mu.x, d0, fmaf(Mu.y, d1, Mu.z * d2));
+    const float b = fmaf(Mv.x, d0, fmaf(Mv.y, d1, Mv.z * d2));
+    const float r = __frcp_rn(z);
+    const float u = a * r, v = b * r;
+    const float ea = 8.0f * F3D_U24 * Mu.w * S, eb = 8.0f * F3D_U24 * Mv.w * S;
+    const float eu = 1.125f * (ea + fabsf(u) * ez) * r + 8.0f * F3D_U24 * fabsf(u) + 1.0e-4f;
+    const float ev = 1.125f * (eb + fabsf(v) * ez) * r + 8.0f * F3D_U24 * fabsf(v) + 1.0e-4f;
+    const float sl = fmaf(s[5].w, d0, fmaf(s[6].w, d1, s[7].w * d2));   // (p - eye) . lookat
+    const float es = 8.0f * F3D_U24 * S + 1.0e-6f * A1.w;
+    if ((u + eu < 0.f) || (u - eu >= fW) || (v + ev < 0.f) || (v - ev >= fH) || (sl - es > A1.w)) return c;
+    const float fu = floorf(u), fv = floorf(v);
+    const bool cu = (u - fu >= eu) && (fu + 1.0f - u > eu);
+    const bool cv = (v - fv >= ev) && (fv + 1.0f - v > ev);
+    const bool cf = (sl + es < A1.w);
+    c.g_in = (u >= 0.f) && (fu < fW) && (v >= 0.f) && (fv < fH) && (sl < A1.w);
+    const int iu = min(max((int)fu, 0), 65535), iv = min(max((int)fv, 0), 65535);
+    c.puv = (uint32_t)iu | ((uint32_t)iv << 16);
+    c.st = (cu && cv && cf) ? 1 : 2;
+    return c;
+}
+
+// fp32 single-pixel criterion ||modPoints[pix] - p|| < radius in metric camera space, with its rounding band.
+//   returns 1 = certainly inside, 0 = certainly outside, 3 = inside the band (g = fp32 guess)
+__device__ __forceinline__ int distance_test(const float4* __restrict__ s, const float4 pt, const uint32_t puv, const float dm,
+                                             const FuseParams& P, int& g) {
+    const float4 A0 = s[0], A1 = s[1];
+    const float d0 = (pt.x - A0.x) - A1.x;
+    const float d1 = (pt.y - A0.y) - A1.y;
+    const float d2 = (pt.z - A0.z) - A1.z;
+    const float S = fabsf(d0) + fabsf(d1) + fabsf(d2) + 1.0e-9f;
+    const float4 R0 = s[5], R1 = s[6], R2 = s[7];
+    const float X = fmaf(R0.x, d0, fmaf(R0.y, d1, R0.z * d2));
+    const float Y = fmaf(R1.x, d0, fmaf(R1.y, d1, R1.z * d2));
+    const float Z = fmaf(R2.x, d0, fmaf(R2.y, d1, R2.z * d2));
+    const float ds = dm * A0.w;                                   // depth scaled by |q|^2 (un-normalised rotate)
+    const float xn = ((float)(puv & 0xffffu) - P.cx) * P.inv_fx, yn = ((float)(puv >> 16) - P.cy) * P.inv_fy;
+    const float qx = X - xn * ds, qy = Y - yn * ds, qz = Z - ds;
+    const float dist2 = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
+    const float del = 16.0f * F3D_U24 * (S + ds * (1.0f + fabsf(xn) + fabsf(yn)));
+    const float rlo = fmaxf(P.radius - del, 0.f), rhi = P.radius + del;
+    g = dist2 < P.radius * P.radius;
+    if (dist2 < rlo * rlo * (1.0f - 16.0f * F3D_U24)) return 1;
+    if (dist2 > rhi * rhi * (1.0f + 16.0f * F3D_U24)) return 0;
+    return 3;
+}
+
+// One deferred (uncertain) point-view: evaluated in fp64 after the fp32 sweep, one queue entry per thread, so the
+// expensive exact path runs with full warps instead of one or two live lanes per warp.
+//   w0 = owner thread | frame (relative) << 16 ;  w1 = pixel guess (26 bits) | g_in/zq-low ... see pack below
+struct Deferred {
+    uint32_t w0, w1, w2;
+};
+#define FUSE_QCAP 176   // deferred entries per CTA (12 B each); overflow falls back to inline evaluation
+
 template <int MODE, int FMT>
-__global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P) {
+__device__ __forceinline__ void resolve_exact(const FuseParams& P, const FrameRecord* __restrict__ frec, uint16_t* hist, int RS,
+                                              int64_t tile_base, int owner, int frel, float px, float py, float pz, int st,
+                                              int g_in, int pix, bool fast_seen, uint32_t fast_zq, bool owner_is_self,
+                                              unsigned& n_exact, unsigned& n_div, unsigned& n_edge, unsigned& n_seen,
+                                              unsigned& n_bad) {
+    const int HW = P.H * P.W;
+    ExactOut eo;
+    exact_eval<MODE, FMT>(P, &frec[P.f_begin + frel].exact, frel, px, py, pz, eo);
+    const bool e_seen = (MODE == MODE_SPLAT) ? (eo.in != 0) : (eo.vis != 0);
+    const uint32_t e_zq = (MODE == MODE_SPLAT && eo.in) ? quantise_mm(eo.zcam) : 0u;
+    if (st >= 2) {
+        ++n_exact;
+        bool diverged;
+        if (st == 2) diverged = (g_in != eo.in) || (eo.in && pix != eo.pix);
+        else if (MODE == MODE_SPLAT) diverged = (!eo.in) || (pix != eo.pix) || ((uint32_t)g_in != e_zq);
+        else diverged = (g_in != eo.vis) || (eo.in && pix != eo.pix);
+        n_div += diverged ? 1u : 0u;
+    } else {
+        // audit: a certified fp32 outcome must equal the fp64 outcome
+        const bool bad = (fast_seen != e_seen) || (fast_seen && pix != eo.pix) || (fast_seen && MODE == MODE_SPLAT && fast_zq != e_zq);
+        n_bad += bad ? 1u : 0u;
+    }
+    n_edge += (eo.in && eo.near_edge) ? 1u : 0u;
+    if (e_seen) {
+        ++n_seen;
+        const size_t off = (size_t)frel * (size_t)HW + (size_t)eo.pix;
+        if (MODE == MODE_VOTE) {
+            const int cls = __ldg(P.mask + off);
+            if (cls < P.C1) {
+                if (owner_is_self) {
+                    hist[owner * RS + cls] += 1;
+                } else {
+                    // another thread's row: 32-bit atomic on the word holding the uint16 counter (cannot carry: <= 65535 frames)
+                    const int h = owner * RS + cls;
+                    atomicAdd(reinterpret_cast<unsigned*>(hist) + (h >> 1), (h & 1) ? 0x10000u : 1u);
+                }
+            }
+        } else if (MODE == MODE_SPLAT) {
+            atomicMin(P.zbuf + off, e_zq);
+        } else {
+            atomicMax(P.uv2pt + off, (int)(tile_base + owner));
+        }
+    }
+}
+
+template <int MODE, int FMT>
+__global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P, const FuseResolve RP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [stage FrameFast x FUSE_STAGE][cand u16 x FUSE_FCHUNK][red float x 48 + ints][hist u16 x C1*(BLOCK+PAD)]
+    // layout: [2 x stage FrameFast x FUSE_STAGE][cand u16 x FUSE_FCHUNK][red: 48 floats | ncand | nq | 2 mbarriers]
+    //         [deferred queue][hist]
     float4* stage = reinterpret_cast<float4*>(smem_raw);
-    uint16_t* cand = reinterpret_cast<uint16_t*>(smem_raw + FUSE_STAGE * sizeof(FrameFast));
-    float* red = reinterpret_cast<float*>(smem_raw + FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t));
+    uint16_t* cand = reinterpret_cast<uint16_t*>(smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast));
+    float* red = reinterpret_cast<float*>(smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t));
     int* ncand_s = reinterpret_cast<int*>(red + 48);
-    uint16_t* hist = reinterpret_cast<uint16_t*>(red + 64);
-    const int HS = FUSE_BLOCK + HIST_PAD;
+    int* nq_s = reinterpret_cast<int*>(red + 49);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 52);   // two barriers (16-byte aligned offset)
+    Deferred* queue = reinterpret_cast<Deferred*>(red + 64);
+    uint16_t* hist = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(queue) + FUSE_QCAP * sizeof(Deferred));
+    const int RS = P.RS;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -130,14 +302,21 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P)
     const int64_t gi = tile_base + tid;
     const bool active = gi < P.N;
     const int HW = P.H * P.W;
+    const float fW = (float)P.W, fH = (float)P.H;
 
     float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) pt = __ldg(P.points + gi);
 
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        *nq_s = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (MODE == MODE_VOTE) {
-        uint32_t* h32 = reinterpret_cast<uint32_t*>(hist);
-        const int nwords = (P.C1 * HS + 1) / 2;
-        for (int i = tid; i < nwords; i += FUSE_BLOCK) h32[i] = 0u;
+        uint4* h128 = reinterpret_cast<uint4*>(hist);
+        const int n128 = (FUSE_BLOCK * RS * 2 + 15) / 16;
+        for (int i = tid; i < n128; i += FUSE_BLOCK) h128[i] = make_uint4(0u, 0u, 0u, 0u);
     }
 
     // ---- tile bounding box (exact min / max of the float32 coordinates)
@@ -179,6 +358,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P)
     const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
 
     unsigned n_cand = 0, n_exact = 0, n_div = 0, n_edge = 0, n_seen = 0, n_bad = 0;
+    unsigned phase_bits = 0;   // parity of the two staging barriers
 
     for (int cbase = P.f_begin; cbase < P.f_end; cbase += FUSE_FCHUNK) {
         __syncthreads();   // previous chunk's candidate list fully consumed; red[] reads done
@@ -210,173 +390,208 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P)
         __syncthreads();
         const int ncand = *ncand_s;
         if (active) n_cand += (unsigned)ncand;
+        const int nbatch = (ncand + FUSE_STAGE - 1) / FUSE_STAGE;
 
-        for (int b0 = 0; b0 < ncand; b0 += FUSE_STAGE) {
+        // TMA producer (warp 0): lane 0 arms the barrier with the batch's byte count, lane k issues the 128-byte bulk
+        // copy of candidate k's projection tile
+        auto issue = [&](int batch) {
+            const int buf = batch & 1;
+            const int b0 = batch * FUSE_STAGE;
             const int nb = min(FUSE_STAGE, ncand - b0);
-            __syncthreads();   // previous batch consumed
-            if (tid < nb * 8) {
-                const int k = tid >> 3;
-                stage[tid] = __ldg(reinterpret_cast<const float4*>(&frec[P.f_begin + cand[b0 + k]].fast) + (tid & 7));
-            }
-            __syncthreads();
-            if (!active) continue;
-            for (int k = 0; k < nb; ++k) {
-                const float4* s = stage + k * 8;
-                const int frel = cand[b0 + k];
-                const float4 A0 = s[0], A1 = s[1];
-                const float d0 = (pt.x - A0.x) - A1.x;
-                const float d1 = (pt.y - A0.y) - A1.y;
-                const float d2 = (pt.z - A0.z) - A1.z;
-                const float S = fabsf(d0) + fabsf(d1) + fabsf(d2) + 1.0e-9f;
-                const float4 Mz = s[4];
-                const float z = fmaf(Mz.x, d0, fmaf(Mz.y, d1, Mz.z * d2));
-                const float ez = 8.0f * F3D_U24 * Mz.w * S;
+            if (lane == 0) mbar_expect_tx(&mbar[buf], (unsigned)(nb * sizeof(FrameFast)));
+            __syncwarp();
+            if (lane < nb)
+                tma_bulk_g2s(stage + (buf * FUSE_STAGE + lane) * 8, &frec[P.f_begin + cand[b0 + lane]].fast, sizeof(FrameFast),
+                             &mbar[buf]);
+        };
+        if (warp == 0 && nbatch > 0) issue(0);
 
-                int st;          // 0 = certainly not seen, 1 = pixel certified, 2 = unsure -> fp64
-                int pix = 0;
-                int g_in = 0;    // fp32 best guess (for divergence logging)
-                float zc = 0.f;
-                if (z < -16.0f * ez) {
-                    st = 0;
-                } else if (z <= 16.0f * ez) {
-                    st = 2;
-                } else {
-                    const float4 Mu = s[2], Mv = s[3];
-                    const float a = fmaf(Mu.x, d0, fmaf(Mu.y, d1, Mu.z * d2));
-                    const float b = fmaf(Mv.x, d0, fmaf(Mv.y, d1, Mv.z * d2));
-                    const float r = __frcp_rn(z);
-                    const float u = a * r, v = b * r;
-                    const float ea = 8.0f * F3D_U24 * Mu.w * S, eb = 8.0f * F3D_U24 * Mv.w * S;
-                    const float eu = 1.125f * (ea + fabsf(u) * ez) * r + 8.0f * F3D_U24 * fabsf(u) + 1.0e-4f;
-                    const float ev = 1.125f * (eb + fabsf(v) * ez) * r + 8.0f * F3D_U24 * fabsf(v) + 1.0e-4f;
-                    const float4 R0 = s[5], R1 = s[6], R2 = s[7];
-                    const float sl = fmaf(R0.w, d0, fmaf(R1.w, d1, R2.w * d2));   // (p - eye) . lookat
-                    const float es = 8.0f * F3D_U24 * S + 1.0e-6f * A1.w;
-                    const float fW = (float)P.W, fH = (float)P.H;
-                    const float fu = floorf(u), fv = floorf(v);
-                    if ((u + eu < 0.f) || (u - eu >= fW) || (v + ev < 0.f) || (v - ev >= fH) || (sl - es > A1.w)) {
-                        st = 0;
-                    } else {
-                        const bool cu = (u - fu >= eu) && (fu + 1.0f - u > eu);
-                        const bool cv = (v - fv >= ev) && (fv + 1.0f - v > ev);
-                        const bool cf = (sl + es < A1.w);
-                        g_in = (u >= 0.f) && (fu < fW) && (v >= 0.f) && (fv < fH) && (sl < A1.w);
-                        pix = (int)fv * P.W + (int)fu;
-                        st = (cu && cv && cf) ? 1 : 2;
-                    }
-                    zc = z;
-                    if (st == 1 && MODE != MODE_SPLAT) {
-                        // ---- z-test against the frame's depth (valid range + single-pixel criterion)
-                        const size_t off = (size_t)frel * (size_t)HW + (size_t)pix;
-                        float dm;   // depth sample in metres
-                        bool valid;
-                        if (FMT == F3D_DEPTH_U16_MM) {
-                            const uint32_t d = __ldg(reinterpret_cast<const uint16_t*>(P.depth) + off);
-                            valid = (d >= P.d_lo) && (d <= P.d_hi);
-                            dm = (float)d * 0.001f;
-                        } else {
-                            const float d = __ldg(reinterpret_cast<const float*>(P.depth) + off);
-                            valid = ((double)d > P.zmin) && ((double)d <= P.zmax);
-                            dm = d;
+        for (int batch = 0; batch < nbatch; ++batch) {
+            const int buf = batch & 1;
+            const int b0 = batch * FUSE_STAGE;
+            const int nb = min(FUSE_STAGE, ncand - b0);
+            // buffer buf^1 was consumed by every thread before the barrier at the end of the previous iteration
+            if (warp == 0 && batch + 1 < nbatch) issue(batch + 1);
+            mbar_wait(&mbar[buf], (phase_bits >> buf) & 1u);
+            phase_bits ^= (1u << buf);
+            if (active) {
+                for (int k0 = 0; k0 < nb; k0 += FUSE_NB) {
+                    // ---- phase 1: fp32 projection + certification of NB candidates
+                    uint32_t puv[FUSE_NB];
+                    uint32_t dv[FUSE_NB];      // depth sample bits; for uint16 depth the mask byte rides in bits 16..23
+                    uint32_t mv = 0, mv2 = 0;  // mask bytes for float depth (4 per register)
+                    unsigned stw = 0;          // 4 bits per candidate: st | g_in << 3
+                    float zc[MODE == MODE_SPLAT ? FUSE_NB : 1];
+#pragma unroll
+                    for (int k = 0; k < FUSE_NB; ++k) {
+                        puv[k] = 0;
+                        dv[k] = 0;
+                        if (k0 + k < nb) {
+                            const Cls c = classify(stage + (buf * FUSE_STAGE + k0 + k) * 8, pt, fW, fH);
+                            puv[k] = c.puv;
+                            stw |= (unsigned)(c.st | (c.g_in << 3)) << (4 * k);
+                            if (MODE == MODE_SPLAT) zc[k] = c.z;
                         }
-                        if (!valid) {
-                            st = 0;
-                        } else {
-                            // metric camera coordinates of the cloud point and of the depth pixel (scaled by |q|^2)
-                            const float X = fmaf(R0.x, d0, fmaf(R0.y, d1, R0.z * d2));
-                            const float Y = fmaf(R1.x, d0, fmaf(R1.y, d1, R1.z * d2));
-                            const float Z = fmaf(R2.x, d0, fmaf(R2.y, d1, R2.z * d2));
-                            const float ds = dm * A0.w;
-                            const float xn = (fu - P.cx) * P.inv_fx, yn = (fv - P.cy) * P.inv_fy;
-                            const float qx = X - xn * ds, qy = Y - yn * ds, qz = Z - ds;
-                            const float dist2 = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
-                            const float del = 16.0f * F3D_U24 * (S + ds * (1.0f + fabsf(xn) + fabsf(yn)));
-                            const float rlo = fmaxf(P.radius - del, 0.f), rhi = P.radius + del;
-                            if (dist2 < rlo * rlo * (1.0f - 16.0f * F3D_U24)) {
-                                st = 1;
-                            } else if (dist2 > rhi * rhi * (1.0f + 16.0f * F3D_U24)) {
-                                st = 0;
+                    }
+                    if (stw == 0 && !P.audit) continue;
+                    // ---- phase 2: all gathers of the certified candidates in flight together
+                    if (MODE != MODE_SPLAT) {
+#pragma unroll
+                        for (int k = 0; k < FUSE_NB; ++k) {
+                            if (((stw >> (4 * k)) & 7u) == 1u) {
+                                const size_t off = (size_t)cand[b0 + k0 + k] * (size_t)HW + (size_t)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
+                                if (FMT == F3D_DEPTH_U16_MM) dv[k] = __ldg(reinterpret_cast<const uint16_t*>(P.depth) + off);
+                                else dv[k] = __float_as_uint(__ldg(reinterpret_cast<const float*>(P.depth) + off));
+                                if (MODE == MODE_VOTE) {
+                                    const uint32_t m = __ldg(P.mask + off);
+                                    if (FMT == F3D_DEPTH_U16_MM) dv[k] |= m << 16;
+                                    else if (k < 4) mv |= m << (8 * k);
+                                    else mv2 |= m << (8 * (k - 4));
+                                }
+                            }
+                        }
+                    }
+                    // ---- phase 3: depth validity + distance criterion, votes; uncertain pairs are deferred
+#pragma unroll
+                    for (int k = 0; k < FUSE_NB; ++k) {
+                        int st = (int)((stw >> (4 * k)) & 7u);
+                        if (st == 0 && !P.audit) continue;
+                        if (k0 + k >= nb) continue;
+                        const int frel = cand[b0 + k0 + k];
+                        const float4* s = stage + (buf * FUSE_STAGE + k0 + k) * 8;
+                        int g_in = (int)((stw >> (4 * k + 3)) & 1u);
+                        const int pix = (int)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
+                        uint32_t zq = 0;
+                        int cls = 0;
+                        if (st == 1 && MODE != MODE_SPLAT) {
+                            float dm;
+                            bool valid;
+                            if (FMT == F3D_DEPTH_U16_MM) {
+                                const uint32_t d = dv[k] & 0xffffu;
+                                valid = (d >= P.d_lo) && (d <= P.d_hi);
+                                dm = (float)d * 0.001f;
+                                cls = (int)(dv[k] >> 16);
                             } else {
-                                st = 3;   // distance inside its band
-                                g_in = dist2 < P.radius * P.radius;
+                                dm = __uint_as_float(dv[k]);
+                                valid = ((double)dm > P.zmin) && ((double)dm <= P.zmax);
+                                cls = (int)(((k < 4 ? mv >> (8 * k) : mv2 >> (8 * (k - 4)))) & 0xffu);
+                            }
+                            st = valid ? distance_test(s, pt, puv[k], dm, P, g_in) : 0;
+                        }
+                        if (MODE == MODE_SPLAT && st == 1) {
+                            // quantised camera z: floor(z*1000 + 0.5); certify the floor
+                            const float zm = fmaf(zc[k], 1000.0f, 0.5f);
+                            const float fz = floorf(zm);
+                            const float ez = 8.0f * F3D_U24 * s[4].w *
+                                             (fabsf((pt.x - s[0].x) - s[1].x) + fabsf((pt.y - s[0].y) - s[1].y) +
+                                              fabsf((pt.z - s[0].z) - s[1].z) + 1.0e-9f);
+                            const float eq = 1010.0f * ez + 8.0f * F3D_U24 * zm;
+                            if ((zm - fz >= eq) && (fz + 1.0f - zm > eq)) {
+                                zq = (uint32_t)fminf(fmaxf(fz, 1.0f), 65535.0f);
+                            } else {
+                                st = 3;
+                                g_in = (int)fminf(fmaxf(fz, 1.0f), 65535.0f);
+                            }
+                        }
+                        const bool seen = (st == 1);
+                        if (st >= 2 || P.audit) {
+                            // defer to the dense fp64 pass (queue full or audit sweep: evaluate inline)
+                            const int slot = (st >= 2 && !P.audit) ? atomicAdd(nq_s, 1) : FUSE_QCAP;
+                            if (slot < FUSE_QCAP) {
+                                queue[slot].w0 = (uint32_t)tid | ((uint32_t)frel << 16);
+                                queue[slot].w1 = (uint32_t)pix;
+                                queue[slot].w2 = (uint32_t)st | ((uint32_t)g_in << 8);
+                            } else {
+                                resolve_exact<MODE, FMT>(P, frec, hist, RS, tile_base, tid, frel, pt.x, pt.y, pt.z, st, g_in, pix, seen,
+                                                         zq, true, n_exact, n_div, n_edge, n_seen, n_bad);
+                            }
+                        } else if (seen) {
+                            ++n_seen;
+                            if (MODE == MODE_VOTE) {
+                                if (cls < P.C1) hist[tid * RS + cls] += 1;
+                            } else {
+                                const size_t off = (size_t)frel * (size_t)HW + (size_t)pix;
+                                if (MODE == MODE_SPLAT) atomicMin(P.zbuf + off, zq);
+                                else atomicMax(P.uv2pt + off, (int)gi);
                             }
                         }
                     }
                 }
+            }
+            __syncthreads();   // every thread is done with stage buffer `buf` -> it may be refilled next iteration
+        }
+    }
 
-                bool seen = (st == 1);
-                uint32_t zq = 0;
-                if (MODE == MODE_SPLAT && st == 1) {
-                    // quantised camera z: floor(z*1000 + 0.5); certify the floor
-                    const float zm = fmaf(zc, 1000.0f, 0.5f);
-                    const float fz = floorf(zm);
-                    const float eq = 1010.0f * ez + 8.0f * F3D_U24 * zm;
-                    if ((zm - fz >= eq) && (fz + 1.0f - zm > eq)) {
-                        zq = (uint32_t)fminf(fmaxf(fz, 1.0f), 65535.0f);
-                    } else {
-                        st = 3;
-                        g_in = (int)fminf(fmaxf(fz, 1.0f), 65535.0f);
-                    }
+    // ---- dense fp64 pass over the deferred point-views (one entry per thread)
+    __syncthreads();
+    {
+        const int nq = min(*nq_s, FUSE_QCAP);
+        for (int q = tid; q < nq; q += FUSE_BLOCK) {
+            const Deferred d = queue[q];
+            const int owner = (int)(d.w0 & 0xffffu), frel = (int)(d.w0 >> 16);
+            const float4 op = __ldg(P.points + tile_base + owner);
+            resolve_exact<MODE, FMT>(P, frec, hist, RS, tile_base, owner, frel, op.x, op.y, op.z, (int)(d.w2 & 0xffu), (int)(d.w2 >> 8),
+                                     (int)d.w1, false, 0u, false, n_exact, n_div, n_edge, n_seen, n_bad);
+        }
+    }
+
+    // ---- epilogue: histogram -> HBM, written once with 16-byte stores; optional fused label resolve
+    if (MODE == MODE_VOTE) {
+        __syncthreads();
+        const int npts_tile = (int)min((int64_t)FUSE_BLOCK, P.N - tile_base);
+        if (P.votes) {
+            const int total = npts_tile * P.C1;
+            int32_t* __restrict__ out = P.votes + tile_base * P.C1;
+            if (RS == P.C1 && !P.accumulate) {
+                // rows are dense (RS == C1): the histogram is the output tile, widened from uint16 to int32
+                const uint2* __restrict__ h64 = reinterpret_cast<const uint2*>(hist);
+                const int n4 = total >> 2;     // C1 even and 256 rows => total % 4 == 0 for full tiles
+                for (int i = tid; i < n4; i += FUSE_BLOCK) {
+                    const uint2 w = h64[i];
+                    *reinterpret_cast<int4*>(out + 4 * i) =
+                        make_int4((int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16));
                 }
-
-                if (st >= 2 || P.audit) {
-                    ExactOut eo;
-                    exact_eval<MODE, FMT>(P, &frec[P.f_begin + frel].exact, frel, pt.x, pt.y, pt.z, eo);
-                    bool e_seen = (MODE == MODE_SPLAT) ? (eo.in != 0) : (eo.vis != 0);
-                    uint32_t e_zq = (MODE == MODE_SPLAT && eo.in) ? quantise_mm(eo.zcam) : 0u;
-                    if (st >= 2) {
-                        ++n_exact;
-                        bool diverged;
-                        if (st == 2) diverged = (g_in != eo.in) || (eo.in && pix != eo.pix);
-                        else if (MODE == MODE_SPLAT) diverged = (!eo.in) || (pix != eo.pix) || ((uint32_t)g_in != e_zq);
-                        else diverged = (g_in != eo.vis) || (eo.in && pix != eo.pix);
-                        n_div += diverged ? 1u : 0u;
-                    } else {
-                        // audit: a certified fp32 outcome must equal the fp64 outcome
-                        bool bad = (seen != e_seen) || (seen && pix != eo.pix) || (seen && MODE == MODE_SPLAT && zq != e_zq);
-                        n_bad += bad ? 1u : 0u;
-                    }
-                    n_edge += (eo.in && eo.near_edge) ? 1u : 0u;
-                    seen = e_seen;
-                    pix = eo.pix;
-                    zq = e_zq;
-                }
-
-                if (seen) {
-                    ++n_seen;
-                    const size_t off = (size_t)frel * (size_t)HW + (size_t)pix;
-                    if (MODE == MODE_VOTE) {
-                        const int cls = __ldg(P.mask + off);
-                        if (cls < P.C1) hist[cls * HS + tid] += 1;
-                    } else if (MODE == MODE_SPLAT) {
-                        atomicMin(P.zbuf + off, zq);
-                    } else {
-                        atomicMax(P.uv2pt + off, (int)gi);
+                for (int e = (n4 << 2) + tid; e < total; e += FUSE_BLOCK) out[e] = (int)hist[e];
+            } else {
+                // a warp per row, lanes over classes (coalesced within the 4*C1-byte row)
+                for (int j = warp; j < npts_tile; j += FUSE_BLOCK / 32) {
+                    for (int c = lane; c < P.C1; c += 32) {
+                        const int v = (int)hist[j * RS + c];
+                        if (!P.accumulate) out[j * P.C1 + c] = v;   // overwrite mode writes every cell exactly once
+                        else if (v) out[j * P.C1 + c] += v;         // accumulate mode touches only the sparse non-zero cells
                     }
                 }
             }
         }
-    }
-
-    // ---- epilogue: histogram -> HBM, written once, coalesced
-    if (MODE == MODE_VOTE) {
-        __syncthreads();
-        const int64_t npts_tile = min((int64_t)FUSE_BLOCK, P.N - tile_base);
-        const int total = (int)npts_tile * P.C1;
-        int32_t* __restrict__ out = P.votes + tile_base * P.C1;
-        int j = tid / P.C1, c = tid - j * P.C1;
-        const int dj = FUSE_BLOCK / P.C1, dc = FUSE_BLOCK - dj * P.C1;
-        for (int e = tid; e < total; e += FUSE_BLOCK) {
-            const int v = hist[c * HS + j];
-            // accumulate mode touches only the (sparse) non-zero cells; overwrite mode writes every cell once
-            if (!P.accumulate) out[e] = v;
-            else if (v) out[e] += v;
-            j += dj;
-            c += dc;
-            if (c >= P.C1) {
-                c -= P.C1;
-                ++j;
+        if (RP.enabled && active) {
+            // VotingSegmentation.segment straight from the histogram row (voting.py:120-135); rows are sparse, so the
+            // row is scanned as 32-bit words and only non-zero counters compete (a zero can never win, voting.py:131)
+            const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(hist + tid * RS);
+            int total = 0, best = 0, bpos = 0x7fff;
+            const int nw = (P.C1 + 1) >> 1;
+            for (int w = 0; w < nw; ++w) {
+                const uint32_t x = row[w];
+                if (x == 0u) continue;
+                const int v0 = (int)(x & 0xffffu), v1 = (2 * w + 1 < P.C1) ? (int)(x >> 16) : 0;
+                total += v0 + v1;
+                if (v0) {
+                    const int pos = RP.fpos[2 * w];
+                    if (pos >= 0 && (v0 > best || (v0 == best && pos < bpos))) {
+                        best = v0;
+                        bpos = pos;
+                    }
+                }
+                if (v1) {
+                    const int pos = RP.fpos[2 * w + 1];
+                    if (pos >= 0 && (v1 > best || (v1 == best && pos < bpos))) {
+                        best = v1;
+                        bpos = pos;
+                    }
+                }
             }
+            bool unc = (total <= 0) || (best <= 0);                                   // voting.py:126,131
+            if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;          // voting.py:128-130
+            P.labels[gi] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
         }
     }
 
@@ -405,21 +620,27 @@ __global__ void zbuf_finalize_kernel(const uint32_t* __restrict__ zbuf, uint16_t
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
+static int hist_row_stride(int C1) {
+    int rs = (C1 + 1) & ~1;            // even number of uint16
+    if (((rs / 2) & 1) == 0) rs += 2;  // odd number of 32-bit words per row: lanes hit distinct banks
+    return rs;
+}
+
 static size_t fuse_smem_bytes(int mode, int C1) {
-    size_t b = FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t) + 64 * sizeof(float);
-    if (mode == MODE_VOTE) b += ((size_t)C1 * (FUSE_BLOCK + HIST_PAD) * sizeof(uint16_t) + 15) & ~(size_t)15;
+    size_t b = 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t) + 64 * sizeof(float) + FUSE_QCAP * sizeof(Deferred);
+    if (mode == MODE_VOTE) b += ((size_t)FUSE_BLOCK * hist_row_stride(C1) * sizeof(uint16_t) + 15) & ~(size_t)15;
     return b;
 }
 
 template <int MODE, int FMT>
-static int launch_fuse(const FuseParams& P, cudaStream_t stream) {
+static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t stream) {
     size_t smem = fuse_smem_bytes(MODE, P.C1);
     if (smem > 227 * 1024) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: nclasses+1 too large for the shared-memory histogram");
     cudaError_t e = cudaFuncSetAttribute(fuse_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute)");
     int64_t tiles = (P.N + FUSE_BLOCK - 1) / FUSE_BLOCK;
     if (tiles > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: too many points for one launch");
-    fuse_kernel<MODE, FMT><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P);
+    fuse_kernel<MODE, FMT><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
     return f3d_check_launch("f3d_fuse");
 }
 
@@ -429,7 +650,7 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     if (!points || !table || !h_K9 || N < 0 || fb < 0 || fe < fb || H <= 0 || W <= 0)
         return f3d_fail(F3D_ERR_ARG, "f3d_fuse: bad argument");
     if (fmt != F3D_DEPTH_U16_MM && fmt != F3D_DEPTH_F32_M) return f3d_fail(F3D_ERR_ARG, "f3d_fuse: unknown depth format");
-    if ((int64_t)H * W > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: image too large");
+    if ((int64_t)H * W > 0x7fffffff || H > 65535 || W > 65535) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: image too large");
     P.points = reinterpret_cast<const float4*>(points);
     P.N = N;
     P.table = table;
@@ -441,7 +662,6 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.cy = (float)h_K9[5];
     P.inv_fx = (float)(1.0 / h_K9[0]);
     P.inv_fy = (float)(1.0 / h_K9[4]);
-    P.dunit = fmt == F3D_DEPTH_U16_MM ? 0.001f : 1.0f;
     P.radius = (float)radius;
     P.radius_d = radius;
     P.zmin = zmin;
@@ -463,28 +683,62 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.uv2pt = nullptr;
     P.zbuf = nullptr;
     P.mask = nullptr;
+    P.labels = nullptr;
     P.C1 = 0;
+    P.RS = 0;
     P.accumulate = 0;
+    return F3D_OK;
+}
+
+// composed sequential remap `for i, cls in enumerate(filter): pc[pc == i] = cls` (voting.py:133-135) and the
+// column -> filter position table, shared with f3d_resolve_labels
+int f3d_build_resolve(int C1, double threshold, const int32_t* h_filter, int nfilter, int nclasses_id, FuseResolve& rp) {
+    if (C1 > RES_MAXC || nfilter > RES_MAXC) return f3d_fail(F3D_ERR_UNSUPPORTED, "label resolve: more than 256 columns / filter classes");
+    rp.enabled = 1;
+    rp.nfilter = nfilter;
+    rp.threshold = threshold;
+    for (int c = 0; c < RES_MAXC; ++c) {
+        rp.fpos[c] = nfilter > 0 ? (int16_t)-1 : (int16_t)c;
+        rp.remap[c] = c;
+    }
+    for (int k = nfilter - 1; k >= 0; --k) {
+        if (h_filter[k] < 0 || h_filter[k] >= C1) return f3d_fail(F3D_ERR_ARG, "label resolve: filter class out of range");
+        rp.fpos[h_filter[k]] = (int16_t)k;   // first position wins
+    }
+    rp.unclassified = nclasses_id;
+    for (int start = 0; start <= nfilter; ++start) {
+        int v = start < nfilter ? start : nclasses_id;
+        for (int i = 0; i < nfilter; ++i)
+            if (v == i) v = h_filter[i];
+        if (start < nfilter) rp.remap[start] = v;
+        else rp.unclassified = v;
+    }
     return F3D_OK;
 }
 
 // frames are processed in launches of at most 65535 (uint16 candidate ids and histogram counters)
 #define F3D_MAX_FRAMES_PER_LAUNCH 65535
 
-extern "C" int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
-                                     int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
-                                     int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                                     int32_t* votes, int32_t C1, int32_t accumulate, uint64_t* stats, int32_t flags,
-                                     void* stream) {
+static int fuse_vote_impl(const void* points, int64_t N, const void* frame_table, int32_t frame_begin, int32_t frame_end,
+                          const void* depth, int32_t depth_fmt, const uint8_t* mask, int32_t H, int32_t W,
+                          const double* h_K9, double radius, double zmin, double zmax, int32_t* votes, int32_t C1,
+                          int32_t accumulate, const FuseResolve& RP, int64_t* labels, uint64_t* stats, int32_t flags,
+                          void* stream) {
     FuseParams P;
     int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
                          zmax, stats, flags);
     if (rc) return rc;
-    if (!votes || C1 <= 0 || C1 > 256 || (frame_end > frame_begin && (!depth || !mask)))
+    if ((!votes && !labels) || C1 <= 0 || C1 > 256 || (frame_end > frame_begin && (!depth || !mask)))
         return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote: bad argument (votes/mask/depth NULL or C1 not in 1..256)");
+    if (labels && (accumulate || frame_end - frame_begin > F3D_MAX_FRAMES_PER_LAUNCH))
+        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_resolve: fused labels need all frames in one non-accumulating launch");
+    if (votes && (reinterpret_cast<uintptr_t>(votes) & 15u))
+        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote: votes must be 16-byte aligned");
     if (N == 0) return F3D_OK;
     P.votes = votes;
+    P.labels = labels;
     P.C1 = C1;
+    P.RS = hist_row_stride(C1);
     const size_t esz = depth_fmt == F3D_DEPTH_U16_MM ? 2 : 4;
     int fb = frame_begin;
     bool first = true;
@@ -495,13 +749,40 @@ extern "C" int f3d_fuse_project_vote(const void* points, int64_t N, const void* 
         P.depth = reinterpret_cast<const char*>(depth) + (size_t)(fb - frame_begin) * H * W * esz;
         P.mask = mask + (size_t)(fb - frame_begin) * H * W;
         P.accumulate = (first && !accumulate) ? 0 : 1;
-        rc = depth_fmt == F3D_DEPTH_U16_MM ? launch_fuse<MODE_VOTE, F3D_DEPTH_U16_MM>(P, (cudaStream_t)stream)
-                                           : launch_fuse<MODE_VOTE, F3D_DEPTH_F32_M>(P, (cudaStream_t)stream);
+        rc = depth_fmt == F3D_DEPTH_U16_MM ? launch_fuse<MODE_VOTE, F3D_DEPTH_U16_MM>(P, RP, (cudaStream_t)stream)
+                                           : launch_fuse<MODE_VOTE, F3D_DEPTH_F32_M>(P, RP, (cudaStream_t)stream);
         if (rc) return rc;
         first = false;
         fb = fe;
     } while (fb < frame_end);
     return F3D_OK;
+}
+
+extern "C" int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                                     int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
+                                     int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
+                                     int32_t* votes, int32_t C1, int32_t accumulate, uint64_t* stats, int32_t flags,
+                                     void* stream) {
+    if (!votes) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote: votes is NULL");
+    FuseResolve RP;
+    RP.enabled = 0;
+    return fuse_vote_impl(points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, mask, H, W, h_K9, radius, zmin,
+                          zmax, votes, C1, accumulate, RP, nullptr, stats, flags, stream);
+}
+
+extern "C" int f3d_fuse_project_vote_resolve(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                                             int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
+                                             int32_t H, int32_t W, const double* h_K9, double radius, double zmin,
+                                             double zmax, int32_t* votes, int32_t C1, double threshold,
+                                             const int32_t* h_filter, int32_t nfilter, int32_t nclasses_id, int64_t* labels,
+                                             uint64_t* stats, int32_t flags, void* stream) {
+    if (!labels || nfilter < 0 || (nfilter > 0 && !h_filter))
+        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_resolve: bad argument");
+    FuseResolve RP;
+    int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
+    if (rc) return rc;
+    return fuse_vote_impl(points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, mask, H, W, h_K9, radius, zmin,
+                          zmax, votes, C1, 0, RP, labels, stats, flags, stream);
 }
 
 extern "C" int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
@@ -515,6 +796,8 @@ extern "C" int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_t
     if (!uv2pt || !depth) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_uv2pt: bad argument");
     if (N == 0 || frame_end == frame_begin) return F3D_OK;
     if (N > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_uv2pt: point index does not fit int32");
+    FuseResolve RP;
+    RP.enabled = 0;
     const size_t esz = depth_fmt == F3D_DEPTH_U16_MM ? 2 : 4;
     for (int fb = frame_begin; fb < frame_end; fb += F3D_MAX_FRAMES_PER_LAUNCH) {
         int fe = frame_end - fb > F3D_MAX_FRAMES_PER_LAUNCH ? fb + F3D_MAX_FRAMES_PER_LAUNCH : frame_end;
@@ -522,8 +805,8 @@ extern "C" int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_t
         P.f_end = fe;
         P.depth = reinterpret_cast<const char*>(depth) + (size_t)(fb - frame_begin) * H * W * esz;
         P.uv2pt = uv2pt + (size_t)(fb - frame_begin) * H * W;
-        rc = depth_fmt == F3D_DEPTH_U16_MM ? launch_fuse<MODE_UV2PT, F3D_DEPTH_U16_MM>(P, (cudaStream_t)stream)
-                                           : launch_fuse<MODE_UV2PT, F3D_DEPTH_F32_M>(P, (cudaStream_t)stream);
+        rc = depth_fmt == F3D_DEPTH_U16_MM ? launch_fuse<MODE_UV2PT, F3D_DEPTH_U16_MM>(P, RP, (cudaStream_t)stream)
+                                           : launch_fuse<MODE_UV2PT, F3D_DEPTH_F32_M>(P, RP, (cudaStream_t)stream);
         if (rc) return rc;
     }
     return F3D_OK;
@@ -542,13 +825,15 @@ extern "C" int f3d_zbuffer_splat(const void* points, int64_t N, const void* fram
     const int64_t total = (int64_t)nf * H * W;
     cudaError_t e = cudaMemsetAsync(zbuf, 0xff, (size_t)total * sizeof(uint32_t), (cudaStream_t)stream);
     if (e != cudaSuccess) return f3d_check_launch("f3d_zbuffer_splat(memset)");
+    FuseResolve RP;
+    RP.enabled = 0;
     if (N > 0) {
         for (int fb = frame_begin; fb < frame_end; fb += F3D_MAX_FRAMES_PER_LAUNCH) {
             int fe = frame_end - fb > F3D_MAX_FRAMES_PER_LAUNCH ? fb + F3D_MAX_FRAMES_PER_LAUNCH : frame_end;
             P.f_begin = fb;
             P.f_end = fe;
             P.zbuf = zbuf + (size_t)(fb - frame_begin) * H * W;
-            rc = launch_fuse<MODE_SPLAT, F3D_DEPTH_U16_MM>(P, (cudaStream_t)stream);
+            rc = launch_fuse<MODE_SPLAT, F3D_DEPTH_U16_MM>(P, RP, (cudaStream_t)stream);
             if (rc) return rc;
         }
     }

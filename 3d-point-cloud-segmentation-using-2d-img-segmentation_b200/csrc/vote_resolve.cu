@@ -62,46 +62,70 @@ __global__ void resize_nearest_kernel(const uint8_t* __restrict__ src, int sh, i
 #define RES_MAX_FILTER 256
 struct ResolveParams {
     int nfilter;                       // 0 = all columns
-    int32_t filter[RES_MAX_FILTER];    // column ids in caller order
-    int32_t remap[RES_MAX_FILTER + 1]; // composed sequential remap (voting.py:133-135) for arg-max index i
+    int16_t fpos[RES_MAX_FILTER];      // column -> first position in the filter list (-1 = not considered)
+    int32_t remap[RES_MAX_FILTER + 1]; // composed sequential remap (voting.py:133-135) for arg-max position i
     int32_t unclassified;              // value for "unclassified" after the same remap
     double threshold;
 };
 
-// One warp per point row: lanes stride over the C1 int32 counters (coalesced 128 B segments), a shuffle reduction
-// gives the row total and the first maximum among the filter columns, lane 0 applies the float64 tests of
-// voting.py:126-131.  HBM-bound: 4*C1 bytes read + 8 bytes written per point.
-template <bool FILTERED>
+// Eight lanes per point row, four rows per warp.  A lane streams its share of the row's int32 counters with 8-byte
+// loads (row stride 4*C1 bytes: 8-byte aligned when C1 is even), keeps the row total and the first maximum among
+// the considered columns, three xor-shuffles combine the eight partials, and one lane applies the float64 tests
+// of voting.py:126-131.  HBM-bound: 4*C1 bytes read + 8 bytes written per point.
+__device__ __forceinline__ void res_take(int v, int pos, int& best, int& bpos) {
+    // zero cells can never win (max == 0 resolves to "unclassified", voting.py:131), so only v > 0 competes
+    if (v > 0 && pos >= 0 && (v > best || (v == best && pos < bpos))) {
+        best = v;
+        bpos = pos;
+    }
+}
+
+template <bool FILTERED, bool VEC2>
 __global__ void __launch_bounds__(256) resolve_kernel(const int32_t* __restrict__ votes, int64_t N, int C1,
                                                       const ResolveParams rp, int64_t* __restrict__ labels) {
-    __shared__ int32_t s_fpos[RES_MAX_FILTER];   // column -> first position in the filter list, or INT_MAX
-    const int lane = threadIdx.x & 31;
+    __shared__ int16_t s_fpos[RES_MAX_FILTER];
     if (FILTERED) {
-        for (int c = threadIdx.x; c < C1 && c < RES_MAX_FILTER; c += blockDim.x) {
-            int pos = 0x7fffffff;
-            for (int k = rp.nfilter - 1; k >= 0; --k)
-                if (rp.filter[k] == c) pos = k;
-            s_fpos[c] = pos;
-        }
+        for (int c = threadIdx.x; c < RES_MAX_FILTER; c += blockDim.x) s_fpos[c] = rp.fpos[c];
         __syncthreads();
     }
-    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < N; row += warps_total) {
-        const int32_t* __restrict__ r = votes + row * C1;
+    const int sub = threadIdx.x & 7;
+    const int64_t rows_per_pass = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    const int64_t row0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t passes = (N + rows_per_pass - 1) / rows_per_pass;   // uniform trip count: shuffles see full warps
+    for (int64_t p = 0; p < passes; ++p) {
+        const int64_t row = row0 + p * rows_per_pass;
+        const bool live = row < N;
         long long total = 0;
-        int best = -1;               // maximum vote among considered columns
-        int bpos = 0x7fffffff;       // its position (first maximum wins: smallest position among equal values)
-        for (int c = lane; c < C1; c += 32) {
-            const int v = __ldg(r + c);
-            total += v;
-            const int pos = FILTERED ? s_fpos[c] : c;
-            if (pos != 0x7fffffff && (v > best || (v == best && pos < bpos))) {
-                best = v;
-                bpos = pos;
+        int best = 0, bpos = 0x7fff;
+        if (live) {
+            const int32_t* __restrict__ r = votes + row * C1;
+            if (VEC2) {
+                const int2* __restrict__ r2 = reinterpret_cast<const int2*>(r);
+                const int n2 = C1 >> 1;
+                int2 buf[4];
+                for (int i0 = sub; i0 < n2; i0 += 32) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) buf[u] = (i0 + 8 * u < n2) ? __ldg(r2 + i0 + 8 * u) : make_int2(0, 0);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = 2 * (i0 + 8 * u);
+                        if ((buf[u].x | buf[u].y) != 0) {
+                            total += (long long)buf[u].x + (long long)buf[u].y;
+                            res_take(buf[u].x, FILTERED ? (int)s_fpos[c] : c, best, bpos);
+                            res_take(buf[u].y, FILTERED ? (int)s_fpos[c + 1] : c + 1, best, bpos);
+                        }
+                    }
+                }
+            } else {
+                for (int c = sub; c < C1; c += 8) {
+                    const int v = __ldg(r + c);
+                    total += v;
+                    res_take(v, FILTERED ? (int)s_fpos[c] : c, best, bpos);
+                }
             }
         }
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
+        for (int s = 4; s > 0; s >>= 1) {
             total += __shfl_xor_sync(0xffffffffu, total, s);
             const int ob = __shfl_xor_sync(0xffffffffu, best, s);
             const int op = __shfl_xor_sync(0xffffffffu, bpos, s);
@@ -110,16 +134,10 @@ __global__ void __launch_bounds__(256) resolve_kernel(const int32_t* __restrict_
                 bpos = op;
             }
         }
-        if (lane == 0) {
-            int32_t out;
-            bool unc = (total <= 0) || (best <= 0);                         // voting.py:126,131
-            if (!unc) {
-                const double prob = xdiv((double)best, (double)total);       // voting.py:128
-                unc = prob < rp.threshold;                                   // voting.py:129-130
-            }
-            if (unc) out = rp.unclassified;
-            else out = FILTERED ? rp.remap[bpos] : bpos;
-            labels[row] = (int64_t)out;
+        if (live && sub == 0) {
+            bool unc = (total <= 0) || (best <= 0);                              // voting.py:126,131
+            if (!unc) unc = xdiv((double)best, (double)total) < rp.threshold;     // voting.py:128-130
+            labels[row] = (int64_t)(unc ? rp.unclassified : (FILTERED ? rp.remap[bpos] : bpos));
         }
     }
 }
@@ -178,9 +196,10 @@ extern "C" int f3d_resolve_labels(const int32_t* votes, int64_t N, int32_t C1, d
     rp.nfilter = nfilter;
     rp.threshold = threshold;
     rp.unclassified = nclasses_id;
-    for (int k = 0; k < nfilter; ++k) {
+    for (int c = 0; c < RES_MAX_FILTER; ++c) rp.fpos[c] = -1;
+    for (int k = nfilter - 1; k >= 0; --k) {
         if (h_filter[k] < 0 || h_filter[k] >= C1) return f3d_fail(F3D_ERR_ARG, "f3d_resolve_labels: filter class out of range");
-        rp.filter[k] = h_filter[k];
+        rp.fpos[h_filter[k]] = (int16_t)k;   // the first position of a repeated class wins (argmax over votes[:, filter])
     }
     // compose the sequential remap `for i, cls in enumerate(filter): pc[pc == i] = cls` (voting.py:133-135),
     // including its aliasing, for every start value an arg-max index or the unclassified id can take
@@ -191,8 +210,15 @@ extern "C" int f3d_resolve_labels(const int32_t* votes, int64_t N, int32_t C1, d
         if (start < nfilter) rp.remap[start] = v;
         else rp.unclassified = v;
     }
-    const unsigned grid = grid_for(N * 32, 256, 148 * 8);
-    if (nfilter > 0) resolve_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(votes, N, C1, rp, labels);
-    else resolve_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(votes, N, C1, rp, labels);
+    const unsigned grid = grid_for(N * 8, 256, 148 * 8);
+    const bool vec2 = ((C1 & 1) == 0) && ((reinterpret_cast<uintptr_t>(votes) & 7u) == 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nfilter > 0) {
+        if (vec2) resolve_kernel<true, true><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
+        else resolve_kernel<true, false><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
+    } else {
+        if (vec2) resolve_kernel<false, true><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
+        else resolve_kernel<false, false><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
+    }
     return f3d_check_launch("f3d_resolve_labels");
 }

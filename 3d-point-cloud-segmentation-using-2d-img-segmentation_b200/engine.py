@@ -106,6 +106,27 @@ def fuse_project_vote(points4, table: FrameTable, depth, mask, nclasses1, radius
     return votes
 
 
+def fuse_project_vote_resolve(points4, table: FrameTable, depth, mask, nclasses1, nclasses_id, radius=0.05, zmin=0.1,
+                              zmax=4.0, threshold=0.5, filter_classes=None, votes=None, want_votes=True, labels=None,
+                              stats=None, audit=False, frame_begin=0, frame_end=None):
+    """Kernel (1) with the label resolve fused into its epilogue.  Returns (votes or None, labels int64 [N])."""
+    frame_end = table.F if frame_end is None else frame_end
+    N = points4.shape[0]
+    if votes is None and want_votes:
+        votes = torch.empty((N, nclasses1), dtype=torch.int32, device=points4.device)
+    if labels is None:
+        labels = torch.empty(N, dtype=torch.int64, device=points4.device)
+    filt = None if filter_classes is None else np.ascontiguousarray(np.asarray(filter_classes, dtype=np.int32))
+    nf = frame_end - frame_begin
+    check(load().f3d_fuse_project_vote_resolve(
+        ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth) if nf else None,
+        _depth_fmt(depth) if nf else 0, ptr(mask) if nf else None, table.H, table.W, ptr(table.K), float(radius),
+        float(zmin), float(zmax), ptr(votes), int(nclasses1), float(threshold), ptr(filt),
+        0 if filt is None else int(filt.size), int(nclasses_id), ptr(labels), ptr(stats), int(bool(audit)), stream_ptr()),
+        "f3d_fuse_project_vote_resolve")
+    return votes, labels
+
+
 def fuse_uv2pt(points4, table: FrameTable, depth, radius=0.05, zmin=0.1, zmax=4.0, stats=None, audit=False,
                frame_begin=0, frame_end=None):
     frame_end = table.F if frame_end is None else frame_end

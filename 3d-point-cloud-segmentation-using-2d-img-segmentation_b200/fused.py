@@ -126,13 +126,14 @@ def vote_stream(fl: FusedLabeler, host_depths, host_masks, chunk_frames=64, fram
 
 def fuse_labels_from_host(points, K, width, height, wxyz, translations, host_depths, host_masks,
                           point_range=(0.1, 4.0), radius=0.05, nclasses=133, threshold=0.5, filter_classes=None,
-                          chunk_frames=64):
+                          chunk_frames=64, out=None):
     """Public end-to-end call: everything starts in host memory, labels (int64 [N]) come back to host memory.
     Votes stay on the device (fetch them with `FusedLabeler.votes_numpy()` when needed)."""
     fl = FusedLabeler(points, K, width, height, wxyz, translations, point_range, radius, nclasses)
     vote_stream(fl, host_depths, host_masks, chunk_frames)
     labels = fl.segment(threshold, filter_classes)
-    out = torch.empty(labels.shape, dtype=labels.dtype, pin_memory=True)
+    if out is None:
+        out = torch.empty(labels.shape, dtype=labels.dtype, pin_memory=True)
     out.copy_(labels, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return out.numpy(), fl

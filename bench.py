@@ -126,7 +126,7 @@ def build_scene(scenes, engine, fused, spec, frame_lo, frame_hi, torch):
     return fl, pts, K, wxyz, t, depth, masks
 
 
-def cpu_sample(pts, K, spec, wxyz, t, depth, masks, target_pv=1.6e7):
+def cpu_sample(pts, K, spec, wxyz, t, depth, masks, target_pv=4.8e7):
     """Bounded CPU sample of the same workload: every k-th point x evenly spaced frames (about 10-30 s of CPU work)."""
     F = len(t)
     nf = min(F, 64)
@@ -155,7 +155,7 @@ def run_reference_arm(args, rank, world):
     pts = scenes.make_cloud(spec)
     nf = min(len(t), 64)
     fidx = np.unique(np.linspace(0, len(t) - 1, nf).astype(int))
-    npts = int(min(len(pts), max(1000, 1.6e7 // len(fidx))))
+    npts = int(min(len(pts), max(1000, 4.8e7 // len(fidx))))
     stride = max(1, len(pts) // npts)
     sub = np.ascontiguousarray(pts[::stride][:npts])
     wq, tt = wxyz[fidx], t[fidx]
@@ -235,15 +235,18 @@ def main():
     N, F, H, W, C1 = fl.N, f_hi - f_lo, spec.height, spec.width, NCLASSES + 1
     stats = fl.stats
 
+    labels_buf = torch.empty(N, dtype=torch.int64, device="cuda")
+
     def step_single():
+        # one launch: kernel (1) with the label resolve (kernel 3's arithmetic) fused into its epilogue
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        votes = engine.fuse_project_vote(fl.points4, fl.table, depth, masks, C1, RADIUS, fl.zmin, fl.zmax, votes=fl.votes,
-                                         accumulate=False, stats=stats)
+        votes, labels = engine.fuse_project_vote_resolve(fl.points4, fl.table, depth, masks, C1, NCLASSES, RADIUS, fl.zmin,
+                                                         fl.zmax, THRESHOLD, None, votes=fl.votes, labels=labels_buf,
+                                                         stats=stats)
         e1.record()
         fl.votes = votes
-        labels = engine.resolve_labels(votes, NCLASSES, THRESHOLD, None)
-        return labels, (e0, e1), 2
+        return labels, (e0, e1), 1
 
     def step_multi():
         launches = [0]
@@ -301,7 +304,7 @@ def main():
         peak, how = peaks()
         ach = balg / (kms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "kernel": "fuse_kernel<VOTE,U16>", "kernel_ms": kms, "algorithmic_bytes": balg, "peak_source": how,
+                "kernel": "fuse_kernel<VOTE,U16> (project + z-test + gather + vote + fused resolve)", "kernel_ms": kms, "algorithmic_bytes": balg, "peak_source": how,
                 "bytes_per_point_view": balg / (float(N) * F)}
         prof = ROOT / "profiles" / "fuse_kernel_traffic.json"
         if prof.exists():

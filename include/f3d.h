@@ -71,9 +71,7 @@ int f3d_frames_export(const void* frame_table, int32_t nframes, double* eyes, do
  *   depth    [F,H,W] uint16 mm or float32 m (depth_fmt); mask [F,H,W] uint8 class ids < C1
  *   radius   criterion distance (fusion.py:225, strict <); zmin/zmax valid range (fusion.py:62-63: > / <=)
  *   votes    [N,C1] int32, row-major like the reference's votes[npts, nclasses+1] (voting.py:34).
- *            accumulate = 0: every cell is overwritten (no memset needed); 1: added to.
- *   labels   optional [N] int64: if non-NULL the label resolve of f3d_resolve_labels is fused into the
- *            epilogue (only meaningful when this call sees all frames, i.e. accumulate = 0)
+ *            accumulate = 0: every cell is overwritten (no memset needed); 1: added to.  16-byte aligned.
  *   stats    optional uint64[F3D_NSTATS], accumulated with atomics (caller zeroes)
  *   flags    bit 0: audit mode (fp64 for every candidate, counts F3D_STAT_AUDIT_BAD) */
 int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
@@ -81,6 +79,17 @@ int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table
                           int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
                           int32_t* votes, int32_t C1, int32_t accumulate, uint64_t* stats, int32_t flags,
                           void* stream);
+
+/* f3d_fuse_project_vote with VotingSegmentation.segment (segUtils/voting.py:106-137, see f3d_resolve_labels) fused
+ * into the epilogue: labels [N] int64 are resolved straight from the on-chip histograms, so the vote tensor is
+ * never re-read.  All frames must be covered by this one call (no accumulation).  votes may be NULL: then only
+ * labels are produced and the 4*N*C1-byte vote write is skipped. */
+int f3d_fuse_project_vote_resolve(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                                  int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
+                                  int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
+                                  int32_t* votes, int32_t C1, double threshold, const int32_t* h_filter,
+                                  int32_t nfilter, int32_t nclasses_id, int64_t* labels, uint64_t* stats,
+                                  int32_t flags, void* stream);
 
 /* Same traversal, but writes the reference's exchange format instead of votes: uv2pt [F,H*W] int32,
  * value = highest cloud-point index seen through the pixel, -1 = none (fusion.py:253,297,322).  The caller

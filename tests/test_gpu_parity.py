@@ -146,6 +146,23 @@ def test_level_p_chunked_accumulate_and_empty(engine, scenes):
     assert v0.sum() == 0
 
 
+def test_fused_resolve_epilogue(engine, scenes):
+    """f3d_fuse_project_vote_resolve: labels straight from the on-chip histograms == segment(votes)."""
+    s = small_scene(scenes, orc, npoints=30011, nframes=6, width=320, height=240, seed=53, block=16)
+    ov = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0, 0.05,
+                               0.1, 4.0, 4.0)
+    tab = engine.FrameTable(s["K"], s["W"], s["H"], s["wxyz"], s["t"], 4.0)
+    p4 = engine.pack_points(s["points"])
+    d, m = dev(s["depths"]), dev(s["masks"])
+    for thr, fc, ncls in [(0.5, None, 133), (0.5, [86, 114, 115], 133), (0.3, [1, 0, 5], 133), (0.75, None, 134),
+                          (0.0, list(range(133, -1, -1)), 133)]:
+        votes, labels = engine.fuse_project_vote_resolve(p4, tab, d, m, 134, ncls, 0.05, 0.1, 4.0, thr, fc)
+        assert np.array_equal(votes.cpu().numpy(), ov)
+        assert np.array_equal(labels.cpu().numpy(), orc.segment(ov, ncls, thr, fc)), (thr, fc, ncls)
+    none_votes, labels = engine.fuse_project_vote_resolve(p4, tab, d, m, 134, 133, 0.05, 0.1, 4.0, 0.5, None, want_votes=False)
+    assert none_votes is None and np.array_equal(labels.cpu().numpy(), orc.segment(ov, 133, 0.5, None))
+
+
 def test_unsorted_cloud_same_votes(engine, scenes):
     s = small_scene(scenes, orc, npoints=20000, nframes=4, width=160, height=120, seed=37)
     base, _, _, _ = run_fused(engine, s)

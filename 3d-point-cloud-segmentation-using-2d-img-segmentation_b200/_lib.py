@@ -24,13 +24,15 @@ SIGNATURES = {
     "f3d_frame_table_bytes": (_i64, [_i32]),
     "f3d_frames_setup": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _f64, _vp, _vp]),
     "f3d_frames_export": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
+    "f3d_fuse_workspace_bytes": (_i64, [_i64]),
     "f3d_fuse_project_vote": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64, _f64,
-                                        _vp, _i32, _i32, _vp, _i32, _vp]),
+                                        _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
     "f3d_fuse_project_vote_resolve": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64,
-                                                _f64, _vp, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
+                                                _f64, _vp, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _i32, _vp]),
     "f3d_fuse_uv2pt": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _f64, _f64, _f64, _vp, _vp,
-                                 _i32, _vp]),
-    "f3d_zbuffer_splat": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _vp]),
+                                 _i64, _vp, _i32, _vp]),
+    "f3d_zbuffer_splat": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _i32,
+                                    _vp]),
     "f3d_vote_uv2pt": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _i64, _i32, _vp]),
     "f3d_vote_finalize": (C.c_int, [_vp, _i64, _vp]),
     "f3d_resize_nearest_u8": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),

@@ -26,6 +26,7 @@
 //     no memset.  The label resolve can run straight from that histogram.
 #include "f3d_common.cuh"
 #include "f3d_host.h"
+#include <cstdlib>
 
 #define MODE_VOTE 0
 #define MODE_SPLAT 1
@@ -43,6 +44,14 @@ struct FuseResolve {
     double threshold;
     int16_t fpos[RES_MAXC];        // column -> first position in the filter list (or column itself), -1 = not considered
     int32_t remap[RES_MAXC];       // arg-max position -> label (sequential remap of voting.py:133-135 composed)
+};
+
+// an uncertain point-view handed from the fused sweep to the fix-up kernels through the caller's workspace
+struct GEntry {
+    int32_t pt;        // global point index (-1: reserved but unused slot)
+    uint32_t w;        // frame (relative to f_begin) | st << 16 | seen << 24
+    int32_t pix;       // fp32 pixel guess
+    uint32_t guess;    // fp32 decision guess (visibility / quantised depth)
 };
 
 struct FuseParams {
@@ -64,7 +73,10 @@ struct FuseParams {
     uint32_t* zbuf;
     int64_t* labels;
     unsigned long long* stats;
-    int audit;
+    int audit, dbg;   // dbg: timing experiments only (bits: 1 drop candidates, 2 skip cull, 4 classify only)
+    GEntry* gq;                    // workspace queue of deferred point-views (NULL: evaluate them inside the sweep)
+    unsigned long long* gq_count;
+    unsigned long long gq_cap;
 };
 
 struct ExactOut {
@@ -227,56 +239,77 @@ __device__ __forceinline__ int distance_test(const float4* __restrict__ s, const
     return 3;
 }
 
-// One deferred (uncertain) point-view: evaluated in fp64 after the fp32 sweep, one queue entry per thread, so the
-// expensive exact path runs with full warps instead of one or two live lanes per warp.
-//   w0 = owner thread | frame (relative) << 16 ;  w1 = pixel guess (26 bits) | g_in/zq-low ... see pack below
+// One deferred (uncertain) point-view.  Each warp queues the pairs its fp32 sweep could not certify and evaluates
+// them in fp64 afterwards with one entry per lane, so the expensive exact path runs on dense warps instead of one
+// or two live lanes; no CTA-wide barrier is involved (queue, histogram rows and output rows are all warp-private).
 struct Deferred {
-    uint32_t w0, w1, w2;
+    uint32_t w0, w1, w2;   // owner lane | frame (relative) << 16 ; pixel guess ; st | guess << 8
 };
-#define FUSE_QCAP 176   // deferred entries per CTA (12 B each); overflow falls back to inline evaluation
+#define FUSE_QWARP 20   // deferred entries per warp (12 B each); overflow falls back to inline evaluation
+
+struct Tally {
+    unsigned n_cand, n_exact, n_div, n_edge, n_seen, n_bad;
+    int total, best, bpos;   // running VotingSegmentation.segment state of this thread's point (fused resolve)
+};
+
+// a vote for class `cls` of the thread's own point: bump the histogram and keep the running arg-max exact:
+// best = max count so far, bpos = smallest filter position among the classes whose count equals best.
+__device__ __forceinline__ void cast_vote(uint16_t* hist, int row_off, int cls, const FuseParams& P, const FuseResolve& RP,
+                                          Tally& t) {
+    if (cls >= P.C1) return;
+    const int v = (int)hist[row_off + cls] + 1;
+    hist[row_off + cls] = (uint16_t)v;
+    if (RP.enabled) {
+        ++t.total;
+        const int pos = RP.fpos[cls];
+        if (pos >= 0 && (v > t.best || (v == t.best && pos < t.bpos))) {
+            t.best = v;
+            t.bpos = pos;
+        }
+    }
+}
 
 template <int MODE, int FMT>
-__device__ __forceinline__ void resolve_exact(const FuseParams& P, const FrameRecord* __restrict__ frec, uint16_t* hist, int RS,
-                                              int64_t tile_base, int owner, int frel, float px, float py, float pz, int st,
-                                              int g_in, int pix, bool fast_seen, uint32_t fast_zq, bool owner_is_self,
-                                              unsigned& n_exact, unsigned& n_div, unsigned& n_edge, unsigned& n_seen,
-                                              unsigned& n_bad) {
+__device__ __forceinline__ void resolve_exact(const FuseParams& P, const FuseResolve& RP, const FrameRecord* __restrict__ frec,
+                                              uint16_t* hist, int RS, int64_t tile_base, int owner_tid, int frel, float px, float py,
+                                              float pz, int st, int g_in, int pix, bool fast_seen, uint32_t fast_zq,
+                                              bool owner_is_self, unsigned* dirty_w, Tally& t) {
     const int HW = P.H * P.W;
     ExactOut eo;
     exact_eval<MODE, FMT>(P, &frec[P.f_begin + frel].exact, frel, px, py, pz, eo);
     const bool e_seen = (MODE == MODE_SPLAT) ? (eo.in != 0) : (eo.vis != 0);
     const uint32_t e_zq = (MODE == MODE_SPLAT && eo.in) ? quantise_mm(eo.zcam) : 0u;
     if (st >= 2) {
-        ++n_exact;
+        ++t.n_exact;
         bool diverged;
         if (st == 2) diverged = (g_in != eo.in) || (eo.in && pix != eo.pix);
         else if (MODE == MODE_SPLAT) diverged = (!eo.in) || (pix != eo.pix) || ((uint32_t)g_in != e_zq);
         else diverged = (g_in != eo.vis) || (eo.in && pix != eo.pix);
-        n_div += diverged ? 1u : 0u;
+        t.n_div += diverged ? 1u : 0u;
     } else {
         // audit: a certified fp32 outcome must equal the fp64 outcome
         const bool bad = (fast_seen != e_seen) || (fast_seen && pix != eo.pix) || (fast_seen && MODE == MODE_SPLAT && fast_zq != e_zq);
-        n_bad += bad ? 1u : 0u;
+        t.n_bad += bad ? 1u : 0u;
     }
-    n_edge += (eo.in && eo.near_edge) ? 1u : 0u;
+    t.n_edge += (eo.in && eo.near_edge) ? 1u : 0u;
     if (e_seen) {
-        ++n_seen;
+        ++t.n_seen;
         const size_t off = (size_t)frel * (size_t)HW + (size_t)eo.pix;
         if (MODE == MODE_VOTE) {
             const int cls = __ldg(P.mask + off);
-            if (cls < P.C1) {
-                if (owner_is_self) {
-                    hist[owner * RS + cls] += 1;
-                } else {
-                    // another thread's row: 32-bit atomic on the word holding the uint16 counter (cannot carry: <= 65535 frames)
-                    const int h = owner * RS + cls;
-                    atomicAdd(reinterpret_cast<unsigned*>(hist) + (h >> 1), (h & 1) ? 0x10000u : 1u);
-                }
+            if (owner_is_self) {
+                cast_vote(hist, owner_tid * RS, cls, P, RP, t);
+            } else if (cls < P.C1) {
+                // another lane's row: 32-bit atomic on the word holding the uint16 counter (cannot carry: <= 65535 frames);
+                // the owner re-derives its arg-max from the row afterwards (dirty bit)
+                const int h = owner_tid * RS + cls;
+                atomicAdd(reinterpret_cast<unsigned*>(hist) + (h >> 1), (h & 1) ? 0x10000u : 1u);
+                atomicOr(dirty_w, 1u << (owner_tid & 31));
             }
         } else if (MODE == MODE_SPLAT) {
             atomicMin(P.zbuf + off, e_zq);
         } else {
-            atomicMax(P.uv2pt + off, (int)(tile_base + owner));
+            atomicMax(P.uv2pt + off, (int)(tile_base + owner_tid));
         }
     }
 }
@@ -284,20 +317,22 @@ __device__ __forceinline__ void resolve_exact(const FuseParams& P, const FrameRe
 template <int MODE, int FMT>
 __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P, const FuseResolve RP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [2 x stage FrameFast x FUSE_STAGE][cand u16 x FUSE_FCHUNK][red: 48 floats | ncand | nq | 2 mbarriers]
-    //         [deferred queue][hist]
+    // layout: [2 x stage FrameFast x FUSE_STAGE][cand u16 x FUSE_FCHUNK][red: 48 floats | ncand | 2 mbarriers | 8 nq | 8 dirty]
+    //         [deferred queues: 8 warps x FUSE_QWARP][hist]
     float4* stage = reinterpret_cast<float4*>(smem_raw);
     uint16_t* cand = reinterpret_cast<uint16_t*>(smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast));
     float* red = reinterpret_cast<float*>(smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t));
     int* ncand_s = reinterpret_cast<int*>(red + 48);
-    int* nq_s = reinterpret_cast<int*>(red + 49);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 52);   // two barriers (16-byte aligned offset)
-    Deferred* queue = reinterpret_cast<Deferred*>(red + 64);
-    uint16_t* hist = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(queue) + FUSE_QCAP * sizeof(Deferred));
+    int* nq_s = reinterpret_cast<int*>(red + 56);             // per-warp deferred counts
+    unsigned* dirty_s = reinterpret_cast<unsigned*>(red + 64);
+    Deferred* queue_all = reinterpret_cast<Deferred*>(red + 72);
+    uint16_t* hist = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(queue_all) + (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred));
     const int RS = P.RS;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    Deferred* queue = queue_all + warp * FUSE_QWARP;
     const int64_t tile_base = (int64_t)blockIdx.x * FUSE_BLOCK;
     const int64_t gi = tile_base + tid;
     const bool active = gi < P.N;
@@ -310,8 +345,11 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
-        *nq_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (lane == 0) {
+        nq_s[warp] = 0;
+        dirty_s[warp] = 0u;
     }
     if (MODE == MODE_VOTE) {
         uint4* h128 = reinterpret_cast<uint4*>(hist);
@@ -357,16 +395,20 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
 
     const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
 
-    unsigned n_cand = 0, n_exact = 0, n_div = 0, n_edge = 0, n_seen = 0, n_bad = 0;
+    Tally T;
+    T.n_cand = T.n_exact = T.n_div = T.n_edge = T.n_seen = T.n_bad = 0u;
+    T.total = 0;
+    T.best = 0;
+    T.bpos = 0x7fff;
     unsigned phase_bits = 0;   // parity of the two staging barriers
 
     for (int cbase = P.f_begin; cbase < P.f_end; cbase += FUSE_FCHUNK) {
-        __syncthreads();   // previous chunk's candidate list fully consumed; red[] reads done
+        if (cbase != P.f_begin) __syncthreads();   // previous chunk's candidate list fully consumed
         if (tid == 0) *ncand_s = 0;
         __syncthreads();
         const int cend = min(cbase + FUSE_FCHUNK, P.f_end);
         // ---- conservative tile x frustum cull (fp32 + explicit rounding margin; never drops a visible pair)
-        for (int f0 = cbase; f0 < cend; f0 += FUSE_BLOCK) {
+        for (int f0 = cbase; f0 < cend && !(P.dbg & 2); f0 += FUSE_BLOCK) {
             const int f = f0 + tid;
             bool keep = false;
             if (f < cend) {
@@ -388,8 +430,8 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
             if (keep) cand[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(f - P.f_begin);
         }
         __syncthreads();
-        const int ncand = *ncand_s;
-        if (active) n_cand += (unsigned)ncand;
+        const int ncand = (P.dbg & 3) ? 0 : *ncand_s;
+        if (active) T.n_cand += (unsigned)ncand;
         const int nbatch = (ncand + FUSE_STAGE - 1) / FUSE_STAGE;
 
         // TMA producer (warp 0): lane 0 arms the barrier with the batch's byte count, lane k issues the 128-byte bulk
@@ -410,7 +452,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
             const int buf = batch & 1;
             const int b0 = batch * FUSE_STAGE;
             const int nb = min(FUSE_STAGE, ncand - b0);
-            // buffer buf^1 was consumed by every thread before the barrier at the end of the previous iteration
+            // buffer buf^1 was released by the barrier at the end of iteration batch-1
             if (warp == 0 && batch + 1 < nbatch) issue(batch + 1);
             mbar_wait(&mbar[buf], (phase_bits >> buf) & 1u);
             phase_bits ^= (1u << buf);
@@ -418,14 +460,11 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
                 for (int k0 = 0; k0 < nb; k0 += FUSE_NB) {
                     // ---- phase 1: fp32 projection + certification of NB candidates
                     uint32_t puv[FUSE_NB];
-                    uint32_t dv[FUSE_NB];      // depth sample bits; for uint16 depth the mask byte rides in bits 16..23
-                    uint32_t mv = 0, mv2 = 0;  // mask bytes for float depth (4 per register)
                     unsigned stw = 0;          // 4 bits per candidate: st | g_in << 3
                     float zc[MODE == MODE_SPLAT ? FUSE_NB : 1];
 #pragma unroll
                     for (int k = 0; k < FUSE_NB; ++k) {
                         puv[k] = 0;
-                        dv[k] = 0;
                         if (k0 + k < nb) {
                             const Cls c = classify(stage + (buf * FUSE_STAGE + k0 + k) * 8, pt, fW, fH);
                             puv[k] = c.puv;
@@ -433,23 +472,29 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
                             if (MODE == MODE_SPLAT) zc[k] = c.z;
                         }
                     }
-                    if (stw == 0 && !P.audit) continue;
-                    // ---- phase 2: all gathers of the certified candidates in flight together
+                    if ((stw == 0 && !P.audit) || (P.dbg & 4)) continue;
+                    // ---- phase 2: every gather of the certified candidates is issued before any is consumed
+                    uint32_t dv[MODE == MODE_SPLAT ? 1 : FUSE_NB];
+                    uint32_t mk[MODE == MODE_VOTE ? FUSE_NB : 1];
                     if (MODE != MODE_SPLAT) {
 #pragma unroll
                         for (int k = 0; k < FUSE_NB; ++k) {
+                            dv[k] = 0;
+                            if (MODE == MODE_VOTE) mk[k] = 0;
                             if (((stw >> (4 * k)) & 7u) == 1u) {
                                 const size_t off = (size_t)cand[b0 + k0 + k] * (size_t)HW + (size_t)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
                                 if (FMT == F3D_DEPTH_U16_MM) dv[k] = __ldg(reinterpret_cast<const uint16_t*>(P.depth) + off);
                                 else dv[k] = __float_as_uint(__ldg(reinterpret_cast<const float*>(P.depth) + off));
-                                if (MODE == MODE_VOTE) {
-                                    const uint32_t m = __ldg(P.mask + off);
-                                    if (FMT == F3D_DEPTH_U16_MM) dv[k] |= m << 16;
-                                    else if (k < 4) mv |= m << (8 * k);
-                                    else mv2 |= m << (8 * (k - 4));
-                                }
+                                if (MODE == MODE_VOTE) mk[k] = __ldg(P.mask + off);
                             }
                         }
+                    }
+                    if (P.dbg & 8) {   // timing experiment: consume the gathers trivially
+                        unsigned acc = 0;
+#pragma unroll
+                        for (int k = 0; k < FUSE_NB; ++k) acc ^= dv[MODE == MODE_SPLAT ? 0 : k] ^ mk[MODE == MODE_VOTE ? k : 0];
+                        if (acc == 0xdeadbeefu) T.n_bad++;
+                        continue;
                     }
                     // ---- phase 3: depth validity + distance criterion, votes; uncertain pairs are deferred
 #pragma unroll
@@ -462,19 +507,16 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
                         int g_in = (int)((stw >> (4 * k + 3)) & 1u);
                         const int pix = (int)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
                         uint32_t zq = 0;
-                        int cls = 0;
                         if (st == 1 && MODE != MODE_SPLAT) {
                             float dm;
                             bool valid;
                             if (FMT == F3D_DEPTH_U16_MM) {
-                                const uint32_t d = dv[k] & 0xffffu;
+                                const uint32_t d = dv[k];
                                 valid = (d >= P.d_lo) && (d <= P.d_hi);
                                 dm = (float)d * 0.001f;
-                                cls = (int)(dv[k] >> 16);
                             } else {
                                 dm = __uint_as_float(dv[k]);
                                 valid = ((double)dm > P.zmin) && ((double)dm <= P.zmax);
-                                cls = (int)(((k < 4 ? mv >> (8 * k) : mv2 >> (8 * (k - 4)))) & 0xffu);
                             }
                             st = valid ? distance_test(s, pt, puv[k], dm, P, g_in) : 0;
                         }
@@ -494,21 +536,21 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
                             }
                         }
                         const bool seen = (st == 1);
-                        if (st >= 2 || P.audit) {
-                            // defer to the dense fp64 pass (queue full or audit sweep: evaluate inline)
-                            const int slot = (st >= 2 && !P.audit) ? atomicAdd(nq_s, 1) : FUSE_QCAP;
-                            if (slot < FUSE_QCAP) {
+                        if ((st >= 2 && !(P.dbg & 16)) || P.audit) {
+                            // defer to the warp's dense fp64 pass (queue full or audit sweep: evaluate inline)
+                            const int slot = (st >= 2 && !P.audit) ? atomicAdd(nq_s + warp, 1) : FUSE_QWARP;
+                            if (slot < FUSE_QWARP) {
                                 queue[slot].w0 = (uint32_t)tid | ((uint32_t)frel << 16);
                                 queue[slot].w1 = (uint32_t)pix;
                                 queue[slot].w2 = (uint32_t)st | ((uint32_t)g_in << 8);
                             } else {
-                                resolve_exact<MODE, FMT>(P, frec, hist, RS, tile_base, tid, frel, pt.x, pt.y, pt.z, st, g_in, pix, seen,
-                                                         zq, true, n_exact, n_div, n_edge, n_seen, n_bad);
+                                resolve_exact<MODE, FMT>(P, RP, frec, hist, RS, tile_base, tid, frel, pt.x, pt.y, pt.z, st, g_in, pix,
+                                                         seen, zq, true, dirty_s + warp, T);
                             }
                         } else if (seen) {
-                            ++n_seen;
+                            ++T.n_seen;
                             if (MODE == MODE_VOTE) {
-                                if (cls < P.C1) hist[tid * RS + cls] += 1;
+                                cast_vote(hist, tid * RS, (int)mk[k], P, RP, T);
                             } else {
                                 const size_t off = (size_t)frel * (size_t)HW + (size_t)pix;
                                 if (MODE == MODE_SPLAT) atomicMin(P.zbuf + off, zq);
@@ -518,45 +560,62 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
                     }
                 }
             }
-            __syncthreads();   // every thread is done with stage buffer `buf` -> it may be refilled next iteration
+            if (batch + 1 < nbatch) __syncthreads();   // stage buffer `buf` may be refilled two iterations later
         }
     }
 
-    // ---- dense fp64 pass over the deferred point-views (one entry per thread)
-    __syncthreads();
+    // ---- warp-private dense fp64 pass over the deferred point-views (one entry per lane)
+    __syncwarp();
     {
-        const int nq = min(*nq_s, FUSE_QCAP);
-        for (int q = tid; q < nq; q += FUSE_BLOCK) {
-            const Deferred d = queue[q];
+        const int nq = min(nq_s[warp], FUSE_QWARP);
+        // preferred: hand the uncertain pairs to the dense fix-up kernels through the caller's workspace queue
+        bool flushed = false;
+        if (P.gq && nq > 0) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.gq_count, (unsigned long long)nq);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            flushed = base + (unsigned long long)nq <= P.gq_cap;
+            if (lane < nq && base + lane < P.gq_cap) {
+                const Deferred d = queue[lane];
+                GEntry e;
+                e.pt = flushed ? (int)(tile_base + (d.w0 & 0xffffu)) : -1;   // -1: slot reserved but unused (queue overflow)
+                e.w = (d.w0 >> 16) | ((d.w2 & 0xffu) << 16);
+                e.pix = (int)d.w1;
+                e.guess = d.w2 >> 8;
+                P.gq[base + lane] = e;
+            }
+        }
+        if (!flushed && lane < nq) {
+            const Deferred d = queue[lane];
             const int owner = (int)(d.w0 & 0xffffu), frel = (int)(d.w0 >> 16);
             const float4 op = __ldg(P.points + tile_base + owner);
-            resolve_exact<MODE, FMT>(P, frec, hist, RS, tile_base, owner, frel, op.x, op.y, op.z, (int)(d.w2 & 0xffu), (int)(d.w2 >> 8),
-                                     (int)d.w1, false, 0u, false, n_exact, n_div, n_edge, n_seen, n_bad);
+            resolve_exact<MODE, FMT>(P, RP, frec, hist, RS, tile_base, owner, frel, op.x, op.y, op.z, (int)(d.w2 & 0xffu),
+                                     (int)(d.w2 >> 8), (int)d.w1, false, 0u, false, dirty_s + warp, T);
         }
     }
+    __syncwarp();
 
-    // ---- epilogue: histogram -> HBM, written once with 16-byte stores; optional fused label resolve
+    // ---- epilogue (warp-private rows): histogram -> HBM, written once with 16-byte stores; fused label resolve
     if (MODE == MODE_VOTE) {
-        __syncthreads();
-        const int npts_tile = (int)min((int64_t)FUSE_BLOCK, P.N - tile_base);
-        if (P.votes) {
-            const int total = npts_tile * P.C1;
-            int32_t* __restrict__ out = P.votes + tile_base * P.C1;
+        const int row0 = warp * 32;
+        const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
+        if (P.votes && nrows > 0) {
+            int32_t* __restrict__ out = P.votes + (tile_base + row0) * P.C1;
             if (RS == P.C1 && !P.accumulate) {
-                // rows are dense (RS == C1): the histogram is the output tile, widened from uint16 to int32
-                const uint2* __restrict__ h64 = reinterpret_cast<const uint2*>(hist);
-                const int n4 = total >> 2;     // C1 even and 256 rows => total % 4 == 0 for full tiles
-                for (int i = tid; i < n4; i += FUSE_BLOCK) {
+                // rows are dense (RS == C1): the histogram rows are the output rows, widened from uint16 to int32
+                const uint2* __restrict__ h64 = reinterpret_cast<const uint2*>(hist + row0 * RS);
+                const int total = nrows * P.C1;
+                const int n4 = total >> 2;
+                for (int i = lane; i < n4; i += 32) {
                     const uint2 w = h64[i];
                     *reinterpret_cast<int4*>(out + 4 * i) =
                         make_int4((int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16));
                 }
-                for (int e = (n4 << 2) + tid; e < total; e += FUSE_BLOCK) out[e] = (int)hist[e];
+                for (int e = (n4 << 2) + lane; e < total; e += 32) out[e] = (int)hist[row0 * RS + e];
             } else {
-                // a warp per row, lanes over classes (coalesced within the 4*C1-byte row)
-                for (int j = warp; j < npts_tile; j += FUSE_BLOCK / 32) {
+                for (int j = 0; j < nrows; ++j) {
                     for (int c = lane; c < P.C1; c += 32) {
-                        const int v = (int)hist[j * RS + c];
+                        const int v = (int)hist[(row0 + j) * RS + c];
                         if (!P.accumulate) out[j * P.C1 + c] = v;   // overwrite mode writes every cell exactly once
                         else if (v) out[j * P.C1 + c] += v;         // accumulate mode touches only the sparse non-zero cells
                     }
@@ -564,40 +623,32 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
             }
         }
         if (RP.enabled && active) {
-            // VotingSegmentation.segment straight from the histogram row (voting.py:120-135); rows are sparse, so the
-            // row is scanned as 32-bit words and only non-zero counters compete (a zero can never win, voting.py:131)
-            const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(hist + tid * RS);
-            int total = 0, best = 0, bpos = 0x7fff;
-            const int nw = (P.C1 + 1) >> 1;
-            for (int w = 0; w < nw; ++w) {
-                const uint32_t x = row[w];
-                if (x == 0u) continue;
-                const int v0 = (int)(x & 0xffffu), v1 = (2 * w + 1 < P.C1) ? (int)(x >> 16) : 0;
-                total += v0 + v1;
-                if (v0) {
-                    const int pos = RP.fpos[2 * w];
-                    if (pos >= 0 && (v0 > best || (v0 == best && pos < bpos))) {
-                        best = v0;
-                        bpos = pos;
-                    }
-                }
-                if (v1) {
-                    const int pos = RP.fpos[2 * w + 1];
-                    if (pos >= 0 && (v1 > best || (v1 == best && pos < bpos))) {
-                        best = v1;
-                        bpos = pos;
+            // VotingSegmentation.segment (voting.py:120-135).  The running (total, best, bpos) is exact unless another
+            // lane's deferred pass added votes to this row: then it is re-derived from the row itself.
+            if ((dirty_s[warp] >> lane) & 1u) {
+                const uint16_t* __restrict__ row = hist + tid * RS;
+                T.total = 0;
+                T.best = 0;
+                T.bpos = 0x7fff;
+                for (int c = 0; c < P.C1; ++c) {
+                    const int v = row[c];
+                    T.total += v;
+                    const int pos = RP.fpos[c];
+                    if (v > 0 && pos >= 0 && (v > T.best || (v == T.best && pos < T.bpos))) {
+                        T.best = v;
+                        T.bpos = pos;
                     }
                 }
             }
-            bool unc = (total <= 0) || (best <= 0);                                   // voting.py:126,131
-            if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;          // voting.py:128-130
-            P.labels[gi] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
+            bool unc = (T.total <= 0) || (T.best <= 0);                                  // voting.py:126,131
+            if (!unc) unc = xdiv((double)T.best, (double)T.total) < RP.threshold;         // voting.py:128-130
+            P.labels[gi] = (int64_t)(unc ? RP.unclassified : RP.remap[T.bpos]);
         }
     }
 
     // ---- statistics
     if (P.stats) {
-        unsigned vals[6] = {n_cand, n_exact, n_div, n_edge, n_seen, n_bad};
+        unsigned vals[6] = {T.n_cand, T.n_exact, T.n_div, T.n_edge, T.n_seen, T.n_bad};
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             unsigned v = vals[i];
@@ -605,6 +656,84 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
             for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
             if (lane == 0 && v) atomicAdd(P.stats + i, (unsigned long long)v);
         }
+    }
+}
+
+// ---- fix-up kernels: the deferred point-views, one per thread, in fp64 ------------------------------------------------
+template <int MODE, int FMT>
+__global__ void __launch_bounds__(256) fixup_apply_kernel(const FuseParams P) {
+    const unsigned long long n = min(*P.gq_count, P.gq_cap);
+    const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
+    const int HW = P.H * P.W;
+    unsigned n_exact = 0, n_div = 0, n_edge = 0, n_seen = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        GEntry e = P.gq[i];
+        if (e.pt < 0) continue;
+        const int frel = (int)(e.w & 0xffffu), st = (int)((e.w >> 16) & 0xffu);
+        const float4 p = __ldg(P.points + e.pt);
+        ExactOut eo;
+        exact_eval<MODE, FMT>(P, &frec[P.f_begin + frel].exact, frel, p.x, p.y, p.z, eo);
+        const bool e_seen = (MODE == MODE_SPLAT) ? (eo.in != 0) : (eo.vis != 0);
+        const uint32_t e_zq = (MODE == MODE_SPLAT && eo.in) ? quantise_mm(eo.zcam) : 0u;
+        bool diverged;
+        if (st == 2) diverged = ((int)e.guess != eo.in) || (eo.in && e.pix != eo.pix);
+        else if (MODE == MODE_SPLAT) diverged = (!eo.in) || (e.pix != eo.pix) || (e.guess != e_zq);
+        else diverged = ((int)e.guess != eo.vis) || (eo.in && e.pix != eo.pix);
+        ++n_exact;
+        n_div += diverged ? 1u : 0u;
+        n_edge += (eo.in && eo.near_edge) ? 1u : 0u;
+        if (e_seen) {
+            ++n_seen;
+            const size_t off = (size_t)frel * (size_t)HW + (size_t)eo.pix;
+            if (MODE == MODE_VOTE) {
+                const int cls = __ldg(P.mask + off);
+                if (cls < P.C1) {
+                    atomicAdd(P.votes + (size_t)e.pt * P.C1 + cls, 1);
+                    P.gq[i].w = e.w | (1u << 24);   // this point's label must be re-resolved
+                }
+            } else if (MODE == MODE_SPLAT) {
+                atomicMin(P.zbuf + off, e_zq);
+            } else {
+                atomicMax(P.uv2pt + off, e.pt);
+            }
+        }
+    }
+    if (P.stats) {
+        unsigned vals[4] = {n_exact, n_div, n_edge, n_seen};
+        const int idx[4] = {F3D_STAT_EXACT, F3D_STAT_DIVERGED, F3D_STAT_NEAR_EDGE, F3D_STAT_SEEN};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned v = vals[k];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(P.stats + idx[k], (unsigned long long)v);
+        }
+    }
+}
+
+// labels of the points whose votes changed in fixup_apply_kernel (VotingSegmentation.segment, voting.py:120-135)
+__global__ void __launch_bounds__(256) fixup_labels_kernel(const FuseParams P, const FuseResolve RP) {
+    const unsigned long long n = min(*P.gq_count, P.gq_cap);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const GEntry e = P.gq[i];
+        if (e.pt < 0 || !((e.w >> 24) & 1u)) continue;
+        const int32_t* __restrict__ row = P.votes + (size_t)e.pt * P.C1;
+        long long total = 0;
+        int best = 0, bpos = 0x7fff;
+        for (int c = 0; c < P.C1; ++c) {
+            const int v = row[c];
+            total += v;
+            const int pos = RP.fpos[c];
+            if (v > 0 && pos >= 0 && (v > best || (v == best && pos < bpos))) {
+                best = v;
+                bpos = pos;
+            }
+        }
+        bool unc = (total <= 0) || (best <= 0);
+        if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;
+        P.labels[e.pt] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
     }
 }
 
@@ -627,7 +756,8 @@ static int hist_row_stride(int C1) {
 }
 
 static size_t fuse_smem_bytes(int mode, int C1) {
-    size_t b = 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t) + 64 * sizeof(float) + FUSE_QCAP * sizeof(Deferred);
+    size_t b = 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t) + 72 * sizeof(float) +
+               (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred);
     if (mode == MODE_VOTE) b += ((size_t)FUSE_BLOCK * hist_row_stride(C1) * sizeof(uint16_t) + 15) & ~(size_t)15;
     return b;
 }
@@ -635,13 +765,43 @@ static size_t fuse_smem_bytes(int mode, int C1) {
 template <int MODE, int FMT>
 static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t stream) {
     size_t smem = fuse_smem_bytes(MODE, P.C1);
+    if (const char* ex = getenv("F3D_EXTRA_SMEM")) smem += (size_t)atoi(ex);   // occupancy experiments only
     if (smem > 227 * 1024) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: nclasses+1 too large for the shared-memory histogram");
     cudaError_t e = cudaFuncSetAttribute(fuse_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute)");
     int64_t tiles = (P.N + FUSE_BLOCK - 1) / FUSE_BLOCK;
     if (tiles > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: too many points for one launch");
+    const bool use_queue = P.gq != nullptr;
+    if (use_queue) {
+        e = cudaMemsetAsync(P.gq_count, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(memset)");
+    }
     fuse_kernel<MODE, FMT><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
+    if (use_queue) {
+        // the queue length lives on the device: fixed grids with grid-stride loops, no host synchronisation
+        fixup_apply_kernel<MODE, FMT><<<148 * 4, 256, 0, stream>>>(P);
+        if (MODE == MODE_VOTE && RP.enabled) fixup_labels_kernel<<<148 * 4, 256, 0, stream>>>(P, RP);
+    }
     return f3d_check_launch("f3d_fuse");
+}
+
+// workspace = [count u64][pad u64][GEntry x cap]; returns false when the caller gave none (or too little)
+static bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_bytes) {
+    P.gq = nullptr;
+    P.gq_count = nullptr;
+    P.gq_cap = 0;
+    if (!workspace || workspace_bytes < (int64_t)(16 + sizeof(GEntry)) || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return false;
+    P.gq_count = reinterpret_cast<unsigned long long*>(workspace);
+    P.gq = reinterpret_cast<GEntry*>(reinterpret_cast<char*>(workspace) + 16);
+    P.gq_cap = (unsigned long long)((workspace_bytes - 16) / (int64_t)sizeof(GEntry));
+    return true;
+}
+
+extern "C" int64_t f3d_fuse_workspace_bytes(int64_t npoints) {
+    // room for one uncertain point-view per 4 points (measured: ~0.08 per point on the 1920x1440 scene), at least 1 Mi entries
+    int64_t cap = npoints / 4;
+    if (cap < (1 << 20)) cap = 1 << 20;
+    return 16 + cap * (int64_t)sizeof(GEntry);
 }
 
 static int fill_common(FuseParams& P, const void* points, int64_t N, const void* table, int fb, int fe, const void* depth,
@@ -679,6 +839,7 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.d_hi = hi;
     P.stats = reinterpret_cast<unsigned long long*>(stats);
     P.audit = flags & 1;
+    P.dbg = (flags >> 8) & 0xff;
     P.votes = nullptr;
     P.uv2pt = nullptr;
     P.zbuf = nullptr;
@@ -687,6 +848,9 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.C1 = 0;
     P.RS = 0;
     P.accumulate = 0;
+    P.gq = nullptr;
+    P.gq_count = nullptr;
+    P.gq_cap = 0;
     return F3D_OK;
 }
 
@@ -722,8 +886,8 @@ int f3d_build_resolve(int C1, double threshold, const int32_t* h_filter, int nfi
 static int fuse_vote_impl(const void* points, int64_t N, const void* frame_table, int32_t frame_begin, int32_t frame_end,
                           const void* depth, int32_t depth_fmt, const uint8_t* mask, int32_t H, int32_t W,
                           const double* h_K9, double radius, double zmin, double zmax, int32_t* votes, int32_t C1,
-                          int32_t accumulate, const FuseResolve& RP, int64_t* labels, uint64_t* stats, int32_t flags,
-                          void* stream) {
+                          int32_t accumulate, const FuseResolve& RP, int64_t* labels, void* workspace,
+                          int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
     FuseParams P;
     int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
                          zmax, stats, flags);
@@ -738,6 +902,7 @@ static int fuse_vote_impl(const void* points, int64_t N, const void* frame_table
     P.votes = votes;
     P.labels = labels;
     P.C1 = C1;
+    if (votes && !P.audit && N <= 0x7fffffff) attach_workspace(P, workspace, workspace_bytes);   // labels-only / audit: fp64 inside the sweep
     P.RS = hist_row_stride(C1);
     const size_t esz = depth_fmt == F3D_DEPTH_U16_MM ? 2 : 4;
     int fb = frame_begin;
@@ -761,13 +926,13 @@ static int fuse_vote_impl(const void* points, int64_t N, const void* frame_table
 extern "C" int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                                      int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
                                      int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                                     int32_t* votes, int32_t C1, int32_t accumulate, uint64_t* stats, int32_t flags,
-                                     void* stream) {
+                                     int32_t* votes, int32_t C1, int32_t accumulate, void* workspace,
+                                     int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
     if (!votes) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote: votes is NULL");
     FuseResolve RP;
     RP.enabled = 0;
     return fuse_vote_impl(points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, mask, H, W, h_K9, radius, zmin,
-                          zmax, votes, C1, accumulate, RP, nullptr, stats, flags, stream);
+                          zmax, votes, C1, accumulate, RP, nullptr, workspace, workspace_bytes, stats, flags, stream);
 }
 
 extern "C" int f3d_fuse_project_vote_resolve(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
@@ -775,20 +940,21 @@ extern "C" int f3d_fuse_project_vote_resolve(const void* points, int64_t N, cons
                                              int32_t H, int32_t W, const double* h_K9, double radius, double zmin,
                                              double zmax, int32_t* votes, int32_t C1, double threshold,
                                              const int32_t* h_filter, int32_t nfilter, int32_t nclasses_id, int64_t* labels,
-                                             uint64_t* stats, int32_t flags, void* stream) {
+                                             void* workspace, int64_t workspace_bytes, uint64_t* stats, int32_t flags,
+                                             void* stream) {
     if (!labels || nfilter < 0 || (nfilter > 0 && !h_filter))
         return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_resolve: bad argument");
     FuseResolve RP;
     int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
     if (rc) return rc;
     return fuse_vote_impl(points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, mask, H, W, h_K9, radius, zmin,
-                          zmax, votes, C1, 0, RP, labels, stats, flags, stream);
+                          zmax, votes, C1, 0, RP, labels, workspace, workspace_bytes, stats, flags, stream);
 }
 
 extern "C" int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                               int32_t frame_end, const void* depth, int32_t depth_fmt, int32_t H, int32_t W,
                               const double* h_K9, double radius, double zmin, double zmax, int32_t* uv2pt,
-                              uint64_t* stats, int32_t flags, void* stream) {
+                              void* workspace, int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
     FuseParams P;
     int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
                          zmax, stats, flags);
@@ -796,6 +962,7 @@ extern "C" int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_t
     if (!uv2pt || !depth) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_uv2pt: bad argument");
     if (N == 0 || frame_end == frame_begin) return F3D_OK;
     if (N > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_uv2pt: point index does not fit int32");
+    if (!P.audit) attach_workspace(P, workspace, workspace_bytes);
     FuseResolve RP;
     RP.enabled = 0;
     const size_t esz = depth_fmt == F3D_DEPTH_U16_MM ? 2 : 4;
@@ -814,12 +981,14 @@ extern "C" int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_t
 
 extern "C" int f3d_zbuffer_splat(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                                  int32_t frame_end, int32_t H, int32_t W, const double* h_K9, uint32_t* zbuf,
-                                 uint16_t* depth_out, int32_t border, uint64_t* stats, int32_t flags, void* stream) {
+                                 uint16_t* depth_out, int32_t border, void* workspace, int64_t workspace_bytes,
+                                 uint64_t* stats, int32_t flags, void* stream) {
     FuseParams P;
     int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, nullptr, F3D_DEPTH_U16_MM, H, W, h_K9, 0.0,
                          0.0, 0.0, stats, flags);
     if (rc) return rc;
     if (!zbuf || !depth_out || border < 0) return f3d_fail(F3D_ERR_ARG, "f3d_zbuffer_splat: bad argument");
+    if (!P.audit && N <= 0x7fffffff) attach_workspace(P, workspace, workspace_bytes);
     const int nf = frame_end - frame_begin;
     if (nf == 0) return F3D_OK;
     const int64_t total = (int64_t)nf * H * W;

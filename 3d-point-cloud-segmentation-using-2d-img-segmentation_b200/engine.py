@@ -77,6 +77,21 @@ def _depth_fmt(depth: torch.Tensor) -> int:
     raise TypeError("depth must be uint16 (millimetres) or float32 (metres)")
 
 
+_WORKSPACE = {}
+
+
+def workspace(npoints: int, device) -> torch.Tensor:
+    """Per-device scratch for the deferred fp64 fix-up queue (f3d_fuse_workspace_bytes); grown on demand, shared by
+    calls on the same stream (calls on other streams should pass their own)."""
+    need = int(load().f3d_fuse_workspace_bytes(int(npoints)))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WORKSPACE.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=device)
+        _WORKSPACE[key] = buf
+    return buf
+
+
 def new_stats() -> torch.Tensor:
     return torch.zeros(NSTATS, dtype=torch.int64, device=require_cuda())
 
@@ -98,11 +113,12 @@ def fuse_project_vote(points4, table: FrameTable, depth, mask, nclasses1, radius
     if nf > 0 and (depth.shape[0] != nf or mask.shape[0] != nf or tuple(depth.shape[1:]) != (table.H, table.W)
                    or tuple(mask.shape[1:]) != (table.H, table.W)):
         raise ValueError("depth / mask must be [frame_end-frame_begin, H, W]")
+    ws = workspace(N, points4.device)
     check(load().f3d_fuse_project_vote(
         ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth) if nf else None,
         _depth_fmt(depth) if nf else 0, ptr(mask) if nf else None, table.H, table.W, ptr(table.K), float(radius),
-        float(zmin), float(zmax), ptr(votes), int(nclasses1), int(bool(accumulate)), ptr(stats), int(bool(audit)),
-        stream_ptr()), "f3d_fuse_project_vote")
+        float(zmin), float(zmax), ptr(votes), int(nclasses1), int(bool(accumulate)), ptr(ws), ws.numel(), ptr(stats),
+        int(bool(audit)), stream_ptr()), "f3d_fuse_project_vote")
     return votes
 
 
@@ -118,12 +134,13 @@ def fuse_project_vote_resolve(points4, table: FrameTable, depth, mask, nclasses1
         labels = torch.empty(N, dtype=torch.int64, device=points4.device)
     filt = None if filter_classes is None else np.ascontiguousarray(np.asarray(filter_classes, dtype=np.int32))
     nf = frame_end - frame_begin
+    ws = workspace(N, points4.device)
     check(load().f3d_fuse_project_vote_resolve(
         ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth) if nf else None,
         _depth_fmt(depth) if nf else 0, ptr(mask) if nf else None, table.H, table.W, ptr(table.K), float(radius),
         float(zmin), float(zmax), ptr(votes), int(nclasses1), float(threshold), ptr(filt),
-        0 if filt is None else int(filt.size), int(nclasses_id), ptr(labels), ptr(stats), int(bool(audit)), stream_ptr()),
-        "f3d_fuse_project_vote_resolve")
+        0 if filt is None else int(filt.size), int(nclasses_id), ptr(labels), ptr(ws), ws.numel(), ptr(stats),
+        int(bool(audit)), stream_ptr()), "f3d_fuse_project_vote_resolve")
     return votes, labels
 
 
@@ -133,9 +150,11 @@ def fuse_uv2pt(points4, table: FrameTable, depth, radius=0.05, zmin=0.1, zmax=4.
     nf = frame_end - frame_begin
     uv2pt = torch.full((nf, table.H * table.W), -1, dtype=torch.int32, device=points4.device)
     if nf:
+        ws = workspace(points4.shape[0], points4.device)
         check(load().f3d_fuse_uv2pt(ptr(points4), points4.shape[0], ptr(table.table), frame_begin, frame_end, ptr(depth),
                                     _depth_fmt(depth), table.H, table.W, ptr(table.K), float(radius), float(zmin),
-                                    float(zmax), ptr(uv2pt), ptr(stats), int(bool(audit)), stream_ptr()), "f3d_fuse_uv2pt")
+                                    float(zmax), ptr(uv2pt), ptr(ws), ws.numel(), ptr(stats), int(bool(audit)),
+                                    stream_ptr()), "f3d_fuse_uv2pt")
     return uv2pt
 
 
@@ -150,9 +169,10 @@ def zbuffer_splat(points4, table: FrameTable, border=0, stats=None, audit=False,
     if out is None:
         out = torch.empty((nf, table.H, table.W), dtype=torch.uint16, device=dev)
     if nf:
+        ws = workspace(points4.shape[0], points4.device)
         check(load().f3d_zbuffer_splat(ptr(points4), points4.shape[0], ptr(table.table), frame_begin, frame_end, table.H,
-                                       table.W, ptr(table.K), ptr(zbuf), ptr(out), int(border), ptr(stats),
-                                       int(bool(audit)), stream_ptr()), "f3d_zbuffer_splat")
+                                       table.W, ptr(table.K), ptr(zbuf), ptr(out), int(border), ptr(ws), ws.numel(),
+                                       ptr(stats), int(bool(audit)), stream_ptr()), "f3d_zbuffer_splat")
     return out
 
 

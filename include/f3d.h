@@ -65,6 +65,12 @@ int f3d_frames_export(const void* frame_table, int32_t nframes, double* eyes, do
 
 /* ---- kernel (1): fused project + z-test + mask gather + vote (level P) ---------------------------------- */
 
+/* Optional scratch for the f3d_fuse_* / f3d_zbuffer_splat calls (16-byte aligned device memory, contents
+ * irrelevant): point-views whose fp32 decision is uncertain are queued there and re-evaluated in fp64 by dense
+ * fix-up kernels after the sweep.  Without it (NULL / 0) they are evaluated inside the sweep -- same results,
+ * slower.  A queue that fills up is handled the same way, so the size is a performance knob only. */
+int64_t f3d_fuse_workspace_bytes(int64_t npoints);
+
 /* Replaces, for a FIXED cloud, the per-frame body of Fusion.fuse (fusion.py:248-298: point_inside_polyhedra
  * -> points2pixel -> single-pixel criterion) composed with VotingSegmentation.vote (segUtils/voting.py:89-98).
  *   points   [N] float4 (x,y,z,unused) -- float32 values are the contract (widened exactly to fp64)
@@ -72,13 +78,14 @@ int f3d_frames_export(const void* frame_table, int32_t nframes, double* eyes, do
  *   radius   criterion distance (fusion.py:225, strict <); zmin/zmax valid range (fusion.py:62-63: > / <=)
  *   votes    [N,C1] int32, row-major like the reference's votes[npts, nclasses+1] (voting.py:34).
  *            accumulate = 0: every cell is overwritten (no memset needed); 1: added to.  16-byte aligned.
+ *   workspace optional scratch, see f3d_fuse_workspace_bytes
  *   stats    optional uint64[F3D_NSTATS], accumulated with atomics (caller zeroes)
  *   flags    bit 0: audit mode (fp64 for every candidate, counts F3D_STAT_AUDIT_BAD) */
 int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                           int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
                           int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                          int32_t* votes, int32_t C1, int32_t accumulate, uint64_t* stats, int32_t flags,
-                          void* stream);
+                          int32_t* votes, int32_t C1, int32_t accumulate, void* workspace, int64_t workspace_bytes,
+                          uint64_t* stats, int32_t flags, void* stream);
 
 /* f3d_fuse_project_vote with VotingSegmentation.segment (segUtils/voting.py:106-137, see f3d_resolve_labels) fused
  * into the epilogue: labels [N] int64 are resolved straight from the on-chip histograms, so the vote tensor is
@@ -88,16 +95,16 @@ int f3d_fuse_project_vote_resolve(const void* points, int64_t N, const void* fra
                                   int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
                                   int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
                                   int32_t* votes, int32_t C1, double threshold, const int32_t* h_filter,
-                                  int32_t nfilter, int32_t nclasses_id, int64_t* labels, uint64_t* stats,
-                                  int32_t flags, void* stream);
+                                  int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* workspace,
+                                  int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
 
 /* Same traversal, but writes the reference's exchange format instead of votes: uv2pt [F,H*W] int32,
  * value = highest cloud-point index seen through the pixel, -1 = none (fusion.py:253,297,322).  The caller
  * fills uv2pt with -1 first. */
 int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                    int32_t frame_end, const void* depth, int32_t depth_fmt, int32_t H, int32_t W,
-                   const double* h_K9, double radius, double zmin, double zmax, int32_t* uv2pt,
-                   uint64_t* stats, int32_t flags, void* stream);
+                   const double* h_K9, double radius, double zmin, double zmax, int32_t* uv2pt, void* workspace,
+                   int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
 
 /* ---- kernel (2): z-buffer splat ----------------------------------------------------------------------------- */
 
@@ -107,7 +114,8 @@ int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_table, int32
  *   border: pixels closer than `border` to the image edge are zeroed (ios_rtab.py:105-109). */
 int f3d_zbuffer_splat(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                       int32_t frame_end, int32_t H, int32_t W, const double* h_K9, uint32_t* zbuf,
-                      uint16_t* depth_out, int32_t border, uint64_t* stats, int32_t flags, void* stream);
+                      uint16_t* depth_out, int32_t border, void* workspace, int64_t workspace_bytes, uint64_t* stats,
+                      int32_t flags, void* stream);
 
 /* ---- level V: uv2pt + mask vote --------------------------------------------------------------------------------- */
 

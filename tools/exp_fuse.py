@@ -1,0 +1,40 @@
+"""Timing experiments on the fused kernel (GPU box only): phase switches via the debug bits of `flags`."""
+import importlib, sys, time
+from pathlib import Path
+import numpy as np, torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench
+PKG = bench.PKG_NAME
+engine = importlib.import_module(PKG + ".engine"); scenes = importlib.import_module(PKG + ".scenes"); fused = importlib.import_module(PKG + ".fused")
+from importlib import import_module
+_lib = import_module(PKG + "._lib")
+wl = sys.argv[1] if len(sys.argv) > 1 else "C2"
+spec = scenes.CONFIGS[wl]
+fl, pts, K, wxyz, t, depth, masks = bench.build_scene(scenes, engine, fused, spec, 0, spec.nframes, torch)
+N, C1 = fl.N, 134
+votes = torch.empty((N, C1), dtype=torch.int32, device="cuda"); labels = torch.empty(N, dtype=torch.int64, device="cuda")
+lib = _lib.load()
+ws = engine.workspace(N, fl.points4.device)
+def run(flags, want_votes=True, want_labels=True, reps=5):
+    def call():
+        if want_labels:
+            rc = lib.f3d_fuse_project_vote_resolve(fl.points4.data_ptr(), N, fl.table.table.data_ptr(), 0, fl.table.F, depth.data_ptr(), 0, masks.data_ptr(), fl.table.H, fl.table.W, fl.table.K.ctypes.data, 0.05, 0.1, spec.zmax, votes.data_ptr() if want_votes else None, C1, 0.5, None, 0, 133, labels.data_ptr(), ws.data_ptr(), ws.numel(), None, flags, torch.cuda.current_stream().cuda_stream)
+        else:
+            rc = lib.f3d_fuse_project_vote(fl.points4.data_ptr(), N, fl.table.table.data_ptr(), 0, fl.table.F, depth.data_ptr(), 0, masks.data_ptr(), fl.table.H, fl.table.W, fl.table.K.ctypes.data, 0.05, 0.1, spec.zmax, votes.data_ptr(), C1, 0, ws.data_ptr(), ws.numel(), None, flags, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.f3d_last_error()
+    for _ in range(2): call()
+    torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): call()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+for name, fl_, wv, wl_ in [("full votes+labels", 0, True, True), ("votes only", 0, True, False), ("labels only (no vote write)", 0, False, True),
+                      ("classify only (no gathers)", 0x400, True, True), ("gathers, no phase 3", 0x800, True, True), ("no deferred fp64", 0x1000, True, True), ("cull only, no candidates", 0x100, True, True),
+                      ("no cull, no candidates", 0x200, True, True), ("no cull, labels only", 0x200, False, True)]:
+    print(f"{name:34s} {run(fl_, wv, wl_):8.3f} ms", flush=True)
+# plain memset of the vote tensor for reference
+torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): votes.zero_()
+e1.record(); torch.cuda.synchronize(); print(f"{'torch zero_ of votes (5.36 GB)':34s} {e0.elapsed_time(e1)/5:8.3f} ms")

@@ -3,13 +3,14 @@ device is missing, every operator raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 import torch
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libf3d.so"
+LIB_PATH = Path(os.environ.get("F3D_LIB", PKG / "libf3d.so"))   # F3D_LIB: kernel-variant experiments only
 
 NSTATS = 8
 STAT_NAMES = ("candidates", "exact", "diverged", "near_edge", "seen", "audit_bad")

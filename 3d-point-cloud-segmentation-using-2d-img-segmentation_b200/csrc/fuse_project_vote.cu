@@ -35,7 +35,12 @@
 #define FUSE_BLOCK 256
 #define FUSE_FCHUNK 512   // frames culled per pass (candidate list capacity)
 #define FUSE_STAGE 16     // FrameFast tiles per staging buffer (2 KB); two buffers
+#ifndef FUSE_NB
 #define FUSE_NB 8         // candidates whose gathers are in flight together
+#endif
+#ifndef FUSE_MINB
+#define FUSE_MINB 2       // resident CTAs per SM the register allocation targets (128 registers: keeps all NB gathers in flight)
+#endif
 #define RES_MAXC 256
 
 struct FuseResolve {
@@ -315,7 +320,7 @@ __device__ __forceinline__ void resolve_exact(const FuseParams& P, const FuseRes
 }
 
 template <int MODE, int FMT>
-__global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P, const FuseResolve RP) {
+__global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseParams P, const FuseResolve RP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [2 x stage FrameFast x FUSE_STAGE][cand u16 x FUSE_FCHUNK][red: 48 floats | ncand | 2 mbarriers | 8 nq | 8 dirty]
     //         [deferred queues: 8 warps x FUSE_QWARP][hist]
@@ -460,7 +465,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
                 for (int k0 = 0; k0 < nb; k0 += FUSE_NB) {
                     // ---- phase 1: fp32 projection + certification of NB candidates
                     uint32_t puv[FUSE_NB];
-                    unsigned stw = 0;          // 4 bits per candidate: st | g_in << 3
+                    unsigned long long stw = 0;   // 4 bits per candidate: st | g_in << 3
                     float zc[MODE == MODE_SPLAT ? FUSE_NB : 1];
 #pragma unroll
                     for (int k = 0; k < FUSE_NB; ++k) {
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
                         if (k0 + k < nb) {
                             const Cls c = classify(stage + (buf * FUSE_STAGE + k0 + k) * 8, pt, fW, fH);
                             puv[k] = c.puv;
-                            stw |= (unsigned)(c.st | (c.g_in << 3)) << (4 * k);
+                            stw |= (unsigned long long)(c.st | (c.g_in << 3)) << (4 * k);
                             if (MODE == MODE_SPLAT) zc[k] = c.z;
                         }
                     }
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
                         for (int k = 0; k < FUSE_NB; ++k) {
                             dv[k] = 0;
                             if (MODE == MODE_VOTE) mk[k] = 0;
-                            if (((stw >> (4 * k)) & 7u) == 1u) {
+                            if (((stw >> (4 * k)) & 7ull) == 1ull) {
                                 const size_t off = (size_t)cand[b0 + k0 + k] * (size_t)HW + (size_t)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
                                 if (FMT == F3D_DEPTH_U16_MM) dv[k] = __ldg(reinterpret_cast<const uint16_t*>(P.depth) + off);
                                 else dv[k] = __float_as_uint(__ldg(reinterpret_cast<const float*>(P.depth) + off));
@@ -499,12 +504,12 @@ __global__ void __launch_bounds__(FUSE_BLOCK, 3) fuse_kernel(const FuseParams P,
                     // ---- phase 3: depth validity + distance criterion, votes; uncertain pairs are deferred
 #pragma unroll
                     for (int k = 0; k < FUSE_NB; ++k) {
-                        int st = (int)((stw >> (4 * k)) & 7u);
+                        int st = (int)((stw >> (4 * k)) & 7ull);
                         if (st == 0 && !P.audit) continue;
                         if (k0 + k >= nb) continue;
                         const int frel = cand[b0 + k0 + k];
                         const float4* s = stage + (buf * FUSE_STAGE + k0 + k) * 8;
-                        int g_in = (int)((stw >> (4 * k + 3)) & 1u);
+                        int g_in = (int)((stw >> (4 * k + 3)) & 1ull);
                         const int pix = (int)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
                         uint32_t zq = 0;
                         if (st == 1 && MODE != MODE_SPLAT) {

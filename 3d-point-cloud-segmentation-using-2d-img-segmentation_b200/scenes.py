@@ -185,8 +185,8 @@ def block_masks(spec_or_shape, nframes=None, seed=0, nclasses=133, block=32, unc
     return np.ascontiguousarray(m.astype(np.uint8))
 
 
-def make_boxes(nboxes=200_000, seed=1004, extent=(400.0, 400.0, 12.0), ngroups=16):
-    """C5: axis-aligned instance boxes.  Returns lo [B,3], hi [B,3] float64, group int32 [B], area int64 [B]."""
+def make_boxes(nboxes=200_000, seed=1004, extent=(80.0, 80.0, 5.0), ngroups=16):
+    """C5: axis-aligned instance boxes, dense enough that a box overlaps ~2-3 others of its group.  Returns lo [B,3], hi [B,3] float64, group int32 [B], area int64 [B]."""
     rng = np.random.Generator(np.random.PCG64(seed))
     c = rng.random((nboxes, 3)) * np.asarray(extent)[None, :]
     half = np.exp(rng.normal(np.log(0.4), 0.5, (nboxes, 3)))

@@ -28,6 +28,9 @@ SIGNATURES = {
     "f3d_fuse_workspace_bytes": (_i64, [_i64]),
     "f3d_fuse_project_vote": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64, _f64,
                                         _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
+    "f3d_fuse_project_vote_u16": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64, _f64,
+                                            _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
+    "f3d_resolve_labels_u16": (C.c_int, [_vp, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp]),
     "f3d_fuse_project_vote_resolve": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64,
                                                 _f64, _vp, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _i32, _vp]),
     "f3d_fuse_uv2pt": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _f64, _f64, _f64, _vp, _vp,

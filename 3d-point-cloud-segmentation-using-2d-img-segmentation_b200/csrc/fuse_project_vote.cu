@@ -73,6 +73,7 @@ struct FuseParams {
     double radius_d, zmin, zmax;
     uint32_t d_lo, d_hi;    // uint16 depth: valid <=> d_lo <= d <= d_hi   (fusion.py:62-63 on d/1000)
     int32_t* votes;
+    uint16_t* votes16;      // alternative packed output (uint16 counters): halves the vote write and the multi-GPU exchange
     int C1, RS, accumulate;
     int32_t* uv2pt;
     uint32_t* zbuf;
@@ -604,6 +605,24 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
     if (MODE == MODE_VOTE) {
         const int row0 = warp * 32;
         const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
+        if (P.votes16 && nrows > 0) {
+            uint16_t* __restrict__ out = P.votes16 + (tile_base + row0) * P.C1;
+            if (RS == P.C1 && !P.accumulate) {
+                const uint4* __restrict__ h128 = reinterpret_cast<const uint4*>(hist + row0 * RS);
+                const int total = nrows * P.C1;
+                const int n8 = total >> 3;
+                for (int i = lane; i < n8; i += 32) *reinterpret_cast<uint4*>(out + 8 * i) = h128[i];
+                for (int e = (n8 << 3) + lane; e < total; e += 32) out[e] = hist[row0 * RS + e];
+            } else {
+                for (int j = 0; j < nrows; ++j) {
+                    for (int c = lane; c < P.C1; c += 32) {
+                        const uint16_t v = hist[(row0 + j) * RS + c];
+                        if (!P.accumulate) out[j * P.C1 + c] = v;
+                        else if (v) out[j * P.C1 + c] += v;
+                    }
+                }
+            }
+        }
         if (P.votes && nrows > 0) {
             int32_t* __restrict__ out = P.votes + (tile_base + row0) * P.C1;
             if (RS == P.C1 && !P.accumulate) {
@@ -694,7 +713,12 @@ __global__ void __launch_bounds__(256) fixup_apply_kernel(const FuseParams P) {
             if (MODE == MODE_VOTE) {
                 const int cls = __ldg(P.mask + off);
                 if (cls < P.C1) {
-                    atomicAdd(P.votes + (size_t)e.pt * P.C1 + cls, 1);
+                    if (P.votes16) {
+                        const size_t cell = (size_t)e.pt * P.C1 + cls;   // 32-bit atomic on the word of the uint16 counter
+                        atomicAdd(reinterpret_cast<unsigned*>(P.votes16) + (cell >> 1), (cell & 1) ? 0x10000u : 1u);
+                    } else {
+                        atomicAdd(P.votes + (size_t)e.pt * P.C1 + cls, 1);
+                    }
                     P.gq[i].w = e.w | (1u << 24);   // this point's label must be re-resolved
                 }
             } else if (MODE == MODE_SPLAT) {
@@ -717,28 +741,48 @@ __global__ void __launch_bounds__(256) fixup_apply_kernel(const FuseParams P) {
     }
 }
 
-// labels of the points whose votes changed in fixup_apply_kernel (VotingSegmentation.segment, voting.py:120-135)
+// labels of the points whose votes changed in fixup_apply_kernel (VotingSegmentation.segment, voting.py:120-135);
+// eight lanes per entry stream the point's vote row, like resolve_kernel
 __global__ void __launch_bounds__(256) fixup_labels_kernel(const FuseParams P, const FuseResolve RP) {
     const unsigned long long n = min(*P.gq_count, P.gq_cap);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const GEntry e = P.gq[i];
-        if (e.pt < 0 || !((e.w >> 24) & 1u)) continue;
-        const int32_t* __restrict__ row = P.votes + (size_t)e.pt * P.C1;
+    const int sub = threadIdx.x & 7;
+    const unsigned long long per_pass = ((unsigned long long)gridDim.x * blockDim.x) >> 3;
+    const unsigned long long passes = (n + per_pass - 1) / per_pass;   // uniform trip count: shuffles see full warps
+    unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    for (unsigned long long p = 0; p < passes; ++p, i += per_pass) {
+        GEntry e;
+        e.pt = -1;
+        e.w = 0;
+        if (i < n) e = P.gq[i];
+        const bool live = (e.pt >= 0) && ((e.w >> 24) & 1u);
         long long total = 0;
         int best = 0, bpos = 0x7fff;
-        for (int c = 0; c < P.C1; ++c) {
-            const int v = row[c];
-            total += v;
-            const int pos = RP.fpos[c];
-            if (v > 0 && pos >= 0 && (v > best || (v == best && pos < bpos))) {
-                best = v;
-                bpos = pos;
+        if (live) {
+            for (int c = sub; c < P.C1; c += 8) {
+                const int v = P.votes16 ? (int)P.votes16[(size_t)e.pt * P.C1 + c] : P.votes[(size_t)e.pt * P.C1 + c];
+                total += v;
+                const int pos = RP.fpos[c];
+                if (v > 0 && pos >= 0 && (v > best || (v == best && pos < bpos))) {
+                    best = v;
+                    bpos = pos;
+                }
             }
         }
-        bool unc = (total <= 0) || (best <= 0);
-        if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;
-        P.labels[e.pt] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
+#pragma unroll
+        for (int s = 4; s > 0; s >>= 1) {
+            total += __shfl_xor_sync(0xffffffffu, total, s);
+            const int ob = __shfl_xor_sync(0xffffffffu, best, s);
+            const int op = __shfl_xor_sync(0xffffffffu, bpos, s);
+            if (ob > best || (ob == best && op < bpos)) {
+                best = ob;
+                bpos = op;
+            }
+        }
+        if (live && sub == 0) {
+            bool unc = (total <= 0) || (best <= 0);
+            if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;
+            P.labels[e.pt] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
+        }
     }
 }
 
@@ -784,8 +828,8 @@ static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t 
     fuse_kernel<MODE, FMT><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
     if (use_queue) {
         // the queue length lives on the device: fixed grids with grid-stride loops, no host synchronisation
-        fixup_apply_kernel<MODE, FMT><<<148 * 4, 256, 0, stream>>>(P);
-        if (MODE == MODE_VOTE && RP.enabled) fixup_labels_kernel<<<148 * 4, 256, 0, stream>>>(P, RP);
+        fixup_apply_kernel<MODE, FMT><<<148 * 16, 256, 0, stream>>>(P);
+        if (MODE == MODE_VOTE && RP.enabled) fixup_labels_kernel<<<148 * 16, 256, 0, stream>>>(P, RP);
     }
     return f3d_check_launch("f3d_fuse");
 }
@@ -846,6 +890,7 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.audit = flags & 1;
     P.dbg = (flags >> 8) & 0xff;
     P.votes = nullptr;
+    P.votes16 = nullptr;
     P.uv2pt = nullptr;
     P.zbuf = nullptr;
     P.mask = nullptr;
@@ -890,24 +935,25 @@ int f3d_build_resolve(int C1, double threshold, const int32_t* h_filter, int nfi
 
 static int fuse_vote_impl(const void* points, int64_t N, const void* frame_table, int32_t frame_begin, int32_t frame_end,
                           const void* depth, int32_t depth_fmt, const uint8_t* mask, int32_t H, int32_t W,
-                          const double* h_K9, double radius, double zmin, double zmax, int32_t* votes, int32_t C1,
-                          int32_t accumulate, const FuseResolve& RP, int64_t* labels, void* workspace,
+                          const double* h_K9, double radius, double zmin, double zmax, int32_t* votes, uint16_t* votes16,
+                          int32_t C1, int32_t accumulate, const FuseResolve& RP, int64_t* labels, void* workspace,
                           int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
     FuseParams P;
     int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
                          zmax, stats, flags);
     if (rc) return rc;
-    if ((!votes && !labels) || C1 <= 0 || C1 > 256 || (frame_end > frame_begin && (!depth || !mask)))
+    if ((!votes && !votes16 && !labels) || (votes && votes16) || C1 <= 0 || C1 > 256 || (frame_end > frame_begin && (!depth || !mask)))
         return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote: bad argument (votes/mask/depth NULL or C1 not in 1..256)");
     if (labels && (accumulate || frame_end - frame_begin > F3D_MAX_FRAMES_PER_LAUNCH))
         return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_resolve: fused labels need all frames in one non-accumulating launch");
-    if (votes && (reinterpret_cast<uintptr_t>(votes) & 15u))
+    if ((votes && (reinterpret_cast<uintptr_t>(votes) & 15u)) || (votes16 && (reinterpret_cast<uintptr_t>(votes16) & 15u)))
         return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote: votes must be 16-byte aligned");
     if (N == 0) return F3D_OK;
     P.votes = votes;
+    P.votes16 = votes16;
     P.labels = labels;
     P.C1 = C1;
-    if (votes && !P.audit && N <= 0x7fffffff) attach_workspace(P, workspace, workspace_bytes);   // labels-only / audit: fp64 inside the sweep
+    if ((votes || votes16) && !P.audit && N <= 0x7fffffff) attach_workspace(P, workspace, workspace_bytes);   // labels-only / audit: fp64 inside the sweep
     P.RS = hist_row_stride(C1);
     const size_t esz = depth_fmt == F3D_DEPTH_U16_MM ? 2 : 4;
     int fb = frame_begin;
@@ -937,7 +983,19 @@ extern "C" int f3d_fuse_project_vote(const void* points, int64_t N, const void* 
     FuseResolve RP;
     RP.enabled = 0;
     return fuse_vote_impl(points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, mask, H, W, h_K9, radius, zmin,
-                          zmax, votes, C1, accumulate, RP, nullptr, workspace, workspace_bytes, stats, flags, stream);
+                          zmax, votes, nullptr, C1, accumulate, RP, nullptr, workspace, workspace_bytes, stats, flags, stream);
+}
+
+extern "C" int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                                         int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
+                                         int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
+                                         uint16_t* votes_u16, int32_t C1, int32_t accumulate, void* workspace,
+                                         int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
+    if (!votes_u16) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_u16: votes is NULL");
+    FuseResolve RP;
+    RP.enabled = 0;
+    return fuse_vote_impl(points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, mask, H, W, h_K9, radius, zmin,
+                          zmax, nullptr, votes_u16, C1, accumulate, RP, nullptr, workspace, workspace_bytes, stats, flags, stream);
 }
 
 extern "C" int f3d_fuse_project_vote_resolve(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
@@ -953,7 +1011,7 @@ extern "C" int f3d_fuse_project_vote_resolve(const void* points, int64_t N, cons
     int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
     if (rc) return rc;
     return fuse_vote_impl(points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, mask, H, W, h_K9, radius, zmin,
-                          zmax, votes, C1, 0, RP, labels, workspace, workspace_bytes, stats, flags, stream);
+                          zmax, votes, nullptr, C1, 0, RP, labels, workspace, workspace_bytes, stats, flags, stream);
 }
 
 extern "C" int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,

@@ -80,8 +80,8 @@ __device__ __forceinline__ void res_take(int v, int pos, int& best, int& bpos) {
     }
 }
 
-template <bool FILTERED, bool VEC2>
-__global__ void __launch_bounds__(256) resolve_kernel(const int32_t* __restrict__ votes, int64_t N, int C1,
+template <bool FILTERED, bool VEC2, typename VT>
+__global__ void __launch_bounds__(256) resolve_kernel(const VT* __restrict__ votes, int64_t N, int C1,
                                                       const ResolveParams rp, int64_t* __restrict__ labels) {
     __shared__ int16_t s_fpos[RES_MAX_FILTER];
     if (FILTERED) {
@@ -98,14 +98,24 @@ __global__ void __launch_bounds__(256) resolve_kernel(const int32_t* __restrict_
         long long total = 0;
         int best = 0, bpos = 0x7fff;
         if (live) {
-            const int32_t* __restrict__ r = votes + row * C1;
+            const VT* __restrict__ r = votes + row * C1;
             if (VEC2) {
-                const int2* __restrict__ r2 = reinterpret_cast<const int2*>(r);
+                // two counters per load: an int2 for int32 votes, one 32-bit word for packed uint16 votes
                 const int n2 = C1 >> 1;
                 int2 buf[4];
                 for (int i0 = sub; i0 < n2; i0 += 32) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) buf[u] = (i0 + 8 * u < n2) ? __ldg(r2 + i0 + 8 * u) : make_int2(0, 0);
+                    for (int u = 0; u < 4; ++u) {
+                        buf[u] = make_int2(0, 0);
+                        if (i0 + 8 * u < n2) {
+                            if (sizeof(VT) == 4) {
+                                buf[u] = __ldg(reinterpret_cast<const int2*>(r) + i0 + 8 * u);
+                            } else {
+                                const unsigned w = __ldg(reinterpret_cast<const unsigned*>(r) + i0 + 8 * u);
+                                buf[u] = make_int2((int)(w & 0xffffu), (int)(w >> 16));
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int c = 2 * (i0 + 8 * u);
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const int32_t* __restrict_
                 }
             } else {
                 for (int c = sub; c < C1; c += 8) {
-                    const int v = __ldg(r + c);
+                    const int v = (int)__ldg(r + c);
                     total += v;
                     res_take(v, FILTERED ? (int)s_fpos[c] : c, best, bpos);
                 }
@@ -185,8 +195,9 @@ extern "C" int f3d_resize_nearest_u8(const uint8_t* src, int32_t nimg, int32_t s
     return f3d_check_launch("f3d_resize_nearest_u8");
 }
 
-extern "C" int f3d_resolve_labels(const int32_t* votes, int64_t N, int32_t C1, double threshold, const int32_t* h_filter,
-                                  int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream) {
+template <typename VT>
+static int resolve_impl(const VT* votes, int64_t N, int32_t C1, double threshold, const int32_t* h_filter, int32_t nfilter,
+                        int32_t nclasses_id, int64_t* labels, void* stream) {
     if (!votes || !labels || N < 0 || C1 <= 0 || nfilter < 0 || (nfilter > 0 && !h_filter))
         return f3d_fail(F3D_ERR_ARG, "f3d_resolve_labels: bad argument");
     if (nfilter > RES_MAX_FILTER || (nfilter > 0 && C1 > RES_MAX_FILTER))
@@ -211,14 +222,25 @@ extern "C" int f3d_resolve_labels(const int32_t* votes, int64_t N, int32_t C1, d
         else rp.unclassified = v;
     }
     const unsigned grid = grid_for(N * 8, 256, 148 * 8);
-    const bool vec2 = ((C1 & 1) == 0) && ((reinterpret_cast<uintptr_t>(votes) & 7u) == 0);
+    // rows must start on the vector width: 8 bytes for int32 pairs, 4 bytes for uint16 pairs
+    const bool vec2 = ((C1 & 1) == 0) && ((reinterpret_cast<uintptr_t>(votes) & (2 * sizeof(VT) - 1)) == 0);
     cudaStream_t s = (cudaStream_t)stream;
     if (nfilter > 0) {
-        if (vec2) resolve_kernel<true, true><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
-        else resolve_kernel<true, false><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
+        if (vec2) resolve_kernel<true, true, VT><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
+        else resolve_kernel<true, false, VT><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
     } else {
-        if (vec2) resolve_kernel<false, true><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
-        else resolve_kernel<false, false><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
+        if (vec2) resolve_kernel<false, true, VT><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
+        else resolve_kernel<false, false, VT><<<grid, 256, 0, s>>>(votes, N, C1, rp, labels);
     }
     return f3d_check_launch("f3d_resolve_labels");
+}
+
+extern "C" int f3d_resolve_labels(const int32_t* votes, int64_t N, int32_t C1, double threshold, const int32_t* h_filter,
+                                  int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream) {
+    return resolve_impl<int32_t>(votes, N, C1, threshold, h_filter, nfilter, nclasses_id, labels, stream);
+}
+
+extern "C" int f3d_resolve_labels_u16(const uint16_t* votes, int64_t N, int32_t C1, double threshold, const int32_t* h_filter,
+                                      int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream) {
+    return resolve_impl<uint16_t>(votes, N, C1, threshold, h_filter, nfilter, nclasses_id, labels, stream);
 }

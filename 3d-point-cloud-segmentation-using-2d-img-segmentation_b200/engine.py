@@ -102,19 +102,21 @@ def stats_dict(stats: torch.Tensor) -> dict:
 
 
 def fuse_project_vote(points4, table: FrameTable, depth, mask, nclasses1, radius=0.05, zmin=0.1, zmax=4.0, votes=None,
-                      accumulate=False, stats=None, audit=False, frame_begin=0, frame_end=None):
-    """Kernel (1).  depth / mask: [F', H, W] device tensors covering frames [frame_begin, frame_end)."""
+                      accumulate=False, stats=None, audit=False, frame_begin=0, frame_end=None, packed_u16=False):
+    """Kernel (1).  depth / mask: [F', H, W] device tensors covering frames [frame_begin, frame_end).  `votes` may be
+    int32 (reference layout) or uint16 (packed exchange format, also selected by `packed_u16` when allocating)."""
     frame_end = table.F if frame_end is None else frame_end
     N = points4.shape[0]
     if votes is None:
-        votes = torch.empty((N, nclasses1), dtype=torch.int32, device=points4.device)
+        votes = torch.empty((N, nclasses1), dtype=torch.uint16 if packed_u16 else torch.int32, device=points4.device)
         accumulate = False
     nf = frame_end - frame_begin
     if nf > 0 and (depth.shape[0] != nf or mask.shape[0] != nf or tuple(depth.shape[1:]) != (table.H, table.W)
                    or tuple(mask.shape[1:]) != (table.H, table.W)):
         raise ValueError("depth / mask must be [frame_end-frame_begin, H, W]")
     ws = workspace(N, points4.device)
-    check(load().f3d_fuse_project_vote(
+    fn = load().f3d_fuse_project_vote_u16 if votes.dtype == torch.uint16 else load().f3d_fuse_project_vote
+    check(fn(
         ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth) if nf else None,
         _depth_fmt(depth) if nf else 0, ptr(mask) if nf else None, table.H, table.W, ptr(table.K), float(radius),
         float(zmin), float(zmax), ptr(votes), int(nclasses1), int(bool(accumulate)), ptr(ws), ws.numel(), ptr(stats),
@@ -207,7 +209,8 @@ def resolve_labels(votes, nclasses_id, threshold=0.5, filter_classes=None, out=N
     filt = None if filter_classes is None else np.ascontiguousarray(np.asarray(filter_classes, dtype=np.int32))
     if filt is not None and filt.size == 0:
         raise ValueError("filter_classes must not be empty")
-    check(load().f3d_resolve_labels(ptr(votes), N, C1, float(threshold), ptr(filt), 0 if filt is None else int(filt.size),
+    fn = load().f3d_resolve_labels_u16 if votes.dtype == torch.uint16 else load().f3d_resolve_labels
+    check(fn(ptr(votes), N, C1, float(threshold), ptr(filt), 0 if filt is None else int(filt.size),
                                     int(nclasses_id), ptr(out), stream_ptr()), "f3d_resolve_labels")
     return out
 

@@ -2,14 +2,24 @@
 over the point axis, labels resolved on each rank's shard and all-gathered.
 
 Votes are integer sums over frames (`segUtils/voting.py:89-98`), so any frame partition gives bit-identical
-results.  The point axis is processed in chunks: chunk k is fused on the compute stream while the reduce-scatter
-of chunk k-1 runs on a communication stream (NCCL over NVLink / NVSwitch).  `combine_votes` works on any
-backend (gloo has no reduce_scatter: all_reduce + slice) so the host logic is testable on CPU.
+results.  The point axis is processed in chunks: chunk k is fused on the compute stream while the reduce-scatter /
+resolve / all-gather of chunk k-1 runs on a communication stream (NCCL over NVLink / NVSwitch).  All buffers are
+allocated once (`ShardedPipeline`), so a step issues no allocation and no host synchronisation.  With
+`packed=True` partial votes travel as uint16 counters viewed as int32 pairs: the int32 sum never carries between the
+halves while a vote tensor sees fewer than 65 536 frames, so the exchange is exact at half the bytes.
+The collectives fall back to all_reduce / all_gather lists on gloo (no reduce_scatter there) so the host logic is
+testable on CPU.
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+
+def init_process_group(local_rank: int):
+    """NCCL process group whose internal stream is high priority (see ShardedPipeline)."""
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
 
 
 def frame_shard(nframes: int, rank: int, world: int):
@@ -19,79 +29,107 @@ def frame_shard(nframes: int, rank: int, world: int):
     return a, a + base + (1 if rank < rem else 0)
 
 
-def point_shard(npoints: int, rank: int, world: int):
-    """Rows of a (padded) chunk owned by `rank` after the reduce-scatter: equal shares of ceil(n/world)."""
-    per = -(-npoints // world)
-    return min(rank * per, npoints), min((rank + 1) * per, npoints), per
-
-
-def combine_votes(partial: torch.Tensor, group=None) -> torch.Tensor:
-    """partial [n, C1] int32 on every rank -> this rank's [per, C1] slice of the element-wise sum (rows beyond n
-    are zero padding)."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    n, c1 = partial.shape
-    per = -(-n // world)
-    if per * world != n:
-        pad = torch.zeros((per * world - n, c1), dtype=partial.dtype, device=partial.device)
-        partial = torch.cat([partial, pad], dim=0)
+def _reduce_scatter(out: torch.Tensor, full: torch.Tensor, group=None):
+    """full [per*world, k] (sum over ranks) -> out [per, k] = this rank's slice."""
     if dist.get_backend(group) == "nccl":
-        out = torch.empty((per, c1), dtype=partial.dtype, device=partial.device)
-        dist.reduce_scatter_tensor(out, partial.contiguous(), op=dist.ReduceOp.SUM, group=group)
-        return out
-    full = partial.clone()
-    dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
-    return full[rank * per:(rank + 1) * per].contiguous()
-
-
-def gather_labels(shard: torch.Tensor, n: int, group=None) -> torch.Tensor:
-    """Per-rank label slices [per] -> full [n] on every rank."""
-    world = dist.get_world_size(group)
-    out = torch.empty(shard.numel() * world, dtype=shard.dtype, device=shard.device)
-    if dist.get_backend(group) == "nccl":
-        dist.all_gather_into_tensor(out, shard.contiguous(), group=group)
+        dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=group)
     else:
-        parts = [torch.empty_like(shard) for _ in range(world)]
-        dist.all_gather(parts, shard.contiguous(), group=group)
-        out = torch.cat(parts)
-    return out[:n]
+        tmp = full.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        r, per = dist.get_rank(group), out.shape[0]
+        out.copy_(tmp[r * per:(r + 1) * per])
+
+
+def _all_gather(out: torch.Tensor, shard: torch.Tensor, group=None):
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, shard, group=group)
+    else:
+        parts = [torch.empty_like(shard) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, shard, group=group)
+        out.copy_(torch.cat(parts))
+
+
+class ShardedPipeline:
+    """Chunked fuse -> reduce-scatter -> resolve -> all-gather pipeline with persistent buffers.
+
+    `fuse_into(a, b, out)` must enqueue on the current stream the partial votes of this rank's frames for points
+    [a, b) into `out[:b-a]` (shape [rows, c1], dtype `vote_dtype`); `resolve(votes, out_labels)` must enqueue the label
+    resolve of `votes` [rows, c1] into `out_labels` [rows] int64."""
+
+    def __init__(self, npoints: int, c1: int, nchunks: int, device, group=None, packed=True):
+        self.group, self.device = group, torch.device(device)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.npoints, self.c1 = npoints, c1
+        nchunks = max(1, min(nchunks, max(npoints, 1)))
+        self.bounds = [(i * npoints // nchunks, (i + 1) * npoints // nchunks) for i in range(nchunks)]
+        self.bounds = [(a, b) for a, b in self.bounds if b > a]
+        big = max([b - a for a, b in self.bounds], default=0)
+        self.per = -(-big // self.world) if big else 0
+        self.cuda = self.device.type == "cuda"
+        self.packed = bool(packed and self.cuda and c1 % 2 == 0)
+        self.vote_dtype = torch.uint16 if self.packed else torch.int32
+        rows = self.per * self.world
+        self.part = [torch.zeros((rows, c1), dtype=self.vote_dtype, device=self.device) for _ in range(2)]
+        self.mine = [torch.zeros((self.per, c1), dtype=self.vote_dtype, device=self.device) for _ in range(2)]
+        self.lab = [torch.zeros(self.per, dtype=torch.int64, device=self.device) for _ in range(2)]
+        self.full = [torch.zeros(rows, dtype=torch.int64, device=self.device) for _ in range(2)]
+        self.labels = torch.empty(npoints, dtype=torch.int64, device=self.device)
+        if self.cuda:
+            # high priority: the exchange kernels (NCCL, resolve) are tiny next to a fuse launch that fills every SM and
+            # must be scheduled ahead of its remaining CTAs, otherwise the exchange only starts when the sweep drains
+            self.comm = torch.cuda.Stream(device=self.device, priority=-1)
+            self.ready = [torch.cuda.Event() for _ in range(2)]
+            self.free = [torch.cuda.Event() for _ in range(2)]
+
+    def _exchange(self, s: int, a: int, b: int, resolve):
+        n = b - a
+        part, mine = self.part[s], self.mine[s]
+        if self.packed:   # uint16 pairs summed as int32: exact, half the bytes
+            _reduce_scatter(mine.view(torch.int32), part.view(torch.int32), self.group)
+        else:
+            _reduce_scatter(mine, part, self.group)
+        resolve(mine, self.lab[s])
+        _all_gather(self.full[s], self.lab[s], self.group)
+        self.labels[a:b].copy_(self.full[s][:n])
+
+    def run(self, fuse_into, resolve) -> torch.Tensor:
+        """One pass over every chunk.  Returns the full label vector [npoints] (valid on the current stream)."""
+        if not self.cuda:
+            for (a, b) in self.bounds:
+                self.part[0][b - a:].zero_()
+                fuse_into(a, b, self.part[0])
+                self._exchange(0, a, b, resolve)
+            return self.labels
+        compute = torch.cuda.current_stream(self.device)
+        for e in self.free:
+            e.record(compute)
+        for k, (a, b) in enumerate(self.bounds):
+            s = k & 1
+            compute.wait_event(self.free[s])            # chunk k-2's exchange no longer reads part[s]
+            if b - a < self.part[s].shape[0]:
+                self.part[s][b - a:].zero_()            # padding rows (chunk not divisible by the world size)
+            fuse_into(a, b, self.part[s])
+            self.ready[s].record(compute)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.ready[s])
+                self._exchange(s, a, b, resolve)
+                self.free[s].record(self.comm)
+        for e in self.free:
+            compute.wait_event(e)
+        return self.labels
 
 
 def fuse_sharded(fuse_chunk, resolve, npoints: int, nchunks: int, device, group=None):
-    """Chunked pipeline.  `fuse_chunk(a, b)` -> partial votes [b-a, C1] of this rank's frames for points [a, b)
-    (enqueued on the current stream); `resolve(votes)` -> labels [rows].  Returns full labels [npoints] on every
-    rank.  On CUDA the collective of chunk k-1 overlaps the fusion of chunk k."""
-    use_cuda = torch.device(device).type == "cuda"
-    nchunks = max(1, min(nchunks, npoints)) if npoints else 1
-    bounds = [(i * npoints // nchunks, (i + 1) * npoints // nchunks) for i in range(nchunks)]
-    labels = torch.empty(npoints, dtype=torch.int64, device=device)
-    if use_cuda:
-        compute = torch.cuda.current_stream()
-        comm = torch.cuda.Stream(device=device)
-    keep = []
-    for (a, b) in bounds:
-        if b == a:
-            continue
-        part = fuse_chunk(a, b)
-        if use_cuda:
-            ev = torch.cuda.Event()
-            ev.record(compute)
-            with torch.cuda.stream(comm):
-                comm.wait_event(ev)
-                part.record_stream(comm)
-                mine = combine_votes(part, group)
-                lab = resolve(mine)
-                full = gather_labels(lab, b - a, group)
-                labels[a:b].copy_(full)
-                keep.append((part, mine, lab, full))
-        else:
-            mine = combine_votes(part, group)
-            labels[a:b] = gather_labels(resolve(mine), b - a, group)
-    if use_cuda:
-        done = torch.cuda.Event()
-        done.record(comm)
-        compute.wait_event(done)
-        for tensors in keep:
-            for t in tensors:
-                t.record_stream(compute)
-    return labels
+    """Convenience wrapper (allocates a pipeline per call): `fuse_chunk(a, b)` -> partial int32 votes [b-a, C1],
+    `resolve(votes)` -> labels [rows]."""
+    c1 = None
+
+    def fuse_into(a, b, out):
+        nonlocal c1
+        v = fuse_chunk(a, b)
+        out[:b - a].copy_(v)
+
+    probe = fuse_chunk(0, min(1, npoints)) if npoints else None
+    c1 = probe.shape[1] if probe is not None else 1
+    pipe = ShardedPipeline(npoints, c1, nchunks, device, group, packed=False)
+    return pipe.run(fuse_into, lambda v, out: out.copy_(resolve(v)))

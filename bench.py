@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--chunks", type=int, default=8, help="point chunks of the multi-GPU pipeline")
+    ap.add_argument("--chunks", type=int, default=4, help="point chunks of the multi-GPU pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -218,13 +218,14 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = importlib.import_module(PKG_NAME)
     pkg.load()
     engine = importlib.import_module(PKG_NAME + ".engine")
     scenes = importlib.import_module(PKG_NAME + ".scenes")
     fused = importlib.import_module(PKG_NAME + ".fused")
     parallel = importlib.import_module(PKG_NAME + ".parallel")
+    if world > 1:
+        parallel.init_process_group(local_rank)
 
     cfg_key, desc = WORKLOADS[args.workload]
     base = scenes.CONFIGS[cfg_key] if args.workload != "small" else scenes.scaled_spec("C1", 200_000, 8, 320, 240)
@@ -246,21 +247,23 @@ def main():
                                                          stats=stats)
         e1.record()
         fl.votes = votes
-        return labels, (e0, e1), 1
+        return labels, (e0, e1), 3   # fuse_kernel + fixup_apply + fixup_labels
+
+    pipe = parallel.ShardedPipeline(N, C1, args.chunks, torch.device("cuda", local_rank)) if world > 1 else None
 
     def step_multi():
         launches = [0]
 
-        def fuse_chunk(a, b):
-            launches[0] += 1
-            return engine.fuse_project_vote(fl.points4[a:b], fl.table, depth, masks, C1, RADIUS, fl.zmin, fl.zmax,
-                                            stats=stats)
+        def fuse_into(a, b, out):
+            launches[0] += 3   # fuse_kernel + the two fix-up kernels
+            engine.fuse_project_vote(fl.points4[a:b], fl.table, depth, masks, C1, RADIUS, fl.zmin, fl.zmax, votes=out[:b - a],
+                                     stats=stats)
 
-        def resolve(v):
+        def resolve(v, out):
             launches[0] += 1
-            return engine.resolve_labels(v, NCLASSES, THRESHOLD, None)
+            engine.resolve_labels(v, NCLASSES, THRESHOLD, None, out=out)
 
-        labels = parallel.fuse_sharded(fuse_chunk, resolve, N, args.chunks, torch.device("cuda", local_rank))
+        labels = pipe.run(fuse_into, resolve)
         return labels, None, launches[0]
 
     step = step_single if world == 1 else step_multi
@@ -371,7 +374,7 @@ def main():
                        "nclasses": NCLASSES, "depth": "uint16 mm", "radius": RADIUS, "cache": "inputs larger than L2 "
                        "(depth+masks+votes = %.1f GB per GPU)" % ((F * H * W * 3 + 4 * N * C1) / 1e9),
                        "parallelism": "single GPU" if world == 1 else f"frames sharded over {world} GPUs, "
-                       f"{args.chunks}-chunk reduce-scatter/resolve/all-gather pipeline"},
+                       f"{args.chunks}-chunk pipeline: fuse -> NCCL reduce-scatter of packed uint16 votes -> resolve -> all-gather"},
             "roofline": roof, "cpu_baseline": cpu_b, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "per_step_counts": per_step,
         }

@@ -87,6 +87,15 @@ int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table
                           int32_t* votes, int32_t C1, int32_t accumulate, void* workspace, int64_t workspace_bytes,
                           uint64_t* stats, int32_t flags, void* stream);
 
+/* f3d_fuse_project_vote with packed uint16 counters [N,C1] (valid below 65 536 frames per vote tensor).  Used for
+ * the multi-GPU exchange: two uint16 counters viewed as one int32 add without carries, so an int32 sum
+ * reduce-scatter of the [N,C1/2] view is exact and moves half the bytes. */
+int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                              int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
+                              int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
+                              uint16_t* votes_u16, int32_t C1, int32_t accumulate, void* workspace,
+                              int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
+
 /* f3d_fuse_project_vote with VotingSegmentation.segment (segUtils/voting.py:106-137, see f3d_resolve_labels) fused
  * into the epilogue: labels [N] int64 are resolved straight from the on-chip histograms, so the vote tensor is
  * never re-read.  All frames must be covered by this one call (no accumulation).  votes may be NULL: then only
@@ -139,6 +148,9 @@ int f3d_resize_nearest_u8(const uint8_t* src, int32_t nimg, int32_t src_h, int32
  *   h_filter host int32[nfilter];  labels [N] int64. */
 int f3d_resolve_labels(const int32_t* votes, int64_t N, int32_t C1, double threshold, const int32_t* h_filter,
                        int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream);
+
+int f3d_resolve_labels_u16(const uint16_t* votes_u16, int64_t N, int32_t C1, double threshold,
+                           const int32_t* h_filter, int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream);
 
 /* ---- single-call projection / cull operators (a-1, a-4) ----------------------------------------------------------- */
 

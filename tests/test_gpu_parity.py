@@ -163,6 +163,26 @@ def test_fused_resolve_epilogue(engine, scenes):
     assert none_votes is None and np.array_equal(labels.cpu().numpy(), orc.segment(ov, 133, 0.5, None))
 
 
+def test_packed_uint16_votes(engine, scenes):
+    """The multi-GPU exchange format: uint16 counters, pairs summed as int32, resolved without widening."""
+    s = small_scene(scenes, orc, npoints=20011, nframes=6, width=320, height=240, seed=59, block=16)
+    tab = engine.FrameTable(s["K"], s["W"], s["H"], s["wxyz"], s["t"], 4.0)
+    p4 = engine.pack_points(s["points"])
+    d, m = dev(s["depths"]), dev(s["masks"])
+    v32 = engine.fuse_project_vote(p4, tab, d, m, 134, 0.05, 0.1, 4.0)
+    v16 = engine.fuse_project_vote(p4, tab, d, m, 134, 0.05, 0.1, 4.0, packed_u16=True)
+    assert v16.dtype == torch.uint16 and torch.equal(v16.to(torch.int32), v32)
+    a = engine.fuse_project_vote(p4, tab, d[:3], m[:3], 134, 0.05, 0.1, 4.0, frame_begin=0, frame_end=3, packed_u16=True)
+    b = engine.fuse_project_vote(p4, tab, d[3:], m[3:], 134, 0.05, 0.1, 4.0, frame_begin=3, frame_end=6, packed_u16=True)
+    summed = (a.view(torch.int32) + b.view(torch.int32)).view(torch.uint16)     # what the int32 reduce-scatter computes
+    assert torch.equal(summed.to(torch.int32), v32)
+    acc = engine.fuse_project_vote(p4, tab, d[3:], m[3:], 134, 0.05, 0.1, 4.0, votes=a.clone(), accumulate=True, frame_begin=3,
+                                   frame_end=6)
+    assert torch.equal(acc.to(torch.int32), v32)
+    for thr, fc in [(0.5, None), (0.5, [86, 114, 115]), (0.3, [1, 0, 5])]:
+        assert torch.equal(engine.resolve_labels(v16, 133, thr, fc), engine.resolve_labels(v32, 133, thr, fc))
+
+
 def test_unsorted_cloud_same_votes(engine, scenes):
     s = small_scene(scenes, orc, npoints=20000, nframes=4, width=160, height=120, seed=37)
     base, _, _, _ = run_fused(engine, s)

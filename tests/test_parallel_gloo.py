@@ -53,6 +53,12 @@ def _worker(rank, world, port, out_dir, nchunks):
             full = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134,
                                          0, 0.05, 0.1, 4.0, 4.0)
             np.save(Path(out_dir) / "ref.npy", orc.segment(full, 133, 0.5, None))
+        # the persistent pipeline object, run twice (buffers are reused between steps)
+        pipe = parallel.ShardedPipeline(len(s["points"]), 134, nchunks, "cpu")
+        for _ in range(2):
+            lab2 = pipe.run(lambda a, b, out: out[:b - a].copy_(part_t[a:b]),
+                            lambda v, out: out.copy_(torch.as_tensor(orc.segment(v.numpy(), 133, 0.5, None))))
+        np.save(Path(out_dir) / f"labels2_{rank}.npy", lab2.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -65,6 +71,7 @@ def test_frame_sharded_pipeline_world2(tmp_path, nchunks):
     assert (ref != 133).sum() > 100
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"labels_{r}.npy"), ref)
+        assert np.array_equal(np.load(tmp_path / f"labels2_{r}.npy"), ref)
 
 
 def test_shard_arithmetic():

@@ -684,20 +684,41 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
 }
 
 // ---- fix-up kernels: the deferred point-views, one per thread, in fp64 ------------------------------------------------
+#define FIXUP_THREADS 128
 template <int MODE, int FMT>
-__global__ void __launch_bounds__(256) fixup_apply_kernel(const FuseParams P) {
+__global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const FuseParams P) {
+    // Each lane needs the 448-byte fp64 record of ITS frame.  Reading it field by field would be ~50 fully divergent
+    // loads per lane; instead the warp copies the 32 records one after the other with coalesced 16-byte loads into
+    // shared memory and every lane then evaluates from its own copy.
+    extern __shared__ __align__(16) unsigned char fx_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FrameExact* wbuf = reinterpret_cast<FrameExact*>(fx_smem) + warp * 32;
     const unsigned long long n = min(*P.gq_count, P.gq_cap);
     const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
     const int HW = P.H * P.W;
     unsigned n_exact = 0, n_div = 0, n_edge = 0, n_seen = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        GEntry e = P.gq[i];
-        if (e.pt < 0) continue;
+    const unsigned long long warps_total = (unsigned long long)gridDim.x * (FIXUP_THREADS / 32);
+    for (unsigned long long base = ((unsigned long long)blockIdx.x * (FIXUP_THREADS / 32) + warp) * 32; base < n;
+         base += warps_total * 32) {
+        const unsigned long long i = base + lane;
+        GEntry e;
+        e.pt = -1;
+        e.w = 0;
+        e.pix = 0;
+        e.guess = 0;
+        if (i < n) e = P.gq[i];
         const int frel = (int)(e.w & 0xffffu), st = (int)((e.w >> 16) & 0xffu);
+        __syncwarp();
+        for (int l = 0; l < 32; ++l) {
+            const int fl = __shfl_sync(0xffffffffu, e.pt >= 0 ? frel : -1, l);
+            if (fl >= 0 && lane < (int)(sizeof(FrameExact) / 16))
+                reinterpret_cast<uint4*>(wbuf + l)[lane] = __ldg(reinterpret_cast<const uint4*>(&frec[P.f_begin + fl].exact) + lane);
+        }
+        __syncwarp();
+        if (e.pt < 0) continue;
         const float4 p = __ldg(P.points + e.pt);
         ExactOut eo;
-        exact_eval<MODE, FMT>(P, &frec[P.f_begin + frel].exact, frel, p.x, p.y, p.z, eo);
+        exact_eval<MODE, FMT>(P, wbuf + lane, frel, p.x, p.y, p.z, eo);
         const bool e_seen = (MODE == MODE_SPLAT) ? (eo.in != 0) : (eo.vis != 0);
         const uint32_t e_zq = (MODE == MODE_SPLAT && eo.in) ? quantise_mm(eo.zcam) : 0u;
         bool diverged;
@@ -744,6 +765,9 @@ __global__ void __launch_bounds__(256) fixup_apply_kernel(const FuseParams P) {
 // labels of the points whose votes changed in fixup_apply_kernel (VotingSegmentation.segment, voting.py:120-135);
 // eight lanes per entry stream the point's vote row, like resolve_kernel
 __global__ void __launch_bounds__(256) fixup_labels_kernel(const FuseParams P, const FuseResolve RP) {
+    __shared__ int16_t s_fpos[RES_MAXC];
+    for (int c = threadIdx.x; c < RES_MAXC; c += blockDim.x) s_fpos[c] = RP.fpos[c];
+    __syncthreads();
     const unsigned long long n = min(*P.gq_count, P.gq_cap);
     const int sub = threadIdx.x & 7;
     const unsigned long long per_pass = ((unsigned long long)gridDim.x * blockDim.x) >> 3;
@@ -761,7 +785,7 @@ __global__ void __launch_bounds__(256) fixup_labels_kernel(const FuseParams P, c
             for (int c = sub; c < P.C1; c += 8) {
                 const int v = P.votes16 ? (int)P.votes16[(size_t)e.pt * P.C1 + c] : P.votes[(size_t)e.pt * P.C1 + c];
                 total += v;
-                const int pos = RP.fpos[c];
+                const int pos = s_fpos[c];
                 if (v > 0 && pos >= 0 && (v > best || (v == best && pos < bpos))) {
                     best = v;
                     bpos = pos;
@@ -828,8 +852,11 @@ static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t 
     fuse_kernel<MODE, FMT><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
     if (use_queue) {
         // the queue length lives on the device: fixed grids with grid-stride loops, no host synchronisation
-        fixup_apply_kernel<MODE, FMT><<<148 * 16, 256, 0, stream>>>(P);
-        if (MODE == MODE_VOTE && RP.enabled) fixup_labels_kernel<<<148 * 16, 256, 0, stream>>>(P, RP);
+        const int fx_smem = (FIXUP_THREADS / 32) * 32 * (int)sizeof(FrameExact);
+        e = cudaFuncSetAttribute(fixup_apply_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem);
+        if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute fixup)");
+        fixup_apply_kernel<MODE, FMT><<<148 * 12, FIXUP_THREADS, fx_smem, stream>>>(P);
+        if (MODE == MODE_VOTE && RP.enabled) fixup_labels_kernel<<<148 * 8, 256, 0, stream>>>(P, RP);
     }
     return f3d_check_launch("f3d_fuse");
 }

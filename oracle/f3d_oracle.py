@@ -462,3 +462,69 @@ def merge_bb_sequential(info_sem, ids, hit_fn):
                 if i < len(info_sem):
                     del info_sem[i]
     return info_sem, ids
+
+
+# ----------------------------------------------------------------------------------------------------------
+# next row: instance split
+# ----------------------------------------------------------------------------------------------------------
+
+
+def split_into_instances(classes, indptr, indices, nclasses=133, instance_classes=None, minimum_points=1):
+    """`split_into_instances` (`Fusion3DSeg/segUtils/cv.py:402-500`) restated on a CSR adjacency (indptr, indices):
+    connected components of equal class, numbered class by class in `instance_classes` order and, inside a class,
+    by ascending smallest point index (the BFS seeds are `remaining_points[0]`, `cv.py:473-475`); components with
+    fewer than `minimum_points` points are re-classed `nclasses` and folded into one "small disjoint" instance
+    (`cv.py:478-486`).  Returns (ninstances, ids [N], info list, classes [N])."""
+    classes = np.asarray(classes).copy()
+    n = len(classes)
+    allclasses = np.unique(classes)
+    ids = np.zeros_like(classes)
+    info = []
+    small_id = None
+    if instance_classes is None:                                   # cv.py:448-456
+        inst = allclasses
+        ninst, sem = 0, []
+        if (inst == nclasses).any():
+            inst = inst[inst != nclasses]
+            sem, ninst = [nclasses], 1
+    else:                                                          # cv.py:457-460
+        inst = np.array(instance_classes)
+        sem = np.setdiff1d(allclasses, inst)
+        ninst = len(sem)
+    for k in range(ninst if len(sem) else 0):                      # cv.py:462-470
+        m = classes == sem[k]
+        ids[m] = k
+        info.append({'id': k, 'isthing': False, 'category_id': int(sem[k]), 'area': int(m.sum())})
+        if sem[k] == nclasses:
+            small_id = k
+    for c in inst:                                                 # cv.py:472-499
+        todo = classes == c
+        for seed in np.nonzero(todo)[0]:
+            if not todo[seed]:
+                continue
+            comp, stack, seen = [], [seed], {int(seed)}
+            while stack:                                           # flood fill over equal-class neighbours (cv.py:425-440)
+                p = stack.pop()
+                comp.append(p)
+                for q in indices[indptr[p]:indptr[p + 1]]:
+                    q = int(q)
+                    if q not in seen and classes[q] == c and todo[q]:
+                        seen.add(q)
+                        stack.append(q)
+            comp = np.array(comp)
+            if len(comp) < minimum_points:
+                if small_id is None:
+                    small_id = ninst
+                    info.append({'id': ninst, 'isthing': True, 'category_id': int(nclasses), 'area': 0})
+                    ninst += 1
+                info[small_id]['area'] += int(len(comp))
+                ids[comp] = small_id
+                newc = nclasses
+            else:
+                info.append({'id': ninst, 'isthing': True, 'category_id': int(c), 'area': int(len(comp))})
+                ids[comp] = ninst
+                ninst += 1
+                newc = c
+            todo[comp] = False
+            classes[comp] = newc
+    return ninst, ids, info, classes

@@ -33,6 +33,7 @@ from Fusion3DSeg.fusion import Fusion as RefFusion, FrameData as RefFrameData  #
 from Fusion3DSeg.intersections import point_inside_polyhedra as ref_pip  # noqa: E402
 from Fusion3DSeg.segUtils.voting import VotingSegmentation as RefVoting  # noqa: E402
 from RTAB_utils.spatQuad import SpatQuadranion as RefQuat  # noqa: E402
+from Fusion3DSeg.segUtils.cv import split_into_instances as ref_split  # noqa: E402
 
 
 def ref_mod_points(depth_u16, K, wxyz, t):
@@ -160,6 +161,25 @@ def main():
         rs[f"src{k}"] = src
         rs[f"dst{k}"] = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_NEAREST)
     out["g4_resize"] = rs
+
+    # ---- G5: instance split (connected components per class) through the reference's BFS ---------------------------
+    from sklearn.neighbors import KDTree
+    import json
+    spec5 = scenes.scaled_spec("C1", npoints=6000, nframes=1, seed=99)
+    p5 = scenes.make_cloud(spec5).astype(np.float64)
+    adj = KDTree(p5).query_radius(p5, r=0.18)                    # as fusion.py:374-375 (r = 2 * radius)
+    cell = (np.floor(p5[:, 0] / 1.3) * 7 + np.floor(p5[:, 1] / 1.1) * 3 + np.floor(p5[:, 2] / 1.6)).astype(int)
+    classes5 = np.array([86, 114, 115, 133, 5, 86, 133])[cell % 7].astype(np.int64)
+    indptr = np.concatenate([[0], np.cumsum([len(a) for a in adj])]).astype(np.int64)
+    indices = np.concatenate(adj).astype(np.int64)
+    g5 = dict(classes=classes5, indptr=indptr, indices=indices)
+    for tag, (inst_cls, minpts) in {"a": ([86, 114, 115], 20), "b": (None, 1), "c": ([115, 86], 100), "d": (None, 50)}.items():
+        insts, ids5, info5, cls5 = ref_split(classes5, adj, 133, inst_cls, minpts)
+        g5[f"ids_{tag}"] = ids5
+        g5[f"classes_{tag}"] = cls5
+        g5[f"ninst_{tag}"] = len(insts)
+        g5[f"info_{tag}"] = json.dumps(info5)
+    out["g5_instances"] = g5
 
     for name, d in out.items():
         np.savez_compressed(HERE / f"{name}.npz", **d)

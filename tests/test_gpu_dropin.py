@@ -49,11 +49,6 @@ def test_get3dseg_segment_and_remove_classes(engine, tmp_path):
     removed = np.append(np.setdiff1d(np.arange(133), keep), [133, 134])
     assert mask.dtype == bool and np.array_equal(mask, ~np.isin(cls, removed))
     assert np.array_equal(np.load(tmp_path / "segmentation" / "remaining_mask.npy"), mask)
-    # with an adjacency list the not-yet-built instance split is refused loudly, after the semantic outputs exist
-    with open(tmp_path / "fusion" / "adj.pkl", "wb") as fp:
-        pickle.dump(np.array([np.array([0])] * N, dtype=object), fp)
-    with pytest.raises(NotImplementedError):
-        g3.segment(tmp_path, tmp_path / "masks", verbose=False)
 
 
 def test_fusion_helpers(engine, scenes, tmp_path):

@@ -42,6 +42,7 @@
 #define FUSE_MINB 2       // resident CTAs per SM the register allocation targets (128 registers: keeps all NB gathers in flight)
 #endif
 #define RES_MAXC 256
+#define F3D_MAX_RANKS 16
 
 struct FuseResolve {
     int enabled, nfilter;
@@ -83,7 +84,19 @@ struct FuseParams {
     GEntry* gq;                    // workspace queue of deferred point-views (NULL: evaluate them inside the sweep)
     unsigned long long* gq_count;
     unsigned long long gq_cap;
+    // sparse multi-GPU exchange: non-zero vote cells are appended straight into the owner rank's receive queue
+    // (peer memory over NVLink / NVSwitch) instead of writing a dense vote tensor
+    int sp_G;                                  // 0 = off
+    unsigned long long* sp_queue[F3D_MAX_RANKS];   // this rank's segment inside rank d's receive queue (peer pointers)
+    unsigned long long* sp_cursor;             // [G] local append cursors, one per destination
+    unsigned long long sp_cap;                 // entries per segment
+    long long sp_per;                          // points per owner shard: owner(p) = p / sp_per
+    unsigned* sp_overflow;                     // set when a segment is full (entries are then dropped: caller must check)
 };
+
+__device__ __forceinline__ unsigned long long sp_pack(unsigned key, unsigned count) {
+    return (unsigned long long)key | ((unsigned long long)count << 32);
+}
 
 struct ExactOut {
     int in, pix, vis, near_edge;
@@ -602,7 +615,63 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
     __syncwarp();
 
     // ---- epilogue (warp-private rows): histogram -> HBM, written once with 16-byte stores; fused label resolve
-    if (MODE == MODE_VOTE) {
+    if (MODE == MODE_VOTE && P.sp_G > 0) {
+        // sparse emit: every lane scans its own histogram row; non-zero cells go to the queue of the rank that owns
+        // the point.  A warp's 32 consecutive points belong to one owner (two at a shard boundary).
+        const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(hist + tid * RS);
+        const int nw = (P.C1 + 1) >> 1;
+        int cnt = 0;
+        if (active)
+            for (int w = 0; w < nw; ++w) {
+                const uint32_t x = row[w];
+                cnt += ((x & 0xffffu) != 0u) + ((x >> 16) != 0u);
+            }
+        const int dst = active ? (int)(gi / P.sp_per) : -1;
+        const int dlo = __shfl_sync(0xffffffffu, dst, 0);
+        int dhi = dst;
+#pragma unroll
+        for (int s2 = 16; s2 > 0; s2 >>= 1) dhi = max(dhi, __shfl_xor_sync(0xffffffffu, dhi, s2));
+        for (int d = max(dlo, 0); d <= dhi; ++d) {
+            const int mine = (dst == d) ? cnt : 0;
+            int incl = mine;
+#pragma unroll
+            for (int s2 = 1; s2 < 32; s2 <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, s2);
+                if (lane >= s2) incl += o;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.sp_cursor + d, (unsigned long long)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (unsigned long long)total > P.sp_cap) {
+                if (lane == 0) atomicExch(P.sp_overflow, 1u);
+                continue;
+            }
+            // cooperative, coalesced emission: the whole warp walks one row at a time (lanes over the row's 32-bit
+            // words), so consecutive lanes append consecutive queue entries -- the (mostly remote, NVLink) stores of
+            // one instruction cover one contiguous run instead of 32 scattered 8-byte writes.
+            unsigned long long* __restrict__ q = P.sp_queue[d] + base;
+            unsigned run = 0;
+            for (int rr = 0; rr < 32; ++rr) {
+                const int rdst = __shfl_sync(0xffffffffu, dst, rr);
+                const int rcnt = __shfl_sync(0xffffffffu, mine, rr);
+                if (rdst != d || rcnt == 0) continue;            // warp-uniform
+                const uint32_t* __restrict__ rrow = reinterpret_cast<const uint32_t*>(hist + (warp * 32 + rr) * RS);
+                const unsigned key0 = (unsigned)((tile_base + warp * 32 + rr - (long long)d * P.sp_per) * P.C1);
+                for (int w0 = 0; w0 < nw; w0 += 32) {
+                    const int w = w0 + lane;
+                    const uint32_t x = (w < nw) ? rrow[w] : 0u;
+                    const unsigned lo = x & 0xffffu, hi = x >> 16;
+                    const unsigned blo = __ballot_sync(0xffffffffu, lo != 0u), bhi = __ballot_sync(0xffffffffu, hi != 0u);
+                    const unsigned below = (1u << lane) - 1u;
+                    if (lo) q[run + __popc(blo & below)] = sp_pack(key0 + 2 * w, lo);
+                    if (hi) q[run + __popc(blo) + __popc(bhi & below)] = sp_pack(key0 + 2 * w + 1, hi);
+                    run += __popc(blo) + __popc(bhi);
+                }
+            }
+        }
+    } else if (MODE == MODE_VOTE) {
         const int row0 = warp * 32;
         const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
         if (P.votes16 && nrows > 0) {
@@ -733,7 +802,12 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const FusePa
             const size_t off = (size_t)frel * (size_t)HW + (size_t)eo.pix;
             if (MODE == MODE_VOTE) {
                 const int cls = __ldg(P.mask + off);
-                if (cls < P.C1) {
+                if (cls < P.C1 && P.sp_G > 0) {
+                    const int d = (int)(e.pt / P.sp_per);
+                    const unsigned long long at = atomicAdd(P.sp_cursor + d, 1ULL);
+                    if (at < P.sp_cap) P.sp_queue[d][at] = sp_pack((unsigned)((e.pt - (long long)d * P.sp_per) * P.C1 + cls), 1u);
+                    else atomicExch(P.sp_overflow, 1u);
+                } else if (cls < P.C1) {
                     if (P.votes16) {
                         const size_t cell = (size_t)e.pt * P.C1 + cls;   // 32-bit atomic on the word of the uint16 counter
                         atomicAdd(reinterpret_cast<unsigned*>(P.votes16) + (cell >> 1), (cell & 1) ? 0x10000u : 1u);
@@ -928,6 +1002,12 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.gq = nullptr;
     P.gq_count = nullptr;
     P.gq_cap = 0;
+    P.sp_G = 0;
+    P.sp_cursor = nullptr;
+    P.sp_cap = 0;
+    P.sp_per = 1;
+    P.sp_overflow = nullptr;
+    for (int i = 0; i < F3D_MAX_RANKS; ++i) P.sp_queue[i] = nullptr;
     return F3D_OK;
 }
 
@@ -1100,4 +1180,91 @@ extern "C" int f3d_zbuffer_splat(const void* points, int64_t N, const void* fram
     if (blocks > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_zbuffer_splat: too many pixels for one launch");
     zbuf_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(zbuf, depth_out, total, H, W, border);
     return f3d_check_launch("f3d_zbuffer_splat");
+}
+
+
+// ---- sparse vote exchange over peer memory --------------------------------------------------------------------------
+struct PeerPtrs {
+    unsigned long long* p[F3D_MAX_RANKS];
+};
+
+__global__ void sparse_publish_kernel2(const unsigned long long* __restrict__ cursor, PeerPtrs counts, int rank, int G,
+                                       unsigned long long cap) {
+    const int d = threadIdx.x;
+    if (d < G) counts.p[d][rank] = min(cursor[d], cap);
+}
+
+// owner side: scatter-add every received (cell, count) entry into the dense int32 shard
+__global__ void __launch_bounds__(256) sparse_accumulate_kernel(const unsigned long long* __restrict__ rx,
+                                                                const unsigned long long* __restrict__ rx_count, unsigned long long cap,
+                                                                int32_t* __restrict__ votes, unsigned long long ncells) {
+    const int src = blockIdx.y;
+    const unsigned long long n = min(rx_count[src], cap);
+    const unsigned long long* __restrict__ seg = rx + (unsigned long long)src * cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = seg[i];
+        const unsigned key = (unsigned)(e & 0xffffffffu);
+        if (key < ncells) atomicAdd(votes + key, (int)(e >> 32));
+    }
+}
+
+extern "C" int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                                            int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
+                                            int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
+                                            int32_t C1, const uint64_t* h_peer_queues, int32_t nranks, int64_t segment_cap,
+                                            int64_t points_per_shard, uint64_t* cursors, uint32_t* overflow, void* workspace,
+                                            int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
+    FuseParams P;
+    int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
+                         zmax, stats, flags);
+    if (rc) return rc;
+    if (!h_peer_queues || nranks < 1 || nranks > F3D_MAX_RANKS || segment_cap <= 0 || points_per_shard <= 0 || !cursors ||
+        !overflow || C1 <= 0 || C1 > 256 || (frame_end > frame_begin && (!depth || !mask)))
+        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_sparse: bad argument");
+    if (frame_end - frame_begin > F3D_MAX_FRAMES_PER_LAUNCH)
+        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: more than 65535 frames per call");
+    if ((int64_t)points_per_shard * C1 > 0xffffffffLL)
+        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: shard cell index does not fit 32 bits");
+    if (N == 0) return F3D_OK;
+    P.C1 = C1;
+    P.RS = hist_row_stride(C1);
+    P.f_begin = frame_begin;
+    P.f_end = frame_end;
+    P.mask = mask;
+    P.sp_G = nranks;
+    for (int i = 0; i < nranks; ++i) P.sp_queue[i] = reinterpret_cast<unsigned long long*>(h_peer_queues[i]);
+    P.sp_cursor = reinterpret_cast<unsigned long long*>(cursors);
+    P.sp_cap = (unsigned long long)segment_cap;
+    P.sp_per = points_per_shard;
+    P.sp_overflow = overflow;
+    if (!P.audit && N <= 0x7fffffff) attach_workspace(P, workspace, workspace_bytes);
+    FuseResolve RP;
+    RP.enabled = 0;
+    return depth_fmt == F3D_DEPTH_U16_MM ? launch_fuse<MODE_VOTE, F3D_DEPTH_U16_MM>(P, RP, (cudaStream_t)stream)
+                                         : launch_fuse<MODE_VOTE, F3D_DEPTH_F32_M>(P, RP, (cudaStream_t)stream);
+}
+
+extern "C" int f3d_sparse_publish(const uint64_t* cursors, const uint64_t* h_peer_counts, int32_t rank, int32_t nranks,
+                                  int64_t segment_cap, void* stream) {
+    if (!cursors || !h_peer_counts || nranks < 1 || nranks > F3D_MAX_RANKS || rank < 0 || rank >= nranks)
+        return f3d_fail(F3D_ERR_ARG, "f3d_sparse_publish: bad argument");
+    PeerPtrs pp;
+    for (int i = 0; i < F3D_MAX_RANKS; ++i) pp.p[i] = i < nranks ? reinterpret_cast<unsigned long long*>(h_peer_counts[i]) : nullptr;
+    sparse_publish_kernel2<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(cursors), pp, rank, nranks,
+                                                               (unsigned long long)segment_cap);
+    return f3d_check_launch("f3d_sparse_publish");
+}
+
+extern "C" int f3d_sparse_accumulate(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
+                                     int32_t* votes, int64_t nrows, int32_t C1, void* stream) {
+    if (!rx || !rx_count || !votes || nranks < 1 || nranks > F3D_MAX_RANKS || segment_cap <= 0 || nrows < 0 || C1 <= 0)
+        return f3d_fail(F3D_ERR_ARG, "f3d_sparse_accumulate: bad argument");
+    if (nrows == 0) return F3D_OK;
+    dim3 grid(148 * 4, (unsigned)nranks);
+    sparse_accumulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(rx),
+                                                                    reinterpret_cast<const unsigned long long*>(rx_count),
+                                                                    (unsigned long long)segment_cap, votes,
+                                                                    (unsigned long long)nrows * (unsigned long long)C1);
+    return f3d_check_launch("f3d_sparse_accumulate");
 }

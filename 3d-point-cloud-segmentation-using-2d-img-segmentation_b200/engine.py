@@ -146,6 +146,32 @@ def fuse_project_vote_resolve(points4, table: FrameTable, depth, mask, nclasses1
     return votes, labels
 
 
+def fuse_project_vote_sparse(points4, table: FrameTable, depth, mask, nclasses1, peer_queue_ptrs, segment_cap, points_per_shard,
+                             cursors, overflow, radius=0.05, zmin=0.1, zmax=4.0, stats=None, frame_begin=0, frame_end=None):
+    """Kernel (1) in sparse-exchange mode: non-zero vote cells are appended to the owner ranks' receive queues through
+    the peer pointers in `peer_queue_ptrs` (numpy uint64 [G]); no dense vote tensor is written."""
+    frame_end = table.F if frame_end is None else frame_end
+    N = points4.shape[0]
+    ws = workspace(N, points4.device)
+    q = np.ascontiguousarray(np.asarray(peer_queue_ptrs, dtype=np.uint64))
+    check(load().f3d_fuse_project_vote_sparse(
+        ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth), _depth_fmt(depth), ptr(mask), table.H, table.W,
+        ptr(table.K), float(radius), float(zmin), float(zmax), int(nclasses1), ptr(q), int(q.size), int(segment_cap),
+        int(points_per_shard), ptr(cursors), ptr(overflow), ptr(ws), ws.numel(), ptr(stats), 0, stream_ptr()),
+        "f3d_fuse_project_vote_sparse")
+
+
+def sparse_publish(cursors, peer_count_ptrs, rank, segment_cap):
+    c = np.ascontiguousarray(np.asarray(peer_count_ptrs, dtype=np.uint64))
+    check(load().f3d_sparse_publish(ptr(cursors), ptr(c), int(rank), int(c.size), int(segment_cap), stream_ptr()),
+          "f3d_sparse_publish")
+
+
+def sparse_accumulate(rx, rx_count, nranks, segment_cap, votes):
+    check(load().f3d_sparse_accumulate(ptr(rx), ptr(rx_count), int(nranks), int(segment_cap), ptr(votes), votes.shape[0],
+                                       votes.shape[1], stream_ptr()), "f3d_sparse_accumulate")
+
+
 def fuse_uv2pt(points4, table: FrameTable, depth, radius=0.05, zmin=0.1, zmax=4.0, stats=None, audit=False,
                frame_begin=0, frame_end=None):
     frame_end = table.F if frame_end is None else frame_end

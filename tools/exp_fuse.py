@@ -38,3 +38,15 @@ torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.
 e0.record()
 for _ in range(5): votes.zero_()
 e1.record(); torch.cuda.synchronize(); print(f"{'torch zero_ of votes (5.36 GB)':34s} {e0.elapsed_time(e1)/5:8.3f} ms")
+# sparse-emit mode with a purely local queue (G = 1): isolates the cost of the emission logic from NVLink stores
+cap = 80_000_000
+queue = torch.empty(cap, dtype=torch.int64, device="cuda"); cursors = torch.zeros(1, dtype=torch.int64, device="cuda"); ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
+qptr = np.array([queue.data_ptr()], dtype=np.uint64)
+def sparse_local():
+    cursors.zero_()
+    engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, qptr, cap, N, cursors, ovf, 0.05, 0.1, spec.zmax)
+for _ in range(2): sparse_local()
+torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): sparse_local()
+e1.record(); torch.cuda.synchronize(); print(f"{'sparse emit, local queue (G=1)':34s} {e0.elapsed_time(e1)/5:8.3f} ms  entries={int(cursors.item())} overflow={int(ovf.item())}")

@@ -46,7 +46,27 @@ res = {"fuse 1 launch": timeit(fuse_all), "fuse 8 chunks": timeit(fuse_chunks), 
        "reduce_scatter 2.68GB": timeit(rs_half), "resolve shard": timeit(resolve_shard), "pipeline 8 chunks": timeit(full),
        "pipeline 4 chunks": timeit(lambda: full(4)), "pipeline 16 chunks": timeit(lambda: full(16)),
        "pipeline 8 chunks int32": timeit(lambda: full(8, False))}
+sp = parallel.SparseExchange(N, C1, torch.device("cuda", lr))
+def sparse_step():
+    return sp.run(lambda q, cap, per, cur, ovf: engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, q, cap, per, cur, ovf, 0.05, 0.1, spec.zmax),
+                  lambda v, out: engine.resolve_labels(v, 133, 0.5, None, out=out))
+def sp_fuse_only():
+    sp.cursors.zero_()
+    engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, sp.peer_queue_ptrs, sp.cap, sp.per, sp.cursors, sp.overflow, 0.05, 0.1, spec.zmax)
+def sp_accum_only():
+    sp.shard.zero_(); engine.sparse_accumulate(sp.rx, sp.rx_count, world, sp.cap, sp.shard)
+def sp_barriers():
+    sp.hdl.barrier(channel=0); sp.hdl.barrier(channel=1)
+res["sparse: fuse+emit only"] = timeit(sp_fuse_only)
+engine.sparse_publish(sp.cursors, sp.peer_count_ptrs, rank, sp.cap); torch.cuda.synchronize(); dist.barrier()
+res["sparse: memset+accumulate only"] = timeit(sp_accum_only)
+res["sparse: 2 barriers"] = timeit(sp_barriers)
+res["sparse: resolve shard"] = timeit(lambda: engine.resolve_labels(sp.shard, 133, 0.5, None, out=sp.lab))
+res["sparse exchange"] = timeit(sparse_step)
+if rank == 0: print(f"{'sparse exchange':32s} {res['sparse exchange']:8.3f} ms  cursors={sp.cursors.tolist()}", flush=True)
+sp.check_overflow()
 ref = full(8, False).clone(); torch.cuda.synchronize()
+assert torch.equal(sparse_step(), ref), "sparse exchange disagrees with the dense pipeline"
 assert torch.equal(full(8), ref) and torch.equal(full(16), ref), "packed / chunked pipelines disagree"
 single = engine.resolve_labels(votes, 133, 0.5, None) if world == 1 else None
 if rank == 0:

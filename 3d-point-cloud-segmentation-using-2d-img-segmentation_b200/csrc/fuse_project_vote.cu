@@ -41,6 +41,18 @@
 #ifndef FUSE_MINB
 #define FUSE_MINB 2       // resident CTAs per SM the register allocation targets (128 registers: keeps all NB gathers in flight)
 #endif
+// Byte-histogram build of the vote kernel (HB = 1): uint8 counters halve the shared-memory footprint, so twice the CTAs
+// are resident and their latency-bound phases (cull, frame staging, gathers, vote write) overlap.  A counter can hold
+// 255: the sweep flushes the warp's rows to HBM (first flush overwrites, later ones add) before more than
+// FUSE_LIMIT8 candidates have been swept since the last flush, so no count is ever lost.
+#ifndef FUSE_NB8
+#define FUSE_NB8 4        // gather batch of the byte-histogram build
+#endif
+#ifndef FUSE_MINB8
+#define FUSE_MINB8 3      // resident CTAs per SM of the byte-histogram build (80 registers; 64 spills and is slower)
+#endif
+#define FUSE_QWARP 20     // deferred entries per warp (12 B each); overflow falls back to inline evaluation
+#define FUSE_LIMIT8 (255 - FUSE_QWARP)   // the warp's deferred pass can add up to FUSE_QWARP votes to one cell at the end
 #define RES_MAXC 256
 #define F3D_MAX_RANKS 16
 
@@ -264,8 +276,6 @@ __device__ __forceinline__ int distance_test(const float4* __restrict__ s, const
 struct Deferred {
     uint32_t w0, w1, w2;   // owner lane | frame (relative) << 16 ; pixel guess ; st | guess << 8
 };
-#define FUSE_QWARP 20   // deferred entries per warp (12 B each); overflow falls back to inline evaluation
-
 struct Tally {
     unsigned n_cand, n_exact, n_div, n_edge, n_seen, n_bad;
     int total, best, bpos;   // running VotingSegmentation.segment state of this thread's point (fused resolve)
@@ -273,11 +283,12 @@ struct Tally {
 
 // a vote for class `cls` of the thread's own point: bump the histogram and keep the running arg-max exact:
 // best = max count so far, bpos = smallest filter position among the classes whose count equals best.
-__device__ __forceinline__ void cast_vote(uint16_t* hist, int row_off, int cls, const FuseParams& P, const FuseResolve& RP,
+template <typename CellT>
+__device__ __forceinline__ void cast_vote(CellT* hist, int row_off, int cls, const FuseParams& P, const FuseResolve& RP,
                                           Tally& t) {
     if (cls >= P.C1) return;
     const int v = (int)hist[row_off + cls] + 1;
-    hist[row_off + cls] = (uint16_t)v;
+    hist[row_off + cls] = (CellT)v;
     if (RP.enabled) {
         ++t.total;
         const int pos = RP.fpos[cls];
@@ -288,9 +299,9 @@ __device__ __forceinline__ void cast_vote(uint16_t* hist, int row_off, int cls, 
     }
 }
 
-template <int MODE, int FMT>
+template <int MODE, int FMT, typename CellT>
 __device__ __forceinline__ void resolve_exact(const FuseParams& P, const FuseResolve& RP, const FrameRecord* __restrict__ frec,
-                                              uint16_t* hist, int RS, int64_t tile_base, int owner_tid, int frel, float px, float py,
+                                              CellT* hist, int RS, int64_t tile_base, int owner_tid, int frel, float px, float py,
                                               float pz, int st, int g_in, int pix, bool fast_seen, uint32_t fast_zq,
                                               bool owner_is_self, unsigned* dirty_w, Tally& t) {
     const int HW = P.H * P.W;
@@ -319,10 +330,12 @@ __device__ __forceinline__ void resolve_exact(const FuseParams& P, const FuseRes
             if (owner_is_self) {
                 cast_vote(hist, owner_tid * RS, cls, P, RP, t);
             } else if (cls < P.C1) {
-                // another lane's row: 32-bit atomic on the word holding the uint16 counter (cannot carry: <= 65535 frames);
-                // the owner re-derives its arg-max from the row afterwards (dirty bit)
+                // another lane's row: 32-bit atomic on the word holding the counter (cannot carry: the counter bound is
+                // enforced by the flush rule / the frames-per-launch limit); the owner re-derives its arg-max from the
+                // row afterwards (dirty bit)
                 const int h = owner_tid * RS + cls;
-                atomicAdd(reinterpret_cast<unsigned*>(hist) + (h >> 1), (h & 1) ? 0x10000u : 1u);
+                if (sizeof(CellT) == 2) atomicAdd(reinterpret_cast<unsigned*>(hist) + (h >> 1), (h & 1) ? 0x10000u : 1u);
+                else atomicAdd(reinterpret_cast<unsigned*>(hist) + (h >> 2), 1u << (8 * (h & 3)));
                 atomicOr(dirty_w, 1u << (owner_tid & 31));
             }
         } else if (MODE == MODE_SPLAT) {
@@ -333,8 +346,136 @@ __device__ __forceinline__ void resolve_exact(const FuseParams& P, const FuseRes
     }
 }
 
-template <int MODE, int FMT>
-__global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseParams P, const FuseResolve RP) {
+template <int HB> struct HistCell { typedef uint16_t T; };
+template <> struct HistCell<1> { typedef uint8_t T; };
+
+// ---- byte-histogram flush: the warp's 32 rows (32*C1 contiguous bytes, row stride == C1) -> HBM ------------------
+// first flush of a non-accumulating launch overwrites (every cell written exactly once, 16-byte stores); later
+// flushes add their non-zero cells.  Rows are warp-private, so no CTA barrier and no atomics are involved.
+__device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int warp, int lane, int64_t tile_base, bool add,
+                                       bool rezero) {
+    const int row0 = warp * 32;
+    const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
+    const int total = nrows * P.C1;
+    const int n4 = total >> 2;
+    uint32_t* __restrict__ h32 = reinterpret_cast<uint32_t*>(hist + row0 * P.C1);   // 32*C1 bytes per warp: word aligned
+    const uint8_t* __restrict__ h8 = hist + row0 * P.C1;
+    if (P.sp_G > 0 && nrows > 0) {
+        // sparse emit: non-zero cells go to the receive queue of the rank that owns the point (peer memory).  A warp's
+        // rows belong to one owner except at the G-1 shard boundaries of the whole launch.
+        const long long p0 = tile_base + row0;
+        const int dlo = (int)(p0 / P.sp_per), dhi = (int)((p0 + nrows - 1) / P.sp_per);
+        for (int d = dlo; d <= dhi; ++d) {
+            const bool single = (dlo == dhi);
+            int cnt = 0;
+            for (int i = lane; i < n4; i += 32) {
+                const uint32_t w = h32[i];
+                if (!w) continue;
+                if (single) cnt += __popc(__vcmpne4(w, 0u)) >> 3;
+                else
+                    for (int b = 0; b < 4; ++b)
+                        cnt += (((w >> (8 * b)) & 0xffu) != 0u) && ((p0 + (4 * i + b) / P.C1) / P.sp_per == d);
+            }
+            for (int e = (n4 << 2) + lane; e < total; e += 32) cnt += (h8[e] != 0) && ((p0 + e / P.C1) / P.sp_per == d);
+#pragma unroll
+            for (int s2 = 16; s2 > 0; s2 >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s2);
+            if (cnt == 0) continue;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.sp_cursor + d, (unsigned long long)cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (unsigned long long)cnt > P.sp_cap) {
+                if (lane == 0) atomicExch(P.sp_overflow, 1u);
+                continue;
+            }
+            // consecutive lanes append consecutive entries (ballot ranks), so the mostly remote stores of one
+            // instruction cover one contiguous run of the queue
+            unsigned long long* __restrict__ q = P.sp_queue[d] + base;
+            const unsigned key0 = (unsigned)((p0 - (long long)d * P.sp_per) * P.C1);
+            const unsigned below = (1u << lane) - 1u;
+            unsigned run = 0;
+            const int n4r = (n4 + 31) & ~31;
+            for (int i0 = 0; i0 < n4r; i0 += 32) {
+                const int i = i0 + lane;
+                const uint32_t w = (i < n4) ? h32[i] : 0u;
+                if (__ballot_sync(0xffffffffu, w != 0u) == 0u) continue;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const unsigned v = (w >> (8 * b)) & 0xffu;
+                    const bool on = (v != 0u) && (single || ((p0 + (4 * i + b) / P.C1) / P.sp_per == d));
+                    const unsigned bal = __ballot_sync(0xffffffffu, on);
+                    if (on) q[run + __popc(bal & below)] = sp_pack(key0 + 4 * i + b, v);
+                    run += __popc(bal);
+                }
+            }
+            for (int e0 = n4 << 2; e0 < total; e0 += 32) {
+                const int e = e0 + lane;
+                const unsigned v = (e < total) ? h8[e] : 0u;
+                const bool on = (v != 0u) && ((p0 + e / P.C1) / P.sp_per == d);
+                const unsigned bal = __ballot_sync(0xffffffffu, on);
+                if (on) q[run + __popc(bal & below)] = sp_pack(key0 + e, v);
+                run += __popc(bal);
+            }
+        }
+    } else if (nrows > 0) {
+        if (P.votes) {
+            int32_t* __restrict__ out = P.votes + (tile_base + row0) * P.C1;
+            if (!add) {
+                for (int i = lane; i < n4; i += 32) {
+                    const uint32_t w = h32[i];
+                    *reinterpret_cast<int4*>(out + 4 * i) =
+                        make_int4((int)(w & 0xffu), (int)((w >> 8) & 0xffu), (int)((w >> 16) & 0xffu), (int)(w >> 24));
+                }
+                for (int e = (n4 << 2) + lane; e < total; e += 32) out[e] = (int)h8[e];
+            } else {
+                for (int i = lane; i < n4; i += 32) {
+                    const uint32_t w = h32[i];
+                    if (!w) continue;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int v = (int)((w >> (8 * b)) & 0xffu);
+                        if (v) out[4 * i + b] += v;
+                    }
+                }
+                for (int e = (n4 << 2) + lane; e < total; e += 32)
+                    if (h8[e]) out[e] += (int)h8[e];
+            }
+        }
+        if (P.votes16) {
+            uint16_t* __restrict__ out = P.votes16 + (tile_base + row0) * P.C1;
+            if (!add) {
+                for (int i = lane; i < n4; i += 32) {
+                    const uint32_t w = h32[i];
+                    *reinterpret_cast<uint2*>(out + 4 * i) =
+                        make_uint2((w & 0xffu) | ((w << 8) & 0xff0000u), ((w >> 16) & 0xffu) | ((w >> 8) & 0xff0000u));
+                }
+                for (int e = (n4 << 2) + lane; e < total; e += 32) out[e] = (uint16_t)h8[e];
+            } else {
+                for (int i = lane; i < n4; i += 32) {
+                    const uint32_t w = h32[i];
+                    if (!w) continue;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const unsigned v = (w >> (8 * b)) & 0xffu;
+                        if (v) out[4 * i + b] += (uint16_t)v;
+                    }
+                }
+                for (int e = (n4 << 2) + lane; e < total; e += 32)
+                    if (h8[e]) out[e] += (uint16_t)h8[e];
+            }
+        }
+    }
+    if (rezero) {
+        __syncwarp();
+        for (int i = lane; i < 8 * P.C1; i += 32) h32[i] = 0u;
+        __syncwarp();
+    }
+}
+
+template <int MODE, int FMT, int HB>
+__global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? FUSE_MINB8 : FUSE_MINB)
+    fuse_kernel(const __grid_constant__ FuseParams P, const __grid_constant__ FuseResolve RP) {
+    typedef typename HistCell<HB>::T CellT;
+    constexpr int NB = (MODE == MODE_VOTE && HB == 1) ? FUSE_NB8 : FUSE_NB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [2 x stage FrameFast x FUSE_STAGE][cand u16 x FUSE_FCHUNK][red: 48 floats | ncand | 2 mbarriers | 8 nq | 8 dirty]
     //         [deferred queues: 8 warps x FUSE_QWARP][hist]
@@ -346,7 +487,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
     int* nq_s = reinterpret_cast<int*>(red + 56);             // per-warp deferred counts
     unsigned* dirty_s = reinterpret_cast<unsigned*>(red + 64);
     Deferred* queue_all = reinterpret_cast<Deferred*>(red + 72);
-    uint16_t* hist = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(queue_all) + (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred));
+    CellT* hist = reinterpret_cast<CellT*>(reinterpret_cast<unsigned char*>(queue_all) + (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred));
     const int RS = P.RS;
 
     const int tid = threadIdx.x;
@@ -372,7 +513,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
     }
     if (MODE == MODE_VOTE) {
         uint4* h128 = reinterpret_cast<uint4*>(hist);
-        const int n128 = (FUSE_BLOCK * RS * 2 + 15) / 16;
+        const int n128 = (FUSE_BLOCK * RS * (int)sizeof(CellT) + 15) / 16;
         for (int i = tid; i < n128; i += FUSE_BLOCK) h128[i] = make_uint4(0u, 0u, 0u, 0u);
     }
 
@@ -420,6 +561,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
     T.best = 0;
     T.bpos = 0x7fff;
     unsigned phase_bits = 0;   // parity of the two staging barriers
+    int since_flush = 0, nflush = 0;   // byte histogram: candidates swept since the last flush, flushes so far (CTA-uniform)
 
     for (int cbase = P.f_begin; cbase < P.f_end; cbase += FUSE_FCHUNK) {
         if (cbase != P.f_begin) __syncthreads();   // previous chunk's candidate list fully consumed
@@ -475,14 +617,24 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
             if (warp == 0 && batch + 1 < nbatch) issue(batch + 1);
             mbar_wait(&mbar[buf], (phase_bits >> buf) & 1u);
             phase_bits ^= (1u << buf);
+            if (MODE == MODE_VOTE && HB == 1) {
+                // a byte counter holds 255: flush the warp's rows before this batch could push a cell past the limit
+                if (since_flush + nb > FUSE_LIMIT8) {
+                    __syncwarp();
+                    flush8(P, reinterpret_cast<uint8_t*>(hist), warp, lane, tile_base, nflush > 0 || P.accumulate, true);
+                    ++nflush;
+                    since_flush = 0;
+                }
+                since_flush += nb;
+            }
             if (active) {
-                for (int k0 = 0; k0 < nb; k0 += FUSE_NB) {
+                for (int k0 = 0; k0 < nb; k0 += NB) {
                     // ---- phase 1: fp32 projection + certification of NB candidates
-                    uint32_t puv[FUSE_NB];
+                    uint32_t puv[NB];
                     unsigned long long stw = 0;   // 4 bits per candidate: st | g_in << 3
-                    float zc[MODE == MODE_SPLAT ? FUSE_NB : 1];
+                    float zc[MODE == MODE_SPLAT ? NB : 1];
 #pragma unroll
-                    for (int k = 0; k < FUSE_NB; ++k) {
+                    for (int k = 0; k < NB; ++k) {
                         puv[k] = 0;
                         if (k0 + k < nb) {
                             const Cls c = classify(stage + (buf * FUSE_STAGE + k0 + k) * 8, pt, fW, fH);
@@ -493,11 +645,11 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
                     }
                     if ((stw == 0 && !P.audit) || (P.dbg & 4)) continue;
                     // ---- phase 2: every gather of the certified candidates is issued before any is consumed
-                    uint32_t dv[MODE == MODE_SPLAT ? 1 : FUSE_NB];
-                    uint32_t mk[MODE == MODE_VOTE ? FUSE_NB : 1];
+                    uint32_t dv[MODE == MODE_SPLAT ? 1 : NB];
+                    uint32_t mk[MODE == MODE_VOTE ? NB : 1];
                     if (MODE != MODE_SPLAT) {
 #pragma unroll
-                        for (int k = 0; k < FUSE_NB; ++k) {
+                        for (int k = 0; k < NB; ++k) {
                             dv[k] = 0;
                             if (MODE == MODE_VOTE) mk[k] = 0;
                             if (((stw >> (4 * k)) & 7ull) == 1ull) {
@@ -511,13 +663,13 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
                     if (P.dbg & 8) {   // timing experiment: consume the gathers trivially
                         unsigned acc = 0;
 #pragma unroll
-                        for (int k = 0; k < FUSE_NB; ++k) acc ^= dv[MODE == MODE_SPLAT ? 0 : k] ^ mk[MODE == MODE_VOTE ? k : 0];
+                        for (int k = 0; k < NB; ++k) acc ^= dv[MODE == MODE_SPLAT ? 0 : k] ^ mk[MODE == MODE_VOTE ? k : 0];
                         if (acc == 0xdeadbeefu) T.n_bad++;
                         continue;
                     }
                     // ---- phase 3: depth validity + distance criterion, votes; uncertain pairs are deferred
 #pragma unroll
-                    for (int k = 0; k < FUSE_NB; ++k) {
+                    for (int k = 0; k < NB; ++k) {
                         int st = (int)((stw >> (4 * k)) & 7ull);
                         if (st == 0 && !P.audit) continue;
                         if (k0 + k >= nb) continue;
@@ -563,7 +715,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
                                 queue[slot].w1 = (uint32_t)pix;
                                 queue[slot].w2 = (uint32_t)st | ((uint32_t)g_in << 8);
                             } else {
-                                resolve_exact<MODE, FMT>(P, RP, frec, hist, RS, tile_base, tid, frel, pt.x, pt.y, pt.z, st, g_in, pix,
+                                resolve_exact<MODE, FMT, CellT>(P, RP, frec, hist, RS, tile_base, tid, frel, pt.x, pt.y, pt.z, st, g_in, pix,
                                                          seen, zq, true, dirty_s + warp, T);
                             }
                         } else if (seen) {
@@ -608,14 +760,45 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
             const Deferred d = queue[lane];
             const int owner = (int)(d.w0 & 0xffffu), frel = (int)(d.w0 >> 16);
             const float4 op = __ldg(P.points + tile_base + owner);
-            resolve_exact<MODE, FMT>(P, RP, frec, hist, RS, tile_base, owner, frel, op.x, op.y, op.z, (int)(d.w2 & 0xffu),
+            resolve_exact<MODE, FMT, CellT>(P, RP, frec, hist, RS, tile_base, owner, frel, op.x, op.y, op.z, (int)(d.w2 & 0xffu),
                                      (int)(d.w2 >> 8), (int)d.w1, false, 0u, false, dirty_s + warp, T);
         }
     }
     __syncwarp();
 
     // ---- epilogue (warp-private rows): histogram -> HBM, written once with 16-byte stores; fused label resolve
-    if (MODE == MODE_VOTE && P.sp_G > 0) {
+    if constexpr (MODE == MODE_VOTE && HB == 1) {
+        uint8_t* hist8 = reinterpret_cast<uint8_t*>(hist);
+        flush8(P, hist8, warp, lane, tile_base, nflush > 0 || P.accumulate, false);
+        if (RP.enabled && active) {
+            // VotingSegmentation.segment (voting.py:120-135).  The running (total, best, bpos) is exact unless another
+            // lane's deferred pass added votes to this row (re-derived from the row) or the tile was flushed more than
+            // once (re-derived from the complete row in HBM, which this warp has just written).
+            const bool multi = nflush > 0 && (P.votes || P.votes16);
+            if (multi) __syncwarp();
+            if (multi || ((dirty_s[warp] >> lane) & 1u)) {
+                T.total = 0;
+                T.best = 0;
+                T.bpos = 0x7fff;
+                for (int c = 0; c < P.C1; ++c) {
+                    int v;
+                    if (!multi) v = hist8[tid * RS + c];
+                    else if (P.votes) v = P.votes[(size_t)gi * P.C1 + c];
+                    else v = P.votes16[(size_t)gi * P.C1 + c];
+                    T.total += v;
+                    const int pos = RP.fpos[c];
+                    if (v > 0 && pos >= 0 && (v > T.best || (v == T.best && pos < T.bpos))) {
+                        T.best = v;
+                        T.bpos = pos;
+                    }
+                }
+            }
+            bool unc = (T.total <= 0) || (T.best <= 0);                                  // voting.py:126,131
+            if (!unc) unc = xdiv((double)T.best, (double)T.total) < RP.threshold;         // voting.py:128-130
+            P.labels[gi] = (int64_t)(unc ? RP.unclassified : RP.remap[T.bpos]);
+        }
+    } else if constexpr (MODE == MODE_VOTE) {
+      if (P.sp_G > 0) {
         // sparse emit: every lane scans its own histogram row; non-zero cells go to the queue of the rank that owns
         // the point.  A warp's 32 consecutive points belong to one owner (two at a shard boundary).
         const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(hist + tid * RS);
@@ -671,7 +854,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
                 }
             }
         }
-    } else if (MODE == MODE_VOTE) {
+      } else {
         const int row0 = warp * 32;
         const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
         if (P.votes16 && nrows > 0) {
@@ -737,6 +920,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
             if (!unc) unc = xdiv((double)T.best, (double)T.total) < RP.threshold;         // voting.py:128-130
             P.labels[gi] = (int64_t)(unc ? RP.unclassified : RP.remap[T.bpos]);
         }
+      }
     }
 
     // ---- statistics
@@ -755,7 +939,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, FUSE_MINB) fuse_kernel(const FuseP
 // ---- fix-up kernels: the deferred point-views, one per thread, in fp64 ------------------------------------------------
 #define FIXUP_THREADS 128
 template <int MODE, int FMT>
-__global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const FuseParams P) {
+__global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid_constant__ FuseParams P) {
     // Each lane needs the 448-byte fp64 record of ITS frame.  Reading it field by field would be ~50 fully divergent
     // loads per lane; instead the warp copies the 32 records one after the other with coalesced 16-byte loads into
     // shared memory and every lane then evaluates from its own copy.
@@ -838,7 +1022,7 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const FusePa
 
 // labels of the points whose votes changed in fixup_apply_kernel (VotingSegmentation.segment, voting.py:120-135);
 // eight lanes per entry stream the point's vote row, like resolve_kernel
-__global__ void __launch_bounds__(256) fixup_labels_kernel(const FuseParams P, const FuseResolve RP) {
+__global__ void __launch_bounds__(256) fixup_labels_kernel(const __grid_constant__ FuseParams P, const __grid_constant__ FuseResolve RP) {
     __shared__ int16_t s_fpos[RES_MAXC];
     for (int c = threadIdx.x; c < RES_MAXC; c += blockDim.x) s_fpos[c] = RP.fpos[c];
     __syncthreads();
@@ -902,19 +1086,36 @@ static int hist_row_stride(int C1) {
     return rs;
 }
 
-static size_t fuse_smem_bytes(int mode, int C1) {
+static size_t fuse_smem_bytes(int mode, int C1, int hb) {
     size_t b = 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t) + 72 * sizeof(float) +
                (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred);
-    if (mode == MODE_VOTE) b += ((size_t)FUSE_BLOCK * hist_row_stride(C1) * sizeof(uint16_t) + 15) & ~(size_t)15;
+    if (mode == MODE_VOTE)
+        b += ((size_t)FUSE_BLOCK * (hb == 1 ? (size_t)C1 : hist_row_stride(C1) * sizeof(uint16_t)) + 15) & ~(size_t)15;
     return b;
 }
 
+template <int MODE, int FMT, int HB>
+static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stream);
+
+// the vote kernel runs on the byte histogram unless the caller wants labels without any vote output from more frames
+// than a byte counter can hold between flushes (there is then nowhere to flush to): that case keeps uint16 counters
 template <int MODE, int FMT>
 static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t stream) {
-    size_t smem = fuse_smem_bytes(MODE, P.C1);
+    if constexpr (MODE == MODE_VOTE) {
+        const bool no_sink = !P.votes && !P.votes16 && P.sp_G == 0;
+        const bool hist16 = (no_sink && P.f_end - P.f_begin > FUSE_LIMIT8) || getenv("F3D_HIST16") != nullptr;
+        if (!hist16) return launch_fuse_hb<MODE, FMT, 1>(P, RP, stream);
+    }
+    return launch_fuse_hb<MODE, FMT, 2>(P, RP, stream);
+}
+
+template <int MODE, int FMT, int HB>
+static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stream) {
+    if (MODE == MODE_VOTE) P.RS = HB == 1 ? P.C1 : hist_row_stride(P.C1);
+    size_t smem = fuse_smem_bytes(MODE, P.C1, HB);
     if (const char* ex = getenv("F3D_EXTRA_SMEM")) smem += (size_t)atoi(ex);   // occupancy experiments only
     if (smem > 227 * 1024) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: nclasses+1 too large for the shared-memory histogram");
-    cudaError_t e = cudaFuncSetAttribute(fuse_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fuse_kernel<MODE, FMT, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute)");
     int64_t tiles = (P.N + FUSE_BLOCK - 1) / FUSE_BLOCK;
     if (tiles > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: too many points for one launch");
@@ -923,7 +1124,7 @@ static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t 
         e = cudaMemsetAsync(P.gq_count, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(memset)");
     }
-    fuse_kernel<MODE, FMT><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
+    fuse_kernel<MODE, FMT, HB><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
     if (use_queue) {
         // the queue length lives on the device: fixed grids with grid-stride loops, no host synchronisation
         const int fx_smem = (FIXUP_THREADS / 32) * 32 * (int)sizeof(FrameExact);
@@ -1037,8 +1238,9 @@ int f3d_build_resolve(int C1, double threshold, const int32_t* h_filter, int nfi
     return F3D_OK;
 }
 
-// frames are processed in launches of at most 65535 (uint16 candidate ids and histogram counters)
-#define F3D_MAX_FRAMES_PER_LAUNCH 65535
+// frames are processed in launches of at most 65535 - FUSE_QWARP (uint16 candidate ids; a uint16 histogram counter
+// must also hold the warp's deferred votes)
+#define F3D_MAX_FRAMES_PER_LAUNCH (65535 - FUSE_QWARP)
 
 static int fuse_vote_impl(const void* points, int64_t N, const void* frame_table, int32_t frame_begin, int32_t frame_end,
                           const void* depth, int32_t depth_fmt, const uint8_t* mask, int32_t H, int32_t W,
@@ -1223,7 +1425,7 @@ extern "C" int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const
         !overflow || C1 <= 0 || C1 > 256 || (frame_end > frame_begin && (!depth || !mask)))
         return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_sparse: bad argument");
     if (frame_end - frame_begin > F3D_MAX_FRAMES_PER_LAUNCH)
-        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: more than 65535 frames per call");
+        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: too many frames per call (limit 65515)");
     if ((int64_t)points_per_shard * C1 > 0xffffffffLL)
         return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: shard cell index does not fit 32 bits");
     if (N == 0) return F3D_OK;

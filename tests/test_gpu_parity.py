@@ -319,3 +319,59 @@ def test_obb_contains_vs_oracle(engine):
     for b in range(5):
         ref = orc.obb_contains(boxes[b, :3], boxes[b, 3:12].reshape(3, 3), boxes[b, 12:], pts)
         assert np.array_equal(out[b], ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# byte-histogram flush rule: more candidate frames per tile than a uint8 counter can hold
+# ---------------------------------------------------------------------------------------------------------------------
+
+def test_byte_histogram_flush_many_views(engine, scenes, monkeypatch):
+    """600 frames that all see the same points (3 poses repeated 300 times): single cells reach counts of several
+    hundred, so the uint8 shared-memory histogram must flush mid-sweep (first flush overwrites, later ones add) and the
+    fused labels must be re-derived from the complete rows.  Checked against 300 x the oracle's 3-frame votes, and
+    against the uint16-histogram build of the same kernel."""
+    rep = 300
+    s = small_scene(scenes, orc, npoints=6001, nframes=3, width=96, height=64, seed=61, block=16)
+    ov3 = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0, 0.05,
+                                0.1, 4.0, 4.0)
+    ov = ov3 * rep
+    assert ov.max() > 255
+    big = dict(s, wxyz=np.tile(s["wxyz"], (rep, 1)), t=np.tile(s["t"], (rep, 1)), depths=np.tile(s["depths"], (rep, 1, 1)),
+               masks=np.tile(s["masks"], (rep, 1, 1)))
+    tab = engine.FrameTable(big["K"], big["W"], big["H"], big["wxyz"], big["t"], 4.0)
+    p4 = engine.pack_points(big["points"])
+    d, m = dev(big["depths"]), dev(big["masks"])
+    for hist16 in (False, True):
+        if hist16:
+            monkeypatch.setenv("F3D_HIST16", "1")
+        else:
+            monkeypatch.delenv("F3D_HIST16", raising=False)
+        st = engine.new_stats()
+        votes = engine.fuse_project_vote(p4, tab, d, m, 134, 0.05, 0.1, 4.0, stats=st)
+        assert np.array_equal(votes.cpu().numpy(), ov) and engine.stats_dict(st)["seen"] == int(ov.sum())
+        v16 = engine.fuse_project_vote(p4, tab, d, m, 134, 0.05, 0.1, 4.0, packed_u16=True)
+        assert np.array_equal(v16.to(torch.int32).cpu().numpy(), ov)
+        # accumulate on top of an earlier launch (every flush adds)
+        acc = engine.fuse_project_vote(p4, tab, d, m, 134, 0.05, 0.1, 4.0, votes=votes.clone(), accumulate=True)
+        assert np.array_equal(acc.cpu().numpy(), 2 * ov)
+        for thr, fc in [(0.5, None), (0.3, [1, 0, 5])]:
+            v, lab = engine.fuse_project_vote_resolve(p4, tab, d, m, 134, 133, 0.05, 0.1, 4.0, thr, fc)
+            assert np.array_equal(v.cpu().numpy(), ov)
+            assert np.array_equal(lab.cpu().numpy(), orc.segment(ov, 133, thr, fc))
+        # labels without a vote tensor: nowhere to flush to, so the library runs the uint16 histogram
+        none_votes, lab = engine.fuse_project_vote_resolve(p4, tab, d, m, 134, 133, 0.05, 0.1, 4.0, 0.5, None, want_votes=False)
+        assert none_votes is None and np.array_equal(lab.cpu().numpy(), orc.segment(ov, 133, 0.5, None))
+        # audit mode evaluates every candidate in fp64 inside the sweep
+        va = engine.fuse_project_vote(p4, tab, d, m, 134, 0.05, 0.1, 4.0, stats=st, audit=True)
+        assert np.array_equal(va.cpu().numpy(), ov) and engine.stats_dict(st)["audit_bad"] == 0
+    monkeypatch.delenv("F3D_HIST16", raising=False)
+
+
+def test_uint16_histogram_build_matches(engine, scenes, monkeypatch):
+    """The uint16-histogram instantiation (used for labels-only launches over many frames) stays bit-identical."""
+    s = small_scene(scenes, orc, npoints=20011, nframes=6, width=320, height=240, seed=67, block=16)
+    base, _, _, _ = run_fused(engine, s)
+    monkeypatch.setenv("F3D_HIST16", "1")
+    alt, _, _, _ = run_fused(engine, s)
+    monkeypatch.delenv("F3D_HIST16", raising=False)
+    assert np.array_equal(base, alt)

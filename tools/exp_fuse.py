@@ -29,6 +29,26 @@ def run(flags, want_votes=True, want_labels=True, reps=5):
     for _ in range(reps): call()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
+quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
+if quick:
+    # every kernel variant under build/variants/ (tools/build_variants.sh) on the same resident scene
+    import ctypes, glob, os
+    ref = None
+    for path in ["default"] + sorted(glob.glob(str(ROOT / "build" / "variants" / "*.so"))) + ["default+F3D_HIST16"]:
+        os.environ.pop("F3D_HIST16", None)
+        if path.startswith("default"):
+            lib = _lib.load()
+            if "HIST16" in path: os.environ["F3D_HIST16"] = "1"
+        else:
+            lib = ctypes.CDLL(path)
+            for name, (res, args) in _lib.SIGNATURES.items():
+                fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
+        t = run(0, True, True, reps=10)
+        tv = run(0, True, False, reps=10)
+        sig = (int(votes.sum()), int(labels.sum()))
+        ref = ref or sig
+        print(f"{os.path.basename(path):28s} votes+labels {t:7.3f} ms   votes only {tv:7.3f} ms   {'same' if sig == ref else 'DIFFERENT ' + str(sig)}", flush=True)
+    sys.exit(0)
 for name, fl_, wv, wl_ in [("full votes+labels", 0, True, True), ("votes only", 0, True, False), ("labels only (no vote write)", 0, False, True),
                       ("classify only (no gathers)", 0x400, True, True), ("gathers, no phase 3", 0x800, True, True), ("no deferred fp64", 0x1000, True, True), ("cull only, no candidates", 0x100, True, True),
                       ("no cull, no candidates", 0x200, True, True), ("no cull, labels only", 0x200, False, True)]:

@@ -23,3 +23,4 @@ int f3d_check_launch(const char* where) {
 
 extern "C" const char* f3d_last_error(void) { return g_err; }
 extern "C" int f3d_version(void) { return 100; }
+

@@ -51,6 +51,7 @@
 #ifndef FUSE_MINB8
 #define FUSE_MINB8 3      // resident CTAs per SM of the byte-histogram build (80 registers; 64 spills and is slower)
 #endif
+#define FUSE_RED_WORDS 96 // small per-CTA scalars (see the layout comment in the kernel)
 #define FUSE_QWARP 20     // deferred entries per warp (12 B each); overflow falls back to inline evaluation
 #define FUSE_LIMIT8 (255 - FUSE_QWARP)   // the warp's deferred pass can add up to FUSE_QWARP votes to one cell at the end
 #define RES_MAXC 256
@@ -277,7 +278,8 @@ struct Deferred {
     uint32_t w0, w1, w2;   // owner lane | frame (relative) << 16 ; pixel guess ; st | guess << 8
 };
 struct Tally {
-    unsigned n_cand, n_exact, n_div, n_edge, n_seen, n_bad;
+    unsigned n_cand, n_seen;   // hot counters (registers); the rare ones (exact / diverged / near-edge / audit-bad) are
+    unsigned* rare;            // shared-memory counters [F3D_STAT_*], bumped with atomics where they occur
     int total, best, bpos;   // running VotingSegmentation.segment state of this thread's point (fused resolve)
 };
 
@@ -310,18 +312,18 @@ __device__ __forceinline__ void resolve_exact(const FuseParams& P, const FuseRes
     const bool e_seen = (MODE == MODE_SPLAT) ? (eo.in != 0) : (eo.vis != 0);
     const uint32_t e_zq = (MODE == MODE_SPLAT && eo.in) ? quantise_mm(eo.zcam) : 0u;
     if (st >= 2) {
-        ++t.n_exact;
+        atomicAdd(t.rare + F3D_STAT_EXACT, 1u);
         bool diverged;
         if (st == 2) diverged = (g_in != eo.in) || (eo.in && pix != eo.pix);
         else if (MODE == MODE_SPLAT) diverged = (!eo.in) || (pix != eo.pix) || ((uint32_t)g_in != e_zq);
         else diverged = (g_in != eo.vis) || (eo.in && pix != eo.pix);
-        t.n_div += diverged ? 1u : 0u;
+        if (diverged) atomicAdd(t.rare + F3D_STAT_DIVERGED, 1u);
     } else {
         // audit: a certified fp32 outcome must equal the fp64 outcome
         const bool bad = (fast_seen != e_seen) || (fast_seen && pix != eo.pix) || (fast_seen && MODE == MODE_SPLAT && fast_zq != e_zq);
-        t.n_bad += bad ? 1u : 0u;
+        if (bad) atomicAdd(t.rare + F3D_STAT_AUDIT_BAD, 1u);
     }
-    t.n_edge += (eo.in && eo.near_edge) ? 1u : 0u;
+    if (eo.in && eo.near_edge) atomicAdd(t.rare + F3D_STAT_NEAR_EDGE, 1u);
     if (e_seen) {
         ++t.n_seen;
         const size_t off = (size_t)frel * (size_t)HW + (size_t)eo.pix;
@@ -422,8 +424,9 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
             if (!add) {
                 for (int i = lane; i < n4; i += 32) {
                     const uint32_t w = h32[i];
-                    *reinterpret_cast<int4*>(out + 4 * i) =
-                        make_int4((int)(w & 0xffu), (int)((w >> 8) & 0xffu), (int)((w >> 16) & 0xffu), (int)(w >> 24));
+                    const int4 v4 = make_int4((int)__byte_perm(w, 0u, 0x4440), (int)__byte_perm(w, 0u, 0x4441),
+                                              (int)__byte_perm(w, 0u, 0x4442), (int)__byte_perm(w, 0u, 0x4443));
+                    *reinterpret_cast<int4*>(out + 4 * i) = v4;
                 }
                 for (int e = (n4 << 2) + lane; e < total; e += 32) out[e] = (int)h8[e];
             } else {
@@ -477,16 +480,20 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     typedef typename HistCell<HB>::T CellT;
     constexpr int NB = (MODE == MODE_VOTE && HB == 1) ? FUSE_NB8 : FUSE_NB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [2 x stage FrameFast x FUSE_STAGE][cand u16 x FUSE_FCHUNK][red: 48 floats | ncand | 2 mbarriers | 8 nq | 8 dirty]
+    // layout: [2 x stage FrameFast x FUSE_STAGE][cand u16 x FUSE_FCHUNK][cmask u8 x FUSE_FCHUNK]
+    //         [red: 48 floats (8 warp boxes) | ncand | 2 mbarriers | 8 nq | 8 dirty | tile box (7) | 8 stat counters]
     //         [deferred queues: 8 warps x FUSE_QWARP][hist]
     float4* stage = reinterpret_cast<float4*>(smem_raw);
     uint16_t* cand = reinterpret_cast<uint16_t*>(smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast));
-    float* red = reinterpret_cast<float*>(smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t));
+    uint8_t* cmask = smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t);   // warps that keep candidate i
+    float* red = reinterpret_cast<float*>(smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * (sizeof(uint16_t) + 1));
     int* ncand_s = reinterpret_cast<int*>(red + 48);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 52);   // two barriers (16-byte aligned offset)
     int* nq_s = reinterpret_cast<int*>(red + 56);             // per-warp deferred counts
     unsigned* dirty_s = reinterpret_cast<unsigned*>(red + 64);
-    Deferred* queue_all = reinterpret_cast<Deferred*>(red + 72);
+    float* tbox = red + 72;                                   // tile box lo[3], hi[3], magnitude
+    unsigned* stat_s = reinterpret_cast<unsigned*>(red + 80); // CTA totals of the statistics, flushed once at the end
+    Deferred* queue_all = reinterpret_cast<Deferred*>(red + FUSE_RED_WORDS);
     CellT* hist = reinterpret_cast<CellT*>(reinterpret_cast<unsigned char*>(queue_all) + (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred));
     const int RS = P.RS;
 
@@ -510,6 +517,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     if (lane == 0) {
         nq_s[warp] = 0;
         dirty_s[warp] = 0u;
+        stat_s[warp] = 0u;
     }
     if (MODE == MODE_VOTE) {
         uint4* h128 = reinterpret_cast<uint4*>(hist);
@@ -539,28 +547,30 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         }
     }
     __syncthreads();
-    float blo[3], bhi[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float l = red[k], h = red[3 + k];
+    if (tid < 3) {
+        float l = red[tid], h = red[3 + tid];
 #pragma unroll
         for (int w = 1; w < FUSE_BLOCK / 32; ++w) {
-            l = fminf(l, red[w * 6 + k]);
-            h = fmaxf(h, red[w * 6 + 3 + k]);
+            l = fminf(l, red[w * 6 + tid]);
+            h = fmaxf(h, red[w * 6 + 3 + tid]);
         }
-        blo[k] = l;
-        bhi[k] = h;
+        tbox[tid] = l;
+        tbox[3 + tid] = h;
     }
-    const float box_mag = fabsf(blo[0]) + fabsf(blo[1]) + fabsf(blo[2]) + fabsf(bhi[0]) + fabsf(bhi[1]) + fabsf(bhi[2]);
+    // (the chunk loop starts with a barrier before the box is read)
 
     const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
 
     Tally T;
-    T.n_cand = T.n_exact = T.n_div = T.n_edge = T.n_seen = T.n_bad = 0u;
+    T.n_cand = T.n_seen = 0u;
+    T.rare = stat_s;
     T.total = 0;
     T.best = 0;
     T.bpos = 0x7fff;
     unsigned phase_bits = 0;   // parity of the two staging barriers
+#ifdef FUSE_PROBE
+    unsigned probe_lane = 0, probe_warp = 0;
+#endif
     int since_flush = 0, nflush = 0;   // byte histogram: candidates swept since the last flush, flushes so far (CTA-uniform)
 
     for (int cbase = P.f_begin; cbase < P.f_end; cbase += FUSE_FCHUNK) {
@@ -569,6 +579,8 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         __syncthreads();
         const int cend = min(cbase + FUSE_FCHUNK, P.f_end);
         // ---- conservative tile x frustum cull (fp32 + explicit rounding margin; never drops a visible pair)
+        const float blo[3] = {tbox[0], tbox[1], tbox[2]}, bhi[3] = {tbox[3], tbox[4], tbox[5]};
+        const float box_mag = fabsf(blo[0]) + fabsf(blo[1]) + fabsf(blo[2]) + fabsf(bhi[0]) + fabsf(bhi[1]) + fabsf(bhi[2]);
         for (int f0 = cbase; f0 < cend && !(P.dbg & 2); f0 += FUSE_BLOCK) {
             const int f = f0 + tid;
             bool keep = false;
@@ -592,7 +604,31 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         }
         __syncthreads();
         const int ncand = (P.dbg & 3) ? 0 : *ncand_s;
-        if (active) T.n_cand += (unsigned)ncand;
+        // ---- second cull level: every surviving frame against the box of each warp's 32 points (8 threads per
+        // candidate, one per warp box).  In a spatially sorted cloud a warp's points are a few centimetres apart, so a
+        // warp is almost always entirely inside or entirely outside a frustum: this drops ~45 % of the (warp, frame)
+        // pairs before any per-point work.  Same conservative rule as the tile test.
+        for (int i0 = 0; i0 < ncand * 8; i0 += FUSE_BLOCK) {
+            const int i = i0 + tid;
+            const int c = i >> 3, wb = i & 7;
+            bool keep = false;
+            if (c < ncand) {
+                keep = true;
+                const float4* pl = frec[P.f_begin + cand[c]].cull.pl;
+                const float* wbox = red + wb * 6;
+                const float l0 = wbox[0], l1 = wbox[1], l2 = wbox[2], h0 = wbox[3], h1 = wbox[4], h2 = wbox[5];
+#pragma unroll
+                for (int m = 0; m < 5; ++m) {
+                    const float4 q = __ldg(pl + m);
+                    const float mx = fmaxf(q.x * l0, q.x * h0) + fmaxf(q.y * l1, q.y * h1) + fmaxf(q.z * l2, q.z * h2) - q.w;
+                    const float margin = 4.0e-6f * (box_mag + fabsf(q.w)) + 1.0e-7f;   // a warp box lies inside the tile box
+                    keep = keep && (mx >= -margin);
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if ((lane & 7) == 0 && c < ncand) cmask[c] = (uint8_t)((bal >> lane) & 0xffu);
+        }
+        __syncthreads();
         const int nbatch = (ncand + FUSE_STAGE - 1) / FUSE_STAGE;
 
         // TMA producer (warp 0): lane 0 arms the barrier with the batch's byte count, lane k issues the 128-byte bulk
@@ -617,18 +653,28 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             if (warp == 0 && batch + 1 < nbatch) issue(batch + 1);
             mbar_wait(&mbar[buf], (phase_bits >> buf) & 1u);
             phase_bits ^= (1u << buf);
+            // this warp's candidates of the batch (bit k: candidate b0 + k)
+            unsigned wm = __ballot_sync(0xffffffffu, lane < nb && ((cmask[b0 + (lane & (FUSE_STAGE - 1))] >> warp) & 1u));
             if (MODE == MODE_VOTE && HB == 1) {
                 // a byte counter holds 255: flush the warp's rows before this batch could push a cell past the limit
-                if (since_flush + nb > FUSE_LIMIT8) {
+                const int nw = __popc(wm);
+                if (since_flush + nw > FUSE_LIMIT8) {
                     __syncwarp();
                     flush8(P, reinterpret_cast<uint8_t*>(hist), warp, lane, tile_base, nflush > 0 || P.accumulate, true);
                     ++nflush;
                     since_flush = 0;
                 }
-                since_flush += nb;
+                since_flush += nw;
             }
             if (active) {
-                for (int k0 = 0; k0 < nb; k0 += NB) {
+                T.n_cand += (unsigned)__popc(wm);
+                while (wm) {
+                    int kk[NB];   // positions (within the batch) of the next NB candidates of this warp; -1 = none
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        kk[k] = wm ? (__ffs(wm) - 1) : -1;
+                        wm &= wm - 1u;
+                    }
                     // ---- phase 1: fp32 projection + certification of NB candidates
                     uint32_t puv[NB];
                     unsigned long long stw = 0;   // 4 bits per candidate: st | g_in << 3
@@ -636,13 +682,21 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
 #pragma unroll
                     for (int k = 0; k < NB; ++k) {
                         puv[k] = 0;
-                        if (k0 + k < nb) {
-                            const Cls c = classify(stage + (buf * FUSE_STAGE + k0 + k) * 8, pt, fW, fH);
+                        if (kk[k] >= 0) {
+                            const Cls c = classify(stage + (buf * FUSE_STAGE + kk[k]) * 8, pt, fW, fH);
                             puv[k] = c.puv;
                             stw |= (unsigned long long)(c.st | (c.g_in << 3)) << (4 * k);
                             if (MODE == MODE_SPLAT) zc[k] = c.z;
                         }
                     }
+#ifdef FUSE_PROBE   // experiment build: how many classified pairs are in-image, and how many (warp, candidate) pairs have any
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        const bool on = ((stw >> (4 * k)) & 7ull) != 0ull;
+                        probe_lane += on ? 1u : 0u;
+                        probe_warp += (lane == 0 && __any_sync(__activemask(), on)) ? 32u : 0u;
+                    }
+#endif
                     if ((stw == 0 && !P.audit) || (P.dbg & 4)) continue;
                     // ---- phase 2: every gather of the certified candidates is issued before any is consumed
                     uint32_t dv[MODE == MODE_SPLAT ? 1 : NB];
@@ -653,7 +707,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
                             dv[k] = 0;
                             if (MODE == MODE_VOTE) mk[k] = 0;
                             if (((stw >> (4 * k)) & 7ull) == 1ull) {
-                                const size_t off = (size_t)cand[b0 + k0 + k] * (size_t)HW + (size_t)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
+                                const size_t off = (size_t)cand[b0 + kk[k]] * (size_t)HW + (size_t)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
                                 if (FMT == F3D_DEPTH_U16_MM) dv[k] = __ldg(reinterpret_cast<const uint16_t*>(P.depth) + off);
                                 else dv[k] = __float_as_uint(__ldg(reinterpret_cast<const float*>(P.depth) + off));
                                 if (MODE == MODE_VOTE) mk[k] = __ldg(P.mask + off);
@@ -664,7 +718,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
                         unsigned acc = 0;
 #pragma unroll
                         for (int k = 0; k < NB; ++k) acc ^= dv[MODE == MODE_SPLAT ? 0 : k] ^ mk[MODE == MODE_VOTE ? k : 0];
-                        if (acc == 0xdeadbeefu) T.n_bad++;
+                        if (acc == 0xdeadbeefu) T.n_seen++;
                         continue;
                     }
                     // ---- phase 3: depth validity + distance criterion, votes; uncertain pairs are deferred
@@ -672,9 +726,9 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
                     for (int k = 0; k < NB; ++k) {
                         int st = (int)((stw >> (4 * k)) & 7ull);
                         if (st == 0 && !P.audit) continue;
-                        if (k0 + k >= nb) continue;
-                        const int frel = cand[b0 + k0 + k];
-                        const float4* s = stage + (buf * FUSE_STAGE + k0 + k) * 8;
+                        if (kk[k] < 0) continue;
+                        const int frel = cand[b0 + kk[k]];
+                        const float4* s = stage + (buf * FUSE_STAGE + kk[k]) * 8;
                         int g_in = (int)((stw >> (4 * k + 3)) & 1ull);
                         const int pix = (int)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
                         uint32_t zq = 0;
@@ -924,15 +978,20 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     }
 
     // ---- statistics
+#ifdef FUSE_PROBE
     if (P.stats) {
-        unsigned vals[6] = {T.n_cand, T.n_exact, T.n_div, T.n_edge, T.n_seen, T.n_bad};
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            unsigned v = vals[i];
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-            if (lane == 0 && v) atomicAdd(P.stats + i, (unsigned long long)v);
+        atomicAdd(P.stats + 6, (unsigned long long)probe_lane);
+        atomicAdd(P.stats + 7, (unsigned long long)probe_warp);
+    }
+#endif
+    if (P.stats) {
+        const unsigned nc = __reduce_add_sync(0xffffffffu, T.n_cand), ns = __reduce_add_sync(0xffffffffu, T.n_seen);
+        if (lane == 0) {
+            if (nc) atomicAdd(stat_s + F3D_STAT_CANDIDATES, nc);
+            if (ns) atomicAdd(stat_s + F3D_STAT_SEEN, ns);
         }
+        __syncthreads();
+        if (tid < 6 && stat_s[tid]) atomicAdd(P.stats + tid, (unsigned long long)stat_s[tid]);   // one atomic per counter per CTA
     }
 }
 
@@ -1087,7 +1146,7 @@ static int hist_row_stride(int C1) {
 }
 
 static size_t fuse_smem_bytes(int mode, int C1, int hb) {
-    size_t b = 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t) + 72 * sizeof(float) +
+    size_t b = 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * (sizeof(uint16_t) + 1) + FUSE_RED_WORDS * sizeof(float) +
                (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred);
     if (mode == MODE_VOTE)
         b += ((size_t)FUSE_BLOCK * (hb == 1 ? (size_t)C1 : hist_row_stride(C1) * sizeof(uint16_t)) + 15) & ~(size_t)15;

@@ -43,6 +43,7 @@ extern "C" {
 const char* f3d_last_error(void);
 int f3d_version(void);
 
+
 /* ---- frame table -------------------------------------------------------------------------------------- */
 
 /* Bytes of packed per-frame data the caller must provide per frame to f3d_frames_setup. */

@@ -29,11 +29,13 @@ def run(flags, want_votes=True, want_labels=True, reps=5):
     for _ in range(reps): call()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
-if quick:
-    # every kernel variant under build/variants/ (tools/build_variants.sh) on the same resident scene
+mode = sys.argv[2] if len(sys.argv) > 2 else ""
+if mode in ("quick", "traffic"):
+    # every kernel variant under build/variants/ (tools/build_variants.sh) on the same resident scene; "traffic" does
+    # three launches per variant (run it under ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum)
     import ctypes, glob, os
     ref = None
+    reps = 10 if mode == "quick" else 1
     for path in ["default"] + sorted(glob.glob(str(ROOT / "build" / "variants" / "*.so"))) + ["default+F3D_HIST16"]:
         os.environ.pop("F3D_HIST16", None)
         if path.startswith("default"):
@@ -43,8 +45,8 @@ if quick:
             lib = ctypes.CDLL(path)
             for name, (res, args) in _lib.SIGNATURES.items():
                 fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
-        t = run(0, True, True, reps=10)
-        tv = run(0, True, False, reps=10)
+        t = run(0, True, True, reps=reps)
+        tv = run(0, True, False, reps=reps) if mode == "quick" else 0.0
         sig = (int(votes.sum()), int(labels.sum()))
         ref = ref or sig
         print(f"{os.path.basename(path):28s} votes+labels {t:7.3f} ms   votes only {tv:7.3f} ms   {'same' if sig == ref else 'DIFFERENT ' + str(sig)}", flush=True)

@@ -139,3 +139,16 @@ struct Intrinsics {
 };
 
 
+
+// ---- label resolve parameters shared by the fused epilogue, the fix-up kernels and the exchange merge ----------------
+#define RES_MAXC 256
+#define F3D_MAX_RANKS 16
+struct FuseResolve {
+    int enabled, nfilter;
+    int32_t unclassified;
+    double threshold;
+    int16_t fpos[RES_MAXC];        // column -> first position in the filter list (or column itself), -1 = not considered
+    int32_t remap[RES_MAXC];       // arg-max position -> label (sequential remap of voting.py:133-135 composed)
+};
+// host: composed sequential remap + column -> filter position table (fuse_project_vote.cu)
+int f3d_build_resolve(int C1, double threshold, const int32_t* h_filter, int nfilter, int nclasses_id, FuseResolve& rp);

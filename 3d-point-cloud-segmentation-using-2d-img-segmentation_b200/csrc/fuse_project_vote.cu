@@ -54,16 +54,6 @@
 #define FUSE_RED_WORDS 96 // small per-CTA scalars (see the layout comment in the kernel)
 #define FUSE_QWARP 20     // deferred entries per warp (12 B each); overflow falls back to inline evaluation
 #define FUSE_LIMIT8 (255 - FUSE_QWARP)   // the warp's deferred pass can add up to FUSE_QWARP votes to one cell at the end
-#define RES_MAXC 256
-#define F3D_MAX_RANKS 16
-
-struct FuseResolve {
-    int enabled, nfilter;
-    int32_t unclassified;
-    double threshold;
-    int16_t fpos[RES_MAXC];        // column -> first position in the filter list (or column itself), -1 = not considered
-    int32_t remap[RES_MAXC];       // arg-max position -> label (sequential remap of voting.py:133-135 composed)
-};
 
 // an uncertain point-view handed from the fused sweep to the fix-up kernels through the caller's workspace
 struct GEntry {
@@ -105,7 +95,13 @@ struct FuseParams {
     unsigned long long sp_cap;                 // entries per segment
     long long sp_per;                          // points per owner shard: owner(p) = p / sp_per
     unsigned* sp_overflow;                     // set when a segment is full (entries are then dropped: caller must check)
+    // slot records (the bulk of the exchange): per (source rank, 32-point block) one 2 KB record [32 slots][32 points] of
+    // uint16 (class | count << 8), written once per launch by the block's warp straight into the owner's memory.
+    // sp_slots[d] = this rank's record array inside rank d's receive buffer (NULL entries: pure (cell, count) queue mode).
+    uint16_t* sp_slots[F3D_MAX_RANKS];
+    int sp_use_slots;
 };
+#define FUSE_NSLOT 32   // distinct classes per point a slot record holds; points with more spill to the (cell, count) queue
 
 __device__ __forceinline__ unsigned long long sp_pack(unsigned key, unsigned count) {
     return (unsigned long long)key | ((unsigned long long)count << 32);
@@ -281,6 +277,8 @@ struct Tally {
     unsigned n_cand, n_seen;   // hot counters (registers); the rare ones (exact / diverged / near-edge / audit-bad) are
     unsigned* rare;            // shared-memory counters [F3D_STAT_*], bumped with atomics where they occur
     int total, best, bpos;   // running VotingSegmentation.segment state of this thread's point (fused resolve)
+    int nlist;               // slot-record mode: distinct classes this point has received since the last flush
+    uint8_t* clist;          // ... and their list, element j at clist[j * FUSE_BLOCK] (NULL outside slot-record mode)
 };
 
 // a vote for class `cls` of the thread's own point: bump the histogram and keep the running arg-max exact:
@@ -291,6 +289,10 @@ __device__ __forceinline__ void cast_vote(CellT* hist, int row_off, int cls, con
     if (cls >= P.C1) return;
     const int v = (int)hist[row_off + cls] + 1;
     hist[row_off + cls] = (CellT)v;
+    if (t.clist && v == 1) {   // first vote for this class: remember it, so the record is built without scanning the row
+        if (t.nlist < FUSE_NSLOT) t.clist[t.nlist * FUSE_BLOCK] = (uint8_t)cls;
+        ++t.nlist;
+    }
     if (RP.enabled) {
         ++t.total;
         const int pos = RP.fpos[cls];
@@ -355,14 +357,51 @@ template <> struct HistCell<1> { typedef uint8_t T; };
 // first flush of a non-accumulating launch overwrites (every cell written exactly once, 16-byte stores); later
 // flushes add their non-zero cells.  Rows are warp-private, so no CTA barrier and no atomics are involved.
 __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int warp, int lane, int64_t tile_base, bool add,
-                                       bool rezero) {
+                                       bool rezero, Tally& T, uint16_t* stg, bool first, bool dirty) {
     const int row0 = warp * 32;
     const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
     const int total = nrows * P.C1;
     const int n4 = total >> 2;
     uint32_t* __restrict__ h32 = reinterpret_cast<uint32_t*>(hist + row0 * P.C1);   // 32*C1 bytes per warp: word aligned
     const uint8_t* __restrict__ h8 = hist + row0 * P.C1;
-    if (P.sp_G > 0 && nrows > 0) {
+    if (P.sp_use_slots) {
+        // slot records: a thread lists the classes of its own point (collected by cast_vote) with their counts into the
+        // warp's staging block [slot][lane]; the block goes to the owner rank with sixteen-byte stores (512 contiguous
+        // bytes per instruction over NVLink).  points_per_shard is a multiple of the tile, so a warp has one owner.
+        const long long p0 = tile_base + row0;
+        const int d = (int)(p0 / P.sp_per);
+        uint4* st4 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st4[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        const bool live = lane < nrows;
+        // the record is written by the first flush only; later flushes, points with more than FUSE_NSLOT classes and
+        // rows another lane's deferred pass touched go cell by cell to the owner's (cell, count) queue
+        const bool spill = live && (!first || T.nlist > FUSE_NSLOT || dirty);
+        const uint8_t* __restrict__ row = h8 + lane * P.C1;
+        if (live && !spill)
+            for (int j = 0; j < T.nlist; ++j) {
+                const unsigned cls = T.clist[j * FUSE_BLOCK];
+                stg[j * 32 + lane] = (uint16_t)(cls | ((unsigned)row[cls] << 8));
+            }
+        if (spill) {
+            const unsigned key0 = (unsigned)((p0 + lane - (long long)d * P.sp_per) * P.C1);
+            for (int c = 0; c < P.C1; ++c) {
+                const unsigned v = row[c];
+                if (!v) continue;
+                const unsigned long long at = atomicAdd(P.sp_cursor + d, 1ULL);
+                if (at < P.sp_cap) P.sp_queue[d][at] = sp_pack(key0 + c, v);
+                else atomicExch(P.sp_overflow, 1u);
+            }
+        }
+        T.nlist = 0;
+        __syncwarp();
+        if (first && nrows > 0) {
+            uint4* __restrict__ dst = reinterpret_cast<uint4*>(P.sp_slots[d] + ((p0 - (long long)d * P.sp_per) >> 5) * (FUSE_NSLOT * 32));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i * 32 + lane] = st4[i * 32 + lane];
+        }
+    } else if (P.sp_G > 0 && nrows > 0) {
         // sparse emit: non-zero cells go to the receive queue of the rank that owns the point (peer memory).  A warp's
         // rows belong to one owner except at the G-1 shard boundaries of the whole launch.
         const long long p0 = tile_base + row0;
@@ -496,6 +535,9 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     Deferred* queue_all = reinterpret_cast<Deferred*>(red + FUSE_RED_WORDS);
     CellT* hist = reinterpret_cast<CellT*>(reinterpret_cast<unsigned char*>(queue_all) + (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred));
     const int RS = P.RS;
+    // slot-record mode only: [class lists u8 x FUSE_NSLOT x FUSE_BLOCK][staging blocks: 8 warps x 2 KB] after the histogram
+    uint8_t* clist_all = reinterpret_cast<uint8_t*>(hist) + (((size_t)FUSE_BLOCK * RS * sizeof(CellT) + 15) & ~(size_t)15);
+    uint16_t* stg_all = reinterpret_cast<uint16_t*>(clist_all + FUSE_NSLOT * FUSE_BLOCK);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -564,6 +606,8 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     Tally T;
     T.n_cand = T.n_seen = 0u;
     T.rare = stat_s;
+    T.nlist = 0;
+    T.clist = (MODE == MODE_VOTE && HB == 1 && P.sp_use_slots) ? clist_all + threadIdx.x : nullptr;
     T.total = 0;
     T.best = 0;
     T.bpos = 0x7fff;
@@ -660,7 +704,8 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
                 const int nw = __popc(wm);
                 if (since_flush + nw > FUSE_LIMIT8) {
                     __syncwarp();
-                    flush8(P, reinterpret_cast<uint8_t*>(hist), warp, lane, tile_base, nflush > 0 || P.accumulate, true);
+                    flush8(P, reinterpret_cast<uint8_t*>(hist), warp, lane, tile_base, nflush > 0 || P.accumulate, true, T,
+                           stg_all + warp * (FUSE_NSLOT * 32), nflush == 0, false);
                     ++nflush;
                     since_flush = 0;
                 }
@@ -823,7 +868,8 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     // ---- epilogue (warp-private rows): histogram -> HBM, written once with 16-byte stores; fused label resolve
     if constexpr (MODE == MODE_VOTE && HB == 1) {
         uint8_t* hist8 = reinterpret_cast<uint8_t*>(hist);
-        flush8(P, hist8, warp, lane, tile_base, nflush > 0 || P.accumulate, false);
+        flush8(P, hist8, warp, lane, tile_base, nflush > 0 || P.accumulate, false, T, stg_all + warp * (FUSE_NSLOT * 32), nflush == 0,
+               ((dirty_s[warp] >> lane) & 1u) != 0u);
         if (RP.enabled && active) {
             // VotingSegmentation.segment (voting.py:120-135).  The running (total, best, bpos) is exact unless another
             // lane's deferred pass added votes to this row (re-derived from the row) or the tile was flushed more than
@@ -1145,11 +1191,12 @@ static int hist_row_stride(int C1) {
     return rs;
 }
 
-static size_t fuse_smem_bytes(int mode, int C1, int hb) {
+static size_t fuse_smem_bytes(int mode, int C1, int hb, bool slots) {
     size_t b = 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * (sizeof(uint16_t) + 1) + FUSE_RED_WORDS * sizeof(float) +
                (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred);
     if (mode == MODE_VOTE)
         b += ((size_t)FUSE_BLOCK * (hb == 1 ? (size_t)C1 : hist_row_stride(C1) * sizeof(uint16_t)) + 15) & ~(size_t)15;
+    if (slots) b += (size_t)FUSE_NSLOT * FUSE_BLOCK + (size_t)(FUSE_BLOCK / 32) * FUSE_NSLOT * 32 * sizeof(uint16_t);
     return b;
 }
 
@@ -1162,7 +1209,7 @@ template <int MODE, int FMT>
 static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t stream) {
     if constexpr (MODE == MODE_VOTE) {
         const bool no_sink = !P.votes && !P.votes16 && P.sp_G == 0;
-        const bool hist16 = (no_sink && P.f_end - P.f_begin > FUSE_LIMIT8) || getenv("F3D_HIST16") != nullptr;
+        const bool hist16 = !P.sp_use_slots && ((no_sink && P.f_end - P.f_begin > FUSE_LIMIT8) || getenv("F3D_HIST16") != nullptr);
         if (!hist16) return launch_fuse_hb<MODE, FMT, 1>(P, RP, stream);
     }
     return launch_fuse_hb<MODE, FMT, 2>(P, RP, stream);
@@ -1171,7 +1218,7 @@ static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t 
 template <int MODE, int FMT, int HB>
 static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stream) {
     if (MODE == MODE_VOTE) P.RS = HB == 1 ? P.C1 : hist_row_stride(P.C1);
-    size_t smem = fuse_smem_bytes(MODE, P.C1, HB);
+    size_t smem = fuse_smem_bytes(MODE, P.C1, HB, MODE == MODE_VOTE && HB == 1 && P.sp_use_slots);
     if (const char* ex = getenv("F3D_EXTRA_SMEM")) smem += (size_t)atoi(ex);   // occupancy experiments only
     if (smem > 227 * 1024) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: nclasses+1 too large for the shared-memory histogram");
     cudaError_t e = cudaFuncSetAttribute(fuse_kernel<MODE, FMT, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1267,7 +1314,11 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.sp_cap = 0;
     P.sp_per = 1;
     P.sp_overflow = nullptr;
-    for (int i = 0; i < F3D_MAX_RANKS; ++i) P.sp_queue[i] = nullptr;
+    P.sp_use_slots = 0;
+    for (int i = 0; i < F3D_MAX_RANKS; ++i) {
+        P.sp_queue[i] = nullptr;
+        P.sp_slots[i] = nullptr;
+    }
     return F3D_OK;
 }
 
@@ -1444,38 +1495,14 @@ extern "C" int f3d_zbuffer_splat(const void* points, int64_t N, const void* fram
 }
 
 
-// ---- sparse vote exchange over peer memory --------------------------------------------------------------------------
-struct PeerPtrs {
-    unsigned long long* p[F3D_MAX_RANKS];
-};
-
-__global__ void sparse_publish_kernel2(const unsigned long long* __restrict__ cursor, PeerPtrs counts, int rank, int G,
-                                       unsigned long long cap) {
-    const int d = threadIdx.x;
-    if (d < G) counts.p[d][rank] = min(cursor[d], cap);
-}
-
-// owner side: scatter-add every received (cell, count) entry into the dense int32 shard
-__global__ void __launch_bounds__(256) sparse_accumulate_kernel(const unsigned long long* __restrict__ rx,
-                                                                const unsigned long long* __restrict__ rx_count, unsigned long long cap,
-                                                                int32_t* __restrict__ votes, unsigned long long ncells) {
-    const int src = blockIdx.y;
-    const unsigned long long n = min(rx_count[src], cap);
-    const unsigned long long* __restrict__ seg = rx + (unsigned long long)src * cap;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long e = seg[i];
-        const unsigned key = (unsigned)(e & 0xffffffffu);
-        if (key < ncells) atomicAdd(votes + key, (int)(e >> 32));
-    }
-}
-
+// ---- sparse / slot-record vote exchange over peer memory: sender side (owner side: vote_exchange.cu) -----------------
 extern "C" int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                                             int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
                                             int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                                            int32_t C1, const uint64_t* h_peer_queues, int32_t nranks, int64_t segment_cap,
-                                            int64_t points_per_shard, uint64_t* cursors, uint32_t* overflow, void* workspace,
-                                            int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
+                                            int32_t C1, const uint64_t* h_peer_queues, const uint64_t* h_peer_slots,
+                                            int32_t nranks, int64_t segment_cap, int64_t points_per_shard, uint64_t* cursors,
+                                            uint32_t* overflow, void* workspace, int64_t workspace_bytes, uint64_t* stats,
+                                            int32_t flags, void* stream) {
     FuseParams P;
     int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
                          zmax, stats, flags);
@@ -1487,6 +1514,8 @@ extern "C" int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const
         return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: too many frames per call (limit 65515)");
     if ((int64_t)points_per_shard * C1 > 0xffffffffLL)
         return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: shard cell index does not fit 32 bits");
+    if (h_peer_slots && (points_per_shard % FUSE_BLOCK) != 0)
+        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_sparse: slot records need points_per_shard to be a multiple of 256");
     if (N == 0) return F3D_OK;
     P.C1 = C1;
     P.RS = hist_row_stride(C1);
@@ -1495,6 +1524,10 @@ extern "C" int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const
     P.mask = mask;
     P.sp_G = nranks;
     for (int i = 0; i < nranks; ++i) P.sp_queue[i] = reinterpret_cast<unsigned long long*>(h_peer_queues[i]);
+    if (h_peer_slots) {
+        P.sp_use_slots = 1;
+        for (int i = 0; i < nranks; ++i) P.sp_slots[i] = reinterpret_cast<uint16_t*>(h_peer_slots[i]);
+    }
     P.sp_cursor = reinterpret_cast<unsigned long long*>(cursors);
     P.sp_cap = (unsigned long long)segment_cap;
     P.sp_per = points_per_shard;
@@ -1506,26 +1539,3 @@ extern "C" int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const
                                          : launch_fuse<MODE_VOTE, F3D_DEPTH_F32_M>(P, RP, (cudaStream_t)stream);
 }
 
-extern "C" int f3d_sparse_publish(const uint64_t* cursors, const uint64_t* h_peer_counts, int32_t rank, int32_t nranks,
-                                  int64_t segment_cap, void* stream) {
-    if (!cursors || !h_peer_counts || nranks < 1 || nranks > F3D_MAX_RANKS || rank < 0 || rank >= nranks)
-        return f3d_fail(F3D_ERR_ARG, "f3d_sparse_publish: bad argument");
-    PeerPtrs pp;
-    for (int i = 0; i < F3D_MAX_RANKS; ++i) pp.p[i] = i < nranks ? reinterpret_cast<unsigned long long*>(h_peer_counts[i]) : nullptr;
-    sparse_publish_kernel2<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(cursors), pp, rank, nranks,
-                                                               (unsigned long long)segment_cap);
-    return f3d_check_launch("f3d_sparse_publish");
-}
-
-extern "C" int f3d_sparse_accumulate(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
-                                     int32_t* votes, int64_t nrows, int32_t C1, void* stream) {
-    if (!rx || !rx_count || !votes || nranks < 1 || nranks > F3D_MAX_RANKS || segment_cap <= 0 || nrows < 0 || C1 <= 0)
-        return f3d_fail(F3D_ERR_ARG, "f3d_sparse_accumulate: bad argument");
-    if (nrows == 0) return F3D_OK;
-    dim3 grid(148 * 4, (unsigned)nranks);
-    sparse_accumulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(rx),
-                                                                    reinterpret_cast<const unsigned long long*>(rx_count),
-                                                                    (unsigned long long)segment_cap, votes,
-                                                                    (unsigned long long)nrows * (unsigned long long)C1);
-    return f3d_check_launch("f3d_sparse_accumulate");
-}

@@ -1,0 +1,236 @@
+// Owner side of the multi-GPU vote exchange (frames sharded over ranks, votes are integer sums over
+// frames -- VotingSegmentation.vote, segUtils/voting.py:89-98 -- so any partition of the frames is bit-exact).
+//
+// Every rank owns a contiguous range of points.  The fused kernel of each source rank writes, straight into the owner's
+// memory over NVLink (fuse_project_vote.cu, flush8):
+//   * slot records: per (source, 32-point block) 2 KB = [32 slots][32 points] of uint16 (class | count << 8), the
+//     classes a point received from that source's frames, in order of first appearance, zero-terminated;
+//   * a (cell, count) queue for what does not fit a record (points with more than 32 classes from one source, later
+//     flushes of very dense scans, the deferred fp64 votes of the fix-up pass).
+// Here the owner merges the G records of each of its points into the dense int32 row the reference keeps
+// (votes[npts, nclasses + 1], voting.py:34), resolves the label (VotingSegmentation.segment, voting.py:106-137) from
+// the on-chip row, then scatter-adds the queue entries and re-resolves the few points they touched.  The merge is a
+// streaming pass: G * 64 B read (less: reading stops at the longest list of the warp) and 4 * C1 + 8 B written per
+// point -- no dense partial vote tensor ever crosses the fabric or HBM.
+#include "f3d_common.cuh"
+#include "f3d_host.h"
+
+#define XCH_BLOCK 256
+#define XCH_NSLOT 32
+
+struct PeerPtrs {
+    unsigned long long* p[F3D_MAX_RANKS];
+};
+
+__global__ void sparse_publish_kernel2(const unsigned long long* __restrict__ cursor, PeerPtrs counts, int rank, int G,
+                                       unsigned long long cap) {
+    const int d = threadIdx.x;
+    if (d < G) counts.p[d][rank] = min(cursor[d], cap);
+}
+
+// scatter-add every received (cell, count) entry into the dense int32 shard
+__global__ void __launch_bounds__(256) sparse_accumulate_kernel(const unsigned long long* __restrict__ rx,
+                                                                const unsigned long long* __restrict__ rx_count, unsigned long long cap,
+                                                                int32_t* __restrict__ votes, unsigned long long ncells) {
+    const int src = blockIdx.y;
+    const unsigned long long n = min(rx_count[src], cap);
+    const unsigned long long* __restrict__ seg = rx + (unsigned long long)src * cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = seg[i];
+        const unsigned key = (unsigned)(e & 0xffffffffu);
+        if (key < ncells) atomicAdd(votes + key, (int)(e >> 32));
+    }
+}
+
+// labels of the points the queue entries touched (eight lanes stream the dense row, like fixup_labels_kernel); a point
+// with several entries is re-resolved several times with the same result
+__global__ void __launch_bounds__(256) sparse_relabel_kernel(const unsigned long long* __restrict__ rx,
+                                                             const unsigned long long* __restrict__ rx_count, unsigned long long cap,
+                                                             const int32_t* __restrict__ votes, long long nrows, int C1,
+                                                             const __grid_constant__ FuseResolve RP, int64_t* __restrict__ labels) {
+    __shared__ int16_t s_fpos[RES_MAXC];
+    for (int c = threadIdx.x; c < RES_MAXC; c += blockDim.x) s_fpos[c] = RP.fpos[c];
+    __syncthreads();
+    const int src = blockIdx.y;
+    const unsigned long long n = min(rx_count[src], cap);
+    const unsigned long long* __restrict__ seg = rx + (unsigned long long)src * cap;
+    const int sub = threadIdx.x & 7;
+    const unsigned long long per_pass = ((unsigned long long)gridDim.x * blockDim.x) >> 3;
+    const unsigned long long passes = (n + per_pass - 1) / per_pass;   // uniform trip count: shuffles see full warps
+    unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    for (unsigned long long p = 0; p < passes; ++p, i += per_pass) {
+        long long pt = -1;
+        if (i < n) pt = (long long)((unsigned)(seg[i] & 0xffffffffu) / (unsigned)C1);
+        const bool live = pt >= 0 && pt < nrows;
+        long long total = 0;
+        int best = 0, bpos = 0x7fff;
+        if (live) {
+            for (int c = sub; c < C1; c += 8) {
+                const int v = votes[(size_t)pt * C1 + c];
+                total += v;
+                const int pos = s_fpos[c];
+                if (v > 0 && pos >= 0 && (v > best || (v == best && pos < bpos))) {
+                    best = v;
+                    bpos = pos;
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 4; s > 0; s >>= 1) {
+            total += __shfl_xor_sync(0xffffffffu, total, s);
+            const int ob = __shfl_xor_sync(0xffffffffu, best, s);
+            const int op = __shfl_xor_sync(0xffffffffu, bpos, s);
+            if (ob > best || (ob == best && op < bpos)) {
+                best = ob;
+                bpos = op;
+            }
+        }
+        if (live && sub == 0) {
+            bool unc = (total <= 0) || (best <= 0);                                    // voting.py:126,131
+            if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;          // voting.py:128-130
+            labels[pt] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
+        }
+    }
+}
+
+// ---- slot-record merge: one thread per owned point, one warp per 32-point block ------------------------------------------
+// shared: uint16 histogram [256][RS] (a thread owns its row; RS/2 odd => conflict-free), written out like the fused
+// kernel's epilogue (warp-private rows, 16-byte stores, every cell exactly once -- no memset of the shard needed).
+__global__ void __launch_bounds__(XCH_BLOCK, 2) slot_merge_kernel(const uint16_t* __restrict__ slots, int G, long long blocks_per_src,
+                                                                  long long nrows, int C1, int RS,
+                                                                  const __grid_constant__ FuseResolve RP,
+                                                                  int32_t* __restrict__ votes, int64_t* __restrict__ labels) {
+    extern __shared__ __align__(16) unsigned char xs[];
+    int16_t* s_fpos = reinterpret_cast<int16_t*>(xs);
+    uint16_t* hist = reinterpret_cast<uint16_t*>(xs + RES_MAXC * sizeof(int16_t));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < RES_MAXC; c += XCH_BLOCK) s_fpos[c] = RP.fpos[c];
+    {
+        uint4* h128 = reinterpret_cast<uint4*>(hist);
+        const int n128 = (XCH_BLOCK * RS * 2 + 15) / 16;
+        for (int i = tid; i < n128; i += XCH_BLOCK) h128[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    const long long blk = (long long)blockIdx.x * (XCH_BLOCK / 32) + warp;   // 32-point block of this warp
+    const long long p = blk * 32 + lane;
+    uint16_t* __restrict__ row = hist + tid * RS;
+    int total = 0, best = 0, bpos = 0x7fff;
+    if (blk < blocks_per_src) {
+        for (int s = 0; s < G; ++s) {
+            const uint16_t* __restrict__ rec = slots + ((size_t)s * blocks_per_src + blk) * (XCH_NSLOT * 32) + lane;
+            for (int j0 = 0; j0 < XCH_NSLOT; j0 += 4) {
+                unsigned pr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pr[k] = __ldg(rec + (j0 + k) * 32);   // 64 contiguous bytes per warp and slot
+                if (!__any_sync(0xffffffffu, pr[0] != 0u)) break;                 // lists are zero-terminated
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int cls = (int)(pr[k] & 0xffu), cnt = (int)(pr[k] >> 8);
+                    if (cnt == 0 || cls >= C1) continue;
+                    const int v = (int)row[cls] + cnt;
+                    row[cls] = (uint16_t)v;
+                    total += cnt;
+                    const int pos = s_fpos[cls];
+                    if (pos >= 0 && (v > best || (v == best && pos < bpos))) {
+                        best = v;
+                        bpos = pos;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const long long row0 = blk * 32;
+    const int nr = (int)max(0LL, min(32LL, nrows - row0));
+    if (votes && nr > 0) {
+        int32_t* __restrict__ out = votes + row0 * C1;
+        if (RS == C1) {
+            const uint2* __restrict__ h64 = reinterpret_cast<const uint2*>(hist + warp * 32 * RS);
+            const int tot = nr * C1, n4 = tot >> 2;
+            for (int i = lane; i < n4; i += 32) {
+                const uint2 w = h64[i];
+                *reinterpret_cast<int4*>(out + 4 * i) =
+                    make_int4((int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16));
+            }
+            for (int e = (n4 << 2) + lane; e < tot; e += 32) out[e] = (int)hist[warp * 32 * RS + e];
+        } else {
+            for (int j = 0; j < nr; ++j)
+                for (int c = lane; c < C1; c += 32) out[j * C1 + c] = (int)hist[(warp * 32 + j) * RS + c];
+        }
+    }
+    if (labels && p < nrows) {
+        bool unc = (total <= 0) || (best <= 0);                                    // voting.py:126,131
+        if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;          // voting.py:128-130
+        labels[p] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
+    }
+}
+
+static int xch_row_stride(int C1) {
+    int rs = (C1 + 1) & ~1;
+    if (((rs / 2) & 1) == 0) rs += 2;
+    return rs;
+}
+
+extern "C" int f3d_sparse_publish(const uint64_t* cursors, const uint64_t* h_peer_counts, int32_t rank, int32_t nranks,
+                                  int64_t segment_cap, void* stream) {
+    if (!cursors || !h_peer_counts || nranks < 1 || nranks > F3D_MAX_RANKS || rank < 0 || rank >= nranks)
+        return f3d_fail(F3D_ERR_ARG, "f3d_sparse_publish: bad argument");
+    PeerPtrs pp;
+    for (int i = 0; i < F3D_MAX_RANKS; ++i) pp.p[i] = i < nranks ? reinterpret_cast<unsigned long long*>(h_peer_counts[i]) : nullptr;
+    sparse_publish_kernel2<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(cursors), pp, rank, nranks,
+                                                               (unsigned long long)segment_cap);
+    return f3d_check_launch("f3d_sparse_publish");
+}
+
+extern "C" int f3d_sparse_accumulate(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
+                                     int32_t* votes, int64_t nrows, int32_t C1, void* stream) {
+    if (!rx || !rx_count || !votes || nranks < 1 || nranks > F3D_MAX_RANKS || segment_cap <= 0 || nrows < 0 || C1 <= 0)
+        return f3d_fail(F3D_ERR_ARG, "f3d_sparse_accumulate: bad argument");
+    if (nrows == 0) return F3D_OK;
+    dim3 grid(148 * 4, (unsigned)nranks);
+    sparse_accumulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(rx),
+                                                                    reinterpret_cast<const unsigned long long*>(rx_count),
+                                                                    (unsigned long long)segment_cap, votes,
+                                                                    (unsigned long long)nrows * (unsigned long long)C1);
+    return f3d_check_launch("f3d_sparse_accumulate");
+}
+
+extern "C" int f3d_sparse_relabel(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
+                                  const int32_t* votes, int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter,
+                                  int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream) {
+    if (!rx || !rx_count || !votes || !labels || nranks < 1 || nranks > F3D_MAX_RANKS || segment_cap <= 0 || nrows < 0 ||
+        C1 <= 0 || nfilter < 0 || (nfilter > 0 && !h_filter))
+        return f3d_fail(F3D_ERR_ARG, "f3d_sparse_relabel: bad argument");
+    if (nrows == 0) return F3D_OK;
+    FuseResolve RP;
+    int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
+    if (rc) return rc;
+    dim3 grid(148 * 2, (unsigned)nranks);
+    sparse_relabel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(rx),
+                                                                 reinterpret_cast<const unsigned long long*>(rx_count),
+                                                                 (unsigned long long)segment_cap, votes, (long long)nrows, C1, RP,
+                                                                 labels);
+    return f3d_check_launch("f3d_sparse_relabel");
+}
+
+extern "C" int f3d_slots_merge(const uint16_t* slots, int32_t nranks, int64_t points_per_shard, int64_t nrows, int32_t C1,
+                               double threshold, const int32_t* h_filter, int32_t nfilter, int32_t nclasses_id, int32_t* votes,
+                               int64_t* labels, void* stream) {
+    if (!slots || nranks < 1 || nranks > F3D_MAX_RANKS || points_per_shard <= 0 || (points_per_shard % XCH_BLOCK) != 0 ||
+        nrows < 0 || nrows > points_per_shard || C1 <= 0 || C1 > 256 || (!votes && !labels) || nfilter < 0 ||
+        (nfilter > 0 && !h_filter) || (votes && (reinterpret_cast<uintptr_t>(votes) & 15u)))
+        return f3d_fail(F3D_ERR_ARG, "f3d_slots_merge: bad argument");
+    if (nrows == 0) return F3D_OK;
+    FuseResolve RP;
+    int rc = f3d_build_resolve(C1, threshold, h_filter ? h_filter : nullptr, nfilter, nclasses_id, RP);
+    if (rc) return rc;
+    const int RS = xch_row_stride(C1);
+    const size_t smem = RES_MAXC * sizeof(int16_t) + (((size_t)XCH_BLOCK * RS * 2 + 15) & ~(size_t)15);
+    cudaError_t e = cudaFuncSetAttribute(slot_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return f3d_check_launch("f3d_slots_merge(cudaFuncSetAttribute)");
+    const long long tiles = (nrows + XCH_BLOCK - 1) / XCH_BLOCK;
+    slot_merge_kernel<<<(unsigned)tiles, XCH_BLOCK, smem, (cudaStream_t)stream>>>(slots, nranks, points_per_shard / 32, (long long)nrows,
+                                                                                C1, RS, RP, votes, labels);
+    return f3d_check_launch("f3d_slots_merge");
+}

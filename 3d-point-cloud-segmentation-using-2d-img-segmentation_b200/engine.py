@@ -146,17 +146,27 @@ def fuse_project_vote_resolve(points4, table: FrameTable, depth, mask, nclasses1
     return votes, labels
 
 
+def _filter_arg(filter_classes):
+    filt = None if filter_classes is None else np.ascontiguousarray(np.asarray(filter_classes, dtype=np.int32))
+    if filt is not None and filt.size == 0:
+        raise ValueError("filter_classes must not be empty")
+    return filt, (0 if filt is None else int(filt.size))
+
+
 def fuse_project_vote_sparse(points4, table: FrameTable, depth, mask, nclasses1, peer_queue_ptrs, segment_cap, points_per_shard,
-                             cursors, overflow, radius=0.05, zmin=0.1, zmax=4.0, stats=None, frame_begin=0, frame_end=None):
-    """Kernel (1) in sparse-exchange mode: non-zero vote cells are appended to the owner ranks' receive queues through
-    the peer pointers in `peer_queue_ptrs` (numpy uint64 [G]); no dense vote tensor is written."""
+                             cursors, overflow, radius=0.05, zmin=0.1, zmax=4.0, stats=None, frame_begin=0, frame_end=None,
+                             peer_slot_ptrs=None):
+    """Kernel (1) with the multi-GPU exchange fused in: the votes of this rank's frames go straight into the owner
+    ranks' memory through the peer pointers (numpy uint64 [G]) -- slot records when `peer_slot_ptrs` is given, the
+    (cell, count) queues otherwise / for what does not fit a record.  No dense vote tensor is written."""
     frame_end = table.F if frame_end is None else frame_end
     N = points4.shape[0]
     ws = workspace(N, points4.device)
     q = np.ascontiguousarray(np.asarray(peer_queue_ptrs, dtype=np.uint64))
+    sl = None if peer_slot_ptrs is None else np.ascontiguousarray(np.asarray(peer_slot_ptrs, dtype=np.uint64))
     check(load().f3d_fuse_project_vote_sparse(
         ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth), _depth_fmt(depth), ptr(mask), table.H, table.W,
-        ptr(table.K), float(radius), float(zmin), float(zmax), int(nclasses1), ptr(q), int(q.size), int(segment_cap),
+        ptr(table.K), float(radius), float(zmin), float(zmax), int(nclasses1), ptr(q), ptr(sl), int(q.size), int(segment_cap),
         int(points_per_shard), ptr(cursors), ptr(overflow), ptr(ws), ws.numel(), ptr(stats), 0, stream_ptr()),
         "f3d_fuse_project_vote_sparse")
 
@@ -167,9 +177,25 @@ def sparse_publish(cursors, peer_count_ptrs, rank, segment_cap):
           "f3d_sparse_publish")
 
 
-def sparse_accumulate(rx, rx_count, nranks, segment_cap, votes):
-    check(load().f3d_sparse_accumulate(ptr(rx), ptr(rx_count), int(nranks), int(segment_cap), ptr(votes), votes.shape[0],
+def slots_merge(slots, nranks, points_per_shard, nrows, nclasses1, nclasses_id, threshold=0.5, filter_classes=None, votes=None,
+                labels=None):
+    """Owner side: merge the slot records of all source ranks into the dense int32 shard rows and the labels."""
+    filt, nf = _filter_arg(filter_classes)
+    check(load().f3d_slots_merge(ptr(slots), int(nranks), int(points_per_shard), int(nrows), int(nclasses1), float(threshold),
+                                 ptr(filt), nf, int(nclasses_id), ptr(votes), ptr(labels), stream_ptr()), "f3d_slots_merge")
+
+
+def sparse_accumulate(rx, rx_count, nranks, segment_cap, votes, nrows=None):
+    nrows = votes.shape[0] if nrows is None else nrows
+    check(load().f3d_sparse_accumulate(ptr(rx), ptr(rx_count), int(nranks), int(segment_cap), ptr(votes), int(nrows),
                                        votes.shape[1], stream_ptr()), "f3d_sparse_accumulate")
+
+
+def sparse_relabel(rx, rx_count, nranks, segment_cap, votes, nrows, nclasses_id, labels, threshold=0.5, filter_classes=None):
+    filt, nf = _filter_arg(filter_classes)
+    check(load().f3d_sparse_relabel(ptr(rx), ptr(rx_count), int(nranks), int(segment_cap), ptr(votes), int(nrows), votes.shape[1],
+                                    float(threshold), ptr(filt), nf, int(nclasses_id), ptr(labels), stream_ptr()),
+          "f3d_sparse_relabel")
 
 
 def fuse_uv2pt(points4, table: FrameTable, depth, radius=0.05, zmin=0.1, zmax=4.0, stats=None, audit=False,

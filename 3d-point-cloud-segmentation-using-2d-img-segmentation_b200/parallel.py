@@ -177,6 +177,84 @@ class SparseExchange:
             raise RuntimeError("sparse vote exchange: a receive segment overflowed; enlarge segment_cap or use ShardedPipeline")
 
 
+def shard_points(npoints: int, world: int, tile: int = 256) -> int:
+    """Points per owner rank of the slot-record exchange: ceil(npoints / world) rounded up to the kernel's point tile."""
+    per = -(-npoints // world)
+    return max(tile, -(-per // tile) * tile)
+
+
+class SlotExchange:
+    """Frame-sharded fusion with the vote exchange fused into the compute kernel as slot records (CUDA only).
+
+    Rank d owns the points [d*per, (d+1)*per), per a multiple of the 256-point tile.  Its receive buffer lives in
+    symmetric memory: per source rank one array of 2 KB records (32 points x 32 slots of class | count << 8) plus one
+    (cell, count) queue segment and a count table.  A step is
+        barrier (peers are done reading the previous step) -> fused kernel: every warp writes its block's record
+        straight into the owner's memory over NVLink, spills / deferred fp64 votes are appended to the owner's queue ->
+        publish cursors -> barrier -> merge the G records of every owned point into the dense int32 shard row and the
+        label -> scatter-add the queue entries, re-resolve the points they touched -> all-gather the labels.
+    Nothing dense crosses the fabric and the sweep never writes a vote tensor; the owner writes its shard once."""
+
+    def __init__(self, npoints: int, c1: int, device, group=None, segment_cap=None):
+        import numpy as np
+        import torch.distributed._symmetric_memory as symm
+        from . import engine
+        self.engine, self.np = engine, np
+        self.group = dist.group.WORLD if group is None else group
+        self.device = torch.device(device)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.npoints, self.c1 = npoints, c1
+        G = self.world
+        self.per = shard_points(npoints, G)
+        self.rows = max(0, min(self.per, npoints - self.rank * self.per))
+        self.cap = int(segment_cap) if segment_cap else max(1 << 20, self.per // 2)
+        # int64 words: [G x cap queue entries][G counts, padded to 64][G x per x 8 words of records]
+        self.q_words, self.c_words, self.s_words = G * self.cap, 64, G * self.per * 8
+        total = self.q_words + self.c_words + self.s_words
+        self.rx = symm.empty(total, dtype=torch.int64, device=self.device)
+        self.rx.zero_()
+        self.hdl = symm.rendezvous(self.rx, self.group)
+        peers = [self.hdl.get_buffer(d, (total,), torch.int64) for d in range(G)]
+        base = [p.data_ptr() for p in peers]
+        self.peer_queue_ptrs = np.array([b + self.rank * self.cap * 8 for b in base], dtype=np.uint64)
+        self.peer_count_ptrs = np.array([b + self.q_words * 8 for b in base], dtype=np.uint64)
+        self.peer_slot_ptrs = np.array([b + (self.q_words + self.c_words + self.rank * self.per * 8) * 8 for b in base],
+                                       dtype=np.uint64)
+        self.rx_queue = self.rx[:self.q_words]
+        self.rx_count = self.rx[self.q_words:self.q_words + G]
+        self.rx_slots = self.rx[self.q_words + self.c_words:]
+        self.cursors = torch.zeros(G, dtype=torch.int64, device=self.device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.shard = torch.zeros((max(self.per, 1), c1), dtype=torch.int32, device=self.device)
+        self.lab = torch.zeros(max(self.per, 1), dtype=torch.int64, device=self.device)
+        self.full = torch.zeros(max(self.per, 1) * G, dtype=torch.int64, device=self.device)
+
+    def run(self, fuse_slots, nclasses_id, threshold=0.5, filter_classes=None) -> torch.Tensor:
+        """`fuse_slots(peer_queue_ptrs, peer_slot_ptrs, cap, per, cursors, overflow)` enqueues the slot-mode fused kernel
+        over this rank's frames.  Returns labels [npoints]; `self.shard[:self.rows]` holds this rank's reduced votes."""
+        eng = self.engine
+        self.hdl.barrier(channel=0)
+        self.cursors.zero_()
+        fuse_slots(self.peer_queue_ptrs, self.peer_slot_ptrs, self.cap, self.per, self.cursors, self.overflow)
+        eng.sparse_publish(self.cursors, self.peer_count_ptrs, self.rank, self.cap)
+        self.hdl.barrier(channel=1)
+        if self.rows > 0:
+            eng.slots_merge(self.rx_slots, self.world, self.per, self.rows, self.c1, nclasses_id, threshold, filter_classes,
+                            votes=self.shard, labels=self.lab)
+            eng.sparse_accumulate(self.rx_queue, self.rx_count, self.world, self.cap, self.shard, nrows=self.rows)
+            eng.sparse_relabel(self.rx_queue, self.rx_count, self.world, self.cap, self.shard, self.rows, nclasses_id, self.lab,
+                               threshold, filter_classes)
+        _all_gather(self.full, self.lab, self.group if self.group is not dist.group.WORLD else None)
+        return self.full[:self.npoints]
+
+    def check_overflow(self):
+        """Host check (synchronises): raises if any queue segment filled up during the steps so far."""
+        t = self.overflow.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if int(t.item()):
+            raise RuntimeError("slot vote exchange: a queue segment overflowed; enlarge segment_cap or use ShardedPipeline")
+
+
 def fuse_sharded(fuse_chunk, resolve, npoints: int, nchunks: int, device, group=None):
     """Convenience wrapper (allocates a pipeline per call): `fuse_chunk(a, b)` -> partial int32 votes [b-a, C1],
     `resolve(votes)` -> labels [rows]."""

@@ -197,8 +197,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--chunks", type=int, default=4, help="point chunks of the multi-GPU pipeline")
-    ap.add_argument("--exchange", default="sparse", choices=["sparse", "dense"],
-                    help="multi-GPU vote exchange: sparse appends over peer memory (default) or dense packed reduce-scatter")
+    ap.add_argument("--exchange", default="slots", choices=["slots", "sparse", "dense"],
+                    help="multi-GPU vote exchange: slot records written by the fused kernel into the owner's memory (default), "
+                         "sparse (cell,count) appends over peer memory, or dense packed reduce-scatter")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -251,11 +252,21 @@ def main():
         fl.votes = votes
         return labels, (e0, e1), 3   # fuse_kernel + fixup_apply + fixup_labels
 
-    pipe = sparse = None
+    pipe = sparse = slotx = None
     if world > 1 and args.exchange == "dense":
         pipe = parallel.ShardedPipeline(N, C1, args.chunks, torch.device("cuda", local_rank))
-    elif world > 1:
+    elif world > 1 and args.exchange == "sparse":
         sparse = parallel.SparseExchange(N, C1, torch.device("cuda", local_rank))
+    elif world > 1:
+        slotx = parallel.SlotExchange(N, C1, torch.device("cuda", local_rank))
+
+    def step_slots():
+        def fuse_slots(qptrs, sptrs, cap, per, cursors, overflow):
+            engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, qptrs, cap, per, cursors, overflow, RADIUS,
+                                            fl.zmin, fl.zmax, stats=stats, peer_slot_ptrs=sptrs)
+
+        labels = slotx.run(fuse_slots, NCLASSES, THRESHOLD, None)
+        return labels, None, 6   # fuse_kernel, fixup_apply, publish, slot_merge, sparse_accumulate, sparse_relabel
 
     def step_sparse():
         def fuse_sparse(qptrs, cap, per, cursors, overflow):
@@ -280,7 +291,7 @@ def main():
         labels = pipe.run(fuse_into, resolve)
         return labels, None, launches[0]
 
-    step = step_single if world == 1 else (step_multi if pipe is not None else step_sparse)
+    step = step_single if world == 1 else (step_multi if pipe is not None else (step_sparse if sparse is not None else step_slots))
     for _ in range(args.warmup):
         labels, _, _ = step()
     torch.cuda.synchronize()
@@ -388,7 +399,9 @@ def main():
                        "nclasses": NCLASSES, "depth": "uint16 mm", "radius": RADIUS, "cache": "inputs larger than L2 "
                        "(depth+masks+votes = %.1f GB per GPU)" % ((F * H * W * 3 + 4 * N * C1) / 1e9),
                        "parallelism": "single GPU" if world == 1 else f"frames sharded over {world} GPUs, "
-                       + ("sparse (cell,count) vote exchange written by the fused kernel into peer memory over NVLink, "
+                       + ("slot-record vote exchange written by the fused kernel into the owner's memory over NVLink, "
+                          "owner-side merge into the dense shard + labels, all-gather of labels" if args.exchange == "slots" else
+                          "sparse (cell,count) vote exchange written by the fused kernel into peer memory over NVLink, "
                           "owner-side scatter-add + resolve, all-gather of labels" if args.exchange == "sparse" else
                           f"{args.chunks}-chunk pipeline: fuse -> NCCL reduce-scatter of packed uint16 votes -> resolve -> "
                           "all-gather")},
@@ -399,6 +412,8 @@ def main():
     if world > 1:
         if sparse is not None:
             sparse.check_overflow()
+        if slotx is not None:
+            slotx.check_overflow()
         dist.destroy_process_group()
 
 

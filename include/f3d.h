@@ -97,27 +97,43 @@ int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_t
                               uint16_t* votes_u16, int32_t C1, int32_t accumulate, void* workspace,
                               int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
 
-/* ---- sparse multi-GPU vote exchange over peer memory (NVLink / NVSwitch) --------------------------------------
- * Votes are ~95 % zeros.  Instead of writing a dense partial vote tensor and reduce-scattering it, the fused kernel
- * appends every non-zero (cell, count) of its on-chip histograms directly into the receive queue of the rank that
- * owns the point (owner(p) = p / points_per_shard), i.e. the exchange happens inside the compute kernel through
- * peer-mapped pointers.  Each destination queue has one segment of `segment_cap` uint64 entries per source rank:
- *   h_peer_queues[d] = device pointer (peer mapped) to THIS rank's segment inside rank d's queue,
- *   cursors [nranks] uint64 local append cursors (caller zeroes before the call), overflow: set to 1 if a segment
- *   filled up (entries dropped -- the caller must check it and fall back to the dense exchange).
- * f3d_sparse_publish then stores the cursors into every destination's count table (h_peer_counts[d] = peer pointer
- * to rank d's uint64[nranks] table; slot [rank] is written).  After a cross-rank barrier the owner calls
- * f3d_sparse_accumulate to scatter-add all segments into its dense int32 shard [nrows, C1] (caller zeroes it). */
+/* ---- multi-GPU vote exchange over peer memory (NVLink / NVSwitch), fused into the compute kernel ------------------
+ * Reference semantics: votes are integer sums over frames (VotingSegmentation.vote, segUtils/voting.py:89-98), so frames
+ * can be sharded over ranks and the partial votes added in any order -- bit-exact for every rank count.
+ * Votes are ~95 % zeros, so no dense partial vote tensor is written or reduce-scattered.  Rank d owns the points
+ * [d * points_per_shard, (d+1) * points_per_shard).  The fused kernel of every source rank writes, straight into the
+ * owner's memory through peer-mapped pointers:
+ *   - slot records (when h_peer_slots != NULL; points_per_shard must be a multiple of 256): per (source, 32-point block)
+ *     2 KB = [32 slots][32 points] uint16 (class | count << 8), zero-terminated lists in order of first appearance.
+ *     h_peer_slots[d] = device pointer (peer mapped) to THIS rank's record array [points_per_shard / 32][32][32] inside
+ *     rank d's receive buffer.  Every record is rewritten on every call (no clearing needed);
+ *   - a (cell, count) queue for everything else (all votes when h_peer_slots == NULL; otherwise points with more than
+ *     32 classes, later flushes of a tile with more than 235 candidate frames, deferred fp64 votes):
+ *     h_peer_queues[d] = peer pointer to THIS rank's segment of `segment_cap` uint64 entries
+ *     (cell = local_point * C1 + class in the low half, count in the high half) inside rank d's queue;
+ *     cursors [nranks] uint64 local append cursors (caller zeroes them before the call); *overflow is set to 1 when a
+ *     segment filled up (entries dropped: the caller must check it and enlarge the segment or fall back).
+ * f3d_sparse_publish then stores the cursors into every destination's count table (h_peer_counts[d] = peer pointer to
+ * rank d's uint64[nranks] table; slot [rank] is written).  After a cross-rank barrier the owner runs
+ *   f3d_slots_merge      (records of all sources -> dense int32 shard rows [nrows, C1] written once + labels), then
+ *   f3d_sparse_accumulate (queue entries scatter-added into the shard; without slot records the caller zeroes it first)
+ *   f3d_sparse_relabel    (labels of the points the queue entries touched, VotingSegmentation.segment voting.py:106-137). */
 int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                                  int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
                                  int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                                 int32_t C1, const uint64_t* h_peer_queues, int32_t nranks, int64_t segment_cap,
-                                 int64_t points_per_shard, uint64_t* cursors, uint32_t* overflow, void* workspace,
-                                 int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
+                                 int32_t C1, const uint64_t* h_peer_queues, const uint64_t* h_peer_slots, int32_t nranks,
+                                 int64_t segment_cap, int64_t points_per_shard, uint64_t* cursors, uint32_t* overflow,
+                                 void* workspace, int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
 int f3d_sparse_publish(const uint64_t* cursors, const uint64_t* h_peer_counts, int32_t rank, int32_t nranks,
                        int64_t segment_cap, void* stream);
+int f3d_slots_merge(const uint16_t* slots, int32_t nranks, int64_t points_per_shard, int64_t nrows, int32_t C1,
+                    double threshold, const int32_t* h_filter, int32_t nfilter, int32_t nclasses_id, int32_t* votes,
+                    int64_t* labels, void* stream);
 int f3d_sparse_accumulate(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
                           int32_t* votes, int64_t nrows, int32_t C1, void* stream);
+int f3d_sparse_relabel(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
+                       const int32_t* votes, int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter,
+                       int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream);
 
 /* f3d_fuse_project_vote with VotingSegmentation.segment (segUtils/voting.py:106-137, see f3d_resolve_labels) fused
  * into the epilogue: labels [N] int64 are resolved straight from the on-chip histograms, so the vote tensor is

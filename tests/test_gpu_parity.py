@@ -375,3 +375,82 @@ def test_uint16_histogram_build_matches(engine, scenes, monkeypatch):
     alt, _, _, _ = run_fused(engine, s)
     monkeypatch.delenv("F3D_HIST16", raising=False)
     assert np.array_equal(base, alt)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# multi-GPU vote exchange, emulated on one device: every "rank" fuses its frame shard into the owners' receive buffers
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _emulated_exchange(engine, s, world, use_slots, cap=None, nclasses_id=133, thr=0.5, fc=None):
+    parallel = importlib.import_module(PKG_NAME + ".parallel")
+    N, C1, F = len(s["points"]), 134, len(s["t"])
+    tab = engine.FrameTable(s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["zmax"])
+    p4 = engine.pack_points(s["points"])
+    d, m = dev(s["depths"]), dev(s["masks"])
+    per = parallel.shard_points(N, world)
+    cap = cap or max(1 << 16, 40 * per)
+    # owner o: queue [world][cap] + counts [world] + records [world][per/32][32][32] u16
+    queues = [torch.zeros(world * cap, dtype=torch.int64, device="cuda") for _ in range(world)]
+    counts = [torch.zeros(world, dtype=torch.int64, device="cuda") for _ in range(world)]
+    slots = [torch.full((world * per * 32,), 0x7b7b, dtype=torch.uint16, device="cuda") for _ in range(world)]   # garbage: must be overwritten
+    overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = engine.new_stats()
+    for r in range(world):                                              # source ranks, one after the other
+        fb, fe = parallel.frame_shard(F, r, world)
+        cursors = torch.zeros(world, dtype=torch.int64, device="cuda")
+        qptrs = np.array([queues[o].data_ptr() + r * cap * 8 for o in range(world)], dtype=np.uint64)
+        sptrs = np.array([slots[o].data_ptr() + r * per * 64 for o in range(world)], dtype=np.uint64) if use_slots else None
+        engine.fuse_project_vote_sparse(p4, tab, d[fb:fe], m[fb:fe], C1, qptrs, cap, per, cursors, overflow, 0.05, 0.1,
+                                        s["zmax"], stats=st, frame_begin=fb, frame_end=fe, peer_slot_ptrs=sptrs)
+        cptrs = np.array([counts[o].data_ptr() for o in range(world)], dtype=np.uint64)
+        engine.sparse_publish(cursors, cptrs, r, cap)
+    torch.cuda.synchronize()
+    assert int(overflow.item()) == 0
+    votes, labels = [], []
+    for o in range(world):                                              # owner ranks
+        rows = max(0, min(per, N - o * per))
+        shard = torch.full((per, C1), 77, dtype=torch.int32, device="cuda") if use_slots else torch.zeros((per, C1), dtype=torch.int32, device="cuda")
+        lab = torch.zeros(per, dtype=torch.int64, device="cuda")
+        if rows:
+            if use_slots:
+                engine.slots_merge(slots[o], world, per, rows, C1, nclasses_id, thr, fc, votes=shard, labels=lab)
+            engine.sparse_accumulate(queues[o], counts[o], world, cap, shard, nrows=rows)
+            if use_slots:
+                engine.sparse_relabel(queues[o], counts[o], world, cap, shard, rows, nclasses_id, lab, thr, fc)
+            else:
+                engine.resolve_labels(shard[:rows], nclasses_id, thr, fc, out=lab[:rows])
+        votes.append(shard[:rows])
+        labels.append(lab[:rows])
+    torch.cuda.synchronize()
+    return torch.cat(votes).cpu().numpy(), torch.cat(labels).cpu().numpy(), engine.stats_dict(st), [int(c.sum()) for c in counts]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("use_slots", [True, False])
+def test_vote_exchange_emulated_ranks(engine, scenes, world, use_slots):
+    s = small_scene(scenes, orc, npoints=20011, nframes=9, width=320, height=240, seed=71, block=16)
+    ov = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0, 0.05,
+                               0.1, 4.0, 4.0)
+    for thr, fc in [(0.5, None), (0.3, [1, 0, 5])]:
+        votes, labels, st, _ = _emulated_exchange(engine, s, world, use_slots, thr=thr, fc=fc)
+        assert np.array_equal(votes, ov)
+        assert np.array_equal(labels, orc.segment(ov, 133, thr, fc))
+        assert st["seen"] == int(ov.sum())
+
+
+def test_vote_exchange_spills_and_flushes(engine, scenes):
+    """300 frames (3 poses x 100) with a different random mask each: points collect far more than 32 distinct classes
+    from one source (record spill -> queue) and tiles sweep more than 235 candidate frames (mid-sweep flush: the first
+    flush writes the record, later ones go to the queue)."""
+    rep = 100
+    base = small_scene(scenes, orc, npoints=5003, nframes=3, width=96, height=64, seed=73, block=16)
+    F = 3 * rep
+    s = dict(base, wxyz=np.tile(base["wxyz"], (rep, 1)), t=np.tile(base["t"], (rep, 1)), depths=np.tile(base["depths"], (rep, 1, 1)),
+             masks=scenes.block_masks((base["H"], base["W"]), F, seed=79, block=16))
+    ov = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0, 0.05,
+                               0.1, 4.0, 4.0)
+    assert ((ov > 0).sum(axis=1) > 32).sum() > 100                      # many points need the spill path
+    for world in (1, 2):
+        votes, labels, _, nq = _emulated_exchange(engine, s, world, True, cap=1 << 21)
+        assert np.array_equal(votes, ov) and sum(nq) > 0
+        assert np.array_equal(labels, orc.segment(ov, 133, 0.5, None))

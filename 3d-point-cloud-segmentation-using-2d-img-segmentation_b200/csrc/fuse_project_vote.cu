@@ -95,13 +95,18 @@ struct FuseParams {
     unsigned long long sp_cap;                 // entries per segment
     long long sp_per;                          // points per owner shard: owner(p) = p / sp_per
     unsigned* sp_overflow;                     // set when a segment is full (entries are then dropped: caller must check)
-    // slot records (the bulk of the exchange): per (source rank, 32-point block) one 2 KB record [32 slots][32 points] of
-    // uint16 (class | count << 8), written once per launch by the block's warp straight into the owner's memory.
-    // sp_slots[d] = this rank's record array inside rank d's receive buffer (NULL entries: pure (cell, count) queue mode).
+    // slot records (the bulk of the exchange): per (source rank, 32-point block) one variable-length record of L rows,
+    // row j = the j-th class (in order of first appearance) of each of the block's 32 points as uint16 class | count << 8
+    // (64 B per row, 0 = none), L = the longest list in the block.  The block's warp reserves L rows in the owner's
+    // record region with one atomic on a local cursor, writes them and the directory entry (offset, L) straight into
+    // the owner's memory.  sp_slots[d] / sp_dir[d]: this rank's record region / directory inside rank d's receive buffer.
     uint16_t* sp_slots[F3D_MAX_RANKS];
+    uint2* sp_dir[F3D_MAX_RANKS];
+    unsigned long long sp_slot_cap;            // rows (64 B) per record region
+    unsigned long long* sp_slot_cursor;        // [G] local row cursors, one per destination
     int sp_use_slots;
 };
-#define FUSE_NSLOT 32   // distinct classes per point a slot record holds; points with more spill to the (cell, count) queue
+#define FUSE_NSLOT 32   // classes per point remembered by cast_vote and rows per staging chunk; longer lists are re-read from the row
 
 __device__ __forceinline__ unsigned long long sp_pack(unsigned key, unsigned count) {
     return (unsigned long long)key | ((unsigned long long)count << 32);
@@ -365,28 +370,62 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
     uint32_t* __restrict__ h32 = reinterpret_cast<uint32_t*>(hist + row0 * P.C1);   // 32*C1 bytes per warp: word aligned
     const uint8_t* __restrict__ h8 = hist + row0 * P.C1;
     if (P.sp_use_slots) {
-        // slot records: a thread lists the classes of its own point (collected by cast_vote) with their counts into the
-        // warp's staging block [slot][lane]; the block goes to the owner rank with sixteen-byte stores (512 contiguous
-        // bytes per instruction over NVLink).  points_per_shard is a multiple of the tile, so a warp has one owner.
+        // slot records.  points_per_shard is a multiple of the tile, so a warp's 32 points have one owner.
         const long long p0 = tile_base + row0;
         const int d = (int)(p0 / P.sp_per);
-        uint4* st4 = reinterpret_cast<uint4*>(stg);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) st4[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
-        __syncwarp();
         const bool live = lane < nrows;
-        // the record is written by the first flush only; later flushes, points with more than FUSE_NSLOT classes and
-        // rows another lane's deferred pass touched go cell by cell to the owner's (cell, count) queue
-        const bool spill = live && (!first || T.nlist > FUSE_NSLOT || dirty);
-        const uint8_t* __restrict__ row = h8 + lane * P.C1;
-        if (live && !spill)
-            for (int j = 0; j < T.nlist; ++j) {
-                const unsigned cls = T.clist[j * FUSE_BLOCK];
-                stg[j * 32 + lane] = (uint16_t)(cls | ((unsigned)row[cls] << 8));
+        // the record is written by the first flush only; later flushes and rows another lane's deferred pass touched
+        // go cell by cell to the owner's (cell, count) queue
+        bool spill = live && (!first || dirty);
+        const int C1 = P.C1;
+        const uint8_t* __restrict__ row = h8 + lane * C1;
+        int n = (live && !spill) ? min(T.nlist, C1) : 0;      // classes of this lane's point
+        int L = n;
+#pragma unroll
+        for (int s2 = 16; s2 > 0; s2 >>= 1) L = max(L, __shfl_xor_sync(0xffffffffu, L, s2));
+        unsigned long long off = 0;
+        if (first) {
+            if (lane == 0 && L > 0) off = atomicAdd(P.sp_slot_cursor + d, (unsigned long long)L);
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (off + (unsigned long long)L > P.sp_slot_cap) {   // record region full: everything of this block goes to the queue
+                spill = live;
+                n = 0;
+                L = 0;
             }
+            if (lane == 0 && nrows > 0)
+                P.sp_dir[d][(p0 - (long long)d * P.sp_per) >> 5] = make_uint2((unsigned)off, (unsigned)L);
+        }
+        uint4* st4 = reinterpret_cast<uint4*>(stg);
+        uint4* __restrict__ dst = reinterpret_cast<uint4*>(P.sp_slots[d] + off * 32ull);
+        int scan_c = 0;                                           // row-scan position of a long list (n > FUSE_NSLOT)
+        for (int j0 = 0; j0 < L; j0 += FUSE_NSLOT) {
+            const int rows_here = min(FUSE_NSLOT, L - j0);
+            for (int i = lane; i < rows_here * 4; i += 32) st4[i] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            if (n <= FUSE_NSLOT) {
+                if (j0 == 0)
+                    for (int j = 0; j < n; ++j) {                 // the classes cast_vote remembered
+                        const unsigned cls = T.clist[j * FUSE_BLOCK];
+                        stg[j * 32 + lane] = (uint16_t)(cls | ((unsigned)row[cls] << 8));
+                    }
+            } else {
+                int j = 0;                                        // long list: next FUSE_NSLOT non-zero cells of the row
+                while (j < rows_here && scan_c < C1) {
+                    const unsigned v = row[scan_c];
+                    if (v) {
+                        stg[j * 32 + lane] = (uint16_t)((unsigned)scan_c | (v << 8));
+                        ++j;
+                    }
+                    ++scan_c;
+                }
+            }
+            __syncwarp();
+            for (int i = lane; i < rows_here * 4; i += 32) dst[j0 * 4 + i] = st4[i];
+            __syncwarp();
+        }
         if (spill) {
-            const unsigned key0 = (unsigned)((p0 + lane - (long long)d * P.sp_per) * P.C1);
-            for (int c = 0; c < P.C1; ++c) {
+            const unsigned key0 = (unsigned)((p0 + lane - (long long)d * P.sp_per) * C1);
+            for (int c = 0; c < C1; ++c) {
                 const unsigned v = row[c];
                 if (!v) continue;
                 const unsigned long long at = atomicAdd(P.sp_cursor + d, 1ULL);
@@ -395,12 +434,6 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
             }
         }
         T.nlist = 0;
-        __syncwarp();
-        if (first && nrows > 0) {
-            uint4* __restrict__ dst = reinterpret_cast<uint4*>(P.sp_slots[d] + ((p0 - (long long)d * P.sp_per) >> 5) * (FUSE_NSLOT * 32));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i * 32 + lane] = st4[i * 32 + lane];
-        }
     } else if (P.sp_G > 0 && nrows > 0) {
         // sparse emit: non-zero cells go to the receive queue of the rank that owns the point (peer memory).  A warp's
         // rows belong to one owner except at the G-1 shard boundaries of the whole launch.
@@ -1315,9 +1348,12 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.sp_per = 1;
     P.sp_overflow = nullptr;
     P.sp_use_slots = 0;
+    P.sp_slot_cap = 0;
+    P.sp_slot_cursor = nullptr;
     for (int i = 0; i < F3D_MAX_RANKS; ++i) {
         P.sp_queue[i] = nullptr;
         P.sp_slots[i] = nullptr;
+        P.sp_dir[i] = nullptr;
     }
     return F3D_OK;
 }
@@ -1500,9 +1536,10 @@ extern "C" int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const
                                             int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
                                             int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
                                             int32_t C1, const uint64_t* h_peer_queues, const uint64_t* h_peer_slots,
-                                            int32_t nranks, int64_t segment_cap, int64_t points_per_shard, uint64_t* cursors,
-                                            uint32_t* overflow, void* workspace, int64_t workspace_bytes, uint64_t* stats,
-                                            int32_t flags, void* stream) {
+                                            const uint64_t* h_peer_dirs, int64_t slot_rows_cap, int32_t nranks,
+                                            int64_t segment_cap, int64_t points_per_shard, uint64_t* cursors, uint32_t* overflow,
+                                            void* workspace, int64_t workspace_bytes, uint64_t* stats, int32_t flags,
+                                            void* stream) {
     FuseParams P;
     int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
                          zmax, stats, flags);
@@ -1514,8 +1551,9 @@ extern "C" int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const
         return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: too many frames per call (limit 65515)");
     if ((int64_t)points_per_shard * C1 > 0xffffffffLL)
         return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: shard cell index does not fit 32 bits");
-    if (h_peer_slots && (points_per_shard % FUSE_BLOCK) != 0)
-        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_sparse: slot records need points_per_shard to be a multiple of 256");
+    if (h_peer_slots && ((points_per_shard % FUSE_BLOCK) != 0 || !h_peer_dirs || slot_rows_cap <= 0 || slot_rows_cap > 0xffffffffLL))
+        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_sparse: slot records need points_per_shard to be a multiple of 256, "
+                                     "directory pointers and a row capacity below 2^32");
     if (N == 0) return F3D_OK;
     P.C1 = C1;
     P.RS = hist_row_stride(C1);
@@ -1526,7 +1564,12 @@ extern "C" int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const
     for (int i = 0; i < nranks; ++i) P.sp_queue[i] = reinterpret_cast<unsigned long long*>(h_peer_queues[i]);
     if (h_peer_slots) {
         P.sp_use_slots = 1;
-        for (int i = 0; i < nranks; ++i) P.sp_slots[i] = reinterpret_cast<uint16_t*>(h_peer_slots[i]);
+        for (int i = 0; i < nranks; ++i) {
+            P.sp_slots[i] = reinterpret_cast<uint16_t*>(h_peer_slots[i]);
+            P.sp_dir[i] = reinterpret_cast<uint2*>(h_peer_dirs[i]);
+        }
+        P.sp_slot_cap = (unsigned long long)slot_rows_cap;
+        P.sp_slot_cursor = reinterpret_cast<unsigned long long*>(cursors) + nranks;   // cursors: [G queue][G record rows]
     }
     P.sp_cursor = reinterpret_cast<unsigned long long*>(cursors);
     P.sp_cap = (unsigned long long)segment_cap;

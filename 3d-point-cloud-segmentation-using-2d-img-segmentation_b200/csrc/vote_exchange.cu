@@ -3,15 +3,16 @@
 //
 // Every rank owns a contiguous range of points.  The fused kernel of each source rank writes, straight into the owner's
 // memory over NVLink (fuse_project_vote.cu, flush8):
-//   * slot records: per (source, 32-point block) 2 KB = [32 slots][32 points] of uint16 (class | count << 8), the
-//     classes a point received from that source's frames, in order of first appearance, zero-terminated;
-//   * a (cell, count) queue for what does not fit a record (points with more than 32 classes from one source, later
-//     flushes of very dense scans, the deferred fp64 votes of the fix-up pass).
+//   * slot records: per (source, 32-point block) L rows of 64 B, row j = the j-th class (order of first appearance) of
+//     each of the block's 32 points as uint16 (class | count << 8, 0 = none), L = the longest list in the block; a
+//     directory entry (row offset, L) per block says where the rows are inside that source's record region;
+//   * a (cell, count) queue for what does not go into a record (a full record region, later flushes of very dense
+//     scans, the deferred fp64 votes of the fix-up pass).
 // Here the owner merges the G records of each of its points into the dense int32 row the reference keeps
 // (votes[npts, nclasses + 1], voting.py:34), resolves the label (VotingSegmentation.segment, voting.py:106-137) from
 // the on-chip row, then scatter-adds the queue entries and re-resolves the few points they touched.  The merge is a
-// streaming pass: G * 64 B read (less: reading stops at the longest list of the warp) and 4 * C1 + 8 B written per
-// point -- no dense partial vote tensor ever crosses the fabric or HBM.
+// streaming pass: 2 B per non-zero (point, class, source) cell (padded to the block's longest list) read and
+// 4 * C1 + 8 B written per point -- no dense partial vote tensor ever crosses the fabric or HBM.
 #include "f3d_common.cuh"
 #include "f3d_host.h"
 
@@ -97,7 +98,8 @@ __global__ void __launch_bounds__(256) sparse_relabel_kernel(const unsigned long
 // ---- slot-record merge: one thread per owned point, one warp per 32-point block ------------------------------------------
 // shared: uint16 histogram [256][RS] (a thread owns its row; RS/2 odd => conflict-free), written out like the fused
 // kernel's epilogue (warp-private rows, 16-byte stores, every cell exactly once -- no memset of the shard needed).
-__global__ void __launch_bounds__(XCH_BLOCK, 2) slot_merge_kernel(const uint16_t* __restrict__ slots, int G, long long blocks_per_src,
+__global__ void __launch_bounds__(XCH_BLOCK, 2) slot_merge_kernel(const uint16_t* __restrict__ slots, const uint2* __restrict__ dir,
+                                                                  int G, long long rows_cap, long long blocks_per_src,
                                                                   long long nrows, int C1, int RS,
                                                                   const __grid_constant__ FuseResolve RP,
                                                                   int32_t* __restrict__ votes, int64_t* __restrict__ labels) {
@@ -116,14 +118,19 @@ __global__ void __launch_bounds__(XCH_BLOCK, 2) slot_merge_kernel(const uint16_t
     const long long p = blk * 32 + lane;
     uint16_t* __restrict__ row = hist + tid * RS;
     int total = 0, best = 0, bpos = 0x7fff;
-    if (blk < blocks_per_src) {
+    if (blk * 32 < nrows) {
+        // the G directory entries of this block, one per lane
+        uint2 de = make_uint2(0u, 0u);
+        if (lane < G) de = __ldg(dir + (size_t)lane * blocks_per_src + blk);
         for (int s = 0; s < G; ++s) {
-            const uint16_t* __restrict__ rec = slots + ((size_t)s * blocks_per_src + blk) * (XCH_NSLOT * 32) + lane;
-            for (int j0 = 0; j0 < XCH_NSLOT; j0 += 4) {
+            const unsigned off = __shfl_sync(0xffffffffu, de.x, s);
+            const int L = (int)min((unsigned long long)__shfl_sync(0xffffffffu, de.y, s),
+                                   (unsigned long long)max(0LL, rows_cap - (long long)off));
+            const uint16_t* __restrict__ rec = slots + ((size_t)s * rows_cap + off) * 32 + lane;
+            for (int j0 = 0; j0 < L; j0 += 4) {
                 unsigned pr[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) pr[k] = __ldg(rec + (j0 + k) * 32);   // 64 contiguous bytes per warp and slot
-                if (!__any_sync(0xffffffffu, pr[0] != 0u)) break;                 // lists are zero-terminated
+                for (int k = 0; k < 4; ++k) pr[k] = (j0 + k < L) ? (unsigned)__ldg(rec + (size_t)(j0 + k) * 32) : 0u;   // 64 contiguous bytes per row
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int cls = (int)(pr[k] & 0xffu), cnt = (int)(pr[k] >> 8);
@@ -214,23 +221,24 @@ extern "C" int f3d_sparse_relabel(const uint64_t* rx, const uint64_t* rx_count, 
     return f3d_check_launch("f3d_sparse_relabel");
 }
 
-extern "C" int f3d_slots_merge(const uint16_t* slots, int32_t nranks, int64_t points_per_shard, int64_t nrows, int32_t C1,
-                               double threshold, const int32_t* h_filter, int32_t nfilter, int32_t nclasses_id, int32_t* votes,
-                               int64_t* labels, void* stream) {
-    if (!slots || nranks < 1 || nranks > F3D_MAX_RANKS || points_per_shard <= 0 || (points_per_shard % XCH_BLOCK) != 0 ||
-        nrows < 0 || nrows > points_per_shard || C1 <= 0 || C1 > 256 || (!votes && !labels) || nfilter < 0 ||
-        (nfilter > 0 && !h_filter) || (votes && (reinterpret_cast<uintptr_t>(votes) & 15u)))
+extern "C" int f3d_slots_merge(const uint16_t* slots, const void* dir, int32_t nranks, int64_t slot_rows_cap,
+                               int64_t points_per_shard, int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter,
+                               int32_t nfilter, int32_t nclasses_id, int32_t* votes, int64_t* labels, void* stream) {
+    if (!slots || !dir || nranks < 1 || nranks > F3D_MAX_RANKS || slot_rows_cap <= 0 || points_per_shard <= 0 ||
+        (points_per_shard % XCH_BLOCK) != 0 || nrows < 0 || nrows > points_per_shard || C1 <= 0 || C1 > 256 || (!votes && !labels) ||
+        nfilter < 0 || (nfilter > 0 && !h_filter) || (votes && (reinterpret_cast<uintptr_t>(votes) & 15u)))
         return f3d_fail(F3D_ERR_ARG, "f3d_slots_merge: bad argument");
     if (nrows == 0) return F3D_OK;
     FuseResolve RP;
-    int rc = f3d_build_resolve(C1, threshold, h_filter ? h_filter : nullptr, nfilter, nclasses_id, RP);
+    int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
     if (rc) return rc;
     const int RS = xch_row_stride(C1);
     const size_t smem = RES_MAXC * sizeof(int16_t) + (((size_t)XCH_BLOCK * RS * 2 + 15) & ~(size_t)15);
     cudaError_t e = cudaFuncSetAttribute(slot_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return f3d_check_launch("f3d_slots_merge(cudaFuncSetAttribute)");
     const long long tiles = (nrows + XCH_BLOCK - 1) / XCH_BLOCK;
-    slot_merge_kernel<<<(unsigned)tiles, XCH_BLOCK, smem, (cudaStream_t)stream>>>(slots, nranks, points_per_shard / 32, (long long)nrows,
-                                                                                C1, RS, RP, votes, labels);
+    slot_merge_kernel<<<(unsigned)tiles, XCH_BLOCK, smem, (cudaStream_t)stream>>>(slots, reinterpret_cast<const uint2*>(dir), nranks,
+                                                                                (long long)slot_rows_cap, points_per_shard / 32,
+                                                                                (long long)nrows, C1, RS, RP, votes, labels);
     return f3d_check_launch("f3d_slots_merge");
 }

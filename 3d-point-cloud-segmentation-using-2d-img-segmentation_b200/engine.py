@@ -155,20 +155,24 @@ def _filter_arg(filter_classes):
 
 def fuse_project_vote_sparse(points4, table: FrameTable, depth, mask, nclasses1, peer_queue_ptrs, segment_cap, points_per_shard,
                              cursors, overflow, radius=0.05, zmin=0.1, zmax=4.0, stats=None, frame_begin=0, frame_end=None,
-                             peer_slot_ptrs=None):
+                             peer_slot_ptrs=None, peer_dir_ptrs=None, slot_rows_cap=0):
     """Kernel (1) with the multi-GPU exchange fused in: the votes of this rank's frames go straight into the owner
-    ranks' memory through the peer pointers (numpy uint64 [G]) -- slot records when `peer_slot_ptrs` is given, the
-    (cell, count) queues otherwise / for what does not fit a record.  No dense vote tensor is written."""
+    ranks' memory through the peer pointers (numpy uint64 [G]) -- slot records + directory when `peer_slot_ptrs` is
+    given, the (cell, count) queues otherwise / for what does not go into a record.  `cursors` is uint64 [2G] (queue
+    entries, record rows), zeroed by the caller.  No dense vote tensor is written."""
     frame_end = table.F if frame_end is None else frame_end
     N = points4.shape[0]
     ws = workspace(N, points4.device)
     q = np.ascontiguousarray(np.asarray(peer_queue_ptrs, dtype=np.uint64))
     sl = None if peer_slot_ptrs is None else np.ascontiguousarray(np.asarray(peer_slot_ptrs, dtype=np.uint64))
+    dr = None if peer_dir_ptrs is None else np.ascontiguousarray(np.asarray(peer_dir_ptrs, dtype=np.uint64))
+    if cursors.numel() < 2 * q.size:
+        raise ValueError("cursors must hold 2 * nranks uint64")
     check(load().f3d_fuse_project_vote_sparse(
         ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth), _depth_fmt(depth), ptr(mask), table.H, table.W,
-        ptr(table.K), float(radius), float(zmin), float(zmax), int(nclasses1), ptr(q), ptr(sl), int(q.size), int(segment_cap),
-        int(points_per_shard), ptr(cursors), ptr(overflow), ptr(ws), ws.numel(), ptr(stats), 0, stream_ptr()),
-        "f3d_fuse_project_vote_sparse")
+        ptr(table.K), float(radius), float(zmin), float(zmax), int(nclasses1), ptr(q), ptr(sl), ptr(dr), int(slot_rows_cap),
+        int(q.size), int(segment_cap), int(points_per_shard), ptr(cursors), ptr(overflow), ptr(ws), ws.numel(), ptr(stats), 0,
+        stream_ptr()), "f3d_fuse_project_vote_sparse")
 
 
 def sparse_publish(cursors, peer_count_ptrs, rank, segment_cap):
@@ -177,12 +181,13 @@ def sparse_publish(cursors, peer_count_ptrs, rank, segment_cap):
           "f3d_sparse_publish")
 
 
-def slots_merge(slots, nranks, points_per_shard, nrows, nclasses1, nclasses_id, threshold=0.5, filter_classes=None, votes=None,
-                labels=None):
+def slots_merge(slots, dirs, nranks, slot_rows_cap, points_per_shard, nrows, nclasses1, nclasses_id, threshold=0.5,
+                filter_classes=None, votes=None, labels=None):
     """Owner side: merge the slot records of all source ranks into the dense int32 shard rows and the labels."""
     filt, nf = _filter_arg(filter_classes)
-    check(load().f3d_slots_merge(ptr(slots), int(nranks), int(points_per_shard), int(nrows), int(nclasses1), float(threshold),
-                                 ptr(filt), nf, int(nclasses_id), ptr(votes), ptr(labels), stream_ptr()), "f3d_slots_merge")
+    check(load().f3d_slots_merge(ptr(slots), ptr(dirs), int(nranks), int(slot_rows_cap), int(points_per_shard), int(nrows),
+                                 int(nclasses1), float(threshold), ptr(filt), nf, int(nclasses_id), ptr(votes), ptr(labels),
+                                 stream_ptr()), "f3d_slots_merge")
 
 
 def sparse_accumulate(rx, rx_count, nranks, segment_cap, votes, nrows=None):

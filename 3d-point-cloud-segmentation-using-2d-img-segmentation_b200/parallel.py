@@ -149,7 +149,7 @@ class SparseExchange:
         self.peer_queue_ptrs = np.array([p.data_ptr() + self.rank * self.cap * 8 for p in peers], dtype=np.uint64)
         self.peer_count_ptrs = np.array([p.data_ptr() + G * self.cap * 8 for p in peers], dtype=np.uint64)
         self.rx_count = self.rx[G * self.cap:G * self.cap + G]
-        self.cursors = torch.zeros(G, dtype=torch.int64, device=self.device)
+        self.cursors = torch.zeros(2 * G, dtype=torch.int64, device=self.device)   # [queue entries x G][unused record rows x G]
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.shard = torch.zeros((max(self.per, 1), c1), dtype=torch.int32, device=self.device)
         self.lab = torch.zeros(max(self.per, 1), dtype=torch.int64, device=self.device)
@@ -187,15 +187,16 @@ class SlotExchange:
     """Frame-sharded fusion with the vote exchange fused into the compute kernel as slot records (CUDA only).
 
     Rank d owns the points [d*per, (d+1)*per), per a multiple of the 256-point tile.  Its receive buffer lives in
-    symmetric memory: per source rank one array of 2 KB records (32 points x 32 slots of class | count << 8) plus one
-    (cell, count) queue segment and a count table.  A step is
-        barrier (peers are done reading the previous step) -> fused kernel: every warp writes its block's record
-        straight into the owner's memory over NVLink, spills / deferred fp64 votes are appended to the owner's queue ->
-        publish cursors -> barrier -> merge the G records of every owned point into the dense int32 shard row and the
-        label -> scatter-add the queue entries, re-resolve the points they touched -> all-gather the labels.
+    symmetric memory: per source rank a record region (variable-length records: per 32-point block L rows of 64 B,
+    row j = the j-th class | count << 8 of each point), a directory (row offset, L) per block, one (cell, count) queue
+    segment and a count table.  A step is
+        barrier (peers are done reading the previous step) -> fused kernel: every warp writes its block's record and
+        directory entry straight into the owner's memory over NVLink, spills / deferred fp64 votes are appended to the
+        owner's queue -> publish cursors -> barrier -> merge the G records of every owned point into the dense int32
+        shard row and the label -> scatter-add the queue entries, re-resolve the points they touched -> all-gather labels.
     Nothing dense crosses the fabric and the sweep never writes a vote tensor; the owner writes its shard once."""
 
-    def __init__(self, npoints: int, c1: int, device, group=None, segment_cap=None):
+    def __init__(self, npoints: int, c1: int, device, group=None, segment_cap=None, rows_per_block=40):
         import numpy as np
         import torch.distributed._symmetric_memory as symm
         from . import engine
@@ -208,39 +209,46 @@ class SlotExchange:
         self.per = shard_points(npoints, G)
         self.rows = max(0, min(self.per, npoints - self.rank * self.per))
         self.cap = int(segment_cap) if segment_cap else max(1 << 20, self.per // 2)
-        # int64 words: [G x cap queue entries][G counts, padded to 64][G x per x 8 words of records]
-        self.q_words, self.c_words, self.s_words = G * self.cap, 64, G * self.per * 8
-        total = self.q_words + self.c_words + self.s_words
+        self.blocks = self.per // 32
+        self.rows_cap = self.blocks * int(rows_per_block)          # 64-byte record rows per source
+        # int64 words: [G x cap queue entries][counts, padded to 64][G x blocks directory entries][G x rows_cap x 8 record words]
+        self.q_words, self.c_words, self.d_words, self.s_words = G * self.cap, 64, G * self.blocks, G * self.rows_cap * 8
+        total = self.q_words + self.c_words + self.d_words + self.s_words
         self.rx = symm.empty(total, dtype=torch.int64, device=self.device)
         self.rx.zero_()
         self.hdl = symm.rendezvous(self.rx, self.group)
-        peers = [self.hdl.get_buffer(d, (total,), torch.int64) for d in range(G)]
-        base = [p.data_ptr() for p in peers]
+        base = [self.hdl.get_buffer(d, (total,), torch.int64).data_ptr() for d in range(G)]
+        o_c, o_d, o_s = self.q_words, self.q_words + self.c_words, self.q_words + self.c_words + self.d_words
         self.peer_queue_ptrs = np.array([b + self.rank * self.cap * 8 for b in base], dtype=np.uint64)
-        self.peer_count_ptrs = np.array([b + self.q_words * 8 for b in base], dtype=np.uint64)
-        self.peer_slot_ptrs = np.array([b + (self.q_words + self.c_words + self.rank * self.per * 8) * 8 for b in base],
-                                       dtype=np.uint64)
-        self.rx_queue = self.rx[:self.q_words]
-        self.rx_count = self.rx[self.q_words:self.q_words + G]
-        self.rx_slots = self.rx[self.q_words + self.c_words:]
-        self.cursors = torch.zeros(G, dtype=torch.int64, device=self.device)
+        self.peer_count_ptrs = np.array([b + o_c * 8 for b in base], dtype=np.uint64)
+        self.peer_dir_ptrs = np.array([b + (o_d + self.rank * self.blocks) * 8 for b in base], dtype=np.uint64)
+        self.peer_slot_ptrs = np.array([b + (o_s + self.rank * self.rows_cap * 8) * 8 for b in base], dtype=np.uint64)
+        self.rx_queue, self.rx_count = self.rx[:self.q_words], self.rx[o_c:o_c + G]
+        self.rx_dir, self.rx_slots = self.rx[o_d:o_s], self.rx[o_s:]
+        self.cursors = torch.zeros(2 * G, dtype=torch.int64, device=self.device)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.shard = torch.zeros((max(self.per, 1), c1), dtype=torch.int32, device=self.device)
         self.lab = torch.zeros(max(self.per, 1), dtype=torch.int64, device=self.device)
         self.full = torch.zeros(max(self.per, 1) * G, dtype=torch.int64, device=self.device)
 
+    def fuse_args(self):
+        """Keyword arguments of engine.fuse_project_vote_sparse that describe this exchange."""
+        return dict(peer_queue_ptrs=self.peer_queue_ptrs, segment_cap=self.cap, points_per_shard=self.per, cursors=self.cursors,
+                    overflow=self.overflow, peer_slot_ptrs=self.peer_slot_ptrs, peer_dir_ptrs=self.peer_dir_ptrs,
+                    slot_rows_cap=self.rows_cap)
+
     def run(self, fuse_slots, nclasses_id, threshold=0.5, filter_classes=None) -> torch.Tensor:
-        """`fuse_slots(peer_queue_ptrs, peer_slot_ptrs, cap, per, cursors, overflow)` enqueues the slot-mode fused kernel
-        over this rank's frames.  Returns labels [npoints]; `self.shard[:self.rows]` holds this rank's reduced votes."""
+        """`fuse_slots(**self.fuse_args())` enqueues the slot-mode fused kernel over this rank's frames.  Returns labels
+        [npoints]; `self.shard[:self.rows]` holds this rank's reduced votes."""
         eng = self.engine
         self.hdl.barrier(channel=0)
         self.cursors.zero_()
-        fuse_slots(self.peer_queue_ptrs, self.peer_slot_ptrs, self.cap, self.per, self.cursors, self.overflow)
+        fuse_slots(**self.fuse_args())
         eng.sparse_publish(self.cursors, self.peer_count_ptrs, self.rank, self.cap)
         self.hdl.barrier(channel=1)
         if self.rows > 0:
-            eng.slots_merge(self.rx_slots, self.world, self.per, self.rows, self.c1, nclasses_id, threshold, filter_classes,
-                            votes=self.shard, labels=self.lab)
+            eng.slots_merge(self.rx_slots, self.rx_dir, self.world, self.rows_cap, self.per, self.rows, self.c1, nclasses_id,
+                            threshold, filter_classes, votes=self.shard, labels=self.lab)
             eng.sparse_accumulate(self.rx_queue, self.rx_count, self.world, self.cap, self.shard, nrows=self.rows)
             eng.sparse_relabel(self.rx_queue, self.rx_count, self.world, self.cap, self.shard, self.rows, nclasses_id, self.lab,
                                threshold, filter_classes)

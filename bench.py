@@ -261,9 +261,9 @@ def main():
         slotx = parallel.SlotExchange(N, C1, torch.device("cuda", local_rank))
 
     def step_slots():
-        def fuse_slots(qptrs, sptrs, cap, per, cursors, overflow):
-            engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, qptrs, cap, per, cursors, overflow, RADIUS,
-                                            fl.zmin, fl.zmax, stats=stats, peer_slot_ptrs=sptrs)
+        def fuse_slots(**xargs):
+            engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, radius=RADIUS, zmin=fl.zmin, zmax=fl.zmax,
+                                            stats=stats, **xargs)
 
         labels = slotx.run(fuse_slots, NCLASSES, THRESHOLD, None)
         return labels, None, 6   # fuse_kernel, fixup_apply, publish, slot_merge, sparse_accumulate, sparse_relabel

@@ -104,14 +104,18 @@ int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_t
  * [d * points_per_shard, (d+1) * points_per_shard).  The fused kernel of every source rank writes, straight into the
  * owner's memory through peer-mapped pointers:
  *   - slot records (when h_peer_slots != NULL; points_per_shard must be a multiple of 256): per (source, 32-point block)
- *     2 KB = [32 slots][32 points] uint16 (class | count << 8), zero-terminated lists in order of first appearance.
- *     h_peer_slots[d] = device pointer (peer mapped) to THIS rank's record array [points_per_shard / 32][32][32] inside
- *     rank d's receive buffer.  Every record is rewritten on every call (no clearing needed);
+ *     L rows of 64 B; row j holds, for each of the block's 32 points, its j-th class in order of first appearance as
+ *     uint16 (class | count << 8, 0 = none); L = the longest list in the block.  The block's warp reserves the rows with
+ *     one atomic on cursors[nranks + d] and writes a directory entry {uint32 row offset, uint32 L}.
+ *     h_peer_slots[d] / h_peer_dirs[d] = device pointers (peer mapped) to THIS rank's record region (slot_rows_cap rows)
+ *     and directory [points_per_shard / 32] inside rank d's receive buffer.  Every directory entry is rewritten on every
+ *     call (no clearing needed); a block that finds the region full goes to the queue instead;
  *   - a (cell, count) queue for everything else (all votes when h_peer_slots == NULL; otherwise points with more than
- *     32 classes, later flushes of a tile with more than 235 candidate frames, deferred fp64 votes):
+ *     a full record region, later flushes of a tile with more than 235 candidate frames, deferred fp64 votes):
  *     h_peer_queues[d] = peer pointer to THIS rank's segment of `segment_cap` uint64 entries
  *     (cell = local_point * C1 + class in the low half, count in the high half) inside rank d's queue;
- *     cursors [nranks] uint64 local append cursors (caller zeroes them before the call); *overflow is set to 1 when a
+ *     cursors [2 * nranks] uint64 local cursors (queue entries, then record rows; the caller zeroes them before the
+ *     call); *overflow is set to 1 when a
  *     segment filled up (entries dropped: the caller must check it and enlarge the segment or fall back).
  * f3d_sparse_publish then stores the cursors into every destination's count table (h_peer_counts[d] = peer pointer to
  * rank d's uint64[nranks] table; slot [rank] is written).  After a cross-rank barrier the owner runs
@@ -121,14 +125,15 @@ int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_t
 int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                                  int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
                                  int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                                 int32_t C1, const uint64_t* h_peer_queues, const uint64_t* h_peer_slots, int32_t nranks,
-                                 int64_t segment_cap, int64_t points_per_shard, uint64_t* cursors, uint32_t* overflow,
-                                 void* workspace, int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
+                                 int32_t C1, const uint64_t* h_peer_queues, const uint64_t* h_peer_slots,
+                                 const uint64_t* h_peer_dirs, int64_t slot_rows_cap, int32_t nranks, int64_t segment_cap,
+                                 int64_t points_per_shard, uint64_t* cursors, uint32_t* overflow, void* workspace,
+                                 int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
 int f3d_sparse_publish(const uint64_t* cursors, const uint64_t* h_peer_counts, int32_t rank, int32_t nranks,
                        int64_t segment_cap, void* stream);
-int f3d_slots_merge(const uint16_t* slots, int32_t nranks, int64_t points_per_shard, int64_t nrows, int32_t C1,
-                    double threshold, const int32_t* h_filter, int32_t nfilter, int32_t nclasses_id, int32_t* votes,
-                    int64_t* labels, void* stream);
+int f3d_slots_merge(const uint16_t* slots, const void* dir, int32_t nranks, int64_t slot_rows_cap, int64_t points_per_shard,
+                    int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter, int32_t nfilter,
+                    int32_t nclasses_id, int32_t* votes, int64_t* labels, void* stream);
 int f3d_sparse_accumulate(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
                           int32_t* votes, int64_t nrows, int32_t C1, void* stream);
 int f3d_sparse_relabel(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,

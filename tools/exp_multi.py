@@ -33,19 +33,19 @@ res["single-GPU style fuse (dense votes)"] = timeit(lambda: engine.fuse_project_
 del votes
 if "slots" in what:
     sx = parallel.SlotExchange(N, C1, torch.device("cuda", lr))
-    def sx_fuse(q, s_, cap, per, cur, ovf): engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, q, cap, per, cur, ovf, 0.05, 0.1, spec.zmax, peer_slot_ptrs=s_)
+    def sx_fuse(**xa): engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, radius=0.05, zmin=0.1, zmax=spec.zmax, **xa)
     def sx_fuse_only():
-        sx.cursors.zero_(); sx_fuse(sx.peer_queue_ptrs, sx.peer_slot_ptrs, sx.cap, sx.per, sx.cursors, sx.overflow)
+        sx.cursors.zero_(); sx_fuse(**sx.fuse_args())
     res["slots: fuse + remote records"] = timeit(sx_fuse_only)
     engine.sparse_publish(sx.cursors, sx.peer_count_ptrs, rank, sx.cap); torch.cuda.synchronize(); dist.barrier()
-    res["slots: merge (shard + labels)"] = timeit(lambda: engine.slots_merge(sx.rx_slots, world, sx.per, sx.rows, C1, 133, 0.5, None, votes=sx.shard, labels=sx.lab))
+    res["slots: merge (shard + labels)"] = timeit(lambda: engine.slots_merge(sx.rx_slots, sx.rx_dir, world, sx.rows_cap, sx.per, sx.rows, C1, 133, 0.5, None, votes=sx.shard, labels=sx.lab))
     res["slots: queue accumulate"] = timeit(lambda: engine.sparse_accumulate(sx.rx_queue, sx.rx_count, world, sx.cap, sx.shard, nrows=sx.rows))
     res["slots: queue relabel"] = timeit(lambda: engine.sparse_relabel(sx.rx_queue, sx.rx_count, world, sx.cap, sx.shard, sx.rows, 133, sx.lab, 0.5, None))
     res["slots: 2 barriers"] = timeit(lambda: (sx.hdl.barrier(channel=0), sx.hdl.barrier(channel=1)))
     res["slots: all-gather labels"] = timeit(lambda: dist.all_gather_into_tensor(sx.full, sx.lab))
     res["slots: whole step"] = timeit(lambda: sx.run(sx_fuse, 133, 0.5, None), reps=10)
     labels["slots"] = sx.run(sx_fuse, 133, 0.5, None).clone()
-    if rank == 0: print("slots: queue cursors", sx.cursors.tolist(), "per", sx.per, "cap", sx.cap, flush=True)
+    if rank == 0: print("slots: cursors [queue x G, record rows x G]", sx.cursors.tolist(), "per", sx.per, "queue cap", sx.cap, "rows cap", sx.rows_cap, flush=True)
     sx.check_overflow()
 if "sparse" in what:
     sp = parallel.SparseExchange(N, C1, torch.device("cuda", lr))

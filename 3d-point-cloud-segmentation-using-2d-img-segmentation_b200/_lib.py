@@ -31,12 +31,12 @@ SIGNATURES = {
     "f3d_fuse_project_vote_u16": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64, _f64,
                                             _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
     "f3d_resolve_labels_u16": (C.c_int, [_vp, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp]),
-    "f3d_fuse_project_vote_sparse": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64, _f64,
-                                               _i32, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _vp]),
-    "f3d_sparse_publish": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp]),
-    "f3d_slots_merge": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _vp]),
-    "f3d_sparse_accumulate": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _vp]),
-    "f3d_sparse_relabel": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp]),
+    "f3d_exchange_constants": (C.c_int, [_vp]),
+    "f3d_fuse_project_vote_exchange": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64, _f64,
+                                                 _i32, _i32, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _vp]),
+    "f3d_exchange_publish": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp]),
+    "f3d_exchange_merge": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "f3d_exchange_queue_apply": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp]),
     "f3d_fuse_project_vote_resolve": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64,
                                                 _f64, _vp, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _i32, _vp]),
     "f3d_fuse_uv2pt": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _f64, _f64, _f64, _vp, _vp,

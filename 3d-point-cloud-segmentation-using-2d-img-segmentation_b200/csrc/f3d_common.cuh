@@ -152,3 +152,45 @@ struct FuseResolve {
 };
 // host: composed sequential remap + column -> filter position table (fuse_project_vote.cu)
 int f3d_build_resolve(int C1, double threshold, const int32_t* h_filter, int nfilter, int nclasses_id, FuseResolve& rp);
+
+// ---- multi-GPU vote exchange layout constants (see FuseParams in fuse_project_vote.cu and vote_exchange.cu) ----------
+#define F3D_XCH_NREG 1024      // record sub-regions per (source, owner): row cursors are spread so warps never queue on one
+#define F3D_XCH_NSUB 2048      // (cell, count) sub-queues per (source, owner)
+#define F3D_XCH_NSUB_FIX 1776  // the first sub-queues belong to the fix-up kernel's blocks (one each, no global atomics)
+
+// Eight lanes (sub = 0..7) stream one int32 vote row: all loads of a lane are issued before any is used (8-byte loads
+// when the row allows it), partial (total, best, first position) per lane; the caller combines with three xor-shuffles.
+__device__ __forceinline__ void row_partial8(const int32_t* __restrict__ r, int C1, const int16_t* __restrict__ s_fpos, int sub,
+                                             long long& total, int& best, int& bpos) {
+    if ((C1 & 1) == 0 && C1 <= 144 && (reinterpret_cast<uintptr_t>(r) & 7u) == 0) {
+        const int n2 = C1 >> 1;
+        int2 buf[9];
+#pragma unroll
+        for (int u = 0; u < 9; ++u) buf[u] = (sub + 8 * u < n2) ? __ldg(reinterpret_cast<const int2*>(r) + sub + 8 * u) : make_int2(0, 0);
+#pragma unroll
+        for (int u = 0; u < 9; ++u) {
+            const int c = 2 * (sub + 8 * u);
+            if ((buf[u].x | buf[u].y) == 0) continue;
+            total += (long long)buf[u].x + (long long)buf[u].y;
+            const int p0 = s_fpos[c], p1 = s_fpos[c + 1];
+            if (buf[u].x > 0 && p0 >= 0 && (buf[u].x > best || (buf[u].x == best && p0 < bpos))) {
+                best = buf[u].x;
+                bpos = p0;
+            }
+            if (buf[u].y > 0 && p1 >= 0 && (buf[u].y > best || (buf[u].y == best && p1 < bpos))) {
+                best = buf[u].y;
+                bpos = p1;
+            }
+        }
+    } else {
+        for (int c = sub; c < C1; c += 8) {
+            const int v = __ldg(r + c);
+            total += v;
+            const int pos = s_fpos[c];
+            if (v > 0 && pos >= 0 && (v > best || (v == best && pos < bpos))) {
+                best = v;
+                bpos = pos;
+            }
+        }
+    }
+}

@@ -87,29 +87,33 @@ struct FuseParams {
     GEntry* gq;                    // workspace queue of deferred point-views (NULL: evaluate them inside the sweep)
     unsigned long long* gq_count;
     unsigned long long gq_cap;
-    // sparse multi-GPU exchange: non-zero vote cells are appended straight into the owner rank's receive queue
-    // (peer memory over NVLink / NVSwitch) instead of writing a dense vote tensor
-    int sp_G;                                  // 0 = off
-    unsigned long long* sp_queue[F3D_MAX_RANKS];   // this rank's segment inside rank d's receive queue (peer pointers)
-    unsigned long long* sp_cursor;             // [G] local append cursors, one per destination
-    unsigned long long sp_cap;                 // entries per segment
-    long long sp_per;                          // points per owner shard: owner(p) = p / sp_per
-    unsigned* sp_overflow;                     // set when a segment is full (entries are then dropped: caller must check)
-    // slot records (the bulk of the exchange): per (source rank, 32-point block) one variable-length record of L rows,
-    // row j = the j-th class (in order of first appearance) of each of the block's 32 points as uint16 class | count << 8
-    // (64 B per row, 0 = none), L = the longest list in the block.  The block's warp reserves L rows in the owner's
-    // record region with one atomic on a local cursor, writes them and the directory entry (offset, L) straight into
-    // the owner's memory.  sp_slots[d] / sp_dir[d]: this rank's record region / directory inside rank d's receive buffer.
-    uint16_t* sp_slots[F3D_MAX_RANKS];
-    uint2* sp_dir[F3D_MAX_RANKS];
-    unsigned long long sp_slot_cap;            // rows (64 B) per record region
-    unsigned long long* sp_slot_cursor;        // [G] local row cursors, one per destination
-    int sp_use_slots;
+    // ---- multi-GPU vote exchange fused into the kernel (sender side; the owner side is vote_exchange.cu) -------------
+    // Rank d owns the points [d * xg_per, (d + 1) * xg_per), xg_per a multiple of the tile, so a CTA has one owner.
+    // Slot records: per 32-point block L rows of 64 B, row j = the j-th class (in order of first appearance) of each of the
+    // block's points as uint16 class | count << 8 (0 = none), L = the longest list in the block.  The block's warp reserves
+    // L rows in one of F3D_XCH_NREG sub-regions of this rank's record region at the owner (an atomic on a local cursor
+    // that only ~300 warps share -- a single cursor serialises at ~10 ns per warp in L2 and binds the whole kernel),
+    // writes them and the directory entry {row offset, L} straight into the owner's memory over NVLink.
+    // What cannot go into a record (region full, later flushes of a tile with more than FUSE_LIMIT8 candidate frames,
+    // and the deferred fp64 votes of the fix-up kernel) is appended as (cell, count) to one of F3D_XCH_NSUB sub-queues:
+    // fix-up block b owns sub-queue b (no global atomics at all), spills take the sub-queues above F3D_XCH_NSUB_FIX.
+    int xg_G;                                  // 0 = off
+    long long xg_per;                          // points per owner shard: owner(p) = p / xg_per
+    uint16_t* xg_slots[F3D_MAX_RANKS];         // this rank's record region inside rank d's receive buffer (peer pointers)
+    uint2* xg_dir[F3D_MAX_RANKS];              // ... its directory [xg_per / 32]
+    unsigned long long* xg_queue[F3D_MAX_RANKS];   // ... its (cell, count) queue [F3D_XCH_NSUB][xg_subcap]
+    unsigned* xg_rowcur;                       // local [G][F3D_XCH_NREG] row cursors (caller zeroes them per call)
+    unsigned* xg_qcur;                         // local [G][F3D_XCH_NSUB] queue cursors (ditto); published to the owners afterwards
+    unsigned xg_subrows, xg_subcap;            // rows per record sub-region, entries per sub-queue
+    unsigned* xg_overflow;                     // set when a sub-queue is full (entries are then dropped: caller must check)
 };
-#define FUSE_NSLOT 32   // classes per point remembered by cast_vote and rows per staging chunk; longer lists are re-read from the row
+#define FUSE_NSLOT 32   // classes per point remembered by cast_vote; longer lists are re-read from the histogram row
+#define FUSE_STG_ROWS 8 // record rows per staging chunk (512 B per warp: shared memory taken here is L1 taken from the gathers)
 
-__device__ __forceinline__ unsigned long long sp_pack(unsigned key, unsigned count) {
-    return (unsigned long long)key | ((unsigned long long)count << 32);
+// one (cell, count) entry for owner d through sub-queue `sub`
+__device__ __forceinline__ void xg_append(const FuseParams& P, int d, unsigned sub, unsigned at, unsigned key, unsigned count) {
+    if (at < P.xg_subcap) P.xg_queue[d][(size_t)sub * P.xg_subcap + at] = (unsigned long long)key | ((unsigned long long)count << 32);
+    else atomicExch(P.xg_overflow, 1u);
 }
 
 struct ExactOut {
@@ -369,13 +373,13 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
     const int n4 = total >> 2;
     uint32_t* __restrict__ h32 = reinterpret_cast<uint32_t*>(hist + row0 * P.C1);   // 32*C1 bytes per warp: word aligned
     const uint8_t* __restrict__ h8 = hist + row0 * P.C1;
-    if (P.sp_use_slots) {
-        // slot records.  points_per_shard is a multiple of the tile, so a warp's 32 points have one owner.
+    if (P.xg_G > 0) {
+        // slot records (see FuseParams)
         const long long p0 = tile_base + row0;
-        const int d = (int)(p0 / P.sp_per);
+        const int d = (int)(p0 / P.xg_per);
         const bool live = lane < nrows;
         // the record is written by the first flush only; later flushes and rows another lane's deferred pass touched
-        // go cell by cell to the owner's (cell, count) queue
+        // go cell by cell to the owner's queue
         bool spill = live && (!first || dirty);
         const int C1 = P.C1;
         const uint8_t* __restrict__ row = h8 + lane * C1;
@@ -383,33 +387,34 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
         int L = n;
 #pragma unroll
         for (int s2 = 16; s2 > 0; s2 >>= 1) L = max(L, __shfl_xor_sync(0xffffffffu, L, s2));
-        unsigned long long off = 0;
+        unsigned off = 0;
         if (first) {
-            if (lane == 0 && L > 0) off = atomicAdd(P.sp_slot_cursor + d, (unsigned long long)L);
+            const unsigned reg = (blockIdx.x * (FUSE_BLOCK / 32) + warp) & (F3D_XCH_NREG - 1);
+            if (lane == 0 && L > 0) off = atomicAdd(P.xg_rowcur + d * F3D_XCH_NREG + reg, (unsigned)L);
             off = __shfl_sync(0xffffffffu, off, 0);
-            if (off + (unsigned long long)L > P.sp_slot_cap) {   // record region full: everything of this block goes to the queue
+            if (off + (unsigned)L > P.xg_subrows) {   // sub-region full: everything of this block goes to the queue
                 spill = live;
                 n = 0;
                 L = 0;
             }
-            if (lane == 0 && nrows > 0)
-                P.sp_dir[d][(p0 - (long long)d * P.sp_per) >> 5] = make_uint2((unsigned)off, (unsigned)L);
+            off += reg * P.xg_subrows;
+            if (lane == 0 && nrows > 0) P.xg_dir[d][(p0 - (long long)d * P.xg_per) >> 5] = make_uint2(off, (unsigned)L);
         }
         uint4* st4 = reinterpret_cast<uint4*>(stg);
-        uint4* __restrict__ dst = reinterpret_cast<uint4*>(P.sp_slots[d] + off * 32ull);
+        uint4* __restrict__ dst = reinterpret_cast<uint4*>(P.xg_slots[d] + (size_t)off * 32);
         int scan_c = 0;                                           // row-scan position of a long list (n > FUSE_NSLOT)
-        for (int j0 = 0; j0 < L; j0 += FUSE_NSLOT) {
-            const int rows_here = min(FUSE_NSLOT, L - j0);
+        for (int j0 = 0; j0 < L; j0 += FUSE_STG_ROWS) {           // FUSE_STG_ROWS rows (512 B) at a time through the staging block
+            const int rows_here = min(FUSE_STG_ROWS, L - j0);
             for (int i = lane; i < rows_here * 4; i += 32) st4[i] = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
             if (n <= FUSE_NSLOT) {
-                if (j0 == 0)
-                    for (int j = 0; j < n; ++j) {                 // the classes cast_vote remembered
-                        const unsigned cls = T.clist[j * FUSE_BLOCK];
-                        stg[j * 32 + lane] = (uint16_t)(cls | ((unsigned)row[cls] << 8));
-                    }
+                const int j1 = min(n, j0 + FUSE_STG_ROWS);
+                for (int j = j0; j < j1; ++j) {                   // the classes cast_vote remembered
+                    const unsigned cls = T.clist[j * FUSE_BLOCK];
+                    stg[(j - j0) * 32 + lane] = (uint16_t)(cls | ((unsigned)row[cls] << 8));
+                }
             } else {
-                int j = 0;                                        // long list: next FUSE_NSLOT non-zero cells of the row
+                int j = 0;                                        // long list: next non-zero cells of the row
                 while (j < rows_here && scan_c < C1) {
                     const unsigned v = row[scan_c];
                     if (v) {
@@ -424,72 +429,14 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
             __syncwarp();
         }
         if (spill) {
-            const unsigned key0 = (unsigned)((p0 + lane - (long long)d * P.sp_per) * C1);
+            const unsigned key0 = (unsigned)((p0 + lane - (long long)d * P.xg_per) * C1);
+            const unsigned sub = F3D_XCH_NSUB_FIX + blockIdx.x % (F3D_XCH_NSUB - F3D_XCH_NSUB_FIX);
             for (int c = 0; c < C1; ++c) {
                 const unsigned v = row[c];
-                if (!v) continue;
-                const unsigned long long at = atomicAdd(P.sp_cursor + d, 1ULL);
-                if (at < P.sp_cap) P.sp_queue[d][at] = sp_pack(key0 + c, v);
-                else atomicExch(P.sp_overflow, 1u);
+                if (v) xg_append(P, d, sub, atomicAdd(P.xg_qcur + d * F3D_XCH_NSUB + sub, 1u), key0 + c, v);
             }
         }
         T.nlist = 0;
-    } else if (P.sp_G > 0 && nrows > 0) {
-        // sparse emit: non-zero cells go to the receive queue of the rank that owns the point (peer memory).  A warp's
-        // rows belong to one owner except at the G-1 shard boundaries of the whole launch.
-        const long long p0 = tile_base + row0;
-        const int dlo = (int)(p0 / P.sp_per), dhi = (int)((p0 + nrows - 1) / P.sp_per);
-        for (int d = dlo; d <= dhi; ++d) {
-            const bool single = (dlo == dhi);
-            int cnt = 0;
-            for (int i = lane; i < n4; i += 32) {
-                const uint32_t w = h32[i];
-                if (!w) continue;
-                if (single) cnt += __popc(__vcmpne4(w, 0u)) >> 3;
-                else
-                    for (int b = 0; b < 4; ++b)
-                        cnt += (((w >> (8 * b)) & 0xffu) != 0u) && ((p0 + (4 * i + b) / P.C1) / P.sp_per == d);
-            }
-            for (int e = (n4 << 2) + lane; e < total; e += 32) cnt += (h8[e] != 0) && ((p0 + e / P.C1) / P.sp_per == d);
-#pragma unroll
-            for (int s2 = 16; s2 > 0; s2 >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s2);
-            if (cnt == 0) continue;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(P.sp_cursor + d, (unsigned long long)cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (unsigned long long)cnt > P.sp_cap) {
-                if (lane == 0) atomicExch(P.sp_overflow, 1u);
-                continue;
-            }
-            // consecutive lanes append consecutive entries (ballot ranks), so the mostly remote stores of one
-            // instruction cover one contiguous run of the queue
-            unsigned long long* __restrict__ q = P.sp_queue[d] + base;
-            const unsigned key0 = (unsigned)((p0 - (long long)d * P.sp_per) * P.C1);
-            const unsigned below = (1u << lane) - 1u;
-            unsigned run = 0;
-            const int n4r = (n4 + 31) & ~31;
-            for (int i0 = 0; i0 < n4r; i0 += 32) {
-                const int i = i0 + lane;
-                const uint32_t w = (i < n4) ? h32[i] : 0u;
-                if (__ballot_sync(0xffffffffu, w != 0u) == 0u) continue;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const unsigned v = (w >> (8 * b)) & 0xffu;
-                    const bool on = (v != 0u) && (single || ((p0 + (4 * i + b) / P.C1) / P.sp_per == d));
-                    const unsigned bal = __ballot_sync(0xffffffffu, on);
-                    if (on) q[run + __popc(bal & below)] = sp_pack(key0 + 4 * i + b, v);
-                    run += __popc(bal);
-                }
-            }
-            for (int e0 = n4 << 2; e0 < total; e0 += 32) {
-                const int e = e0 + lane;
-                const unsigned v = (e < total) ? h8[e] : 0u;
-                const bool on = (v != 0u) && ((p0 + e / P.C1) / P.sp_per == d);
-                const unsigned bal = __ballot_sync(0xffffffffu, on);
-                if (on) q[run + __popc(bal & below)] = sp_pack(key0 + e, v);
-                run += __popc(bal);
-            }
-        }
     } else if (nrows > 0) {
         if (P.votes) {
             int32_t* __restrict__ out = P.votes + (tile_base + row0) * P.C1;
@@ -568,7 +515,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     Deferred* queue_all = reinterpret_cast<Deferred*>(red + FUSE_RED_WORDS);
     CellT* hist = reinterpret_cast<CellT*>(reinterpret_cast<unsigned char*>(queue_all) + (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred));
     const int RS = P.RS;
-    // slot-record mode only: [class lists u8 x FUSE_NSLOT x FUSE_BLOCK][staging blocks: 8 warps x 2 KB] after the histogram
+    // exchange mode only: [class lists u8 x FUSE_NSLOT x FUSE_BLOCK][staging blocks: 8 warps x 512 B] after the histogram
     uint8_t* clist_all = reinterpret_cast<uint8_t*>(hist) + (((size_t)FUSE_BLOCK * RS * sizeof(CellT) + 15) & ~(size_t)15);
     uint16_t* stg_all = reinterpret_cast<uint16_t*>(clist_all + FUSE_NSLOT * FUSE_BLOCK);
 
@@ -640,7 +587,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     T.n_cand = T.n_seen = 0u;
     T.rare = stat_s;
     T.nlist = 0;
-    T.clist = (MODE == MODE_VOTE && HB == 1 && P.sp_use_slots) ? clist_all + threadIdx.x : nullptr;
+    T.clist = (MODE == MODE_VOTE && HB == 1 && P.xg_G > 0) ? clist_all + threadIdx.x : nullptr;
     T.total = 0;
     T.best = 0;
     T.bpos = 0x7fff;
@@ -738,7 +685,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
                 if (since_flush + nw > FUSE_LIMIT8) {
                     __syncwarp();
                     flush8(P, reinterpret_cast<uint8_t*>(hist), warp, lane, tile_base, nflush > 0 || P.accumulate, true, T,
-                           stg_all + warp * (FUSE_NSLOT * 32), nflush == 0, false);
+                           stg_all + warp * (FUSE_STG_ROWS * 32), nflush == 0, false);
                     ++nflush;
                     since_flush = 0;
                 }
@@ -901,7 +848,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     // ---- epilogue (warp-private rows): histogram -> HBM, written once with 16-byte stores; fused label resolve
     if constexpr (MODE == MODE_VOTE && HB == 1) {
         uint8_t* hist8 = reinterpret_cast<uint8_t*>(hist);
-        flush8(P, hist8, warp, lane, tile_base, nflush > 0 || P.accumulate, false, T, stg_all + warp * (FUSE_NSLOT * 32), nflush == 0,
+        flush8(P, hist8, warp, lane, tile_base, nflush > 0 || P.accumulate, false, T, stg_all + warp * (FUSE_STG_ROWS * 32), nflush == 0,
                ((dirty_s[warp] >> lane) & 1u) != 0u);
         if (RP.enabled && active) {
             // VotingSegmentation.segment (voting.py:120-135).  The running (total, best, bpos) is exact unless another
@@ -931,63 +878,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             P.labels[gi] = (int64_t)(unc ? RP.unclassified : RP.remap[T.bpos]);
         }
     } else if constexpr (MODE == MODE_VOTE) {
-      if (P.sp_G > 0) {
-        // sparse emit: every lane scans its own histogram row; non-zero cells go to the queue of the rank that owns
-        // the point.  A warp's 32 consecutive points belong to one owner (two at a shard boundary).
-        const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(hist + tid * RS);
-        const int nw = (P.C1 + 1) >> 1;
-        int cnt = 0;
-        if (active)
-            for (int w = 0; w < nw; ++w) {
-                const uint32_t x = row[w];
-                cnt += ((x & 0xffffu) != 0u) + ((x >> 16) != 0u);
-            }
-        const int dst = active ? (int)(gi / P.sp_per) : -1;
-        const int dlo = __shfl_sync(0xffffffffu, dst, 0);
-        int dhi = dst;
-#pragma unroll
-        for (int s2 = 16; s2 > 0; s2 >>= 1) dhi = max(dhi, __shfl_xor_sync(0xffffffffu, dhi, s2));
-        for (int d = max(dlo, 0); d <= dhi; ++d) {
-            const int mine = (dst == d) ? cnt : 0;
-            int incl = mine;
-#pragma unroll
-            for (int s2 = 1; s2 < 32; s2 <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, incl, s2);
-                if (lane >= s2) incl += o;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total == 0) continue;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(P.sp_cursor + d, (unsigned long long)total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (unsigned long long)total > P.sp_cap) {
-                if (lane == 0) atomicExch(P.sp_overflow, 1u);
-                continue;
-            }
-            // cooperative, coalesced emission: the whole warp walks one row at a time (lanes over the row's 32-bit
-            // words), so consecutive lanes append consecutive queue entries -- the (mostly remote, NVLink) stores of
-            // one instruction cover one contiguous run instead of 32 scattered 8-byte writes.
-            unsigned long long* __restrict__ q = P.sp_queue[d] + base;
-            unsigned run = 0;
-            for (int rr = 0; rr < 32; ++rr) {
-                const int rdst = __shfl_sync(0xffffffffu, dst, rr);
-                const int rcnt = __shfl_sync(0xffffffffu, mine, rr);
-                if (rdst != d || rcnt == 0) continue;            // warp-uniform
-                const uint32_t* __restrict__ rrow = reinterpret_cast<const uint32_t*>(hist + (warp * 32 + rr) * RS);
-                const unsigned key0 = (unsigned)((tile_base + warp * 32 + rr - (long long)d * P.sp_per) * P.C1);
-                for (int w0 = 0; w0 < nw; w0 += 32) {
-                    const int w = w0 + lane;
-                    const uint32_t x = (w < nw) ? rrow[w] : 0u;
-                    const unsigned lo = x & 0xffffu, hi = x >> 16;
-                    const unsigned blo = __ballot_sync(0xffffffffu, lo != 0u), bhi = __ballot_sync(0xffffffffu, hi != 0u);
-                    const unsigned below = (1u << lane) - 1u;
-                    if (lo) q[run + __popc(blo & below)] = sp_pack(key0 + 2 * w, lo);
-                    if (hi) q[run + __popc(blo) + __popc(bhi & below)] = sp_pack(key0 + 2 * w + 1, hi);
-                    run += __popc(blo) + __popc(bhi);
-                }
-            }
-        }
-      } else {
+      {
         const int row0 = warp * 32;
         const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
         if (P.votes16 && nrows > 0) {
@@ -1082,8 +973,11 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid
     // loads per lane; instead the warp copies the 32 records one after the other with coalesced 16-byte loads into
     // shared memory and every lane then evaluates from its own copy.
     extern __shared__ __align__(16) unsigned char fx_smem[];
+    __shared__ unsigned s_qcnt[F3D_MAX_RANKS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FrameExact* wbuf = reinterpret_cast<FrameExact*>(fx_smem) + warp * 32;
+    if (threadIdx.x < F3D_MAX_RANKS) s_qcnt[threadIdx.x] = 0u;
+    __syncthreads();
     const unsigned long long n = min(*P.gq_count, P.gq_cap);
     const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
     const int HW = P.H * P.W;
@@ -1100,10 +994,20 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid
         if (i < n) e = P.gq[i];
         const int frel = (int)(e.w & 0xffffu), st = (int)((e.w >> 16) & 0xffu);
         __syncwarp();
-        for (int l = 0; l < 32; ++l) {
-            const int fl = __shfl_sync(0xffffffffu, e.pt >= 0 ? frel : -1, l);
-            if (fl >= 0 && lane < (int)(sizeof(FrameExact) / 16))
-                reinterpret_cast<uint4*>(wbuf + l)[lane] = __ldg(reinterpret_cast<const uint4*>(&frec[P.f_begin + fl].exact) + lane);
+        // eight records per round: all eight 16-byte loads of a lane are in flight before the first store (one L2
+        // round trip per round instead of one per record)
+        for (int l0 = 0; l0 < 32; l0 += 8) {
+            uint4 tmp[8];
+            int fls[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                fls[k] = __shfl_sync(0xffffffffu, e.pt >= 0 ? frel : -1, l0 + k);
+                if (fls[k] >= 0 && lane < (int)(sizeof(FrameExact) / 16))
+                    tmp[k] = __ldg(reinterpret_cast<const uint4*>(&frec[P.f_begin + fls[k]].exact) + lane);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (fls[k] >= 0 && lane < (int)(sizeof(FrameExact) / 16)) reinterpret_cast<uint4*>(wbuf + l0 + k)[lane] = tmp[k];
         }
         __syncwarp();
         if (e.pt < 0) continue;
@@ -1124,11 +1028,10 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid
             const size_t off = (size_t)frel * (size_t)HW + (size_t)eo.pix;
             if (MODE == MODE_VOTE) {
                 const int cls = __ldg(P.mask + off);
-                if (cls < P.C1 && P.sp_G > 0) {
-                    const int d = (int)(e.pt / P.sp_per);
-                    const unsigned long long at = atomicAdd(P.sp_cursor + d, 1ULL);
-                    if (at < P.sp_cap) P.sp_queue[d][at] = sp_pack((unsigned)((e.pt - (long long)d * P.sp_per) * P.C1 + cls), 1u);
-                    else atomicExch(P.sp_overflow, 1u);
+                if (cls < P.C1 && P.xg_G > 0) {
+                    // exchange mode: the vote goes to the owner's queue through this block's own sub-queue (shared-memory cursor)
+                    const int d = (int)(e.pt / P.xg_per);
+                    xg_append(P, d, blockIdx.x, atomicAdd(&s_qcnt[d], 1u), (unsigned)((e.pt - (long long)d * P.xg_per) * P.C1 + cls), 1u);
                 } else if (cls < P.C1) {
                     if (P.votes16) {
                         const size_t cell = (size_t)e.pt * P.C1 + cls;   // 32-bit atomic on the word of the uint16 counter
@@ -1144,6 +1047,10 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid
                 atomicMax(P.uv2pt + off, e.pt);
             }
         }
+    }
+    if (P.xg_G > 0) {
+        __syncthreads();
+        if ((int)threadIdx.x < P.xg_G) P.xg_qcur[threadIdx.x * F3D_XCH_NSUB + blockIdx.x] = min(s_qcnt[threadIdx.x], P.xg_subcap);
     }
     if (P.stats) {
         unsigned vals[4] = {n_exact, n_div, n_edge, n_seen};
@@ -1177,9 +1084,11 @@ __global__ void __launch_bounds__(256) fixup_labels_kernel(const __grid_constant
         const bool live = (e.pt >= 0) && ((e.w >> 24) & 1u);
         long long total = 0;
         int best = 0, bpos = 0x7fff;
-        if (live) {
+        if (live && !P.votes16) {
+            row_partial8(P.votes + (size_t)e.pt * P.C1, P.C1, s_fpos, sub, total, best, bpos);
+        } else if (live) {
             for (int c = sub; c < P.C1; c += 8) {
-                const int v = P.votes16 ? (int)P.votes16[(size_t)e.pt * P.C1 + c] : P.votes[(size_t)e.pt * P.C1 + c];
+                const int v = (int)P.votes16[(size_t)e.pt * P.C1 + c];
                 total += v;
                 const int pos = s_fpos[c];
                 if (v > 0 && pos >= 0 && (v > best || (v == best && pos < bpos))) {
@@ -1229,7 +1138,7 @@ static size_t fuse_smem_bytes(int mode, int C1, int hb, bool slots) {
                (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred);
     if (mode == MODE_VOTE)
         b += ((size_t)FUSE_BLOCK * (hb == 1 ? (size_t)C1 : hist_row_stride(C1) * sizeof(uint16_t)) + 15) & ~(size_t)15;
-    if (slots) b += (size_t)FUSE_NSLOT * FUSE_BLOCK + (size_t)(FUSE_BLOCK / 32) * FUSE_NSLOT * 32 * sizeof(uint16_t);
+    if (slots) b += (size_t)FUSE_NSLOT * FUSE_BLOCK + (size_t)(FUSE_BLOCK / 32) * FUSE_STG_ROWS * 32 * sizeof(uint16_t);
     return b;
 }
 
@@ -1241,8 +1150,8 @@ static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stre
 template <int MODE, int FMT>
 static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t stream) {
     if constexpr (MODE == MODE_VOTE) {
-        const bool no_sink = !P.votes && !P.votes16 && P.sp_G == 0;
-        const bool hist16 = !P.sp_use_slots && ((no_sink && P.f_end - P.f_begin > FUSE_LIMIT8) || getenv("F3D_HIST16") != nullptr);
+        const bool no_sink = !P.votes && !P.votes16 && P.xg_G == 0;
+        const bool hist16 = P.xg_G == 0 && ((no_sink && P.f_end - P.f_begin > FUSE_LIMIT8) || getenv("F3D_HIST16") != nullptr);
         if (!hist16) return launch_fuse_hb<MODE, FMT, 1>(P, RP, stream);
     }
     return launch_fuse_hb<MODE, FMT, 2>(P, RP, stream);
@@ -1251,7 +1160,7 @@ static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t 
 template <int MODE, int FMT, int HB>
 static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stream) {
     if (MODE == MODE_VOTE) P.RS = HB == 1 ? P.C1 : hist_row_stride(P.C1);
-    size_t smem = fuse_smem_bytes(MODE, P.C1, HB, MODE == MODE_VOTE && HB == 1 && P.sp_use_slots);
+    size_t smem = fuse_smem_bytes(MODE, P.C1, HB, MODE == MODE_VOTE && HB == 1 && P.xg_G > 0);
     if (const char* ex = getenv("F3D_EXTRA_SMEM")) smem += (size_t)atoi(ex);   // occupancy experiments only
     if (smem > 227 * 1024) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: nclasses+1 too large for the shared-memory histogram");
     cudaError_t e = cudaFuncSetAttribute(fuse_kernel<MODE, FMT, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1269,7 +1178,8 @@ static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stre
         const int fx_smem = (FIXUP_THREADS / 32) * 32 * (int)sizeof(FrameExact);
         e = cudaFuncSetAttribute(fixup_apply_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem);
         if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute fixup)");
-        fixup_apply_kernel<MODE, FMT><<<148 * 12, FIXUP_THREADS, fx_smem, stream>>>(P);
+        static_assert(F3D_XCH_NSUB_FIX == 148 * 12, "one sub-queue per fix-up block");
+        fixup_apply_kernel<MODE, FMT><<<F3D_XCH_NSUB_FIX, FIXUP_THREADS, fx_smem, stream>>>(P);
         if (MODE == MODE_VOTE && RP.enabled) fixup_labels_kernel<<<148 * 8, 256, 0, stream>>>(P, RP);
     }
     return f3d_check_launch("f3d_fuse");
@@ -1342,18 +1252,17 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.gq = nullptr;
     P.gq_count = nullptr;
     P.gq_cap = 0;
-    P.sp_G = 0;
-    P.sp_cursor = nullptr;
-    P.sp_cap = 0;
-    P.sp_per = 1;
-    P.sp_overflow = nullptr;
-    P.sp_use_slots = 0;
-    P.sp_slot_cap = 0;
-    P.sp_slot_cursor = nullptr;
+    P.xg_G = 0;
+    P.xg_per = 1;
+    P.xg_rowcur = nullptr;
+    P.xg_qcur = nullptr;
+    P.xg_subrows = 0;
+    P.xg_subcap = 0;
+    P.xg_overflow = nullptr;
     for (int i = 0; i < F3D_MAX_RANKS; ++i) {
-        P.sp_queue[i] = nullptr;
-        P.sp_slots[i] = nullptr;
-        P.sp_dir[i] = nullptr;
+        P.xg_queue[i] = nullptr;
+        P.xg_slots[i] = nullptr;
+        P.xg_dir[i] = nullptr;
     }
     return F3D_OK;
 }
@@ -1531,54 +1440,50 @@ extern "C" int f3d_zbuffer_splat(const void* points, int64_t N, const void* fram
 }
 
 
-// ---- sparse / slot-record vote exchange over peer memory: sender side (owner side: vote_exchange.cu) -----------------
-extern "C" int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
-                                            int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
-                                            int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                                            int32_t C1, const uint64_t* h_peer_queues, const uint64_t* h_peer_slots,
-                                            const uint64_t* h_peer_dirs, int64_t slot_rows_cap, int32_t nranks,
-                                            int64_t segment_cap, int64_t points_per_shard, uint64_t* cursors, uint32_t* overflow,
-                                            void* workspace, int64_t workspace_bytes, uint64_t* stats, int32_t flags,
-                                            void* stream) {
+// ---- vote exchange over peer memory: sender side (owner side: vote_exchange.cu) ---------------------------------------
+extern "C" int f3d_fuse_project_vote_exchange(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                                              int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
+                                              int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
+                                              int32_t C1, int32_t nranks, int64_t points_per_shard, const uint64_t* h_peer_slots,
+                                              const uint64_t* h_peer_dirs, const uint64_t* h_peer_queues, int64_t sub_rows,
+                                              int64_t sub_cap, uint32_t* cursors, uint32_t* overflow, void* workspace,
+                                              int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
     FuseParams P;
     int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
                          zmax, stats, flags);
     if (rc) return rc;
-    if (!h_peer_queues || nranks < 1 || nranks > F3D_MAX_RANKS || segment_cap <= 0 || points_per_shard <= 0 || !cursors ||
-        !overflow || C1 <= 0 || C1 > 256 || (frame_end > frame_begin && (!depth || !mask)))
-        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_sparse: bad argument");
+    if (!h_peer_slots || !h_peer_dirs || !h_peer_queues || nranks < 1 || nranks > F3D_MAX_RANKS || points_per_shard <= 0 ||
+        (points_per_shard % FUSE_BLOCK) != 0 || sub_rows <= 0 || sub_cap <= 0 || sub_rows * F3D_XCH_NREG > 0xffffffffLL ||
+        sub_cap > 0x7fffffffLL || !cursors || !overflow || C1 <= 0 || C1 > 256 || (frame_end > frame_begin && (!depth || !mask)))
+        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_exchange: bad argument (points_per_shard must be a multiple of 256)");
     if (frame_end - frame_begin > F3D_MAX_FRAMES_PER_LAUNCH)
-        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: too many frames per call (limit 65515)");
+        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_exchange: too many frames per call (limit 65515)");
     if ((int64_t)points_per_shard * C1 > 0xffffffffLL)
-        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_sparse: shard cell index does not fit 32 bits");
-    if (h_peer_slots && ((points_per_shard % FUSE_BLOCK) != 0 || !h_peer_dirs || slot_rows_cap <= 0 || slot_rows_cap > 0xffffffffLL))
-        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_sparse: slot records need points_per_shard to be a multiple of 256, "
-                                     "directory pointers and a row capacity below 2^32");
+        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_exchange: shard cell index does not fit 32 bits");
+    if (points_per_shard * nranks < N)
+        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_exchange: nranks * points_per_shard does not cover the cloud");
     if (N == 0) return F3D_OK;
     P.C1 = C1;
-    P.RS = hist_row_stride(C1);
     P.f_begin = frame_begin;
     P.f_end = frame_end;
     P.mask = mask;
-    P.sp_G = nranks;
-    for (int i = 0; i < nranks; ++i) P.sp_queue[i] = reinterpret_cast<unsigned long long*>(h_peer_queues[i]);
-    if (h_peer_slots) {
-        P.sp_use_slots = 1;
-        for (int i = 0; i < nranks; ++i) {
-            P.sp_slots[i] = reinterpret_cast<uint16_t*>(h_peer_slots[i]);
-            P.sp_dir[i] = reinterpret_cast<uint2*>(h_peer_dirs[i]);
-        }
-        P.sp_slot_cap = (unsigned long long)slot_rows_cap;
-        P.sp_slot_cursor = reinterpret_cast<unsigned long long*>(cursors) + nranks;   // cursors: [G queue][G record rows]
+    P.xg_G = nranks;
+    P.xg_per = points_per_shard;
+    for (int i = 0; i < nranks; ++i) {
+        P.xg_slots[i] = reinterpret_cast<uint16_t*>(h_peer_slots[i]);
+        P.xg_dir[i] = reinterpret_cast<uint2*>(h_peer_dirs[i]);
+        P.xg_queue[i] = reinterpret_cast<unsigned long long*>(h_peer_queues[i]);
     }
-    P.sp_cursor = reinterpret_cast<unsigned long long*>(cursors);
-    P.sp_cap = (unsigned long long)segment_cap;
-    P.sp_per = points_per_shard;
-    P.sp_overflow = overflow;
-    if (!P.audit && N <= 0x7fffffff) attach_workspace(P, workspace, workspace_bytes);
+    P.xg_rowcur = cursors;
+    P.xg_qcur = cursors + (size_t)nranks * F3D_XCH_NREG;
+    P.xg_subrows = (unsigned)sub_rows;
+    P.xg_subcap = (unsigned)sub_cap;
+    P.xg_overflow = overflow;
+    // the fix-up kernel's blocks own the first F3D_XCH_NSUB_FIX sub-queues: the deferred queue is mandatory here
+    if (P.audit || N > 0x7fffffff || !attach_workspace(P, workspace, workspace_bytes))
+        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_exchange: needs the workspace of f3d_fuse_workspace_bytes (no audit mode)");
     FuseResolve RP;
     RP.enabled = 0;
     return depth_fmt == F3D_DEPTH_U16_MM ? launch_fuse<MODE_VOTE, F3D_DEPTH_U16_MM>(P, RP, (cudaStream_t)stream)
                                          : launch_fuse<MODE_VOTE, F3D_DEPTH_F32_M>(P, RP, (cudaStream_t)stream);
 }
-

@@ -5,9 +5,10 @@
 // memory over NVLink (fuse_project_vote.cu, flush8):
 //   * slot records: per (source, 32-point block) L rows of 64 B, row j = the j-th class (order of first appearance) of
 //     each of the block's 32 points as uint16 (class | count << 8, 0 = none), L = the longest list in the block; a
-//     directory entry (row offset, L) per block says where the rows are inside that source's record region;
-//   * a (cell, count) queue for what does not go into a record (a full record region, later flushes of very dense
-//     scans, the deferred fp64 votes of the fix-up pass).
+//     directory entry (row offset, L) per block says where the rows are inside that source's record region (the region is
+//     split into F3D_XCH_NREG sub-regions so that the senders' row cursors never become an atomic hot spot);
+//   * (cell, count) entries in F3D_XCH_NSUB sub-queues for what does not go into a record (a full record sub-region,
+//     later flushes of very dense scans, the deferred fp64 votes of the fix-up pass -- fix-up block b owns sub-queue b).
 // Here the owner merges the G records of each of its points into the dense int32 row the reference keeps
 // (votes[npts, nclasses + 1], voting.py:34), resolves the label (VotingSegmentation.segment, voting.py:106-137) from
 // the on-chip row, then scatter-adds the queue entries and re-resolves the few points they touched.  The merge is a
@@ -17,80 +18,72 @@
 #include "f3d_host.h"
 
 #define XCH_BLOCK 256
-#define XCH_NSLOT 32
 
 struct PeerPtrs {
-    unsigned long long* p[F3D_MAX_RANKS];
+    unsigned* p[F3D_MAX_RANKS];
 };
 
-__global__ void sparse_publish_kernel2(const unsigned long long* __restrict__ cursor, PeerPtrs counts, int rank, int G,
-                                       unsigned long long cap) {
-    const int d = threadIdx.x;
-    if (d < G) counts.p[d][rank] = min(cursor[d], cap);
+// this rank's queue cursors [G][F3D_XCH_NSUB] -> row [rank] of every owner's count table [G][F3D_XCH_NSUB]
+__global__ void exchange_publish_kernel(const unsigned* __restrict__ qcur, PeerPtrs counts, int rank, int G, unsigned subcap) {
+    const int d = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < G && i < F3D_XCH_NSUB) counts.p[d][(size_t)rank * F3D_XCH_NSUB + i] = min(qcur[(size_t)d * F3D_XCH_NSUB + i], subcap);
 }
 
-// scatter-add every received (cell, count) entry into the dense int32 shard
-__global__ void __launch_bounds__(256) sparse_accumulate_kernel(const unsigned long long* __restrict__ rx,
-                                                                const unsigned long long* __restrict__ rx_count, unsigned long long cap,
-                                                                int32_t* __restrict__ votes, unsigned long long ncells) {
+// scatter-add every received (cell, count) entry into the dense int32 shard: block (x, y) walks the sub-queues
+// x, x + gridDim.x, ... of source y
+__global__ void __launch_bounds__(256) queue_accumulate_kernel(const unsigned long long* __restrict__ rx,
+                                                               const unsigned* __restrict__ counts, unsigned subcap,
+                                                               int32_t* __restrict__ votes, unsigned long long ncells) {
     const int src = blockIdx.y;
-    const unsigned long long n = min(rx_count[src], cap);
-    const unsigned long long* __restrict__ seg = rx + (unsigned long long)src * cap;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long e = seg[i];
-        const unsigned key = (unsigned)(e & 0xffffffffu);
-        if (key < ncells) atomicAdd(votes + key, (int)(e >> 32));
+    for (int sub = blockIdx.x; sub < F3D_XCH_NSUB; sub += gridDim.x) {
+        const unsigned n = min(counts[(size_t)src * F3D_XCH_NSUB + sub], subcap);
+        const unsigned long long* __restrict__ seg = rx + ((size_t)src * F3D_XCH_NSUB + sub) * subcap;
+        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long e = seg[i];
+            const unsigned key = (unsigned)(e & 0xffffffffu);
+            if (key < ncells) atomicAdd(votes + key, (int)(e >> 32));
+        }
     }
 }
 
-// labels of the points the queue entries touched (eight lanes stream the dense row, like fixup_labels_kernel); a point
-// with several entries is re-resolved several times with the same result
-__global__ void __launch_bounds__(256) sparse_relabel_kernel(const unsigned long long* __restrict__ rx,
-                                                             const unsigned long long* __restrict__ rx_count, unsigned long long cap,
-                                                             const int32_t* __restrict__ votes, long long nrows, int C1,
-                                                             const __grid_constant__ FuseResolve RP, int64_t* __restrict__ labels) {
+// labels of the points the queue entries touched (eight lanes stream the dense row with batched loads); a point with
+// several entries is re-resolved several times with the same result
+__global__ void __launch_bounds__(256) queue_relabel_kernel(const unsigned long long* __restrict__ rx,
+                                                            const unsigned* __restrict__ counts, unsigned subcap,
+                                                            const int32_t* __restrict__ votes, long long nrows, int C1,
+                                                            const __grid_constant__ FuseResolve RP, int64_t* __restrict__ labels) {
     __shared__ int16_t s_fpos[RES_MAXC];
     for (int c = threadIdx.x; c < RES_MAXC; c += blockDim.x) s_fpos[c] = RP.fpos[c];
     __syncthreads();
     const int src = blockIdx.y;
-    const unsigned long long n = min(rx_count[src], cap);
-    const unsigned long long* __restrict__ seg = rx + (unsigned long long)src * cap;
-    const int sub = threadIdx.x & 7;
-    const unsigned long long per_pass = ((unsigned long long)gridDim.x * blockDim.x) >> 3;
-    const unsigned long long passes = (n + per_pass - 1) / per_pass;   // uniform trip count: shuffles see full warps
-    unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    for (unsigned long long p = 0; p < passes; ++p, i += per_pass) {
-        long long pt = -1;
-        if (i < n) pt = (long long)((unsigned)(seg[i] & 0xffffffffu) / (unsigned)C1);
-        const bool live = pt >= 0 && pt < nrows;
-        long long total = 0;
-        int best = 0, bpos = 0x7fff;
-        if (live) {
-            for (int c = sub; c < C1; c += 8) {
-                const int v = votes[(size_t)pt * C1 + c];
-                total += v;
-                const int pos = s_fpos[c];
-                if (v > 0 && pos >= 0 && (v > best || (v == best && pos < bpos))) {
-                    best = v;
-                    bpos = pos;
+    const int sub8 = threadIdx.x & 7;
+    for (int sub = blockIdx.x; sub < F3D_XCH_NSUB; sub += gridDim.x) {
+        const unsigned n = min(counts[(size_t)src * F3D_XCH_NSUB + sub], subcap);
+        const unsigned long long* __restrict__ seg = rx + ((size_t)src * F3D_XCH_NSUB + sub) * subcap;
+        for (unsigned i0 = 0; i0 < n; i0 += blockDim.x >> 3) {             // block-uniform trip count
+            const unsigned i = i0 + (threadIdx.x >> 3);
+            long long pt = -1;
+            if (i < n) pt = (long long)((unsigned)(seg[i] & 0xffffffffu) / (unsigned)C1);
+            const bool live = pt >= 0 && pt < nrows;
+            long long total = 0;
+            int best = 0, bpos = 0x7fff;
+            if (live) row_partial8(votes + (size_t)pt * C1, C1, s_fpos, sub8, total, best, bpos);
+#pragma unroll
+            for (int s = 4; s > 0; s >>= 1) {
+                total += __shfl_xor_sync(0xffffffffu, total, s);
+                const int ob = __shfl_xor_sync(0xffffffffu, best, s);
+                const int op = __shfl_xor_sync(0xffffffffu, bpos, s);
+                if (ob > best || (ob == best && op < bpos)) {
+                    best = ob;
+                    bpos = op;
                 }
             }
-        }
-#pragma unroll
-        for (int s = 4; s > 0; s >>= 1) {
-            total += __shfl_xor_sync(0xffffffffu, total, s);
-            const int ob = __shfl_xor_sync(0xffffffffu, best, s);
-            const int op = __shfl_xor_sync(0xffffffffu, bpos, s);
-            if (ob > best || (ob == best && op < bpos)) {
-                best = ob;
-                bpos = op;
+            if (live && sub8 == 0) {
+                bool unc = (total <= 0) || (best <= 0);                                    // voting.py:126,131
+                if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;          // voting.py:128-130
+                labels[pt] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
             }
-        }
-        if (live && sub == 0) {
-            bool unc = (total <= 0) || (best <= 0);                                    // voting.py:126,131
-            if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;          // voting.py:128-130
-            labels[pt] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
         }
     }
 }
@@ -179,55 +172,54 @@ static int xch_row_stride(int C1) {
     return rs;
 }
 
-extern "C" int f3d_sparse_publish(const uint64_t* cursors, const uint64_t* h_peer_counts, int32_t rank, int32_t nranks,
-                                  int64_t segment_cap, void* stream) {
-    if (!cursors || !h_peer_counts || nranks < 1 || nranks > F3D_MAX_RANKS || rank < 0 || rank >= nranks)
-        return f3d_fail(F3D_ERR_ARG, "f3d_sparse_publish: bad argument");
-    PeerPtrs pp;
-    for (int i = 0; i < F3D_MAX_RANKS; ++i) pp.p[i] = i < nranks ? reinterpret_cast<unsigned long long*>(h_peer_counts[i]) : nullptr;
-    sparse_publish_kernel2<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(cursors), pp, rank, nranks,
-                                                               (unsigned long long)segment_cap);
-    return f3d_check_launch("f3d_sparse_publish");
+extern "C" int f3d_exchange_constants(int32_t* out3) {
+    if (!out3) return f3d_fail(F3D_ERR_ARG, "f3d_exchange_constants: NULL");
+    out3[0] = F3D_XCH_NREG;
+    out3[1] = F3D_XCH_NSUB;
+    out3[2] = F3D_XCH_NSUB_FIX;
+    return F3D_OK;
 }
 
-extern "C" int f3d_sparse_accumulate(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
-                                     int32_t* votes, int64_t nrows, int32_t C1, void* stream) {
-    if (!rx || !rx_count || !votes || nranks < 1 || nranks > F3D_MAX_RANKS || segment_cap <= 0 || nrows < 0 || C1 <= 0)
-        return f3d_fail(F3D_ERR_ARG, "f3d_sparse_accumulate: bad argument");
+extern "C" int f3d_exchange_publish(const uint32_t* cursors, const uint64_t* h_peer_counts, int32_t rank, int32_t nranks,
+                                    int64_t sub_cap, void* stream) {
+    if (!cursors || !h_peer_counts || nranks < 1 || nranks > F3D_MAX_RANKS || rank < 0 || rank >= nranks || sub_cap <= 0)
+        return f3d_fail(F3D_ERR_ARG, "f3d_exchange_publish: bad argument");
+    PeerPtrs pp;
+    for (int i = 0; i < F3D_MAX_RANKS; ++i) pp.p[i] = i < nranks ? reinterpret_cast<unsigned*>(h_peer_counts[i]) : nullptr;
+    dim3 grid(F3D_XCH_NSUB / 256, (unsigned)nranks);
+    exchange_publish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cursors + (size_t)nranks * F3D_XCH_NREG, pp, rank, nranks,
+                                                                    (unsigned)sub_cap);
+    return f3d_check_launch("f3d_exchange_publish");
+}
+
+extern "C" int f3d_exchange_queue_apply(const uint64_t* queue, const uint32_t* counts, int32_t nranks, int64_t sub_cap,
+                                        int32_t* votes, int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter,
+                                        int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream) {
+    if (!queue || !counts || !votes || nranks < 1 || nranks > F3D_MAX_RANKS || sub_cap <= 0 || nrows < 0 || C1 <= 0 || C1 > 256 ||
+        nfilter < 0 || (nfilter > 0 && !h_filter))
+        return f3d_fail(F3D_ERR_ARG, "f3d_exchange_queue_apply: bad argument");
     if (nrows == 0) return F3D_OK;
     dim3 grid(148 * 4, (unsigned)nranks);
-    sparse_accumulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(rx),
-                                                                    reinterpret_cast<const unsigned long long*>(rx_count),
-                                                                    (unsigned long long)segment_cap, votes,
-                                                                    (unsigned long long)nrows * (unsigned long long)C1);
-    return f3d_check_launch("f3d_sparse_accumulate");
+    queue_accumulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(queue), counts,
+                                                                   (unsigned)sub_cap, votes,
+                                                                   (unsigned long long)nrows * (unsigned long long)C1);
+    if (labels) {
+        FuseResolve RP;
+        int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
+        if (rc) return rc;
+        queue_relabel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(queue), counts,
+                                                                    (unsigned)sub_cap, votes, (long long)nrows, C1, RP, labels);
+    }
+    return f3d_check_launch("f3d_exchange_queue_apply");
 }
 
-extern "C" int f3d_sparse_relabel(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
-                                  const int32_t* votes, int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter,
-                                  int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream) {
-    if (!rx || !rx_count || !votes || !labels || nranks < 1 || nranks > F3D_MAX_RANKS || segment_cap <= 0 || nrows < 0 ||
-        C1 <= 0 || nfilter < 0 || (nfilter > 0 && !h_filter))
-        return f3d_fail(F3D_ERR_ARG, "f3d_sparse_relabel: bad argument");
-    if (nrows == 0) return F3D_OK;
-    FuseResolve RP;
-    int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
-    if (rc) return rc;
-    dim3 grid(148 * 2, (unsigned)nranks);
-    sparse_relabel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(rx),
-                                                                 reinterpret_cast<const unsigned long long*>(rx_count),
-                                                                 (unsigned long long)segment_cap, votes, (long long)nrows, C1, RP,
-                                                                 labels);
-    return f3d_check_launch("f3d_sparse_relabel");
-}
-
-extern "C" int f3d_slots_merge(const uint16_t* slots, const void* dir, int32_t nranks, int64_t slot_rows_cap,
-                               int64_t points_per_shard, int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter,
-                               int32_t nfilter, int32_t nclasses_id, int32_t* votes, int64_t* labels, void* stream) {
-    if (!slots || !dir || nranks < 1 || nranks > F3D_MAX_RANKS || slot_rows_cap <= 0 || points_per_shard <= 0 ||
+extern "C" int f3d_exchange_merge(const uint16_t* slots, const void* dir, int32_t nranks, int64_t sub_rows,
+                                  int64_t points_per_shard, int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter,
+                                  int32_t nfilter, int32_t nclasses_id, int32_t* votes, int64_t* labels, void* stream) {
+    if (!slots || !dir || nranks < 1 || nranks > F3D_MAX_RANKS || sub_rows <= 0 || points_per_shard <= 0 ||
         (points_per_shard % XCH_BLOCK) != 0 || nrows < 0 || nrows > points_per_shard || C1 <= 0 || C1 > 256 || (!votes && !labels) ||
         nfilter < 0 || (nfilter > 0 && !h_filter) || (votes && (reinterpret_cast<uintptr_t>(votes) & 15u)))
-        return f3d_fail(F3D_ERR_ARG, "f3d_slots_merge: bad argument");
+        return f3d_fail(F3D_ERR_ARG, "f3d_exchange_merge: bad argument");
     if (nrows == 0) return F3D_OK;
     FuseResolve RP;
     int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
@@ -235,10 +227,11 @@ extern "C" int f3d_slots_merge(const uint16_t* slots, const void* dir, int32_t n
     const int RS = xch_row_stride(C1);
     const size_t smem = RES_MAXC * sizeof(int16_t) + (((size_t)XCH_BLOCK * RS * 2 + 15) & ~(size_t)15);
     cudaError_t e = cudaFuncSetAttribute(slot_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return f3d_check_launch("f3d_slots_merge(cudaFuncSetAttribute)");
+    if (e != cudaSuccess) return f3d_check_launch("f3d_exchange_merge(cudaFuncSetAttribute)");
     const long long tiles = (nrows + XCH_BLOCK - 1) / XCH_BLOCK;
     slot_merge_kernel<<<(unsigned)tiles, XCH_BLOCK, smem, (cudaStream_t)stream>>>(slots, reinterpret_cast<const uint2*>(dir), nranks,
-                                                                                (long long)slot_rows_cap, points_per_shard / 32,
-                                                                                (long long)nrows, C1, RS, RP, votes, labels);
-    return f3d_check_launch("f3d_slots_merge");
+                                                                                (long long)sub_rows * F3D_XCH_NREG,
+                                                                                points_per_shard / 32, (long long)nrows, C1, RS, RP,
+                                                                                votes, labels);
+    return f3d_check_launch("f3d_exchange_merge");
 }

@@ -153,54 +153,58 @@ def _filter_arg(filter_classes):
     return filt, (0 if filt is None else int(filt.size))
 
 
-def fuse_project_vote_sparse(points4, table: FrameTable, depth, mask, nclasses1, peer_queue_ptrs, segment_cap, points_per_shard,
-                             cursors, overflow, radius=0.05, zmin=0.1, zmax=4.0, stats=None, frame_begin=0, frame_end=None,
-                             peer_slot_ptrs=None, peer_dir_ptrs=None, slot_rows_cap=0):
+def exchange_constants():
+    """(NREG, NSUB, NSUB_FIX): record sub-regions, sub-queues and fix-up-owned sub-queues per (source, owner)."""
+    out = np.zeros(3, dtype=np.int32)
+    check(load().f3d_exchange_constants(ptr(out)), "f3d_exchange_constants")
+    return int(out[0]), int(out[1]), int(out[2])
+
+
+def fuse_project_vote_exchange(points4, table: FrameTable, depth, mask, nclasses1, nranks, points_per_shard, peer_slot_ptrs,
+                               peer_dir_ptrs, peer_queue_ptrs, sub_rows, sub_cap, cursors, overflow, radius=0.05, zmin=0.1,
+                               zmax=4.0, stats=None, frame_begin=0, frame_end=None):
     """Kernel (1) with the multi-GPU exchange fused in: the votes of this rank's frames go straight into the owner
-    ranks' memory through the peer pointers (numpy uint64 [G]) -- slot records + directory when `peer_slot_ptrs` is
-    given, the (cell, count) queues otherwise / for what does not go into a record.  `cursors` is uint64 [2G] (queue
-    entries, record rows), zeroed by the caller.  No dense vote tensor is written."""
+    ranks' memory through the peer pointers (numpy uint64 [G] each) as slot records + directory entries, and as
+    (cell, count) queue entries for what does not go into a record.  `cursors` is uint32 [G * (NREG + NSUB)], zeroed
+    by the caller.  No dense vote tensor is written."""
     frame_end = table.F if frame_end is None else frame_end
     N = points4.shape[0]
     ws = workspace(N, points4.device)
-    q = np.ascontiguousarray(np.asarray(peer_queue_ptrs, dtype=np.uint64))
-    sl = None if peer_slot_ptrs is None else np.ascontiguousarray(np.asarray(peer_slot_ptrs, dtype=np.uint64))
-    dr = None if peer_dir_ptrs is None else np.ascontiguousarray(np.asarray(peer_dir_ptrs, dtype=np.uint64))
-    if cursors.numel() < 2 * q.size:
-        raise ValueError("cursors must hold 2 * nranks uint64")
-    check(load().f3d_fuse_project_vote_sparse(
+    arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.uint64)) for a in (peer_slot_ptrs, peer_dir_ptrs, peer_queue_ptrs)]
+    if any(a.size != nranks for a in arrs):
+        raise ValueError("peer pointer arrays must have one entry per rank")
+    nreg, nsub, _ = exchange_constants()
+    if cursors.dtype != torch.int32 or cursors.numel() < nranks * (nreg + nsub):
+        raise ValueError("cursors must be int32 [nranks * (NREG + NSUB)]")
+    check(load().f3d_fuse_project_vote_exchange(
         ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth), _depth_fmt(depth), ptr(mask), table.H, table.W,
-        ptr(table.K), float(radius), float(zmin), float(zmax), int(nclasses1), ptr(q), ptr(sl), ptr(dr), int(slot_rows_cap),
-        int(q.size), int(segment_cap), int(points_per_shard), ptr(cursors), ptr(overflow), ptr(ws), ws.numel(), ptr(stats), 0,
-        stream_ptr()), "f3d_fuse_project_vote_sparse")
+        ptr(table.K), float(radius), float(zmin), float(zmax), int(nclasses1), int(nranks), int(points_per_shard), ptr(arrs[0]),
+        ptr(arrs[1]), ptr(arrs[2]), int(sub_rows), int(sub_cap), ptr(cursors), ptr(overflow), ptr(ws), ws.numel(), ptr(stats), 0,
+        stream_ptr()), "f3d_fuse_project_vote_exchange")
 
 
-def sparse_publish(cursors, peer_count_ptrs, rank, segment_cap):
+def exchange_publish(cursors, peer_count_ptrs, rank, sub_cap):
     c = np.ascontiguousarray(np.asarray(peer_count_ptrs, dtype=np.uint64))
-    check(load().f3d_sparse_publish(ptr(cursors), ptr(c), int(rank), int(c.size), int(segment_cap), stream_ptr()),
-          "f3d_sparse_publish")
+    check(load().f3d_exchange_publish(ptr(cursors), ptr(c), int(rank), int(c.size), int(sub_cap), stream_ptr()),
+          "f3d_exchange_publish")
 
 
-def slots_merge(slots, dirs, nranks, slot_rows_cap, points_per_shard, nrows, nclasses1, nclasses_id, threshold=0.5,
-                filter_classes=None, votes=None, labels=None):
+def exchange_merge(slots, dirs, nranks, sub_rows, points_per_shard, nrows, nclasses1, nclasses_id, threshold=0.5,
+                   filter_classes=None, votes=None, labels=None):
     """Owner side: merge the slot records of all source ranks into the dense int32 shard rows and the labels."""
     filt, nf = _filter_arg(filter_classes)
-    check(load().f3d_slots_merge(ptr(slots), ptr(dirs), int(nranks), int(slot_rows_cap), int(points_per_shard), int(nrows),
-                                 int(nclasses1), float(threshold), ptr(filt), nf, int(nclasses_id), ptr(votes), ptr(labels),
-                                 stream_ptr()), "f3d_slots_merge")
+    check(load().f3d_exchange_merge(ptr(slots), ptr(dirs), int(nranks), int(sub_rows), int(points_per_shard), int(nrows),
+                                    int(nclasses1), float(threshold), ptr(filt), nf, int(nclasses_id), ptr(votes), ptr(labels),
+                                    stream_ptr()), "f3d_exchange_merge")
 
 
-def sparse_accumulate(rx, rx_count, nranks, segment_cap, votes, nrows=None):
-    nrows = votes.shape[0] if nrows is None else nrows
-    check(load().f3d_sparse_accumulate(ptr(rx), ptr(rx_count), int(nranks), int(segment_cap), ptr(votes), int(nrows),
-                                       votes.shape[1], stream_ptr()), "f3d_sparse_accumulate")
-
-
-def sparse_relabel(rx, rx_count, nranks, segment_cap, votes, nrows, nclasses_id, labels, threshold=0.5, filter_classes=None):
+def exchange_queue_apply(queue, counts, nranks, sub_cap, votes, nrows, nclasses_id, labels=None, threshold=0.5,
+                         filter_classes=None):
+    """Owner side: scatter-add the received (cell, count) entries into the shard and re-resolve the touched points."""
     filt, nf = _filter_arg(filter_classes)
-    check(load().f3d_sparse_relabel(ptr(rx), ptr(rx_count), int(nranks), int(segment_cap), ptr(votes), int(nrows), votes.shape[1],
-                                    float(threshold), ptr(filt), nf, int(nclasses_id), ptr(labels), stream_ptr()),
-          "f3d_sparse_relabel")
+    check(load().f3d_exchange_queue_apply(ptr(queue), ptr(counts), int(nranks), int(sub_cap), ptr(votes), int(nrows),
+                                          votes.shape[1], float(threshold), ptr(filt), nf, int(nclasses_id), ptr(labels),
+                                          stream_ptr()), "f3d_exchange_queue_apply")
 
 
 def fuse_uv2pt(points4, table: FrameTable, depth, radius=0.05, zmin=0.1, zmax=4.0, stats=None, audit=False,

@@ -119,84 +119,26 @@ class ShardedPipeline:
         return self.labels
 
 
-class SparseExchange:
-    """Frame-sharded fusion with the vote exchange fused into the compute kernel (CUDA only).
-
-    Every rank owns the points [rank*per, (rank+1)*per).  Its receive queue lives in symmetric memory
-    (`torch.distributed._symmetric_memory`): one segment of `cap` uint64 (cell, count) entries per source rank plus a
-    count table.  A step is: barrier (peers are done reading the previous step) -> fused kernel appends its non-zero
-    vote cells straight into the owners' queues over NVLink -> publish cursors -> barrier -> scatter-add the received
-    entries into the dense int32 shard -> resolve the shard -> all-gather labels.  Nothing dense crosses the fabric
-    (votes are ~95 % zeros) and the sweep never writes a vote tensor."""
-
-    def __init__(self, npoints: int, c1: int, device, group=None, segment_cap=None):
-        import numpy as np
-        import torch.distributed._symmetric_memory as symm
-        from . import engine
-        self.engine, self.np = engine, np
-        self.group = dist.group.WORLD if group is None else group
-        self.device = torch.device(device)
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.npoints, self.c1 = npoints, c1
-        self.per = -(-npoints // self.world)
-        self.rows = max(0, min(self.per, npoints - self.rank * self.per))
-        self.cap = int(segment_cap) if segment_cap else max(1 << 20, 8 * self.per)
-        G = self.world
-        self.rx = symm.empty(G * self.cap + 64, dtype=torch.int64, device=self.device)
-        self.rx.zero_()
-        self.hdl = symm.rendezvous(self.rx, self.group)
-        peers = [self.hdl.get_buffer(d, (G * self.cap + 64,), torch.int64) for d in range(G)]
-        self.peer_queue_ptrs = np.array([p.data_ptr() + self.rank * self.cap * 8 for p in peers], dtype=np.uint64)
-        self.peer_count_ptrs = np.array([p.data_ptr() + G * self.cap * 8 for p in peers], dtype=np.uint64)
-        self.rx_count = self.rx[G * self.cap:G * self.cap + G]
-        self.cursors = torch.zeros(2 * G, dtype=torch.int64, device=self.device)   # [queue entries x G][unused record rows x G]
-        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.shard = torch.zeros((max(self.per, 1), c1), dtype=torch.int32, device=self.device)
-        self.lab = torch.zeros(max(self.per, 1), dtype=torch.int64, device=self.device)
-        self.full = torch.zeros(max(self.per, 1) * G, dtype=torch.int64, device=self.device)
-
-    def run(self, fuse_sparse, resolve) -> torch.Tensor:
-        """`fuse_sparse(peer_queue_ptrs, cap, per, cursors, overflow)` enqueues the sparse-mode fused kernel over this
-        rank's frames; `resolve(votes, out_labels)` enqueues the label resolve.  Returns labels [npoints]."""
-        self.hdl.barrier(channel=0)
-        self.cursors.zero_()
-        fuse_sparse(self.peer_queue_ptrs, self.cap, self.per, self.cursors, self.overflow)
-        self.engine.sparse_publish(self.cursors, self.peer_count_ptrs, self.rank, self.cap)
-        self.hdl.barrier(channel=1)
-        self.shard.zero_()
-        self.engine.sparse_accumulate(self.rx, self.rx_count, self.world, self.cap, self.shard)
-        resolve(self.shard, self.lab)
-        _all_gather(self.full, self.lab, self.group if self.group is not dist.group.WORLD else None)
-        return self.full[:self.npoints]
-
-    def check_overflow(self):
-        """Host check (synchronises): raises if any receive segment filled up during the steps so far."""
-        t = self.overflow.clone()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if int(t.item()):
-            raise RuntimeError("sparse vote exchange: a receive segment overflowed; enlarge segment_cap or use ShardedPipeline")
-
-
 def shard_points(npoints: int, world: int, tile: int = 256) -> int:
-    """Points per owner rank of the slot-record exchange: ceil(npoints / world) rounded up to the kernel's point tile."""
+    """Points per owner rank of the record exchange: ceil(npoints / world) rounded up to the kernel's point tile."""
     per = -(-npoints // world)
     return max(tile, -(-per // tile) * tile)
 
 
-class SlotExchange:
-    """Frame-sharded fusion with the vote exchange fused into the compute kernel as slot records (CUDA only).
+class VoteExchange:
+    """Frame-sharded fusion with the vote exchange fused into the compute kernel (CUDA only).
 
     Rank d owns the points [d*per, (d+1)*per), per a multiple of the 256-point tile.  Its receive buffer lives in
-    symmetric memory: per source rank a record region (variable-length records: per 32-point block L rows of 64 B,
-    row j = the j-th class | count << 8 of each point), a directory (row offset, L) per block, one (cell, count) queue
-    segment and a count table.  A step is
+    symmetric memory (`torch.distributed._symmetric_memory`); per source rank it holds a record region (NREG
+    sub-regions of variable-length records: per 32-point block L rows of 64 B, row j = the j-th class | count << 8 of
+    each point), a directory {row offset, L} per block, NSUB (cell, count) sub-queues and their count table.  A step is
         barrier (peers are done reading the previous step) -> fused kernel: every warp writes its block's record and
-        directory entry straight into the owner's memory over NVLink, spills / deferred fp64 votes are appended to the
-        owner's queue -> publish cursors -> barrier -> merge the G records of every owned point into the dense int32
-        shard row and the label -> scatter-add the queue entries, re-resolve the points they touched -> all-gather labels.
+        directory entry straight into the owner's memory over NVLink; deferred fp64 votes and spills go to the owner's
+        sub-queues -> publish the queue counts -> barrier -> merge the G records of every owned point into the dense
+        int32 shard row and the label -> apply the queue entries -> all-gather the labels.
     Nothing dense crosses the fabric and the sweep never writes a vote tensor; the owner writes its shard once."""
 
-    def __init__(self, npoints: int, c1: int, device, group=None, segment_cap=None, rows_per_block=40):
+    def __init__(self, npoints: int, c1: int, device, group=None, rows_per_block=40, sub_cap=None):
         import numpy as np
         import torch.distributed._symmetric_memory as symm
         from . import engine
@@ -206,61 +148,65 @@ class SlotExchange:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.npoints, self.c1 = npoints, c1
         G = self.world
+        self.nreg, self.nsub, self.nsub_fix = engine.exchange_constants()
         self.per = shard_points(npoints, G)
         self.rows = max(0, min(self.per, npoints - self.rank * self.per))
-        self.cap = int(segment_cap) if segment_cap else max(1 << 20, self.per // 2)
         self.blocks = self.per // 32
-        self.rows_cap = self.blocks * int(rows_per_block)          # 64-byte record rows per source
-        # int64 words: [G x cap queue entries][counts, padded to 64][G x blocks directory entries][G x rows_cap x 8 record words]
-        self.q_words, self.c_words, self.d_words, self.s_words = G * self.cap, 64, G * self.blocks, G * self.rows_cap * 8
+        self.sub_rows = max(256, -(-self.blocks * int(rows_per_block) // self.nreg))     # 64-byte rows per record sub-region
+        self.sub_cap = int(sub_cap) if sub_cap else max(512, -(-self.per // self.nsub))    # entries per sub-queue
+        # int64 words: [queue: G x NSUB x sub_cap][counts: G x NSUB uint32][directory: G x blocks][records: G x NREG x sub_rows x 8]
+        self.q_words = G * self.nsub * self.sub_cap
+        self.c_words = G * self.nsub // 2
+        self.d_words = G * self.blocks
+        self.s_words = G * self.nreg * self.sub_rows * 8
         total = self.q_words + self.c_words + self.d_words + self.s_words
         self.rx = symm.empty(total, dtype=torch.int64, device=self.device)
         self.rx.zero_()
         self.hdl = symm.rendezvous(self.rx, self.group)
         base = [self.hdl.get_buffer(d, (total,), torch.int64).data_ptr() for d in range(G)]
         o_c, o_d, o_s = self.q_words, self.q_words + self.c_words, self.q_words + self.c_words + self.d_words
-        self.peer_queue_ptrs = np.array([b + self.rank * self.cap * 8 for b in base], dtype=np.uint64)
+        r = self.rank
+        self.peer_queue_ptrs = np.array([b + r * self.nsub * self.sub_cap * 8 for b in base], dtype=np.uint64)
         self.peer_count_ptrs = np.array([b + o_c * 8 for b in base], dtype=np.uint64)
-        self.peer_dir_ptrs = np.array([b + (o_d + self.rank * self.blocks) * 8 for b in base], dtype=np.uint64)
-        self.peer_slot_ptrs = np.array([b + (o_s + self.rank * self.rows_cap * 8) * 8 for b in base], dtype=np.uint64)
-        self.rx_queue, self.rx_count = self.rx[:self.q_words], self.rx[o_c:o_c + G]
+        self.peer_dir_ptrs = np.array([b + (o_d + r * self.blocks) * 8 for b in base], dtype=np.uint64)
+        self.peer_slot_ptrs = np.array([b + (o_s + r * self.nreg * self.sub_rows * 8) * 8 for b in base], dtype=np.uint64)
+        self.rx_queue, self.rx_count = self.rx[:self.q_words], self.rx[o_c:o_d]
         self.rx_dir, self.rx_slots = self.rx[o_d:o_s], self.rx[o_s:]
-        self.cursors = torch.zeros(2 * G, dtype=torch.int64, device=self.device)
+        self.cursors = torch.zeros(G * (self.nreg + self.nsub), dtype=torch.int32, device=self.device)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.shard = torch.zeros((max(self.per, 1), c1), dtype=torch.int32, device=self.device)
         self.lab = torch.zeros(max(self.per, 1), dtype=torch.int64, device=self.device)
         self.full = torch.zeros(max(self.per, 1) * G, dtype=torch.int64, device=self.device)
 
     def fuse_args(self):
-        """Keyword arguments of engine.fuse_project_vote_sparse that describe this exchange."""
-        return dict(peer_queue_ptrs=self.peer_queue_ptrs, segment_cap=self.cap, points_per_shard=self.per, cursors=self.cursors,
-                    overflow=self.overflow, peer_slot_ptrs=self.peer_slot_ptrs, peer_dir_ptrs=self.peer_dir_ptrs,
-                    slot_rows_cap=self.rows_cap)
+        """Keyword arguments of engine.fuse_project_vote_exchange that describe this exchange."""
+        return dict(nranks=self.world, points_per_shard=self.per, peer_slot_ptrs=self.peer_slot_ptrs,
+                    peer_dir_ptrs=self.peer_dir_ptrs, peer_queue_ptrs=self.peer_queue_ptrs, sub_rows=self.sub_rows,
+                    sub_cap=self.sub_cap, cursors=self.cursors, overflow=self.overflow)
 
-    def run(self, fuse_slots, nclasses_id, threshold=0.5, filter_classes=None) -> torch.Tensor:
-        """`fuse_slots(**self.fuse_args())` enqueues the slot-mode fused kernel over this rank's frames.  Returns labels
+    def run(self, fuse, nclasses_id, threshold=0.5, filter_classes=None) -> torch.Tensor:
+        """`fuse(**self.fuse_args())` enqueues the exchange-mode fused kernel over this rank's frames.  Returns labels
         [npoints]; `self.shard[:self.rows]` holds this rank's reduced votes."""
         eng = self.engine
         self.hdl.barrier(channel=0)
         self.cursors.zero_()
-        fuse_slots(**self.fuse_args())
-        eng.sparse_publish(self.cursors, self.peer_count_ptrs, self.rank, self.cap)
+        fuse(**self.fuse_args())
+        eng.exchange_publish(self.cursors, self.peer_count_ptrs, self.rank, self.sub_cap)
         self.hdl.barrier(channel=1)
         if self.rows > 0:
-            eng.slots_merge(self.rx_slots, self.rx_dir, self.world, self.rows_cap, self.per, self.rows, self.c1, nclasses_id,
-                            threshold, filter_classes, votes=self.shard, labels=self.lab)
-            eng.sparse_accumulate(self.rx_queue, self.rx_count, self.world, self.cap, self.shard, nrows=self.rows)
-            eng.sparse_relabel(self.rx_queue, self.rx_count, self.world, self.cap, self.shard, self.rows, nclasses_id, self.lab,
-                               threshold, filter_classes)
+            eng.exchange_merge(self.rx_slots, self.rx_dir, self.world, self.sub_rows, self.per, self.rows, self.c1, nclasses_id,
+                               threshold, filter_classes, votes=self.shard, labels=self.lab)
+            eng.exchange_queue_apply(self.rx_queue, self.rx_count, self.world, self.sub_cap, self.shard, self.rows, nclasses_id,
+                                     self.lab, threshold, filter_classes)
         _all_gather(self.full, self.lab, self.group if self.group is not dist.group.WORLD else None)
         return self.full[:self.npoints]
 
     def check_overflow(self):
-        """Host check (synchronises): raises if any queue segment filled up during the steps so far."""
+        """Host check (synchronises): raises if any sub-queue filled up during the steps so far."""
         t = self.overflow.clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if int(t.item()):
-            raise RuntimeError("slot vote exchange: a queue segment overflowed; enlarge segment_cap or use ShardedPipeline")
+            raise RuntimeError("vote exchange: a sub-queue overflowed; enlarge sub_cap or use ShardedPipeline")
 
 
 def fuse_sharded(fuse_chunk, resolve, npoints: int, nchunks: int, device, group=None):

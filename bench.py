@@ -197,9 +197,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--chunks", type=int, default=4, help="point chunks of the multi-GPU pipeline")
-    ap.add_argument("--exchange", default="slots", choices=["slots", "sparse", "dense"],
-                    help="multi-GPU vote exchange: slot records written by the fused kernel into the owner's memory (default), "
-                         "sparse (cell,count) appends over peer memory, or dense packed reduce-scatter")
+    ap.add_argument("--exchange", default="records", choices=["records", "dense"],
+                    help="multi-GPU vote exchange: slot records written by the fused kernel into the owner's memory over "
+                         "NVLink (default), or dense packed-uint16 reduce-scatter through NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -252,29 +252,19 @@ def main():
         fl.votes = votes
         return labels, (e0, e1), 3   # fuse_kernel + fixup_apply + fixup_labels
 
-    pipe = sparse = slotx = None
+    pipe = xchg = None
     if world > 1 and args.exchange == "dense":
         pipe = parallel.ShardedPipeline(N, C1, args.chunks, torch.device("cuda", local_rank))
-    elif world > 1 and args.exchange == "sparse":
-        sparse = parallel.SparseExchange(N, C1, torch.device("cuda", local_rank))
     elif world > 1:
-        slotx = parallel.SlotExchange(N, C1, torch.device("cuda", local_rank))
+        xchg = parallel.VoteExchange(N, C1, torch.device("cuda", local_rank))
 
-    def step_slots():
-        def fuse_slots(**xargs):
-            engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, radius=RADIUS, zmin=fl.zmin, zmax=fl.zmax,
-                                            stats=stats, **xargs)
+    def step_records():
+        def fuse(**xargs):
+            engine.fuse_project_vote_exchange(fl.points4, fl.table, depth, masks, C1, radius=RADIUS, zmin=fl.zmin, zmax=fl.zmax,
+                                              stats=stats, **xargs)
 
-        labels = slotx.run(fuse_slots, NCLASSES, THRESHOLD, None)
-        return labels, None, 6   # fuse_kernel, fixup_apply, publish, slot_merge, sparse_accumulate, sparse_relabel
-
-    def step_sparse():
-        def fuse_sparse(qptrs, cap, per, cursors, overflow):
-            engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, qptrs, cap, per, cursors, overflow, RADIUS,
-                                            fl.zmin, fl.zmax, stats=stats)
-
-        labels = sparse.run(fuse_sparse, lambda v, out: engine.resolve_labels(v, NCLASSES, THRESHOLD, None, out=out))
-        return labels, None, 5   # fuse_kernel, fixup_apply, publish, accumulate, resolve
+        labels = xchg.run(fuse, NCLASSES, THRESHOLD, None)
+        return labels, None, 6   # fuse_kernel, fixup_apply, publish, slot_merge, queue_accumulate, queue_relabel
 
     def step_multi():
         launches = [0]
@@ -291,7 +281,7 @@ def main():
         labels = pipe.run(fuse_into, resolve)
         return labels, None, launches[0]
 
-    step = step_single if world == 1 else (step_multi if pipe is not None else (step_sparse if sparse is not None else step_slots))
+    step = step_single if world == 1 else (step_multi if pipe is not None else step_records)
     for _ in range(args.warmup):
         labels, _, _ = step()
     torch.cuda.synchronize()
@@ -399,10 +389,8 @@ def main():
                        "nclasses": NCLASSES, "depth": "uint16 mm", "radius": RADIUS, "cache": "inputs larger than L2 "
                        "(depth+masks+votes = %.1f GB per GPU)" % ((F * H * W * 3 + 4 * N * C1) / 1e9),
                        "parallelism": "single GPU" if world == 1 else f"frames sharded over {world} GPUs, "
-                       + ("slot-record vote exchange written by the fused kernel into the owner's memory over NVLink, "
-                          "owner-side merge into the dense shard + labels, all-gather of labels" if args.exchange == "slots" else
-                          "sparse (cell,count) vote exchange written by the fused kernel into peer memory over NVLink, "
-                          "owner-side scatter-add + resolve, all-gather of labels" if args.exchange == "sparse" else
+                       + ("vote exchange fused into the kernel: slot records written into the owner's memory over NVLink, "
+                          "owner-side merge into the dense shard + labels, all-gather of labels" if args.exchange == "records" else
                           f"{args.chunks}-chunk pipeline: fuse -> NCCL reduce-scatter of packed uint16 votes -> resolve -> "
                           "all-gather")},
             "roofline": roof, "cpu_baseline": cpu_b, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -410,10 +398,8 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
-        if sparse is not None:
-            sparse.check_overflow()
-        if slotx is not None:
-            slotx.check_overflow()
+        if xchg is not None:
+            xchg.check_overflow()
         dist.destroy_process_group()
 
 

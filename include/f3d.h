@@ -101,44 +101,44 @@ int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_t
  * Reference semantics: votes are integer sums over frames (VotingSegmentation.vote, segUtils/voting.py:89-98), so frames
  * can be sharded over ranks and the partial votes added in any order -- bit-exact for every rank count.
  * Votes are ~95 % zeros, so no dense partial vote tensor is written or reduce-scattered.  Rank d owns the points
- * [d * points_per_shard, (d+1) * points_per_shard).  The fused kernel of every source rank writes, straight into the
- * owner's memory through peer-mapped pointers:
- *   - slot records (when h_peer_slots != NULL; points_per_shard must be a multiple of 256): per (source, 32-point block)
- *     L rows of 64 B; row j holds, for each of the block's 32 points, its j-th class in order of first appearance as
- *     uint16 (class | count << 8, 0 = none); L = the longest list in the block.  The block's warp reserves the rows with
- *     one atomic on cursors[nranks + d] and writes a directory entry {uint32 row offset, uint32 L}.
- *     h_peer_slots[d] / h_peer_dirs[d] = device pointers (peer mapped) to THIS rank's record region (slot_rows_cap rows)
- *     and directory [points_per_shard / 32] inside rank d's receive buffer.  Every directory entry is rewritten on every
- *     call (no clearing needed); a block that finds the region full goes to the queue instead;
- *   - a (cell, count) queue for everything else (all votes when h_peer_slots == NULL; otherwise points with more than
- *     a full record region, later flushes of a tile with more than 235 candidate frames, deferred fp64 votes):
- *     h_peer_queues[d] = peer pointer to THIS rank's segment of `segment_cap` uint64 entries
- *     (cell = local_point * C1 + class in the low half, count in the high half) inside rank d's queue;
- *     cursors [2 * nranks] uint64 local cursors (queue entries, then record rows; the caller zeroes them before the
- *     call); *overflow is set to 1 when a
- *     segment filled up (entries dropped: the caller must check it and enlarge the segment or fall back).
- * f3d_sparse_publish then stores the cursors into every destination's count table (h_peer_counts[d] = peer pointer to
- * rank d's uint64[nranks] table; slot [rank] is written).  After a cross-rank barrier the owner runs
- *   f3d_slots_merge      (records of all sources -> dense int32 shard rows [nrows, C1] written once + labels), then
- *   f3d_sparse_accumulate (queue entries scatter-added into the shard; without slot records the caller zeroes it first)
- *   f3d_sparse_relabel    (labels of the points the queue entries touched, VotingSegmentation.segment voting.py:106-137). */
-int f3d_fuse_project_vote_sparse(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
-                                 int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
-                                 int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                                 int32_t C1, const uint64_t* h_peer_queues, const uint64_t* h_peer_slots,
-                                 const uint64_t* h_peer_dirs, int64_t slot_rows_cap, int32_t nranks, int64_t segment_cap,
-                                 int64_t points_per_shard, uint64_t* cursors, uint32_t* overflow, void* workspace,
-                                 int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
-int f3d_sparse_publish(const uint64_t* cursors, const uint64_t* h_peer_counts, int32_t rank, int32_t nranks,
-                       int64_t segment_cap, void* stream);
-int f3d_slots_merge(const uint16_t* slots, const void* dir, int32_t nranks, int64_t slot_rows_cap, int64_t points_per_shard,
-                    int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter, int32_t nfilter,
-                    int32_t nclasses_id, int32_t* votes, int64_t* labels, void* stream);
-int f3d_sparse_accumulate(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
-                          int32_t* votes, int64_t nrows, int32_t C1, void* stream);
-int f3d_sparse_relabel(const uint64_t* rx, const uint64_t* rx_count, int32_t nranks, int64_t segment_cap,
-                       const int32_t* votes, int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter,
-                       int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream);
+ * [d * points_per_shard, (d+1) * points_per_shard), points_per_shard a multiple of 256.  f3d_exchange_constants returns
+ * {NREG, NSUB, NSUB_FIX}.  The fused kernel of every source rank writes, straight into the owner's memory through
+ * peer-mapped pointers:
+ *   - slot records: per (source, 32-point block) L rows of 64 B; row j holds, for each of the block's 32 points, its
+ *     j-th class in order of first appearance as uint16 (class | count << 8, 0 = none); L = the longest list in the
+ *     block.  The block's warp reserves the rows in one of NREG sub-regions (sub_rows rows each) of its record region
+ *     and writes a directory entry {uint32 row offset, uint32 L}.
+ *     h_peer_slots[d] / h_peer_dirs[d] = device pointers (peer mapped) to THIS rank's record region
+ *     [NREG * sub_rows rows] and directory [points_per_shard / 32] inside rank d's receive buffer.  Every directory
+ *     entry is rewritten on every call (no clearing needed);
+ *   - (cell, count) entries for everything else (a full sub-region, later flushes of a tile with more than 235
+ *     candidate frames, the deferred fp64 votes): h_peer_queues[d] = peer pointer to THIS rank's queue
+ *     [NSUB][sub_cap] uint64 (cell = local_point * C1 + class in the low half, count in the high half) inside rank d's
+ *     buffer; the fix-up kernel's block b owns sub-queue b < NSUB_FIX, the rest take spills.
+ * cursors: local uint32 [nranks * (NREG + NSUB)] (row cursors, then queue cursors), zeroed by the caller before the call;
+ * *overflow is set to 1 when a sub-queue filled up (entries dropped: the caller must check it and enlarge sub_cap or
+ * fall back to the dense exchange).  The deferred-fp64 workspace (f3d_fuse_workspace_bytes) is mandatory here.
+ * f3d_exchange_publish then copies the queue cursors into every destination's count table (h_peer_counts[d] = peer
+ * pointer to rank d's uint32 [nranks][NSUB] table; row [rank] is written).  After a cross-rank barrier the owner runs
+ *   f3d_exchange_merge       (records of all sources -> dense int32 shard rows [nrows, C1], every cell written once, and
+ *                             labels: VotingSegmentation.segment, voting.py:106-137), then
+ *   f3d_exchange_queue_apply (queue entries scatter-added into the shard, labels of the touched points re-resolved). */
+int f3d_exchange_constants(int32_t* out3);
+int f3d_fuse_project_vote_exchange(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
+                                   int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
+                                   int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
+                                   int32_t C1, int32_t nranks, int64_t points_per_shard, const uint64_t* h_peer_slots,
+                                   const uint64_t* h_peer_dirs, const uint64_t* h_peer_queues, int64_t sub_rows,
+                                   int64_t sub_cap, uint32_t* cursors, uint32_t* overflow, void* workspace,
+                                   int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
+int f3d_exchange_publish(const uint32_t* cursors, const uint64_t* h_peer_counts, int32_t rank, int32_t nranks,
+                         int64_t sub_cap, void* stream);
+int f3d_exchange_merge(const uint16_t* slots, const void* dir, int32_t nranks, int64_t sub_rows, int64_t points_per_shard,
+                       int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter, int32_t nfilter,
+                       int32_t nclasses_id, int32_t* votes, int64_t* labels, void* stream);
+int f3d_exchange_queue_apply(const uint64_t* queue, const uint32_t* counts, int32_t nranks, int64_t sub_cap, int32_t* votes,
+                             int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter, int32_t nfilter,
+                             int32_t nclasses_id, int64_t* labels, void* stream);
 
 /* f3d_fuse_project_vote with VotingSegmentation.segment (segUtils/voting.py:106-137, see f3d_resolve_labels) fused
  * into the epilogue: labels [N] int64 are resolved straight from the on-chip histograms, so the vote tensor is

@@ -381,51 +381,46 @@ def test_uint16_histogram_build_matches(engine, scenes, monkeypatch):
 # multi-GPU vote exchange, emulated on one device: every "rank" fuses its frame shard into the owners' receive buffers
 # ---------------------------------------------------------------------------------------------------------------------
 
-def _emulated_exchange(engine, s, world, use_slots, cap=None, nclasses_id=133, thr=0.5, fc=None, rows_cap=None):
+def _emulated_exchange(engine, s, world, nclasses_id=133, thr=0.5, fc=None, sub_rows=None, sub_cap=None):
     parallel = importlib.import_module(PKG_NAME + ".parallel")
     N, C1, F = len(s["points"]), 134, len(s["t"])
     tab = engine.FrameTable(s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["zmax"])
     p4 = engine.pack_points(s["points"])
     d, m = dev(s["depths"]), dev(s["masks"])
+    nreg, nsub, nfix = engine.exchange_constants()
     per = parallel.shard_points(N, world)
-    cap = cap or max(1 << 16, 40 * per)
-    # owner o: queue [world][cap] + counts [world] + directory [world][per/32] + record regions [world][rows_cap] x 64 B
     blocks = per // 32
-    rows_cap = rows_cap or blocks * 40
-    queues = [torch.zeros(world * cap, dtype=torch.int64, device="cuda") for _ in range(world)]
-    counts = [torch.zeros(world, dtype=torch.int64, device="cuda") for _ in range(world)]
+    sub_rows = sub_rows or max(64, -(-blocks * 40 // nreg))
+    sub_cap = sub_cap or 256
+    # owner o: queue [world][nsub][sub_cap] + counts [world][nsub] + directory [world][blocks] + records [world][nreg*sub_rows] x 64 B
+    queues = [torch.zeros(world * nsub * sub_cap, dtype=torch.int64, device="cuda") for _ in range(world)]
+    counts = [torch.zeros(world * nsub, dtype=torch.int32, device="cuda") for _ in range(world)]
     dirs = [torch.full((world * blocks,), -1, dtype=torch.int64, device="cuda") for _ in range(world)]        # garbage: must be overwritten
-    slots = [torch.full((world * rows_cap * 32,), 0x7b7b, dtype=torch.uint16, device="cuda") for _ in range(world)]
+    slots = [torch.full((world * nreg * sub_rows * 32,), 0x7b7b, dtype=torch.uint16, device="cuda") for _ in range(world)]
     overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
     st = engine.new_stats()
     nrec = 0
     for r in range(world):                                              # source ranks, one after the other
         fb, fe = parallel.frame_shard(F, r, world)
-        cursors = torch.zeros(2 * world, dtype=torch.int64, device="cuda")
-        qptrs = np.array([queues[o].data_ptr() + r * cap * 8 for o in range(world)], dtype=np.uint64)
-        sptrs = np.array([slots[o].data_ptr() + r * rows_cap * 64 for o in range(world)], dtype=np.uint64) if use_slots else None
-        dptrs = np.array([dirs[o].data_ptr() + r * blocks * 8 for o in range(world)], dtype=np.uint64) if use_slots else None
-        engine.fuse_project_vote_sparse(p4, tab, d[fb:fe], m[fb:fe], C1, qptrs, cap, per, cursors, overflow, 0.05, 0.1,
-                                        s["zmax"], stats=st, frame_begin=fb, frame_end=fe, peer_slot_ptrs=sptrs,
-                                        peer_dir_ptrs=dptrs, slot_rows_cap=rows_cap)
+        cursors = torch.zeros(world * (nreg + nsub), dtype=torch.int32, device="cuda")
+        qptrs = np.array([queues[o].data_ptr() + r * nsub * sub_cap * 8 for o in range(world)], dtype=np.uint64)
+        sptrs = np.array([slots[o].data_ptr() + r * nreg * sub_rows * 64 for o in range(world)], dtype=np.uint64)
+        dptrs = np.array([dirs[o].data_ptr() + r * blocks * 8 for o in range(world)], dtype=np.uint64)
+        engine.fuse_project_vote_exchange(p4, tab, d[fb:fe], m[fb:fe], C1, world, per, sptrs, dptrs, qptrs, sub_rows, sub_cap, cursors,
+                                          overflow, 0.05, 0.1, s["zmax"], stats=st, frame_begin=fb, frame_end=fe)
         cptrs = np.array([counts[o].data_ptr() for o in range(world)], dtype=np.uint64)
-        engine.sparse_publish(cursors, cptrs, r, cap)
-        nrec += int(cursors[world:].sum())
+        engine.exchange_publish(cursors, cptrs, r, sub_cap)
+        nrec += int(cursors[:world * nreg].sum())
     torch.cuda.synchronize()
     assert int(overflow.item()) == 0
     votes, labels = [], []
     for o in range(world):                                              # owner ranks
         rows = max(0, min(per, N - o * per))
-        shard = torch.full((per, C1), 77, dtype=torch.int32, device="cuda") if use_slots else torch.zeros((per, C1), dtype=torch.int32, device="cuda")
+        shard = torch.full((per, C1), 77, dtype=torch.int32, device="cuda")       # garbage: every cell must be written
         lab = torch.zeros(per, dtype=torch.int64, device="cuda")
         if rows:
-            if use_slots:
-                engine.slots_merge(slots[o], dirs[o], world, rows_cap, per, rows, C1, nclasses_id, thr, fc, votes=shard, labels=lab)
-            engine.sparse_accumulate(queues[o], counts[o], world, cap, shard, nrows=rows)
-            if use_slots:
-                engine.sparse_relabel(queues[o], counts[o], world, cap, shard, rows, nclasses_id, lab, thr, fc)
-            else:
-                engine.resolve_labels(shard[:rows], nclasses_id, thr, fc, out=lab[:rows])
+            engine.exchange_merge(slots[o], dirs[o], world, sub_rows, per, rows, C1, nclasses_id, thr, fc, votes=shard, labels=lab)
+            engine.exchange_queue_apply(queues[o], counts[o], world, sub_cap, shard, rows, nclasses_id, lab, thr, fc)
         votes.append(shard[:rows])
         labels.append(lab[:rows])
     torch.cuda.synchronize()
@@ -433,25 +428,23 @@ def _emulated_exchange(engine, s, world, use_slots, cap=None, nclasses_id=133, t
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
-@pytest.mark.parametrize("use_slots", [True, False])
-def test_vote_exchange_emulated_ranks(engine, scenes, world, use_slots):
+def test_vote_exchange_emulated_ranks(engine, scenes, world):
     s = small_scene(scenes, orc, npoints=20011, nframes=9, width=320, height=240, seed=71, block=16)
     ov = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0, 0.05,
                                0.1, 4.0, 4.0)
     for thr, fc in [(0.5, None), (0.3, [1, 0, 5])]:
-        votes, labels, st, nq, nrec = _emulated_exchange(engine, s, world, use_slots, thr=thr, fc=fc)
+        votes, labels, st, nq, nrec = _emulated_exchange(engine, s, world, thr=thr, fc=fc)
         assert np.array_equal(votes, ov)
         assert np.array_equal(labels, orc.segment(ov, 133, thr, fc))
         assert st["seen"] == int(ov.sum())
-        if use_slots:
-            assert sum(nq) < 0.02 * (ov > 0).sum() and nrec > 0          # only deferred fp64 votes use the queue
+        assert sum(nq) < 0.02 * (ov > 0).sum() and nrec > 0             # only deferred fp64 votes use the queue
 
 
 def test_vote_exchange_spills_and_flushes(engine, scenes):
     """300 frames (3 poses x 100) with a different random mask each: points collect far more than 32 distinct classes
     from one source (long lists: several staging chunks, re-read from the histogram row) and tiles sweep more than 235
     candidate frames (mid-sweep flush: the first flush writes the record, later ones go to the queue).  A second pass
-    with a tiny record region forces the region-full fallback to the queue."""
+    with tiny record sub-regions forces the region-full fallback to the queue."""
     rep = 100
     base = small_scene(scenes, orc, npoints=5003, nframes=3, width=96, height=64, seed=73, block=16)
     F = 3 * rep
@@ -460,7 +453,7 @@ def test_vote_exchange_spills_and_flushes(engine, scenes):
     ov = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0, 0.05,
                                0.1, 4.0, 4.0)
     assert ((ov > 0).sum(axis=1) > 32).sum() > 100                      # many points have long lists
-    for world, rows_cap in ((1, 1 << 16), (2, 1 << 16), (2, 64)):
-        votes, labels, _, nq, nrec = _emulated_exchange(engine, s, world, True, cap=1 << 21, rows_cap=rows_cap)
+    for world, sub_rows in ((1, 256), (2, 256), (2, 2)):
+        votes, labels, _, nq, nrec = _emulated_exchange(engine, s, world, sub_rows=sub_rows, sub_cap=1 << 14)
         assert np.array_equal(votes, ov) and sum(nq) > 0
         assert np.array_equal(labels, orc.segment(ov, 133, 0.5, None))

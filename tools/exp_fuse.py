@@ -60,15 +60,25 @@ torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.
 e0.record()
 for _ in range(5): votes.zero_()
 e1.record(); torch.cuda.synchronize(); print(f"{'torch zero_ of votes (5.36 GB)':34s} {e0.elapsed_time(e1)/5:8.3f} ms")
-# sparse-emit mode with a purely local queue (G = 1): isolates the cost of the emission logic from NVLink stores
-cap = 80_000_000
-queue = torch.empty(cap, dtype=torch.int64, device="cuda"); cursors = torch.zeros(1, dtype=torch.int64, device="cuda"); ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
-qptr = np.array([queue.data_ptr()], dtype=np.uint64)
-def sparse_local():
+# exchange mode with purely local buffers (G = 1): isolates the cost of the record logic from NVLink stores
+parallel = importlib.import_module(PKG + ".parallel")
+nreg, nsub, _ = engine.exchange_constants()
+per = parallel.shard_points(N, 1); sub_rows = max(256, -(-(per // 32 * 40) // nreg)); sub_cap = max(512, -(-per // nsub))
+queue = torch.empty(nsub * sub_cap, dtype=torch.int64, device="cuda"); counts = torch.zeros(nsub, dtype=torch.int32, device="cuda")
+cursors = torch.zeros(nreg + nsub, dtype=torch.int32, device="cuda"); ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
+slots = torch.empty(nreg * sub_rows * 32, dtype=torch.uint16, device="cuda"); dirs = torch.empty(per // 32, dtype=torch.int64, device="cuda")
+P = lambda t_: np.array([t_.data_ptr()], dtype=np.uint64)
+def timed(fn, reps=5):
+    for _ in range(2): fn()
+    torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / reps
+def records_local():
     cursors.zero_()
-    engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, qptr, cap, N, cursors, ovf, 0.05, 0.1, spec.zmax)
-for _ in range(2): sparse_local()
-torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(5): sparse_local()
-e1.record(); torch.cuda.synchronize(); print(f"{'sparse emit, local queue (G=1)':34s} {e0.elapsed_time(e1)/5:8.3f} ms  entries={int(cursors.item())} overflow={int(ovf.item())}")
+    engine.fuse_project_vote_exchange(fl.points4, fl.table, depth, masks, C1, 1, per, P(slots), P(dirs), P(queue), sub_rows, sub_cap, cursors, ovf, 0.05, 0.1, spec.zmax)
+print(f"{'exchange records, local (G=1)':34s} {timed(records_local):8.3f} ms  rows={int(cursors[:nreg].sum())} queue={int(cursors[nreg:].sum())} overflow={int(ovf.item())}")
+engine.exchange_publish(cursors, P(counts), 0, sub_cap)
+shard = torch.empty((per, C1), dtype=torch.int32, device="cuda"); lab = torch.empty(per, dtype=torch.int64, device="cuda")
+print(f"{'exchange merge (all points)':34s} {timed(lambda: engine.exchange_merge(slots, dirs, 1, sub_rows, per, N, C1, 133, 0.5, None, votes=shard, labels=lab)):8.3f} ms")
+print(f"{'exchange queue apply':34s} {timed(lambda: engine.exchange_queue_apply(queue, counts, 1, sub_cap, shard, N, 133, lab, 0.5, None)):8.3f} ms")

@@ -17,7 +17,7 @@ spec = scenes.scaled_spec("C2", nframes=base.nframes * world)
 lo, hi = parallel.frame_shard(spec.nframes, rank, world)
 fl, pts, K, wxyz, t, depth, masks = bench.build_scene(scenes, engine, fused, spec, lo, hi, torch)
 N, C1 = fl.N, 134
-what = set(sys.argv[1:]) or {"slots", "sparse", "dense"}
+what = set(sys.argv[1:]) or {"records", "dense"}
 def timeit(fn, reps=5):
     for _ in range(2): fn()
     torch.cuda.synchronize(); dist.barrier()
@@ -31,30 +31,25 @@ res, labels = {}, {}
 votes = torch.empty((N, C1), dtype=torch.int32, device="cuda")
 res["single-GPU style fuse (dense votes)"] = timeit(lambda: engine.fuse_project_vote(fl.points4, fl.table, depth, masks, C1, 0.05, 0.1, spec.zmax, votes=votes))
 del votes
-if "slots" in what:
-    sx = parallel.SlotExchange(N, C1, torch.device("cuda", lr))
-    def sx_fuse(**xa): engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, radius=0.05, zmin=0.1, zmax=spec.zmax, **xa)
+if "records" in what:
+    sx = parallel.VoteExchange(N, C1, torch.device("cuda", lr))
+    def sx_fuse(**xa): engine.fuse_project_vote_exchange(fl.points4, fl.table, depth, masks, C1, radius=0.05, zmin=0.1, zmax=spec.zmax, **xa)
     def sx_fuse_only():
         sx.cursors.zero_(); sx_fuse(**sx.fuse_args())
-    res["slots: fuse + remote records"] = timeit(sx_fuse_only)
-    engine.sparse_publish(sx.cursors, sx.peer_count_ptrs, rank, sx.cap); torch.cuda.synchronize(); dist.barrier()
-    res["slots: merge (shard + labels)"] = timeit(lambda: engine.slots_merge(sx.rx_slots, sx.rx_dir, world, sx.rows_cap, sx.per, sx.rows, C1, 133, 0.5, None, votes=sx.shard, labels=sx.lab))
-    res["slots: queue accumulate"] = timeit(lambda: engine.sparse_accumulate(sx.rx_queue, sx.rx_count, world, sx.cap, sx.shard, nrows=sx.rows))
-    res["slots: queue relabel"] = timeit(lambda: engine.sparse_relabel(sx.rx_queue, sx.rx_count, world, sx.cap, sx.shard, sx.rows, 133, sx.lab, 0.5, None))
-    res["slots: 2 barriers"] = timeit(lambda: (sx.hdl.barrier(channel=0), sx.hdl.barrier(channel=1)))
-    res["slots: all-gather labels"] = timeit(lambda: dist.all_gather_into_tensor(sx.full, sx.lab))
-    res["slots: whole step"] = timeit(lambda: sx.run(sx_fuse, 133, 0.5, None), reps=10)
-    labels["slots"] = sx.run(sx_fuse, 133, 0.5, None).clone()
-    if rank == 0: print("slots: cursors [queue x G, record rows x G]", sx.cursors.tolist(), "per", sx.per, "queue cap", sx.cap, "rows cap", sx.rows_cap, flush=True)
+    res["records: fuse + remote records"] = timeit(sx_fuse_only)
+    engine.exchange_publish(sx.cursors, sx.peer_count_ptrs, rank, sx.sub_cap); torch.cuda.synchronize(); dist.barrier()
+    res["records: merge (shard + labels)"] = timeit(lambda: engine.exchange_merge(sx.rx_slots, sx.rx_dir, world, sx.sub_rows, sx.per, sx.rows, C1, 133, 0.5, None, votes=sx.shard, labels=sx.lab))
+    res["records: queue apply"] = timeit(lambda: engine.exchange_queue_apply(sx.rx_queue, sx.rx_count, world, sx.sub_cap, sx.shard, sx.rows, 133, sx.lab, 0.5, None))
+    res["records: 2 barriers"] = timeit(lambda: (sx.hdl.barrier(channel=0), sx.hdl.barrier(channel=1)))
+    res["records: all-gather labels"] = timeit(lambda: dist.all_gather_into_tensor(sx.full, sx.lab))
+    res["records: whole step"] = timeit(lambda: sx.run(sx_fuse, 133, 0.5, None), reps=10)
+    labels["records"] = sx.run(sx_fuse, 133, 0.5, None).clone()
+    cur = sx.cursors.view(2 if False else 1, -1)[0]
+    if rank == 0:
+        rows = sx.cursors[:world * sx.nreg].view(world, sx.nreg).sum(dim=1).tolist(); q = sx.cursors[world * sx.nreg:].view(world, sx.nsub).sum(dim=1).tolist()
+        print("records: rows per destination", rows, "max sub-region fill", int(sx.cursors[:world * sx.nreg].max()), "of", sx.sub_rows,
+              "; queue entries per destination", q, "max sub-queue fill", int(sx.cursors[world * sx.nreg:].max()), "of", sx.sub_cap, flush=True)
     sx.check_overflow()
-if "sparse" in what:
-    sp = parallel.SparseExchange(N, C1, torch.device("cuda", lr))
-    def sparse_step():
-        return sp.run(lambda q, cap, per, cur, ovf: engine.fuse_project_vote_sparse(fl.points4, fl.table, depth, masks, C1, q, cap, per, cur, ovf, 0.05, 0.1, spec.zmax),
-                      lambda v, out: engine.resolve_labels(v, 133, 0.5, None, out=out))
-    res["sparse: whole step"] = timeit(sparse_step)
-    labels["sparse"] = sparse_step().clone()
-    sp.check_overflow()
 if "dense" in what:
     pipe = parallel.ShardedPipeline(N, C1, 4, torch.device("cuda", lr))
     def dense_step():

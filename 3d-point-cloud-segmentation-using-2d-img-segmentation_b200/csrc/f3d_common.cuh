@@ -157,6 +157,7 @@ int f3d_build_resolve(int C1, double threshold, const int32_t* h_filter, int nfi
 #define F3D_XCH_NREG 1024      // record sub-regions per (source, owner): row cursors are spread so warps never queue on one
 #define F3D_XCH_NSUB 2048      // (cell, count) sub-queues per (source, owner)
 #define F3D_XCH_NSUB_FIX 1776  // the first sub-queues belong to the fix-up kernel's blocks (one each, no global atomics)
+#define F3D_XCH_NLEVEL 4       // records per (source, block): one per flush of the byte histogram (235 candidate frames each)
 
 // Eight lanes (sub = 0..7) stream one int32 vote row: all loads of a lane are issued before any is used (8-byte loads
 // when the row allows it), partial (total, best, first position) per lane; the caller combines with three xor-shuffles.

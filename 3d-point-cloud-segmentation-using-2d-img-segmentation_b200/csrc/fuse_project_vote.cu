@@ -51,7 +51,7 @@
 #ifndef FUSE_MINB8
 #define FUSE_MINB8 3      // resident CTAs per SM of the byte-histogram build (80 registers; 64 spills and is slower)
 #endif
-#define FUSE_RED_WORDS 96 // small per-CTA scalars (see the layout comment in the kernel)
+#define FUSE_RED_WORDS 160 // small per-CTA scalars (see the layout comment in the kernel)
 #define FUSE_QWARP 20     // deferred entries per warp (12 B each); overflow falls back to inline evaluation
 #define FUSE_LIMIT8 (255 - FUSE_QWARP)   // the warp's deferred pass can add up to FUSE_QWARP votes to one cell at the end
 
@@ -93,14 +93,16 @@ struct FuseParams {
     // block's points as uint16 class | count << 8 (0 = none), L = the longest list in the block.  The block's warp reserves
     // L rows in one of F3D_XCH_NREG sub-regions of this rank's record region at the owner (an atomic on a local cursor
     // that only ~300 warps share -- a single cursor serialises at ~10 ns per warp in L2 and binds the whole kernel),
-    // writes them and the directory entry {row offset, L} straight into the owner's memory over NVLink.
-    // What cannot go into a record (region full, later flushes of a tile with more than FUSE_LIMIT8 candidate frames,
-    // and the deferred fp64 votes of the fix-up kernel) is appended as (cell, count) to one of F3D_XCH_NSUB sub-queues:
+    // writes them and the directory entry {row offset, L} straight into the owner's memory over NVLink.  A tile with more
+    // than FUSE_LIMIT8 candidate frames flushes its byte histogram several times: every flush writes its own record, the
+    // directory holds F3D_XCH_NLEVEL of them per block.
+    // What cannot go into a record (sub-region full, more than F3D_XCH_NLEVEL flushes, and the deferred fp64 votes of the
+    // fix-up kernel) is appended as (cell, count) to one of F3D_XCH_NSUB sub-queues:
     // fix-up block b owns sub-queue b (no global atomics at all), spills take the sub-queues above F3D_XCH_NSUB_FIX.
     int xg_G;                                  // 0 = off
     long long xg_per;                          // points per owner shard: owner(p) = p / xg_per
     uint16_t* xg_slots[F3D_MAX_RANKS];         // this rank's record region inside rank d's receive buffer (peer pointers)
-    uint2* xg_dir[F3D_MAX_RANKS];              // ... its directory [xg_per / 32]
+    uint2* xg_dir[F3D_MAX_RANKS];              // ... its directory [xg_per / 32][F3D_XCH_NLEVEL] of {row offset, L}
     unsigned long long* xg_queue[F3D_MAX_RANKS];   // ... its (cell, count) queue [F3D_XCH_NSUB][xg_subcap]
     unsigned* xg_rowcur;                       // local [G][F3D_XCH_NREG] row cursors (caller zeroes them per call)
     unsigned* xg_qcur;                         // local [G][F3D_XCH_NSUB] queue cursors (ditto); published to the owners afterwards
@@ -366,7 +368,7 @@ template <> struct HistCell<1> { typedef uint8_t T; };
 // first flush of a non-accumulating launch overwrites (every cell written exactly once, 16-byte stores); later
 // flushes add their non-zero cells.  Rows are warp-private, so no CTA barrier and no atomics are involved.
 __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int warp, int lane, int64_t tile_base, bool add,
-                                       bool rezero, Tally& T, uint16_t* stg, bool first, bool dirty) {
+                                       bool rezero, Tally& T, uint16_t* stg, int level, bool dirty, uint2* dcache) {
     const int row0 = warp * 32;
     const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
     const int total = nrows * P.C1;
@@ -378,9 +380,10 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
         const long long p0 = tile_base + row0;
         const int d = (int)(p0 / P.xg_per);
         const bool live = lane < nrows;
-        // the record is written by the first flush only; later flushes and rows another lane's deferred pass touched
-        // go cell by cell to the owner's queue
-        bool spill = live && (!first || dirty);
+        // flush number `level` of this warp writes directory level `level`; flushes beyond F3D_XCH_NLEVEL and rows another
+        // lane's deferred pass touched go cell by cell to the owner's queue
+        const bool rec = level < F3D_XCH_NLEVEL;
+        bool spill = live && (!rec || dirty);
         const int C1 = P.C1;
         const uint8_t* __restrict__ row = h8 + lane * C1;
         int n = (live && !spill) ? min(T.nlist, C1) : 0;      // classes of this lane's point
@@ -388,7 +391,7 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
 #pragma unroll
         for (int s2 = 16; s2 > 0; s2 >>= 1) L = max(L, __shfl_xor_sync(0xffffffffu, L, s2));
         unsigned off = 0;
-        if (first) {
+        if (rec) {
             const unsigned reg = (blockIdx.x * (FUSE_BLOCK / 32) + warp) & (F3D_XCH_NREG - 1);
             if (lane == 0 && L > 0) off = atomicAdd(P.xg_rowcur + d * F3D_XCH_NREG + reg, (unsigned)L);
             off = __shfl_sync(0xffffffffu, off, 0);
@@ -398,7 +401,13 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
                 L = 0;
             }
             off += reg * P.xg_subrows;
-            if (lane == 0 && nrows > 0) P.xg_dir[d][(p0 - (long long)d * P.xg_per) >> 5] = make_uint2(off, (unsigned)L);
+            if (lane == 0) dcache[level] = make_uint2(off, (unsigned)L);
+        }
+        if (!rezero && nrows > 0) {
+            // last flush of the tile: publish all directory levels of the block at once (unused levels are zero)
+            __syncwarp();
+            if (lane < F3D_XCH_NLEVEL)
+                P.xg_dir[d][((p0 - (long long)d * P.xg_per) >> 5) * F3D_XCH_NLEVEL + lane] = dcache[lane];
         }
         uint4* st4 = reinterpret_cast<uint4*>(stg);
         uint4* __restrict__ dst = reinterpret_cast<uint4*>(P.xg_slots[d] + (size_t)off * 32);
@@ -500,7 +509,8 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     constexpr int NB = (MODE == MODE_VOTE && HB == 1) ? FUSE_NB8 : FUSE_NB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [2 x stage FrameFast x FUSE_STAGE][cand u16 x FUSE_FCHUNK][cmask u8 x FUSE_FCHUNK]
-    //         [red: 48 floats (8 warp boxes) | ncand | 2 mbarriers | 8 nq | 8 dirty | tile box (7) | 8 stat counters]
+    //         [red: 48 floats (8 warp boxes) | ncand | 2 mbarriers | 8 nq | 8 dirty | tile box (7) | 8 stat counters | pad |
+    //               8 warps x F3D_XCH_NLEVEL directory entries]
     //         [deferred queues: 8 warps x FUSE_QWARP][hist]
     float4* stage = reinterpret_cast<float4*>(smem_raw);
     uint16_t* cand = reinterpret_cast<uint16_t*>(smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast));
@@ -512,6 +522,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     unsigned* dirty_s = reinterpret_cast<unsigned*>(red + 64);
     float* tbox = red + 72;                                   // tile box lo[3], hi[3], magnitude
     unsigned* stat_s = reinterpret_cast<unsigned*>(red + 80); // CTA totals of the statistics, flushed once at the end
+    uint2* dcache_all = reinterpret_cast<uint2*>(red + 96);   // exchange mode: this warp's directory levels {row offset, L}
     Deferred* queue_all = reinterpret_cast<Deferred*>(red + FUSE_RED_WORDS);
     CellT* hist = reinterpret_cast<CellT*>(reinterpret_cast<unsigned char*>(queue_all) + (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred));
     const int RS = P.RS;
@@ -541,6 +552,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         dirty_s[warp] = 0u;
         stat_s[warp] = 0u;
     }
+    if (lane < F3D_XCH_NLEVEL) dcache_all[warp * F3D_XCH_NLEVEL + lane] = make_uint2(0u, 0u);
     if (MODE == MODE_VOTE) {
         uint4* h128 = reinterpret_cast<uint4*>(hist);
         const int n128 = (FUSE_BLOCK * RS * (int)sizeof(CellT) + 15) / 16;
@@ -685,7 +697,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
                 if (since_flush + nw > FUSE_LIMIT8) {
                     __syncwarp();
                     flush8(P, reinterpret_cast<uint8_t*>(hist), warp, lane, tile_base, nflush > 0 || P.accumulate, true, T,
-                           stg_all + warp * (FUSE_STG_ROWS * 32), nflush == 0, false);
+                           stg_all + warp * (FUSE_STG_ROWS * 32), nflush, false, dcache_all + warp * F3D_XCH_NLEVEL);
                     ++nflush;
                     since_flush = 0;
                 }
@@ -848,8 +860,8 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     // ---- epilogue (warp-private rows): histogram -> HBM, written once with 16-byte stores; fused label resolve
     if constexpr (MODE == MODE_VOTE && HB == 1) {
         uint8_t* hist8 = reinterpret_cast<uint8_t*>(hist);
-        flush8(P, hist8, warp, lane, tile_base, nflush > 0 || P.accumulate, false, T, stg_all + warp * (FUSE_STG_ROWS * 32), nflush == 0,
-               ((dirty_s[warp] >> lane) & 1u) != 0u);
+        flush8(P, hist8, warp, lane, tile_base, nflush > 0 || P.accumulate, false, T, stg_all + warp * (FUSE_STG_ROWS * 32), nflush,
+               ((dirty_s[warp] >> lane) & 1u) != 0u, dcache_all + warp * F3D_XCH_NLEVEL);
         if (RP.enabled && active) {
             // VotingSegmentation.segment (voting.py:120-135).  The running (total, best, bpos) is exact unless another
             // lane's deferred pass added votes to this row (re-derived from the row) or the tile was flushed more than

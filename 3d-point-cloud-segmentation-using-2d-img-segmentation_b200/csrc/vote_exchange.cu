@@ -5,7 +5,8 @@
 // memory over NVLink (fuse_project_vote.cu, flush8):
 //   * slot records: per (source, 32-point block) L rows of 64 B, row j = the j-th class (order of first appearance) of
 //     each of the block's 32 points as uint16 (class | count << 8, 0 = none), L = the longest list in the block; a
-//     directory entry (row offset, L) per block says where the rows are inside that source's record region (the region is
+//     directory entry (row offset, L) per block and flush level (F3D_XCH_NLEVEL of them: a tile with more than 235
+//     candidate frames flushes its byte histogram several times) says where the rows are inside that source's record region (the region is
 //     split into F3D_XCH_NREG sub-regions so that the senders' row cursors never become an atomic hot spot);
 //   * (cell, count) entries in F3D_XCH_NSUB sub-queues for what does not go into a record (a full record sub-region,
 //     later flushes of very dense scans, the deferred fp64 votes of the fix-up pass -- fix-up block b owns sub-queue b).
@@ -112,13 +113,18 @@ __global__ void __launch_bounds__(XCH_BLOCK, 2) slot_merge_kernel(const uint16_t
     uint16_t* __restrict__ row = hist + tid * RS;
     int total = 0, best = 0, bpos = 0x7fff;
     if (blk * 32 < nrows) {
-        // the G directory entries of this block, one per lane
-        uint2 de = make_uint2(0u, 0u);
-        if (lane < G) de = __ldg(dir + (size_t)lane * blocks_per_src + blk);
-        for (int s = 0; s < G; ++s) {
-            const unsigned off = __shfl_sync(0xffffffffu, de.x, s);
-            const int L = (int)min((unsigned long long)__shfl_sync(0xffffffffu, de.y, s),
-                                   (unsigned long long)max(0LL, rows_cap - (long long)off));
+        // the G x F3D_XCH_NLEVEL directory entries of this block, one per lane (two rounds cover 16 ranks)
+        uint2 de0 = make_uint2(0u, 0u), de1 = make_uint2(0u, 0u);
+        {
+            const int s0 = lane / F3D_XCH_NLEVEL, k0 = lane % F3D_XCH_NLEVEL;
+            if (s0 < G) de0 = __ldg(dir + ((size_t)s0 * blocks_per_src + blk) * F3D_XCH_NLEVEL + k0);
+            if (s0 + 8 < G) de1 = __ldg(dir + ((size_t)(s0 + 8) * blocks_per_src + blk) * F3D_XCH_NLEVEL + k0);
+        }
+        for (int sk = 0; sk < G * F3D_XCH_NLEVEL; ++sk) {
+            const int s = sk / F3D_XCH_NLEVEL;
+            const unsigned off = (s < 8) ? __shfl_sync(0xffffffffu, de0.x, sk) : __shfl_sync(0xffffffffu, de1.x, sk - 32);
+            const unsigned len = (s < 8) ? __shfl_sync(0xffffffffu, de0.y, sk) : __shfl_sync(0xffffffffu, de1.y, sk - 32);
+            const int L = (int)min((unsigned long long)len, (unsigned long long)max(0LL, rows_cap - (long long)off));
             const uint16_t* __restrict__ rec = slots + ((size_t)s * rows_cap + off) * 32 + lane;
             for (int j0 = 0; j0 < L; j0 += 4) {
                 unsigned pr[4];
@@ -172,11 +178,13 @@ static int xch_row_stride(int C1) {
     return rs;
 }
 
-extern "C" int f3d_exchange_constants(int32_t* out3) {
+extern "C" int f3d_exchange_constants(int32_t* out4) {
+    int32_t* out3 = out4;
     if (!out3) return f3d_fail(F3D_ERR_ARG, "f3d_exchange_constants: NULL");
     out3[0] = F3D_XCH_NREG;
     out3[1] = F3D_XCH_NSUB;
     out3[2] = F3D_XCH_NSUB_FIX;
+    out3[3] = F3D_XCH_NLEVEL;
     return F3D_OK;
 }
 

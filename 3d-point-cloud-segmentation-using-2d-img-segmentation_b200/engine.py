@@ -154,10 +154,11 @@ def _filter_arg(filter_classes):
 
 
 def exchange_constants():
-    """(NREG, NSUB, NSUB_FIX): record sub-regions, sub-queues and fix-up-owned sub-queues per (source, owner)."""
-    out = np.zeros(3, dtype=np.int32)
+    """(NREG, NSUB, NSUB_FIX, NLEVEL): record sub-regions, sub-queues, fix-up-owned sub-queues per (source, owner) and
+    directory levels per 32-point block."""
+    out = np.zeros(4, dtype=np.int32)
     check(load().f3d_exchange_constants(ptr(out)), "f3d_exchange_constants")
-    return int(out[0]), int(out[1]), int(out[2])
+    return tuple(int(v) for v in out)
 
 
 def fuse_project_vote_exchange(points4, table: FrameTable, depth, mask, nclasses1, nranks, points_per_shard, peer_slot_ptrs,
@@ -173,7 +174,7 @@ def fuse_project_vote_exchange(points4, table: FrameTable, depth, mask, nclasses
     arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.uint64)) for a in (peer_slot_ptrs, peer_dir_ptrs, peer_queue_ptrs)]
     if any(a.size != nranks for a in arrs):
         raise ValueError("peer pointer arrays must have one entry per rank")
-    nreg, nsub, _ = exchange_constants()
+    nreg, nsub = exchange_constants()[:2]
     if cursors.dtype != torch.int32 or cursors.numel() < nranks * (nreg + nsub):
         raise ValueError("cursors must be int32 [nranks * (NREG + NSUB)]")
     check(load().f3d_fuse_project_vote_exchange(

@@ -29,6 +29,19 @@ def frame_shard(nframes: int, rank: int, world: int):
     return a, a + base + (1 if rank < rem else 0)
 
 
+def frame_shard_ids(nframes: int, rank: int, world: int, mode: str = "interleaved"):
+    """Global frame indices of `rank`.  "contiguous" = frame_shard; "interleaved" = rank, rank + world, ...: on a loop
+    trajectory a contiguous shard looks at 1/world of the cloud, which concentrates each rank's votes (and histogram
+    flushes) on few tiles and its records on few owners; interleaving gives every rank the whole scene at 1/world of
+    the frame rate.  Votes commute over frames, so both give identical results."""
+    if mode == "contiguous":
+        a, b = frame_shard(nframes, rank, world)
+        return list(range(a, b))
+    if mode != "interleaved":
+        raise ValueError(mode)
+    return list(range(rank, nframes, world))
+
+
 def _reduce_scatter(out: torch.Tensor, full: torch.Tensor, group=None):
     """full [per*world, k] (sum over ranks) -> out [per, k] = this rank's slice."""
     if dist.get_backend(group) == "nccl":
@@ -148,16 +161,16 @@ class VoteExchange:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.npoints, self.c1 = npoints, c1
         G = self.world
-        self.nreg, self.nsub, self.nsub_fix = engine.exchange_constants()
+        self.nreg, self.nsub, self.nsub_fix, self.nlevel = engine.exchange_constants()
         self.per = shard_points(npoints, G)
         self.rows = max(0, min(self.per, npoints - self.rank * self.per))
         self.blocks = self.per // 32
         self.sub_rows = max(256, -(-self.blocks * int(rows_per_block) // self.nreg))     # 64-byte rows per record sub-region
         self.sub_cap = int(sub_cap) if sub_cap else max(512, -(-self.per // self.nsub))    # entries per sub-queue
-        # int64 words: [queue: G x NSUB x sub_cap][counts: G x NSUB uint32][directory: G x blocks][records: G x NREG x sub_rows x 8]
+        # int64 words: [queue: G x NSUB x sub_cap][counts: G x NSUB uint32][directory: G x blocks x NLEVEL][records: G x NREG x sub_rows x 8]
         self.q_words = G * self.nsub * self.sub_cap
         self.c_words = G * self.nsub // 2
-        self.d_words = G * self.blocks
+        self.d_words = G * self.blocks * self.nlevel
         self.s_words = G * self.nreg * self.sub_rows * 8
         total = self.q_words + self.c_words + self.d_words + self.s_words
         self.rx = symm.empty(total, dtype=torch.int64, device=self.device)
@@ -168,7 +181,7 @@ class VoteExchange:
         r = self.rank
         self.peer_queue_ptrs = np.array([b + r * self.nsub * self.sub_cap * 8 for b in base], dtype=np.uint64)
         self.peer_count_ptrs = np.array([b + o_c * 8 for b in base], dtype=np.uint64)
-        self.peer_dir_ptrs = np.array([b + (o_d + r * self.blocks) * 8 for b in base], dtype=np.uint64)
+        self.peer_dir_ptrs = np.array([b + (o_d + r * self.blocks * self.nlevel) * 8 for b in base], dtype=np.uint64)
         self.peer_slot_ptrs = np.array([b + (o_s + r * self.nreg * self.sub_rows * 8) * 8 for b in base], dtype=np.uint64)
         self.rx_queue, self.rx_count = self.rx[:self.q_words], self.rx[o_c:o_d]
         self.rx_dir, self.rx_slots = self.rx[o_d:o_s], self.rx[o_s:]

@@ -95,12 +95,16 @@ def algorithmic_bytes(N, F, H, W, depth_bytes, C1):
     return 16 * N + F * H * W * (1 + depth_bytes) + 64 * F + 4 * N * C1
 
 
-def build_scene(scenes, engine, fused, spec, frame_lo, frame_hi, torch):
+def build_scene(scenes, engine, fused, spec, frame_lo, frame_hi, torch, frame_ids=None):
     """Cloud + poses on the host (seeded numpy), depth = GPU z-buffer splat of the cloud (kernel 2), block masks on
-    the GPU.  Returns the FusedLabeler (cloud + frame table for frames [frame_lo, frame_hi)) and device depth / masks."""
+    the GPU.  Returns the FusedLabeler (cloud + frame table for frames [frame_lo, frame_hi), or the global frame indices
+    `frame_ids`) and device depth / masks."""
     K = scenes.scaled_intrinsics(spec.width, spec.height)
     wxyz, t = scenes.make_poses(spec)
-    wxyz, t = wxyz[frame_lo:frame_hi], t[frame_lo:frame_hi]
+    if frame_ids is None:
+        frame_ids = list(range(frame_lo, frame_hi))
+    frame_lo = frame_ids[0] if len(frame_ids) else 0
+    wxyz, t = np.ascontiguousarray(wxyz[frame_ids]), np.ascontiguousarray(t[frame_ids])
     pts = scenes.make_cloud(spec)
     fl = fused.FusedLabeler(pts, K, spec.width, spec.height, wxyz, t, point_range=(0.1, spec.zmax), radius=RADIUS,
                             nclasses=NCLASSES)
@@ -200,6 +204,8 @@ def main():
     ap.add_argument("--exchange", default="records", choices=["records", "dense"],
                     help="multi-GPU vote exchange: slot records written by the fused kernel into the owner's memory over "
                          "NVLink (default), or dense packed-uint16 reduce-scatter through NCCL")
+    ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
+                    help="how the frames of the N-GPU job are dealt to the ranks (same results either way)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -234,9 +240,9 @@ def main():
     base = scenes.CONFIGS[cfg_key] if args.workload != "small" else scenes.scaled_spec("C1", 200_000, 8, 320, 240)
     fpg = base.nframes                                   # frames per GPU (weak scaling in frames)
     spec = scenes.scaled_spec(cfg_key, npoints=base.npoints, nframes=fpg * world, width=base.width, height=base.height)
-    f_lo, f_hi = parallel.frame_shard(spec.nframes, rank, world)
-    fl, pts, K, wxyz, t, depth, masks = build_scene(scenes, engine, fused, spec, f_lo, f_hi, torch)
-    N, F, H, W, C1 = fl.N, f_hi - f_lo, spec.height, spec.width, NCLASSES + 1
+    fl, pts, K, wxyz, t, depth, masks = build_scene(scenes, engine, fused, spec, 0, 0, torch,
+                                                    frame_ids=parallel.frame_shard_ids(spec.nframes, rank, world, args.shard))
+    N, F, H, W, C1 = fl.N, fl.table.F, spec.height, spec.width, NCLASSES + 1
     stats = fl.stats
 
     labels_buf = torch.empty(N, dtype=torch.int64, device="cuda")
@@ -388,7 +394,7 @@ def main():
             "config": {"workload": desc, "points": N, "frames_per_gpu": F, "frames_total": F * world, "width": W, "height": H,
                        "nclasses": NCLASSES, "depth": "uint16 mm", "radius": RADIUS, "cache": "inputs larger than L2 "
                        "(depth+masks+votes = %.1f GB per GPU)" % ((F * H * W * 3 + 4 * N * C1) / 1e9),
-                       "parallelism": "single GPU" if world == 1 else f"frames sharded over {world} GPUs, "
+                       "parallelism": "single GPU" if world == 1 else f"frames sharded over {world} GPUs ({args.shard}), "
                        + ("vote exchange fused into the kernel: slot records written into the owner's memory over NVLink, "
                           "owner-side merge into the dense shard + labels, all-gather of labels" if args.exchange == "records" else
                           f"{args.chunks}-chunk pipeline: fuse -> NCCL reduce-scatter of packed uint16 votes -> resolve -> "

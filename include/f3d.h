@@ -102,17 +102,18 @@ int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_t
  * can be sharded over ranks and the partial votes added in any order -- bit-exact for every rank count.
  * Votes are ~95 % zeros, so no dense partial vote tensor is written or reduce-scattered.  Rank d owns the points
  * [d * points_per_shard, (d+1) * points_per_shard), points_per_shard a multiple of 256.  f3d_exchange_constants returns
- * {NREG, NSUB, NSUB_FIX}.  The fused kernel of every source rank writes, straight into the owner's memory through
+ * {NREG, NSUB, NSUB_FIX, NLEVEL}.  The fused kernel of every source rank writes, straight into the owner's memory through
  * peer-mapped pointers:
  *   - slot records: per (source, 32-point block) L rows of 64 B; row j holds, for each of the block's 32 points, its
  *     j-th class in order of first appearance as uint16 (class | count << 8, 0 = none); L = the longest list in the
  *     block.  The block's warp reserves the rows in one of NREG sub-regions (sub_rows rows each) of its record region
- *     and writes a directory entry {uint32 row offset, uint32 L}.
+ *     and writes a directory entry {uint32 row offset, uint32 L}; a tile that flushes its byte histogram k times (more than
+ *     235 candidate frames each) writes k records, the directory keeps NLEVEL entries per block.
  *     h_peer_slots[d] / h_peer_dirs[d] = device pointers (peer mapped) to THIS rank's record region
- *     [NREG * sub_rows rows] and directory [points_per_shard / 32] inside rank d's receive buffer.  Every directory
+ *     [NREG * sub_rows rows] and directory [points_per_shard / 32][NLEVEL] inside rank d's receive buffer.  Every directory
  *     entry is rewritten on every call (no clearing needed);
- *   - (cell, count) entries for everything else (a full sub-region, later flushes of a tile with more than 235
- *     candidate frames, the deferred fp64 votes): h_peer_queues[d] = peer pointer to THIS rank's queue
+ *   - (cell, count) entries for everything else (a full sub-region, more than NLEVEL flushes, the deferred fp64
+ *     votes): h_peer_queues[d] = peer pointer to THIS rank's queue
  *     [NSUB][sub_cap] uint64 (cell = local_point * C1 + class in the low half, count in the high half) inside rank d's
  *     buffer; the fix-up kernel's block b owns sub-queue b < NSUB_FIX, the rest take spills.
  * cursors: local uint32 [nranks * (NREG + NSUB)] (row cursors, then queue cursors), zeroed by the caller before the call;
@@ -123,7 +124,7 @@ int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_t
  *   f3d_exchange_merge       (records of all sources -> dense int32 shard rows [nrows, C1], every cell written once, and
  *                             labels: VotingSegmentation.segment, voting.py:106-137), then
  *   f3d_exchange_queue_apply (queue entries scatter-added into the shard, labels of the touched points re-resolved). */
-int f3d_exchange_constants(int32_t* out3);
+int f3d_exchange_constants(int32_t* out4);
 int f3d_fuse_project_vote_exchange(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                                    int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
                                    int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,

@@ -387,7 +387,7 @@ def _emulated_exchange(engine, s, world, nclasses_id=133, thr=0.5, fc=None, sub_
     tab = engine.FrameTable(s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["zmax"])
     p4 = engine.pack_points(s["points"])
     d, m = dev(s["depths"]), dev(s["masks"])
-    nreg, nsub, nfix = engine.exchange_constants()
+    nreg, nsub, nfix, nlev = engine.exchange_constants()
     per = parallel.shard_points(N, world)
     blocks = per // 32
     sub_rows = sub_rows or max(64, -(-blocks * 40 // nreg))
@@ -395,7 +395,7 @@ def _emulated_exchange(engine, s, world, nclasses_id=133, thr=0.5, fc=None, sub_
     # owner o: queue [world][nsub][sub_cap] + counts [world][nsub] + directory [world][blocks] + records [world][nreg*sub_rows] x 64 B
     queues = [torch.zeros(world * nsub * sub_cap, dtype=torch.int64, device="cuda") for _ in range(world)]
     counts = [torch.zeros(world * nsub, dtype=torch.int32, device="cuda") for _ in range(world)]
-    dirs = [torch.full((world * blocks,), -1, dtype=torch.int64, device="cuda") for _ in range(world)]        # garbage: must be overwritten
+    dirs = [torch.full((world * blocks * nlev,), -1, dtype=torch.int64, device="cuda") for _ in range(world)]  # garbage: must be overwritten
     slots = [torch.full((world * nreg * sub_rows * 32,), 0x7b7b, dtype=torch.uint16, device="cuda") for _ in range(world)]
     overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
     st = engine.new_stats()
@@ -405,7 +405,7 @@ def _emulated_exchange(engine, s, world, nclasses_id=133, thr=0.5, fc=None, sub_
         cursors = torch.zeros(world * (nreg + nsub), dtype=torch.int32, device="cuda")
         qptrs = np.array([queues[o].data_ptr() + r * nsub * sub_cap * 8 for o in range(world)], dtype=np.uint64)
         sptrs = np.array([slots[o].data_ptr() + r * nreg * sub_rows * 64 for o in range(world)], dtype=np.uint64)
-        dptrs = np.array([dirs[o].data_ptr() + r * blocks * 8 for o in range(world)], dtype=np.uint64)
+        dptrs = np.array([dirs[o].data_ptr() + r * blocks * nlev * 8 for o in range(world)], dtype=np.uint64)
         engine.fuse_project_vote_exchange(p4, tab, d[fb:fe], m[fb:fe], C1, world, per, sptrs, dptrs, qptrs, sub_rows, sub_cap, cursors,
                                           overflow, 0.05, 0.1, s["zmax"], stats=st, frame_begin=fb, frame_end=fe)
         cptrs = np.array([counts[o].data_ptr() for o in range(world)], dtype=np.uint64)

@@ -62,11 +62,11 @@ for _ in range(5): votes.zero_()
 e1.record(); torch.cuda.synchronize(); print(f"{'torch zero_ of votes (5.36 GB)':34s} {e0.elapsed_time(e1)/5:8.3f} ms")
 # exchange mode with purely local buffers (G = 1): isolates the cost of the record logic from NVLink stores
 parallel = importlib.import_module(PKG + ".parallel")
-nreg, nsub, _ = engine.exchange_constants()
+nreg, nsub, _, nlev = engine.exchange_constants()
 per = parallel.shard_points(N, 1); sub_rows = max(256, -(-(per // 32 * 40) // nreg)); sub_cap = max(512, -(-per // nsub))
 queue = torch.empty(nsub * sub_cap, dtype=torch.int64, device="cuda"); counts = torch.zeros(nsub, dtype=torch.int32, device="cuda")
 cursors = torch.zeros(nreg + nsub, dtype=torch.int32, device="cuda"); ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
-slots = torch.empty(nreg * sub_rows * 32, dtype=torch.uint16, device="cuda"); dirs = torch.empty(per // 32, dtype=torch.int64, device="cuda")
+slots = torch.empty(nreg * sub_rows * 32, dtype=torch.uint16, device="cuda"); dirs = torch.empty(per // 32 * nlev, dtype=torch.int64, device="cuda")
 P = lambda t_: np.array([t_.data_ptr()], dtype=np.uint64)
 def timed(fn, reps=5):
     for _ in range(2): fn()

@@ -14,10 +14,10 @@ fused = importlib.import_module(PKG + ".fused"); parallel = importlib.import_mod
 parallel.init_process_group(lr)
 base = scenes.CONFIGS["C2"]
 spec = scenes.scaled_spec("C2", nframes=base.nframes * world)
-lo, hi = parallel.frame_shard(spec.nframes, rank, world)
-fl, pts, K, wxyz, t, depth, masks = bench.build_scene(scenes, engine, fused, spec, lo, hi, torch)
+shard = "contiguous" if "contiguous" in sys.argv else "interleaved"
+fl, pts, K, wxyz, t, depth, masks = bench.build_scene(scenes, engine, fused, spec, 0, 0, torch, frame_ids=parallel.frame_shard_ids(spec.nframes, rank, world, shard))
 N, C1 = fl.N, 134
-what = set(sys.argv[1:]) or {"records", "dense"}
+what = (set(sys.argv[1:]) - {"contiguous", "interleaved"}) or {"records", "dense"}
 def timeit(fn, reps=5):
     for _ in range(2): fn()
     torch.cuda.synchronize(); dist.barrier()

@@ -51,6 +51,8 @@
 #ifndef FUSE_MINB8
 #define FUSE_MINB8 3      // resident CTAs per SM of the byte-histogram build (80 registers; 64 spills and is slower)
 #endif
+#define FUSE_ST_TILES 16   // tiles per super-tile (4096 points) of the first cull level
+#define FUSE_ST_LCAP 1024  // candidate frames a super-tile list holds
 #define FUSE_RED_WORDS 160 // small per-CTA scalars (see the layout comment in the kernel)
 #define FUSE_QWARP 20     // deferred entries per warp (12 B each); overflow falls back to inline evaluation
 #define FUSE_LIMIT8 (255 - FUSE_QWARP)   // the warp's deferred pass can add up to FUSE_QWARP votes to one cell at the end
@@ -84,6 +86,10 @@ struct FuseParams {
     int64_t* labels;
     unsigned long long* stats;
     int audit, dbg;   // dbg: timing experiments only (bits: 1 drop candidates, 2 skip cull, 4 classify only)
+    // first cull level (optional, from the workspace): candidate frames of every super-tile of FUSE_ST_TILES tiles, found
+    // by supertile_cull_kernel; a tile then tests only its super-tile's list instead of every frame of the launch
+    const unsigned* st_count;      // [super-tiles] list length, 0xFFFFFFFF = list overflowed (scan all frames)
+    const uint16_t* st_list;       // [super-tiles][FUSE_ST_LCAP] frame ids relative to f_begin
     GEntry* gq;                    // workspace queue of deferred point-views (NULL: evaluate them inside the sweep)
     unsigned long long* gq_count;
     unsigned long long gq_cap;
@@ -609,20 +615,27 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
 #endif
     int since_flush = 0, nflush = 0;   // byte histogram: candidates swept since the last flush, flushes so far (CTA-uniform)
 
-    for (int cbase = P.f_begin; cbase < P.f_end; cbase += FUSE_FCHUNK) {
-        if (cbase != P.f_begin) __syncthreads();   // previous chunk's candidate list fully consumed
+    // frames to test: the super-tile's candidate list when the first cull level ran, else every frame of the launch
+    const unsigned st_n = P.st_count ? __ldg(P.st_count + blockIdx.x / FUSE_ST_TILES) : 0xffffffffu;
+    const bool use_list = st_n != 0xffffffffu;
+    const uint16_t* __restrict__ st_list = P.st_list + (size_t)(blockIdx.x / FUSE_ST_TILES) * FUSE_ST_LCAP;
+    const int ntest = use_list ? (int)st_n : P.f_end - P.f_begin;
+    for (int cbase = 0; cbase < ntest; cbase += FUSE_FCHUNK) {
+        if (cbase != 0) __syncthreads();   // previous chunk's candidate list fully consumed
         if (tid == 0) *ncand_s = 0;
         __syncthreads();
-        const int cend = min(cbase + FUSE_FCHUNK, P.f_end);
+        const int cend = min(cbase + FUSE_FCHUNK, ntest);
         // ---- conservative tile x frustum cull (fp32 + explicit rounding margin; never drops a visible pair)
         const float blo[3] = {tbox[0], tbox[1], tbox[2]}, bhi[3] = {tbox[3], tbox[4], tbox[5]};
         const float box_mag = fabsf(blo[0]) + fabsf(blo[1]) + fabsf(blo[2]) + fabsf(bhi[0]) + fabsf(bhi[1]) + fabsf(bhi[2]);
         for (int f0 = cbase; f0 < cend && !(P.dbg & 2); f0 += FUSE_BLOCK) {
-            const int f = f0 + tid;
+            const int fi = f0 + tid;
             bool keep = false;
-            if (f < cend) {
+            int frel = 0;
+            if (fi < cend) {
                 keep = true;
-                const float4* pl = frec[f].cull.pl;
+                frel = use_list ? (int)__ldg(st_list + fi) : fi;
+                const float4* pl = frec[P.f_begin + frel].cull.pl;
 #pragma unroll
                 for (int m = 0; m < 5; ++m) {
                     const float4 q = __ldg(pl + m);
@@ -636,7 +649,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             int base = 0;
             if (lane == 0 && bal) base = atomicAdd(ncand_s, __popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) cand[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(f - P.f_begin);
+            if (keep) cand[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)frel;
         }
         __syncthreads();
         const int ncand = (P.dbg & 3) ? 0 : *ncand_s;
@@ -977,6 +990,80 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     }
 }
 
+// ---- first cull level: candidate frames per super-tile (FUSE_ST_TILES tiles = 4096 consecutive points) -------------------------
+// One CTA per super-tile: exact box of its points, every frame of the launch tested with the same conservative rule as
+// the tile test, surviving frame ids appended to the super-tile's list.  With F frames and T tiles this replaces T*F
+// plane tests inside the fused kernel by T*F/16 here plus (list length) per tile -- what keeps the cull from dominating
+// at thousands of frames (C3 / C4) and keeps the frame table out of the fused kernel's L1.
+__global__ void __launch_bounds__(256) supertile_cull_kernel(const __grid_constant__ FuseParams P, unsigned* __restrict__ st_count,
+                                                             uint16_t* __restrict__ st_list) {
+    __shared__ float s_box[8 * 6];
+    __shared__ unsigned s_n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p0 = (int64_t)blockIdx.x * (FUSE_ST_TILES * FUSE_BLOCK);
+    const float big = 3.0e38f;
+    float lo[3] = {big, big, big}, hi[3] = {-big, -big, -big};
+    for (int k = 0; k < FUSE_ST_TILES; ++k) {
+        const int64_t i = p0 + (int64_t)k * FUSE_BLOCK + tid;
+        if (i < P.N) {
+            const float4 q = __ldg(P.points + i);
+            lo[0] = fminf(lo[0], q.x); hi[0] = fmaxf(hi[0], q.x);
+            lo[1] = fminf(lo[1], q.y); hi[1] = fmaxf(hi[1], q.y);
+            lo[2] = fminf(lo[2], q.z); hi[2] = fmaxf(hi[2], q.z);
+        }
+    }
+#pragma unroll
+    for (int s2 = 16; s2 > 0; s2 >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], s2));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], s2));
+        }
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            s_box[warp * 6 + k] = lo[k];
+            s_box[warp * 6 + 3 + k] = hi[k];
+        }
+    if (tid == 0) s_n = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = s_box[k];
+        hi[k] = s_box[3 + k];
+        for (int w = 1; w < 8; ++w) {
+            lo[k] = fminf(lo[k], s_box[w * 6 + k]);
+            hi[k] = fmaxf(hi[k], s_box[w * 6 + 3 + k]);
+        }
+    }
+    const float box_mag = fabsf(lo[0]) + fabsf(lo[1]) + fabsf(lo[2]) + fabsf(hi[0]) + fabsf(hi[1]) + fabsf(hi[2]);
+    const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
+    const int nf = P.f_end - P.f_begin;
+    uint16_t* __restrict__ list = st_list + (size_t)blockIdx.x * FUSE_ST_LCAP;
+    for (int f0 = 0; f0 < nf; f0 += 256) {
+        const int fi = f0 + tid;
+        bool keep = fi < nf;
+        if (keep) {
+            const float4* pl = frec[P.f_begin + fi].cull.pl;
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                const float4 q = __ldg(pl + m);
+                const float mx = fmaxf(q.x * lo[0], q.x * hi[0]) + fmaxf(q.y * lo[1], q.y * hi[1]) + fmaxf(q.z * lo[2], q.z * hi[2]) - q.w;
+                const float margin = 2.0e-6f * (box_mag + fabsf(q.w)) + 1.0e-7f;
+                keep = keep && (mx >= -margin);
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        unsigned base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_n, (unsigned)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned at = base + __popc(bal & ((1u << lane) - 1u));
+        if (keep && at < FUSE_ST_LCAP) list[at] = (uint16_t)fi;
+    }
+    __syncthreads();
+    if (tid == 0) st_count[blockIdx.x] = s_n > FUSE_ST_LCAP ? 0xffffffffu : s_n;
+}
+
 // ---- fix-up kernels: the deferred point-views, one per thread, in fp64 ------------------------------------------------
 #define FIXUP_THREADS 128
 template <int MODE, int FMT>
@@ -1184,6 +1271,14 @@ static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stre
         e = cudaMemsetAsync(P.gq_count, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(memset)");
     }
+    if (P.st_count) {
+        if (P.f_end - P.f_begin > 32 && !(P.dbg & 2) && !getenv("F3D_NO_SUPERTILE")) {   // env: A/B experiments only
+            const unsigned nst = (unsigned)((tiles + FUSE_ST_TILES - 1) / FUSE_ST_TILES);
+            supertile_cull_kernel<<<nst, 256, 0, stream>>>(P, const_cast<unsigned*>(P.st_count), const_cast<uint16_t*>(P.st_list));
+        } else {
+            P.st_count = nullptr;   // few frames: the per-tile scan is cheaper than another launch
+        }
+    }
     fuse_kernel<MODE, FMT, HB><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
     if (use_queue) {
         // the queue length lives on the device: fixed grids with grid-stride loops, no host synchronisation
@@ -1197,23 +1292,45 @@ static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stre
     return f3d_check_launch("f3d_fuse");
 }
 
-// workspace = [count u64][pad u64][GEntry x cap]; returns false when the caller gave none (or too little)
-static bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_bytes) {
+// workspace = [deferred count u64][pad u64][super-tile counts u32 x S, padded to 16 B][super-tile lists u16 x S x FUSE_ST_LCAP]
+//             [GEntry x cap]; S = super-tiles of the cloud.  The super-tile part is attached whenever it fits, the deferred
+// queue only when the caller's mode wants it; returns whether the queue was attached.
+static int64_t supertile_bytes(int64_t npoints) {
+    const int64_t tiles = (npoints + FUSE_BLOCK - 1) / FUSE_BLOCK;
+    const int64_t S = (tiles + FUSE_ST_TILES - 1) / FUSE_ST_TILES;
+    return ((S * 4 + 15) & ~(int64_t)15) + S * FUSE_ST_LCAP * 2;
+}
+
+static bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_bytes, bool want_queue = true) {
     P.gq = nullptr;
     P.gq_count = nullptr;
     P.gq_cap = 0;
-    if (!workspace || workspace_bytes < (int64_t)(16 + sizeof(GEntry)) || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return false;
+    P.st_count = nullptr;
+    P.st_list = nullptr;
+    if (!workspace || workspace_bytes < 16 || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return false;
+    char* base = reinterpret_cast<char*>(workspace);
+    int64_t off = 16;
+    const int64_t stb = supertile_bytes(P.N);
+    if (workspace_bytes >= off + stb) {
+        const int64_t tiles = (P.N + FUSE_BLOCK - 1) / FUSE_BLOCK;
+        const int64_t S = (tiles + FUSE_ST_TILES - 1) / FUSE_ST_TILES;
+        P.st_count = reinterpret_cast<const unsigned*>(base + off);
+        P.st_list = reinterpret_cast<const uint16_t*>(base + off + ((S * 4 + 15) & ~(int64_t)15));
+        off += stb;
+    }
+    if (!want_queue || workspace_bytes - off < (int64_t)sizeof(GEntry)) return false;
     P.gq_count = reinterpret_cast<unsigned long long*>(workspace);
-    P.gq = reinterpret_cast<GEntry*>(reinterpret_cast<char*>(workspace) + 16);
-    P.gq_cap = (unsigned long long)((workspace_bytes - 16) / (int64_t)sizeof(GEntry));
+    P.gq = reinterpret_cast<GEntry*>(base + off);
+    P.gq_cap = (unsigned long long)((workspace_bytes - off) / (int64_t)sizeof(GEntry));
     return true;
 }
 
 extern "C" int64_t f3d_fuse_workspace_bytes(int64_t npoints) {
-    // room for one uncertain point-view per 4 points (measured: ~0.08 per point on the 1920x1440 scene), at least 1 Mi entries
+    // room for one uncertain point-view per 4 points (measured: ~0.08 per point on the 1920x1440 scene), at least 1 Mi entries,
+    // plus the super-tile candidate lists of the first cull level
     int64_t cap = npoints / 4;
     if (cap < (1 << 20)) cap = 1 << 20;
-    return 16 + cap * (int64_t)sizeof(GEntry);
+    return 16 + supertile_bytes(npoints < 0 ? 0 : npoints) + cap * (int64_t)sizeof(GEntry);
 }
 
 static int fill_common(FuseParams& P, const void* points, int64_t N, const void* table, int fb, int fe, const void* depth,
@@ -1264,6 +1381,8 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.gq = nullptr;
     P.gq_count = nullptr;
     P.gq_cap = 0;
+    P.st_count = nullptr;
+    P.st_list = nullptr;
     P.xg_G = 0;
     P.xg_per = 1;
     P.xg_rowcur = nullptr;
@@ -1329,7 +1448,7 @@ static int fuse_vote_impl(const void* points, int64_t N, const void* frame_table
     P.votes16 = votes16;
     P.labels = labels;
     P.C1 = C1;
-    if ((votes || votes16) && !P.audit && N <= 0x7fffffff) attach_workspace(P, workspace, workspace_bytes);   // labels-only / audit: fp64 inside the sweep
+    attach_workspace(P, workspace, workspace_bytes, (votes || votes16) && !P.audit && N <= 0x7fffffff);   // labels-only / audit: fp64 inside the sweep
     P.RS = hist_row_stride(C1);
     const size_t esz = depth_fmt == F3D_DEPTH_U16_MM ? 2 : 4;
     int fb = frame_begin;
@@ -1401,7 +1520,7 @@ extern "C" int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_t
     if (!uv2pt || !depth) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_uv2pt: bad argument");
     if (N == 0 || frame_end == frame_begin) return F3D_OK;
     if (N > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_uv2pt: point index does not fit int32");
-    if (!P.audit) attach_workspace(P, workspace, workspace_bytes);
+    attach_workspace(P, workspace, workspace_bytes, !P.audit);
     FuseResolve RP;
     RP.enabled = 0;
     const size_t esz = depth_fmt == F3D_DEPTH_U16_MM ? 2 : 4;
@@ -1427,7 +1546,7 @@ extern "C" int f3d_zbuffer_splat(const void* points, int64_t N, const void* fram
                          0.0, 0.0, stats, flags);
     if (rc) return rc;
     if (!zbuf || !depth_out || border < 0) return f3d_fail(F3D_ERR_ARG, "f3d_zbuffer_splat: bad argument");
-    if (!P.audit && N <= 0x7fffffff) attach_workspace(P, workspace, workspace_bytes);
+    attach_workspace(P, workspace, workspace_bytes, !P.audit && N <= 0x7fffffff);
     const int nf = frame_end - frame_begin;
     if (nf == 0) return F3D_OK;
     const int64_t total = (int64_t)nf * H * W;

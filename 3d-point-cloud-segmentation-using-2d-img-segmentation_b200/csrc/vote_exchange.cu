@@ -19,6 +19,7 @@
 #include "f3d_host.h"
 
 #define XCH_BLOCK 256
+#define XCH_Q 4   // records of a block whose first rows are prefetched together by the merge
 
 struct PeerPtrs {
     unsigned* p[F3D_MAX_RANKS];
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) queue_relabel_kernel(const unsigned long 
 // ---- slot-record merge: one thread per owned point, one warp per 32-point block ------------------------------------------
 // shared: uint16 histogram [256][RS] (a thread owns its row; RS/2 odd => conflict-free), written out like the fused
 // kernel's epilogue (warp-private rows, 16-byte stores, every cell exactly once -- no memset of the shard needed).
-__global__ void __launch_bounds__(XCH_BLOCK, 2) slot_merge_kernel(const uint16_t* __restrict__ slots, const uint2* __restrict__ dir,
+__global__ void __launch_bounds__(XCH_BLOCK, 3) slot_merge_kernel(const uint16_t* __restrict__ slots, const uint2* __restrict__ dir,
                                                                   int G, long long rows_cap, long long blocks_per_src,
                                                                   long long nrows, int C1, int RS,
                                                                   const __grid_constant__ FuseResolve RP,
@@ -120,27 +121,49 @@ __global__ void __launch_bounds__(XCH_BLOCK, 2) slot_merge_kernel(const uint16_t
             if (s0 < G) de0 = __ldg(dir + ((size_t)s0 * blocks_per_src + blk) * F3D_XCH_NLEVEL + k0);
             if (s0 + 8 < G) de1 = __ldg(dir + ((size_t)(s0 + 8) * blocks_per_src + blk) * F3D_XCH_NLEVEL + k0);
         }
-        for (int sk = 0; sk < G * F3D_XCH_NLEVEL; ++sk) {
-            const int s = sk / F3D_XCH_NLEVEL;
-            const unsigned off = (s < 8) ? __shfl_sync(0xffffffffu, de0.x, sk) : __shfl_sync(0xffffffffu, de1.x, sk - 32);
-            const unsigned len = (s < 8) ? __shfl_sync(0xffffffffu, de0.y, sk) : __shfl_sync(0xffffffffu, de1.y, sk - 32);
-            const int L = (int)min((unsigned long long)len, (unsigned long long)max(0LL, rows_cap - (long long)off));
-            const uint16_t* __restrict__ rec = slots + ((size_t)s * rows_cap + off) * 32 + lane;
-            for (int j0 = 0; j0 < L; j0 += 4) {
-                unsigned pr[4];
+        auto take = [&](unsigned pair) {
+            const int cls = (int)(pair & 0xffu), cnt = (int)(pair >> 8);
+            if (cnt == 0 || cls >= C1) return;
+            const int v = (int)row[cls] + cnt;
+            row[cls] = (uint16_t)v;
+            total += cnt;
+            const int pos = s_fpos[cls];
+            if (pos >= 0 && (v > best || (v == best && pos < bpos))) {
+                best = v;
+                bpos = pos;
+            }
+        };
+        // non-empty records, four at a time: the first four rows of all four are requested before any is used (two HBM
+        // round trips for a typical block of an 8-rank job instead of eight); longer records continue row by row
+        for (int round = 0; round < 2; ++round) {
+            const uint2 de = round ? de1 : de0;
+            const int base_s = round * 8;
+            unsigned live = __ballot_sync(0xffffffffu, de.y != 0u && base_s + lane / F3D_XCH_NLEVEL < G);
+            while (live) {
+                unsigned pr[XCH_Q][4];
+                int Ls[XCH_Q];
+                const uint16_t* recs[XCH_Q];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) pr[k] = (j0 + k < L) ? (unsigned)__ldg(rec + (size_t)(j0 + k) * 32) : 0u;   // 64 contiguous bytes per row
+                for (int q = 0; q < XCH_Q; ++q) {
+                    const int e = live ? (__ffs(live) - 1) : -1;
+                    live &= live - 1u;
+                    const unsigned off = __shfl_sync(0xffffffffu, de.x, max(e, 0));
+                    const unsigned len = __shfl_sync(0xffffffffu, de.y, max(e, 0));
+                    Ls[q] = e < 0 ? 0 : (int)min((unsigned long long)len, (unsigned long long)max(0LL, rows_cap - (long long)off));
+                    recs[q] = slots + ((size_t)(base_s + max(e, 0) / F3D_XCH_NLEVEL) * rows_cap + off) * 32 + lane;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int cls = (int)(pr[k] & 0xffu), cnt = (int)(pr[k] >> 8);
-                    if (cnt == 0 || cls >= C1) continue;
-                    const int v = (int)row[cls] + cnt;
-                    row[cls] = (uint16_t)v;
-                    total += cnt;
-                    const int pos = s_fpos[cls];
-                    if (pos >= 0 && (v > best || (v == best && pos < bpos))) {
-                        best = v;
-                        bpos = pos;
+                    for (int k = 0; k < 4; ++k) pr[q][k] = (k < Ls[q]) ? (unsigned)__ldg(recs[q] + (size_t)k * 32) : 0u;   // 64 contiguous bytes per row
+                }
+#pragma unroll
+                for (int q = 0; q < XCH_Q; ++q) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) take(pr[q][k]);
+                    for (int j0 = 4; j0 < Ls[q]; j0 += 4) {
+                        unsigned more[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) more[k] = (j0 + k < Ls[q]) ? (unsigned)__ldg(recs[q] + (size_t)(j0 + k) * 32) : 0u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) take(more[k]);
                     }
                 }
             }

@@ -151,7 +151,7 @@ class VoteExchange:
         int32 shard row and the label -> apply the queue entries -> all-gather the labels.
     Nothing dense crosses the fabric and the sweep never writes a vote tensor; the owner writes its shard once."""
 
-    def __init__(self, npoints: int, c1: int, device, group=None, rows_per_block=40, sub_cap=None):
+    def __init__(self, npoints: int, c1: int, device, group=None, rows_per_block=64, sub_cap=None):
         import numpy as np
         import torch.distributed._symmetric_memory as symm
         from . import engine
@@ -190,6 +190,8 @@ class VoteExchange:
         self.shard = torch.zeros((max(self.per, 1), c1), dtype=torch.int32, device=self.device)
         self.lab = torch.zeros(max(self.per, 1), dtype=torch.int64, device=self.device)
         self.full = torch.zeros(max(self.per, 1) * G, dtype=torch.int64, device=self.device)
+        self.lab16 = torch.zeros(max(self.per, 1), dtype=torch.int16, device=self.device)
+        self.full16 = torch.zeros(max(self.per, 1) * G, dtype=torch.int16, device=self.device)
 
     def fuse_args(self):
         """Keyword arguments of engine.fuse_project_vote_exchange that describe this exchange."""
@@ -211,7 +213,15 @@ class VoteExchange:
                                threshold, filter_classes, votes=self.shard, labels=self.lab)
             eng.exchange_queue_apply(self.rx_queue, self.rx_count, self.world, self.sub_cap, self.shard, self.rows, nclasses_id,
                                      self.lab, threshold, filter_classes)
-        _all_gather(self.full, self.lab, self.group if self.group is not dist.group.WORLD else None)
+        # labels are class ids < 2^15 (C1 <= 256 columns, filter values are columns): gather them as int16 (a quarter of
+        # the int64 bytes over the fabric) and widen once
+        grp = self.group if self.group is not dist.group.WORLD else None
+        if 0 <= int(nclasses_id) < 32768:
+            self.lab16.copy_(self.lab)
+            _all_gather(self.full16, self.lab16, grp)
+            self.full.copy_(self.full16)
+        else:
+            _all_gather(self.full, self.lab, grp)
         return self.full[:self.npoints]
 
     def check_overflow(self):

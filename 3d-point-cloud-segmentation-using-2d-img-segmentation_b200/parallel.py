@@ -218,7 +218,7 @@ class VoteExchange:
         grp = self.group if self.group is not dist.group.WORLD else None
         if 0 <= int(nclasses_id) < 32768:
             self.lab16.copy_(self.lab)
-            _all_gather(self.full16, self.lab16, grp)
+            _all_gather(self.full16.view(torch.uint8), self.lab16.view(torch.uint8), grp)   # NCCL has no int16: move bytes
             self.full.copy_(self.full16)
         else:
             _all_gather(self.full, self.lab, grp)

@@ -262,7 +262,21 @@ def main():
     if world > 1 and args.exchange == "dense":
         pipe = parallel.ShardedPipeline(N, C1, args.chunks, torch.device("cuda", local_rank))
     elif world > 1:
-        xchg = parallel.VoteExchange(N, C1, torch.device("cuda", local_rank))
+        # the record exchange needs peer-mapped symmetric memory (NVLink / NVSwitch P2P); every rank must take the same
+        # path, so a failure anywhere falls back to the NCCL reduce-scatter pipeline everywhere
+        err = None
+        try:
+            xchg = parallel.VoteExchange(N, C1, torch.device("cuda", local_rank))
+        except Exception as ex:   # noqa: BLE001
+            err = ex
+        bad = torch.tensor([1 if err is not None else 0], device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            if rank == 0:
+                print(f"bench.py: symmetric-memory vote exchange unavailable ({err}); using the NCCL reduce-scatter pipeline", file=sys.stderr)
+            xchg = None
+            args.exchange = "dense"
+            pipe = parallel.ShardedPipeline(N, C1, args.chunks, torch.device("cuda", local_rank))
 
     def step_records():
         def fuse(**xargs):

@@ -1065,6 +1065,99 @@ __global__ void __launch_bounds__(256) supertile_cull_kernel(const __grid_consta
 }
 
 // ---- fix-up kernels: the deferred point-views, one per thread, in fp64 ------------------------------------------------
+// one deferred point-view: fp64 evaluation against its frame's exact record `fe`, then the vote / depth sample / index goes
+// where the mode wants it (dense votes by atomics, the owner's sub-queue `qsub` in exchange mode, z-buffer, uv2pt)
+template <int MODE, int FMT>
+__device__ __forceinline__ void fixup_entry(const FuseParams& P, const FrameExact* fe, const GEntry& e, unsigned long long i,
+                                            unsigned qsub, unsigned* s_qcnt, unsigned& n_exact, unsigned& n_div, unsigned& n_edge,
+                                            unsigned& n_seen) {
+    const int frel = (int)(e.w & 0xffffu), st = (int)((e.w >> 16) & 0xffu);
+    const int HW = P.H * P.W;
+    const float4 p = __ldg(P.points + e.pt);
+    ExactOut eo;
+    exact_eval<MODE, FMT>(P, fe, frel, p.x, p.y, p.z, eo);
+    const bool e_seen = (MODE == MODE_SPLAT) ? (eo.in != 0) : (eo.vis != 0);
+    const uint32_t e_zq = (MODE == MODE_SPLAT && eo.in) ? quantise_mm(eo.zcam) : 0u;
+    bool diverged;
+    if (st == 2) diverged = ((int)e.guess != eo.in) || (eo.in && e.pix != eo.pix);
+    else if (MODE == MODE_SPLAT) diverged = (!eo.in) || (e.pix != eo.pix) || (e.guess != e_zq);
+    else diverged = ((int)e.guess != eo.vis) || (eo.in && e.pix != eo.pix);
+    ++n_exact;
+    n_div += diverged ? 1u : 0u;
+    n_edge += (eo.in && eo.near_edge) ? 1u : 0u;
+    if (!e_seen) return;
+    ++n_seen;
+    const size_t off = (size_t)frel * (size_t)HW + (size_t)eo.pix;
+    if (MODE == MODE_VOTE) {
+        const int cls = __ldg(P.mask + off);
+        if (cls < P.C1 && P.xg_G > 0) {
+            // exchange mode: the vote goes to the owner's queue through a sub-queue this block owns (shared-memory cursor)
+            const int d = (int)(e.pt / P.xg_per);
+            xg_append(P, d, qsub, atomicAdd(&s_qcnt[d], 1u), (unsigned)((e.pt - (long long)d * P.xg_per) * P.C1 + cls), 1u);
+        } else if (cls < P.C1) {
+            if (P.votes16) {
+                const size_t cell = (size_t)e.pt * P.C1 + cls;   // 32-bit atomic on the word of the uint16 counter
+                atomicAdd(reinterpret_cast<unsigned*>(P.votes16) + (cell >> 1), (cell & 1) ? 0x10000u : 1u);
+            } else {
+                atomicAdd(P.votes + (size_t)e.pt * P.C1 + cls, 1);
+            }
+            P.gq[i].w = e.w | (1u << 24);   // this point's label must be re-resolved
+        }
+    } else if (MODE == MODE_SPLAT) {
+        atomicMin(P.zbuf + off, e_zq);
+    } else {
+        atomicMax(P.uv2pt + off, e.pt);
+    }
+}
+
+__device__ __forceinline__ void fixup_stats(const FuseParams& P, unsigned n_exact, unsigned n_div, unsigned n_edge, unsigned n_seen) {
+    if (!P.stats) return;
+    unsigned vals[4] = {n_exact, n_div, n_edge, n_seen};
+    const int idx[4] = {F3D_STAT_EXACT, F3D_STAT_DIVERGED, F3D_STAT_NEAR_EDGE, F3D_STAT_SEEN};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned v = __reduce_add_sync(0xffffffffu, vals[k]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(P.stats + idx[k], (unsigned long long)v);
+    }
+}
+
+// When the launch has few enough frames, the used part of every frame's exact record (FIXUP_REC_BYTES of 448) fits one
+// SM's shared memory: one 1024-thread block per SM keeps the whole table on chip and every thread evaluates its entries
+// against it directly -- no per-warp staging round trips, 32 warps per SM in flight.
+#define FIXUP_REC_BYTES 368   // q, qi, t, ss, plane_pt, plane_n, lookat = 360 bytes, padded to 16
+#define FIXUP_TABLE_THREADS 1024
+#define FIXUP_TABLE_QSUBS (F3D_XCH_NSUB_FIX / 148)   // sub-queues a table block owns (warps share them round-robin)
+template <int MODE, int FMT>
+__global__ void __launch_bounds__(FIXUP_TABLE_THREADS, 1) fixup_apply_table_kernel(const __grid_constant__ FuseParams P) {
+    extern __shared__ __align__(16) unsigned char fx_smem[];
+    __shared__ unsigned s_qcnt[FIXUP_TABLE_QSUBS][F3D_MAX_RANKS];
+    const int nf = P.f_end - P.f_begin;
+    const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
+    for (int i = threadIdx.x; i < FIXUP_TABLE_QSUBS * F3D_MAX_RANKS; i += blockDim.x) (&s_qcnt[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < nf * (FIXUP_REC_BYTES / 16); i += blockDim.x) {
+        const int f = i / (FIXUP_REC_BYTES / 16), c = i % (FIXUP_REC_BYTES / 16);
+        reinterpret_cast<uint4*>(fx_smem + (size_t)f * FIXUP_REC_BYTES)[c] = __ldg(reinterpret_cast<const uint4*>(&frec[P.f_begin + f].exact) + c);
+    }
+    __syncthreads();
+    const unsigned long long n = min(*P.gq_count, P.gq_cap);
+    const unsigned wsub = (threadIdx.x >> 5) % FIXUP_TABLE_QSUBS;
+    unsigned n_exact = 0, n_div = 0, n_edge = 0, n_seen = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const GEntry e = P.gq[i];
+        if (e.pt < 0) continue;
+        const FrameExact* fe = reinterpret_cast<const FrameExact*>(fx_smem + (size_t)(e.w & 0xffffu) * FIXUP_REC_BYTES);
+        fixup_entry<MODE, FMT>(P, fe, e, i, blockIdx.x * FIXUP_TABLE_QSUBS + wsub, s_qcnt[wsub], n_exact, n_div, n_edge, n_seen);
+    }
+    if (P.xg_G > 0) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < FIXUP_TABLE_QSUBS * P.xg_G; i += blockDim.x) {
+            const int q = i / P.xg_G, d = i % P.xg_G;
+            P.xg_qcur[d * F3D_XCH_NSUB + blockIdx.x * FIXUP_TABLE_QSUBS + q] = min(s_qcnt[q][d], P.xg_subcap);
+        }
+    }
+    fixup_stats(P, n_exact, n_div, n_edge, n_seen);
+}
+
 #define FIXUP_THREADS 128
 template <int MODE, int FMT>
 __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid_constant__ FuseParams P) {
@@ -1079,7 +1172,6 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid
     __syncthreads();
     const unsigned long long n = min(*P.gq_count, P.gq_cap);
     const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
-    const int HW = P.H * P.W;
     unsigned n_exact = 0, n_div = 0, n_edge = 0, n_seen = 0;
     const unsigned long long warps_total = (unsigned long long)gridDim.x * (FIXUP_THREADS / 32);
     for (unsigned long long base = ((unsigned long long)blockIdx.x * (FIXUP_THREADS / 32) + warp) * 32; base < n;
@@ -1091,7 +1183,7 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid
         e.pix = 0;
         e.guess = 0;
         if (i < n) e = P.gq[i];
-        const int frel = (int)(e.w & 0xffffu), st = (int)((e.w >> 16) & 0xffu);
+        const int frel = (int)(e.w & 0xffffu);
         __syncwarp();
         // eight records per round: all eight 16-byte loads of a lane are in flight before the first store (one L2
         // round trip per round instead of one per record)
@@ -1110,58 +1202,13 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid
         }
         __syncwarp();
         if (e.pt < 0) continue;
-        const float4 p = __ldg(P.points + e.pt);
-        ExactOut eo;
-        exact_eval<MODE, FMT>(P, wbuf + lane, frel, p.x, p.y, p.z, eo);
-        const bool e_seen = (MODE == MODE_SPLAT) ? (eo.in != 0) : (eo.vis != 0);
-        const uint32_t e_zq = (MODE == MODE_SPLAT && eo.in) ? quantise_mm(eo.zcam) : 0u;
-        bool diverged;
-        if (st == 2) diverged = ((int)e.guess != eo.in) || (eo.in && e.pix != eo.pix);
-        else if (MODE == MODE_SPLAT) diverged = (!eo.in) || (e.pix != eo.pix) || (e.guess != e_zq);
-        else diverged = ((int)e.guess != eo.vis) || (eo.in && e.pix != eo.pix);
-        ++n_exact;
-        n_div += diverged ? 1u : 0u;
-        n_edge += (eo.in && eo.near_edge) ? 1u : 0u;
-        if (e_seen) {
-            ++n_seen;
-            const size_t off = (size_t)frel * (size_t)HW + (size_t)eo.pix;
-            if (MODE == MODE_VOTE) {
-                const int cls = __ldg(P.mask + off);
-                if (cls < P.C1 && P.xg_G > 0) {
-                    // exchange mode: the vote goes to the owner's queue through this block's own sub-queue (shared-memory cursor)
-                    const int d = (int)(e.pt / P.xg_per);
-                    xg_append(P, d, blockIdx.x, atomicAdd(&s_qcnt[d], 1u), (unsigned)((e.pt - (long long)d * P.xg_per) * P.C1 + cls), 1u);
-                } else if (cls < P.C1) {
-                    if (P.votes16) {
-                        const size_t cell = (size_t)e.pt * P.C1 + cls;   // 32-bit atomic on the word of the uint16 counter
-                        atomicAdd(reinterpret_cast<unsigned*>(P.votes16) + (cell >> 1), (cell & 1) ? 0x10000u : 1u);
-                    } else {
-                        atomicAdd(P.votes + (size_t)e.pt * P.C1 + cls, 1);
-                    }
-                    P.gq[i].w = e.w | (1u << 24);   // this point's label must be re-resolved
-                }
-            } else if (MODE == MODE_SPLAT) {
-                atomicMin(P.zbuf + off, e_zq);
-            } else {
-                atomicMax(P.uv2pt + off, e.pt);
-            }
-        }
+        fixup_entry<MODE, FMT>(P, wbuf + lane, e, i, blockIdx.x, s_qcnt, n_exact, n_div, n_edge, n_seen);
     }
     if (P.xg_G > 0) {
         __syncthreads();
         if ((int)threadIdx.x < P.xg_G) P.xg_qcur[threadIdx.x * F3D_XCH_NSUB + blockIdx.x] = min(s_qcnt[threadIdx.x], P.xg_subcap);
     }
-    if (P.stats) {
-        unsigned vals[4] = {n_exact, n_div, n_edge, n_seen};
-        const int idx[4] = {F3D_STAT_EXACT, F3D_STAT_DIVERGED, F3D_STAT_NEAR_EDGE, F3D_STAT_SEEN};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            unsigned v = vals[k];
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-            if ((threadIdx.x & 31) == 0 && v) atomicAdd(P.stats + idx[k], (unsigned long long)v);
-        }
-    }
+    fixup_stats(P, n_exact, n_div, n_edge, n_seen);
 }
 
 // labels of the points whose votes changed in fixup_apply_kernel (VotingSegmentation.segment, voting.py:120-135);
@@ -1286,7 +1333,14 @@ static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stre
         e = cudaFuncSetAttribute(fixup_apply_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem);
         if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute fixup)");
         static_assert(F3D_XCH_NSUB_FIX == 148 * 12, "one sub-queue per fix-up block");
-        fixup_apply_kernel<MODE, FMT><<<F3D_XCH_NSUB_FIX, FIXUP_THREADS, fx_smem, stream>>>(P);
+        const size_t table_smem = (size_t)(P.f_end - P.f_begin) * FIXUP_REC_BYTES;
+        if (table_smem <= 200 * 1024 && !getenv("F3D_FIXUP_STAGING")) {   // env: A/B experiments only
+            e = cudaFuncSetAttribute(fixup_apply_table_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_smem);
+            if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute fixup table)");
+            fixup_apply_table_kernel<MODE, FMT><<<148, FIXUP_TABLE_THREADS, table_smem, stream>>>(P);
+        } else {
+            fixup_apply_kernel<MODE, FMT><<<F3D_XCH_NSUB_FIX, FIXUP_THREADS, fx_smem, stream>>>(P);
+        }
         if (MODE == MODE_VOTE && RP.enabled) fixup_labels_kernel<<<148 * 8, 256, 0, stream>>>(P, RP);
     }
     return f3d_check_launch("f3d_fuse");

@@ -256,7 +256,7 @@ def main():
                                                          stats=stats)
         e1.record()
         fl.votes = votes
-        return labels, (e0, e1), 3   # fuse_kernel + fixup_apply + fixup_labels
+        return labels, (e0, e1), 4   # supertile_cull + fuse_kernel + fixup_apply + fixup_labels
 
     pipe = xchg = None
     if world > 1 and args.exchange == "dense":
@@ -284,13 +284,13 @@ def main():
                                               stats=stats, **xargs)
 
         labels = xchg.run(fuse, NCLASSES, THRESHOLD, None)
-        return labels, None, 6   # fuse_kernel, fixup_apply, publish, slot_merge, queue_accumulate, queue_relabel
+        return labels, None, 7   # supertile_cull, fuse_kernel, fixup_apply, publish, slot_merge, queue_accumulate, queue_relabel
 
     def step_multi():
         launches = [0]
 
         def fuse_into(a, b, out):
-            launches[0] += 3   # fuse_kernel + the two fix-up kernels
+            launches[0] += 3   # supertile_cull + fuse_kernel + fixup_apply
             engine.fuse_project_vote(fl.points4[a:b], fl.table, depth, masks, C1, RADIUS, fl.zmin, fl.zmax, votes=out[:b - a],
                                      stats=stats)
 

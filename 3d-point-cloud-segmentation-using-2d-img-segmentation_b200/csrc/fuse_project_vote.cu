@@ -90,6 +90,10 @@ struct FuseParams {
     // by supertile_cull_kernel; a tile then tests only its super-tile's list instead of every frame of the launch
     const unsigned* st_count;      // [super-tiles] list length, 0xFFFFFFFF = list overflowed (scan all frames)
     const uint16_t* st_list;       // [super-tiles][FUSE_ST_LCAP] frame ids relative to f_begin
+    // fused labels + deferred queue: per-point resolve state (total | best << 24 | first position << 48) written by the sweep,
+    // advanced by the fix-up kernel with a compare-and-swap per deferred vote, so the labels of the touched points are
+    // re-resolved from 8 bytes instead of re-reading their 4*C1-byte vote rows (NULL: re-read the rows)
+    unsigned long long* summ;
     GEntry* gq;                    // workspace queue of deferred point-views (NULL: evaluate them inside the sweep)
     unsigned long long* gq_count;
     unsigned long long gq_cap;
@@ -117,6 +121,10 @@ struct FuseParams {
 };
 #define FUSE_NSLOT 32   // classes per point remembered by cast_vote; longer lists are re-read from the histogram row
 #define FUSE_STG_ROWS 8 // record rows per staging chunk (512 B per warp: shared memory taken here is L1 taken from the gathers)
+
+__device__ __forceinline__ unsigned long long summ_pack(int total, int best, int bpos) {
+    return (unsigned long long)(unsigned)total | ((unsigned long long)(unsigned)best << 24) | ((unsigned long long)(unsigned)(bpos & 0xffff) << 48);
+}
 
 // one (cell, count) entry for owner d through sub-queue `sub`
 __device__ __forceinline__ void xg_append(const FuseParams& P, int d, unsigned sub, unsigned at, unsigned key, unsigned count) {
@@ -901,6 +909,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             bool unc = (T.total <= 0) || (T.best <= 0);                                  // voting.py:126,131
             if (!unc) unc = xdiv((double)T.best, (double)T.total) < RP.threshold;         // voting.py:128-130
             P.labels[gi] = (int64_t)(unc ? RP.unclassified : RP.remap[T.bpos]);
+            if (P.summ) P.summ[gi] = summ_pack(T.total, T.best, T.bpos);
         }
     } else if constexpr (MODE == MODE_VOTE) {
       {
@@ -968,6 +977,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             bool unc = (T.total <= 0) || (T.best <= 0);                                  // voting.py:126,131
             if (!unc) unc = xdiv((double)T.best, (double)T.total) < RP.threshold;         // voting.py:128-130
             P.labels[gi] = (int64_t)(unc ? RP.unclassified : RP.remap[T.bpos]);
+            if (P.summ) P.summ[gi] = summ_pack(T.total, T.best, T.bpos);
         }
       }
     }
@@ -1068,9 +1078,9 @@ __global__ void __launch_bounds__(256) supertile_cull_kernel(const __grid_consta
 // one deferred point-view: fp64 evaluation against its frame's exact record `fe`, then the vote / depth sample / index goes
 // where the mode wants it (dense votes by atomics, the owner's sub-queue `qsub` in exchange mode, z-buffer, uv2pt)
 template <int MODE, int FMT>
-__device__ __forceinline__ void fixup_entry(const FuseParams& P, const FrameExact* fe, const GEntry& e, unsigned long long i,
-                                            unsigned qsub, unsigned* s_qcnt, unsigned& n_exact, unsigned& n_div, unsigned& n_edge,
-                                            unsigned& n_seen) {
+__device__ __forceinline__ void fixup_entry(const FuseParams& P, const FuseResolve& RP, const FrameExact* fe, const GEntry& e,
+                                            unsigned long long i, unsigned qsub, unsigned* s_qcnt, unsigned& n_exact,
+                                            unsigned& n_div, unsigned& n_edge, unsigned& n_seen) {
     const int frel = (int)(e.w & 0xffffu), st = (int)((e.w >> 16) & 0xffu);
     const int HW = P.H * P.W;
     const float4 p = __ldg(P.points + e.pt);
@@ -1099,7 +1109,21 @@ __device__ __forceinline__ void fixup_entry(const FuseParams& P, const FrameExac
                 const size_t cell = (size_t)e.pt * P.C1 + cls;   // 32-bit atomic on the word of the uint16 counter
                 atomicAdd(reinterpret_cast<unsigned*>(P.votes16) + (cell >> 1), (cell & 1) ? 0x10000u : 1u);
             } else {
-                atomicAdd(P.votes + (size_t)e.pt * P.C1 + cls, 1);
+                const int v = atomicAdd(P.votes + (size_t)e.pt * P.C1 + cls, 1) + 1;
+                if (P.summ) {
+                    // advance the point's resolve state exactly as cast_vote would have: total + 1, and (best, first position)
+                    // if this class now leads.  Order of the updates does not matter (the maximum is the maximum).
+                    const int pos = RP.fpos[cls];
+                    unsigned long long cur = P.summ[e.pt];
+                    for (;;) {
+                        const int total = (int)(cur & 0xffffffu), best = (int)((cur >> 24) & 0xffffffu), bpos = (int)(cur >> 48);
+                        const bool lead = pos >= 0 && (v > best || (v == best && pos < bpos));
+                        const unsigned long long nxt = summ_pack(total + 1, lead ? v : best, lead ? pos : bpos);
+                        const unsigned long long seen = atomicCAS(P.summ + e.pt, cur, nxt);
+                        if (seen == cur) break;
+                        cur = seen;
+                    }
+                }
             }
             P.gq[i].w = e.w | (1u << 24);   // this point's label must be re-resolved
         }
@@ -1128,7 +1152,8 @@ __device__ __forceinline__ void fixup_stats(const FuseParams& P, unsigned n_exac
 #define FIXUP_TABLE_THREADS 1024
 #define FIXUP_TABLE_QSUBS (F3D_XCH_NSUB_FIX / 148)   // sub-queues a table block owns (warps share them round-robin)
 template <int MODE, int FMT>
-__global__ void __launch_bounds__(FIXUP_TABLE_THREADS, 1) fixup_apply_table_kernel(const __grid_constant__ FuseParams P) {
+__global__ void __launch_bounds__(FIXUP_TABLE_THREADS, 1) fixup_apply_table_kernel(const __grid_constant__ FuseParams P,
+                                                                                    const __grid_constant__ FuseResolve RP) {
     extern __shared__ __align__(16) unsigned char fx_smem[];
     __shared__ unsigned s_qcnt[FIXUP_TABLE_QSUBS][F3D_MAX_RANKS];
     const int nf = P.f_end - P.f_begin;
@@ -1146,7 +1171,7 @@ __global__ void __launch_bounds__(FIXUP_TABLE_THREADS, 1) fixup_apply_table_kern
         const GEntry e = P.gq[i];
         if (e.pt < 0) continue;
         const FrameExact* fe = reinterpret_cast<const FrameExact*>(fx_smem + (size_t)(e.w & 0xffffu) * FIXUP_REC_BYTES);
-        fixup_entry<MODE, FMT>(P, fe, e, i, blockIdx.x * FIXUP_TABLE_QSUBS + wsub, s_qcnt[wsub], n_exact, n_div, n_edge, n_seen);
+        fixup_entry<MODE, FMT>(P, RP, fe, e, i, blockIdx.x * FIXUP_TABLE_QSUBS + wsub, s_qcnt[wsub], n_exact, n_div, n_edge, n_seen);
     }
     if (P.xg_G > 0) {
         __syncthreads();
@@ -1160,7 +1185,7 @@ __global__ void __launch_bounds__(FIXUP_TABLE_THREADS, 1) fixup_apply_table_kern
 
 #define FIXUP_THREADS 128
 template <int MODE, int FMT>
-__global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid_constant__ FuseParams P) {
+__global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid_constant__ FuseParams P, const __grid_constant__ FuseResolve RP) {
     // Each lane needs the 448-byte fp64 record of ITS frame.  Reading it field by field would be ~50 fully divergent
     // loads per lane; instead the warp copies the 32 records one after the other with coalesced 16-byte loads into
     // shared memory and every lane then evaluates from its own copy.
@@ -1202,13 +1227,27 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid
         }
         __syncwarp();
         if (e.pt < 0) continue;
-        fixup_entry<MODE, FMT>(P, wbuf + lane, e, i, blockIdx.x, s_qcnt, n_exact, n_div, n_edge, n_seen);
+        fixup_entry<MODE, FMT>(P, RP, wbuf + lane, e, i, blockIdx.x, s_qcnt, n_exact, n_div, n_edge, n_seen);
     }
     if (P.xg_G > 0) {
         __syncthreads();
         if ((int)threadIdx.x < P.xg_G) P.xg_qcur[threadIdx.x * F3D_XCH_NSUB + blockIdx.x] = min(s_qcnt[threadIdx.x], P.xg_subcap);
     }
     fixup_stats(P, n_exact, n_div, n_edge, n_seen);
+}
+
+// labels of the points whose votes changed, from their 8-byte resolve state (VotingSegmentation.segment, voting.py:120-135)
+__global__ void __launch_bounds__(256) fixup_labels_summary_kernel(const __grid_constant__ FuseParams P, const __grid_constant__ FuseResolve RP) {
+    const unsigned long long n = min(*P.gq_count, P.gq_cap);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const GEntry e = P.gq[i];
+        if (e.pt < 0 || !((e.w >> 24) & 1u)) continue;
+        const unsigned long long cur = P.summ[e.pt];
+        const int total = (int)(cur & 0xffffffu), best = (int)((cur >> 24) & 0xffffffu), bpos = (int)(cur >> 48);
+        bool unc = (total <= 0) || (best <= 0);
+        if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;
+        P.labels[e.pt] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
+    }
 }
 
 // labels of the points whose votes changed in fixup_apply_kernel (VotingSegmentation.segment, voting.py:120-135);
@@ -1337,17 +1376,20 @@ static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stre
         if (table_smem <= 200 * 1024 && !getenv("F3D_FIXUP_STAGING")) {   // env: A/B experiments only
             e = cudaFuncSetAttribute(fixup_apply_table_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_smem);
             if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute fixup table)");
-            fixup_apply_table_kernel<MODE, FMT><<<148, FIXUP_TABLE_THREADS, table_smem, stream>>>(P);
+            fixup_apply_table_kernel<MODE, FMT><<<148, FIXUP_TABLE_THREADS, table_smem, stream>>>(P, RP);
         } else {
-            fixup_apply_kernel<MODE, FMT><<<F3D_XCH_NSUB_FIX, FIXUP_THREADS, fx_smem, stream>>>(P);
+            fixup_apply_kernel<MODE, FMT><<<F3D_XCH_NSUB_FIX, FIXUP_THREADS, fx_smem, stream>>>(P, RP);
         }
-        if (MODE == MODE_VOTE && RP.enabled) fixup_labels_kernel<<<148 * 8, 256, 0, stream>>>(P, RP);
+        if (MODE == MODE_VOTE && RP.enabled) {
+            if (P.summ) fixup_labels_summary_kernel<<<148 * 8, 256, 0, stream>>>(P, RP);
+            else fixup_labels_kernel<<<148 * 8, 256, 0, stream>>>(P, RP);
+        }
     }
     return f3d_check_launch("f3d_fuse");
 }
 
 // workspace = [deferred count u64][pad u64][super-tile counts u32 x S, padded to 16 B][super-tile lists u16 x S x FUSE_ST_LCAP]
-//             [GEntry x cap]; S = super-tiles of the cloud.  The super-tile part is attached whenever it fits, the deferred
+//             [resolve states u64 x N (fused labels only)][GEntry x cap]; S = super-tiles of the cloud.  The super-tile part is attached whenever it fits, the deferred
 // queue only when the caller's mode wants it; returns whether the queue was attached.
 static int64_t supertile_bytes(int64_t npoints) {
     const int64_t tiles = (npoints + FUSE_BLOCK - 1) / FUSE_BLOCK;
@@ -1355,7 +1397,8 @@ static int64_t supertile_bytes(int64_t npoints) {
     return ((S * 4 + 15) & ~(int64_t)15) + S * FUSE_ST_LCAP * 2;
 }
 
-static bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_bytes, bool want_queue = true) {
+static bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_bytes, bool want_queue = true, bool want_summ = false) {
+    P.summ = nullptr;
     P.gq = nullptr;
     P.gq_count = nullptr;
     P.gq_cap = 0;
@@ -1372,7 +1415,16 @@ static bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_b
         P.st_list = reinterpret_cast<const uint16_t*>(base + off + ((S * 4 + 15) & ~(int64_t)15));
         off += stb;
     }
-    if (!want_queue || workspace_bytes - off < (int64_t)sizeof(GEntry)) return false;
+    if (!want_queue) return false;
+    // resolve states only when the queue still gets its share (one entry per 8 points) behind them
+    if (want_summ && !getenv("F3D_NO_SUMMARY") && workspace_bytes - off >= P.N * 8 + (P.N / 8 + 1024) * (int64_t)sizeof(GEntry)) {
+        P.summ = reinterpret_cast<unsigned long long*>(base + off);
+        off += P.N * 8;
+    }
+    if (workspace_bytes - off < (int64_t)sizeof(GEntry)) {
+        P.summ = nullptr;
+        return false;
+    }
     P.gq_count = reinterpret_cast<unsigned long long*>(workspace);
     P.gq = reinterpret_cast<GEntry*>(base + off);
     P.gq_cap = (unsigned long long)((workspace_bytes - off) / (int64_t)sizeof(GEntry));
@@ -1381,10 +1433,11 @@ static bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_b
 
 extern "C" int64_t f3d_fuse_workspace_bytes(int64_t npoints) {
     // room for one uncertain point-view per 4 points (measured: ~0.08 per point on the 1920x1440 scene), at least 1 Mi entries,
-    // plus the super-tile candidate lists of the first cull level
+    // plus the super-tile candidate lists of the first cull level and the 8-byte per-point resolve states
     int64_t cap = npoints / 4;
     if (cap < (1 << 20)) cap = 1 << 20;
-    return 16 + supertile_bytes(npoints < 0 ? 0 : npoints) + cap * (int64_t)sizeof(GEntry);
+    if (npoints < 0) npoints = 0;
+    return 16 + supertile_bytes(npoints) + npoints * 8 + cap * (int64_t)sizeof(GEntry);
 }
 
 static int fill_common(FuseParams& P, const void* points, int64_t N, const void* table, int fb, int fe, const void* depth,
@@ -1432,6 +1485,7 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.C1 = 0;
     P.RS = 0;
     P.accumulate = 0;
+    P.summ = nullptr;
     P.gq = nullptr;
     P.gq_count = nullptr;
     P.gq_cap = 0;
@@ -1502,7 +1556,8 @@ static int fuse_vote_impl(const void* points, int64_t N, const void* frame_table
     P.votes16 = votes16;
     P.labels = labels;
     P.C1 = C1;
-    attach_workspace(P, workspace, workspace_bytes, (votes || votes16) && !P.audit && N <= 0x7fffffff);   // labels-only / audit: fp64 inside the sweep
+    attach_workspace(P, workspace, workspace_bytes, (votes || votes16) && !P.audit && N <= 0x7fffffff,
+                     votes && labels && frame_end - frame_begin < (1 << 24));   // labels-only / audit: fp64 inside the sweep
     P.RS = hist_row_stride(C1);
     const size_t esz = depth_fmt == F3D_DEPTH_U16_MM ? 2 : 4;
     int fb = frame_begin;

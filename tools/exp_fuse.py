@@ -36,10 +36,11 @@ if mode in ("quick", "traffic"):
     import ctypes, glob, os
     ref = None
     reps = 10 if mode == "quick" else 1
-    for path in ["default", "default+F3D_NO_SUPERTILE", "default+F3D_FIXUP_STAGING"] + sorted(glob.glob(str(ROOT / "build" / "variants" / "*.so"))) + ["default+F3D_HIST16"]:
-        os.environ.pop("F3D_HIST16", None); os.environ.pop("F3D_NO_SUPERTILE", None); os.environ.pop("F3D_FIXUP_STAGING", None)
+    for path in ["default", "default+F3D_NO_SUPERTILE", "default+F3D_FIXUP_STAGING", "default+F3D_NO_SUMMARY"] + sorted(glob.glob(str(ROOT / "build" / "variants" / "*.so"))) + ["default+F3D_HIST16"]:
+        os.environ.pop("F3D_HIST16", None); os.environ.pop("F3D_NO_SUPERTILE", None); os.environ.pop("F3D_FIXUP_STAGING", None); os.environ.pop("F3D_NO_SUMMARY", None)
         if "NO_SUPERTILE" in path: os.environ["F3D_NO_SUPERTILE"] = "1"
         if "FIXUP_STAGING" in path: os.environ["F3D_FIXUP_STAGING"] = "1"
+        if "NO_SUMMARY" in path: os.environ["F3D_NO_SUMMARY"] = "1"
         if path.startswith("default"):
             lib = _lib.load()
             if "HIST16" in path: os.environ["F3D_HIST16"] = "1"

@@ -22,6 +22,8 @@ _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 SIGNATURES = {
     "f3d_last_error": (C.c_char_p, []),
     "f3d_version": (C.c_int, []),
+    "f3d_fuse_timing_reset": (C.c_int, []),
+    "f3d_fuse_timing_read": (C.c_int, [_vp, _i32]),
     "f3d_frame_table_bytes": (_i64, [_i32]),
     "f3d_frames_setup": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _f64, _vp, _vp]),
     "f3d_frames_export": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),

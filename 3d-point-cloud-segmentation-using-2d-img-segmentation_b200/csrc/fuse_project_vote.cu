@@ -85,6 +85,7 @@ struct FuseParams {
     uint32_t* zbuf;
     int64_t* labels;
     unsigned long long* stats;
+    int time_kernel;  // flags bit 1: CUDA events around the fused kernel (f3d_fuse_timing_*)
     int audit, dbg;   // dbg: timing experiments only (bits: 1 drop candidates, 2 skip cull, 4 classify only)
     // first cull level (optional, from the workspace): candidate frames of every super-tile of FUSE_ST_TILES tiles, found
     // by supertile_cull_kernel; a tile then tests only its super-tile's list instead of every frame of the launch
@@ -636,56 +637,57 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         // ---- conservative tile x frustum cull (fp32 + explicit rounding margin; never drops a visible pair)
         const float blo[3] = {tbox[0], tbox[1], tbox[2]}, bhi[3] = {tbox[3], tbox[4], tbox[5]};
         const float box_mag = fabsf(blo[0]) + fabsf(blo[1]) + fabsf(blo[2]) + fabsf(bhi[0]) + fabsf(bhi[1]) + fabsf(bhi[2]);
+        // Two levels in one pass: a frame that survives the tile box is tested against the box of each warp's 32 points
+        // while its planes are still in registers.  In a spatially sorted cloud a warp's points are a few centimetres
+        // apart, so a warp is almost always entirely inside or entirely outside a frustum: this drops ~45 % of the
+        // (warp, frame) pairs -- and every frame no warp keeps -- before any per-point work.  Same conservative rule.
         for (int f0 = cbase; f0 < cend && !(P.dbg & 2); f0 += FUSE_BLOCK) {
             const int fi = f0 + tid;
             bool keep = false;
             int frel = 0;
+            unsigned wmask = 0u;
             if (fi < cend) {
                 keep = true;
                 frel = use_list ? (int)__ldg(st_list + fi) : fi;
                 const float4* pl = frec[P.f_begin + frel].cull.pl;
+                float4 q[5];
 #pragma unroll
                 for (int m = 0; m < 5; ++m) {
-                    const float4 q = __ldg(pl + m);
-                    float mx = fmaxf(q.x * blo[0], q.x * bhi[0]) + fmaxf(q.y * blo[1], q.y * bhi[1]) +
-                               fmaxf(q.z * blo[2], q.z * bhi[2]) - q.w;
-                    float margin = 2.0e-6f * (box_mag + fabsf(q.w)) + 1.0e-7f;
+                    q[m] = __ldg(pl + m);
+                    float mx = fmaxf(q[m].x * blo[0], q[m].x * bhi[0]) + fmaxf(q[m].y * blo[1], q[m].y * bhi[1]) +
+                               fmaxf(q[m].z * blo[2], q[m].z * bhi[2]) - q[m].w;
+                    float margin = 2.0e-6f * (box_mag + fabsf(q[m].w)) + 1.0e-7f;
                     keep = keep && (mx >= -margin);
+                }
+                if (keep) {
+                    for (int wb = 0; wb < FUSE_BLOCK / 32; ++wb) {
+                        const float* wbox = red + wb * 6;
+                        const float l0 = wbox[0], l1 = wbox[1], l2 = wbox[2], h0 = wbox[3], h1 = wbox[4], h2 = wbox[5];
+                        bool kw = true;
+#pragma unroll
+                        for (int m = 0; m < 5; ++m) {
+                            const float mx = fmaxf(q[m].x * l0, q[m].x * h0) + fmaxf(q[m].y * l1, q[m].y * h1) +
+                                             fmaxf(q[m].z * l2, q[m].z * h2) - q[m].w;
+                            const float margin = 4.0e-6f * (box_mag + fabsf(q[m].w)) + 1.0e-7f;   // a warp box lies inside the tile box
+                            kw = kw && (mx >= -margin);
+                        }
+                        wmask |= kw ? (1u << wb) : 0u;
+                    }
+                    keep = wmask != 0u;
                 }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             int base = 0;
             if (lane == 0 && bal) base = atomicAdd(ncand_s, __popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) cand[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)frel;
+            if (keep) {
+                const int at = base + __popc(bal & ((1u << lane) - 1u));
+                cand[at] = (uint16_t)frel;
+                cmask[at] = (uint8_t)wmask;
+            }
         }
         __syncthreads();
         const int ncand = (P.dbg & 3) ? 0 : *ncand_s;
-        // ---- second cull level: every surviving frame against the box of each warp's 32 points (8 threads per
-        // candidate, one per warp box).  In a spatially sorted cloud a warp's points are a few centimetres apart, so a
-        // warp is almost always entirely inside or entirely outside a frustum: this drops ~45 % of the (warp, frame)
-        // pairs before any per-point work.  Same conservative rule as the tile test.
-        for (int i0 = 0; i0 < ncand * 8; i0 += FUSE_BLOCK) {
-            const int i = i0 + tid;
-            const int c = i >> 3, wb = i & 7;
-            bool keep = false;
-            if (c < ncand) {
-                keep = true;
-                const float4* pl = frec[P.f_begin + cand[c]].cull.pl;
-                const float* wbox = red + wb * 6;
-                const float l0 = wbox[0], l1 = wbox[1], l2 = wbox[2], h0 = wbox[3], h1 = wbox[4], h2 = wbox[5];
-#pragma unroll
-                for (int m = 0; m < 5; ++m) {
-                    const float4 q = __ldg(pl + m);
-                    const float mx = fmaxf(q.x * l0, q.x * h0) + fmaxf(q.y * l1, q.y * h1) + fmaxf(q.z * l2, q.z * h2) - q.w;
-                    const float margin = 4.0e-6f * (box_mag + fabsf(q.w)) + 1.0e-7f;   // a warp box lies inside the tile box
-                    keep = keep && (mx >= -margin);
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if ((lane & 7) == 0 && c < ncand) cmask[c] = (uint8_t)((bal >> lane) & 0xffu);
-        }
-        __syncthreads();
         const int nbatch = (ncand + FUSE_STAGE - 1) / FUSE_STAGE;
 
         // TMA producer (warp 0): lane 0 arms the barrier with the batch's byte count, lane k issues the 128-byte bulk
@@ -1327,6 +1329,38 @@ static size_t fuse_smem_bytes(int mode, int C1, int hb, bool slots) {
     return b;
 }
 
+// ---- optional timing of the fused kernel alone (flags bit 1): event pairs recorded on the launch stream around
+// fuse_kernel, read back after the timed region -- so a benchmark reports the dominant kernel's duration measured live,
+// not the whole call (first cull level + fused kernel + fix-up kernels)
+#define F3D_TIMING_SLOTS 256
+static cudaEvent_t g_tev[F3D_TIMING_SLOTS][2];
+static int g_tev_created = 0, g_tev_used = 0;
+
+extern "C" int f3d_fuse_timing_reset(void) {
+    g_tev_used = 0;
+    return F3D_OK;
+}
+
+extern "C" int f3d_fuse_timing_read(float* ms_out, int32_t max_n) {
+    if (!ms_out || max_n < 0) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_timing_read: bad argument");
+    int n = g_tev_used < max_n ? g_tev_used : max_n;
+    for (int i = 0; i < n; ++i) {
+        if (cudaEventSynchronize(g_tev[i][1]) != cudaSuccess || cudaEventElapsedTime(ms_out + i, g_tev[i][0], g_tev[i][1]) != cudaSuccess)
+            return f3d_check_launch("f3d_fuse_timing_read");
+    }
+    return n;
+}
+
+static bool timing_slot(cudaEvent_t*& pair) {
+    if (g_tev_used >= F3D_TIMING_SLOTS) return false;
+    while (g_tev_created <= g_tev_used) {
+        if (cudaEventCreate(&g_tev[g_tev_created][0]) != cudaSuccess || cudaEventCreate(&g_tev[g_tev_created][1]) != cudaSuccess) return false;
+        ++g_tev_created;
+    }
+    pair = g_tev[g_tev_used++];
+    return true;
+}
+
 template <int MODE, int FMT, int HB>
 static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stream);
 
@@ -1365,7 +1399,10 @@ static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stre
             P.st_count = nullptr;   // few frames: the per-tile scan is cheaper than another launch
         }
     }
+    cudaEvent_t* tev = nullptr;
+    if (P.time_kernel && timing_slot(tev)) cudaEventRecord(tev[0], stream);
     fuse_kernel<MODE, FMT, HB><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
+    if (tev) cudaEventRecord(tev[1], stream);
     if (use_queue) {
         // the queue length lives on the device: fixed grids with grid-stride loops, no host synchronisation
         const int fx_smem = (FIXUP_THREADS / 32) * 32 * (int)sizeof(FrameExact);
@@ -1475,6 +1512,7 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.d_hi = hi;
     P.stats = reinterpret_cast<unsigned long long*>(stats);
     P.audit = flags & 1;
+    P.time_kernel = (flags >> 1) & 1;
     P.dbg = (flags >> 8) & 0xff;
     P.votes = nullptr;
     P.votes16 = nullptr;

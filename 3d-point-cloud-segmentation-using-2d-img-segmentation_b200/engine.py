@@ -126,8 +126,9 @@ def fuse_project_vote(points4, table: FrameTable, depth, mask, nclasses1, radius
 
 def fuse_project_vote_resolve(points4, table: FrameTable, depth, mask, nclasses1, nclasses_id, radius=0.05, zmin=0.1,
                               zmax=4.0, threshold=0.5, filter_classes=None, votes=None, want_votes=True, labels=None,
-                              stats=None, audit=False, frame_begin=0, frame_end=None):
-    """Kernel (1) with the label resolve fused into its epilogue.  Returns (votes or None, labels int64 [N])."""
+                              stats=None, audit=False, frame_begin=0, frame_end=None, time_kernel=False):
+    """Kernel (1) with the label resolve fused into its epilogue.  Returns (votes or None, labels int64 [N]).
+    `time_kernel`: record CUDA events around the fused kernel alone (read them with `fuse_timing_read`)."""
     frame_end = table.F if frame_end is None else frame_end
     N = points4.shape[0]
     if votes is None and want_votes:
@@ -142,8 +143,21 @@ def fuse_project_vote_resolve(points4, table: FrameTable, depth, mask, nclasses1
         _depth_fmt(depth) if nf else 0, ptr(mask) if nf else None, table.H, table.W, ptr(table.K), float(radius),
         float(zmin), float(zmax), ptr(votes), int(nclasses1), float(threshold), ptr(filt),
         0 if filt is None else int(filt.size), int(nclasses_id), ptr(labels), ptr(ws), ws.numel(), ptr(stats),
-        int(bool(audit)), stream_ptr()), "f3d_fuse_project_vote_resolve")
+        int(bool(audit)) | (2 if time_kernel else 0), stream_ptr()), "f3d_fuse_project_vote_resolve")
     return votes, labels
+
+
+def fuse_timing_reset():
+    check(load().f3d_fuse_timing_reset(), "f3d_fuse_timing_reset")
+
+
+def fuse_timing_read(max_n=256):
+    """Durations (ms) of the fused kernel alone for the calls made with time_kernel=True since the last reset."""
+    out = np.zeros(max_n, dtype=np.float32)
+    n = load().f3d_fuse_timing_read(ptr(out), int(max_n))
+    if n < 0:
+        check(n, "f3d_fuse_timing_read")
+    return out[:n].astype(np.float64)
 
 
 def _filter_arg(filter_classes):

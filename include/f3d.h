@@ -43,6 +43,12 @@ extern "C" {
 const char* f3d_last_error(void);
 int f3d_version(void);
 
+/* Timing of the fused kernel alone (not the first cull level or the fix-up kernels of the same call): every f3d_fuse_*
+ * call with flags bit 1 records one event pair (up to 256 since the last reset; process-wide, not thread-safe).
+ * f3d_fuse_timing_read waits for the recorded pairs and writes their durations in milliseconds; returns how many. */
+int f3d_fuse_timing_reset(void);
+int f3d_fuse_timing_read(float* ms_out, int32_t max_n);
+
 
 /* ---- frame table -------------------------------------------------------------------------------------- */
 
@@ -81,7 +87,8 @@ int64_t f3d_fuse_workspace_bytes(int64_t npoints);
  *            accumulate = 0: every cell is overwritten (no memset needed); 1: added to.  16-byte aligned.
  *   workspace optional scratch, see f3d_fuse_workspace_bytes
  *   stats    optional uint64[F3D_NSTATS], accumulated with atomics (caller zeroes)
- *   flags    bit 0: audit mode (fp64 for every candidate, counts F3D_STAT_AUDIT_BAD) */
+ *   flags    bit 0: audit mode (fp64 for every candidate, counts F3D_STAT_AUDIT_BAD)
+ *            bit 1: record CUDA events on `stream` around the fused kernel alone (see f3d_fuse_timing_read) */
 int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                           int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
                           int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,

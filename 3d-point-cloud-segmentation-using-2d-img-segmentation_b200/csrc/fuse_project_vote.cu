@@ -239,7 +239,15 @@ __device__ __forceinline__ Cls classify(const float4* __restrict__ s, const floa
     const float S = fabsf(d0) + fabsf(d1) + fabsf(d2) + 1.0e-9f;
     const float4 Mz = s[4];
     const float z = fmaf(Mz.x, d0, fmaf(Mz.y, d1, Mz.z * d2));
+    // rounding bound of a row: 8 u * sum |M_i| |d_i| (M rounded to fp32: 1 u; d: 2 u; product and two fused adds: 3 u; the
+    // sum itself is computed to 3 u) -- two to three times tighter than 8 u * max|M_i| * sum|d_i|, which is what decides
+    // how many pixel floors have to be re-evaluated in fp64.  The 1e-9 m floor covers the absolute error of d near 0.
+#ifndef FUSE_LOOSE_BOUND
+    const float ad0 = fabsf(d0), ad1 = fabsf(d1), ad2 = fabsf(d2);
+    const float ez = 8.0f * F3D_U24 * fmaf(fabsf(Mz.x), ad0, fmaf(fabsf(Mz.y), ad1, fmaf(fabsf(Mz.z), ad2, Mz.w * 1.0e-9f)));
+#else
     const float ez = 8.0f * F3D_U24 * Mz.w * S;
+#endif
     c.z = z;
     if (z < -16.0f * ez) return c;
     if (z <= 16.0f * ez) {
@@ -251,7 +259,12 @@ __device__ __forceinline__ Cls classify(const float4* __restrict__ s, const floa
     const float b = fmaf(Mv.x, d0, fmaf(Mv.y, d1, Mv.z * d2));
     const float r = __frcp_rn(z);
     const float u = a * r, v = b * r;
+#ifndef FUSE_LOOSE_BOUND
+    const float ea = 8.0f * F3D_U24 * fmaf(fabsf(Mu.x), ad0, fmaf(fabsf(Mu.y), ad1, fmaf(fabsf(Mu.z), ad2, Mu.w * 1.0e-9f)));
+    const float eb = 8.0f * F3D_U24 * fmaf(fabsf(Mv.x), ad0, fmaf(fabsf(Mv.y), ad1, fmaf(fabsf(Mv.z), ad2, Mv.w * 1.0e-9f)));
+#else
     const float ea = 8.0f * F3D_U24 * Mu.w * S, eb = 8.0f * F3D_U24 * Mv.w * S;
+#endif
     const float eu = 1.125f * (ea + fabsf(u) * ez) * r + 8.0f * F3D_U24 * fabsf(u) + 1.0e-4f;
     const float ev = 1.125f * (eb + fabsf(v) * ez) * r + 8.0f * F3D_U24 * fabsf(v) + 1.0e-4f;
     const float sl = fmaf(s[5].w, d0, fmaf(s[6].w, d1, s[7].w * d2));   // (p - eye) . lookat

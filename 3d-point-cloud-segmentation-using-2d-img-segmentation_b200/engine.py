@@ -177,7 +177,7 @@ def exchange_constants():
 
 def fuse_project_vote_exchange(points4, table: FrameTable, depth, mask, nclasses1, nranks, points_per_shard, peer_slot_ptrs,
                                peer_dir_ptrs, peer_queue_ptrs, sub_rows, sub_cap, cursors, overflow, radius=0.05, zmin=0.1,
-                               zmax=4.0, stats=None, frame_begin=0, frame_end=None):
+                               zmax=4.0, stats=None, frame_begin=0, frame_end=None, time_kernel=False):
     """Kernel (1) with the multi-GPU exchange fused in: the votes of this rank's frames go straight into the owner
     ranks' memory through the peer pointers (numpy uint64 [G] each) as slot records + directory entries, and as
     (cell, count) queue entries for what does not go into a record.  `cursors` is uint32 [G * (NREG + NSUB)], zeroed
@@ -194,8 +194,8 @@ def fuse_project_vote_exchange(points4, table: FrameTable, depth, mask, nclasses
     check(load().f3d_fuse_project_vote_exchange(
         ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth), _depth_fmt(depth), ptr(mask), table.H, table.W,
         ptr(table.K), float(radius), float(zmin), float(zmax), int(nclasses1), int(nranks), int(points_per_shard), ptr(arrs[0]),
-        ptr(arrs[1]), ptr(arrs[2]), int(sub_rows), int(sub_cap), ptr(cursors), ptr(overflow), ptr(ws), ws.numel(), ptr(stats), 0,
-        stream_ptr()), "f3d_fuse_project_vote_exchange")
+        ptr(arrs[1]), ptr(arrs[2]), int(sub_rows), int(sub_cap), ptr(cursors), ptr(overflow), ptr(ws), ws.numel(), ptr(stats),
+        2 if time_kernel else 0, stream_ptr()), "f3d_fuse_project_vote_exchange")
 
 
 def exchange_publish(cursors, peer_count_ptrs, rank, sub_cap):

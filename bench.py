@@ -281,7 +281,7 @@ def main():
     def step_records():
         def fuse(**xargs):
             engine.fuse_project_vote_exchange(fl.points4, fl.table, depth, masks, C1, radius=RADIUS, zmin=fl.zmin, zmax=fl.zmax,
-                                              stats=stats, **xargs)
+                                              stats=stats, time_kernel=True, **xargs)
 
         labels = xchg.run(fuse, NCLASSES, THRESHOLD, None)
         return labels, None, 7   # supertile_cull, fuse_kernel, fixup_apply, publish, slot_merge, queue_accumulate, queue_relabel
@@ -357,8 +357,55 @@ def main():
             except Exception:
                 pass
 
+    if roof is None and xchg is not None:
+        kt = engine.fuse_timing_read()
+        if len(kt):
+            kms = float(np.mean(kt))
+            balg = 16 * N + F * H * W * 3 + 64 * F + 4 * xchg.rows * C1    # per rank: the dense vote write is this rank's shard
+            peak, how = peaks()
+            roof = {"bound": "hbm", "achieved": balg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": balg / (kms * 1e-3) / 1e9 / peak, "traffic": None,
+                    "kernel": "fuse_kernel<VOTE,U16MM,HB1> in exchange mode on rank 0 (sweep + slot records written to the owners); "
+                              "the dense shard write happens in slot_merge_kernel", "kernel_ms": kms,
+                    "kernel_launches_timed": int(len(kt)), "algorithmic_bytes": balg, "peak_source": how,
+                    "note": "per-rank bytes: cloud + this rank's frames + this rank's shard of the vote tensor"}
+
     # ---- end to end through the public API: host (pinned) buffers in, host labels out ------------------------------------
     e2e = None
+    if not args.no_e2e and world > 1:
+        # every rank copies its frames from pinned host memory, the exchange step runs, labels land on the host
+        h_depth = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True)
+        h_masks = torch.empty(masks.shape, dtype=masks.dtype, pin_memory=True)
+        h_depth.copy_(depth)
+        h_masks.copy_(masks)
+        h_pts = torch.as_tensor(np.ascontiguousarray(fl.points4.cpu().numpy())).pin_memory()
+        h_out = torch.empty(N, dtype=torch.int64, pin_memory=True)
+        ref_labels = labels.clone()
+        n_e2e = max(2, min(args.steps, 5))
+        torch.cuda.synchronize()
+        dist.barrier()
+        for i in range(1 + n_e2e):
+            if i == 1:
+                torch.cuda.synchronize()
+                dist.barrier()
+                t0 = time.perf_counter()
+            fl.points4.copy_(h_pts, non_blocking=True)
+            depth.copy_(h_depth, non_blocking=True)
+            masks.copy_(h_masks, non_blocking=True)
+            lab = step()[0]
+            h_out.copy_(lab, non_blocking=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sec = (time.perf_counter() - t0) / n_e2e
+        tt = torch.tensor([sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = float(tt.item())
+        assert torch.equal(torch.as_tensor(h_out.numpy()).cuda(), ref_labels), "end-to-end labels differ from the device-resident run"
+        h2d = int(h_pts.numel() * 4 + h_depth.numel() * 2 + h_masks.numel())
+        e2e = {"value": pv_step / sec, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(N * 8) * world,
+               "ms_per_step": sec * 1e3, "steps": n_e2e,
+               "api": "per rank: pinned host cloud + frames -> device, parallel.VoteExchange.run, labels -> pinned host"}
+        del h_depth, h_masks
     if not args.no_e2e and world == 1:
         h_depth = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True)
         h_masks = torch.empty(masks.shape, dtype=masks.dtype, pin_memory=True)

@@ -82,3 +82,19 @@ def test_shard_arithmetic():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_frame_and_point_sharding_helpers():
+    """Host-side sharding rules of the multi-GPU path (no GPU needed)."""
+    import importlib
+    parallel = importlib.import_module(PKG_NAME + ".parallel")
+    for nframes, world in [(500, 1), (4000, 8), (9, 8), (3, 8), (1001, 4)]:
+        for mode in ("interleaved", "contiguous"):
+            ids = [parallel.frame_shard_ids(nframes, r, world, mode) for r in range(world)]
+            flat = sorted(i for part in ids for i in part)
+            assert flat == list(range(nframes))                                  # a partition of the frames
+            assert max(len(p) for p in ids) - min(len(p) for p in ids) <= 1      # balanced
+        assert parallel.frame_shard_ids(nframes, 0, world, "contiguous") == list(range(*parallel.frame_shard(nframes, 0, world)))
+    for n, world in [(10_000_000, 8), (20011, 3), (255, 2), (1, 8)]:
+        per = parallel.shard_points(n, world)
+        assert per % 256 == 0 and per * world >= n and (per - 256) * world < max(n, 256 * world)

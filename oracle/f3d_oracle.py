@@ -305,10 +305,11 @@ def zbuffer_splat(points, K, w, h, quat, t, eye, lookat, face_normals, max_depth
 def zero_border(depth, border=10):
     """10-px zero border the reference multiplies into depth when `padding` is set (`ios_rtab.py:105-109`)."""
     d = depth.copy()
-    d[:border, :] = 0
-    d[-border:, :] = 0
-    d[:, :border] = 0
-    d[:, -border:] = 0
+    if border > 0:                      # (a `-0:` slice would select the whole array)
+        d[:border, :] = 0
+        d[-border:, :] = 0
+        d[:, :border] = 0
+        d[:, -border:] = 0
     return d
 
 

@@ -13,7 +13,8 @@ roots, left to right as written, never fused), because the reference itself leav
 this file.  Pinning: `tests/golden/make_golden.py` runs the UNMODIFIED reference functions (imported from
 `/root/reference` in the build container with the `oracle/refshim` stand-ins for the absent pyquaternion /
 open3d) on seeded scenes and stores their outputs under `tests/golden/`; `tests/test_oracle_golden.py` checks
-this restatement against those vectors.  The box-merge part has no runnable reference in this image
+this restatement against those vectors (`tests/golden/make_golden_ingest.py` does the same for the scan-directory
+readers, which are host code of the product and are compared with the reference's readers directly).  The box-merge part has no runnable reference in this image
 (Open3D absent) -> "parity unpinned" for OBB fitting; the pair predicate and merge drivers are restated from
 the source text only.
 """

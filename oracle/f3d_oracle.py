@@ -530,3 +530,49 @@ def split_into_instances(classes, indptr, indices, nclasses=133, instance_classe
             todo[comp] = False
             classes[comp] = newc
     return ninst, ids, info, classes
+
+
+# ----------------------------------------------------------------------------------------------------------
+# radius adjacency: `KDTree(points).query_radius(points, r=2*ds_radius)`, fusion.py:374-375
+# ----------------------------------------------------------------------------------------------------------
+
+
+def radius_adjacency(points, r, chunk=2048):
+    """CSR (indptr int64 [N+1], indices int64) of `sklearn.neighbors.KDTree(points).query_radius(points, r)` with every
+    row sorted ascending (scikit-learn returns a row in tree-traversal order; `split_into_instances` only uses the
+    rows as sets, `segUtils/cv.py:425-440`).  Membership is scikit-learn's leaf test for the Euclidean metric: the
+    reduced distance `((dx*dx) + dy*dy) + dz*dz` (binary64, left to right, never fused) `<= r*r`; a point is its own
+    neighbour.  Restated on a uniform grid of cell size r (27 cells per query) so that it finishes on 1e5-point clouds.
+    Pinned by `tests/test_oracle_golden.py::test_radius_adjacency_matches_kdtree` against scikit-learn itself."""
+    p = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
+    n = len(p)
+    r = float(r)
+    r2 = r * r
+    if n == 0:
+        return np.zeros(1, np.int64), np.zeros(0, np.int64)
+    cell = np.floor((p - p.min(axis=0)) / max(r, 1e-300)).astype(np.int64)
+    dims = cell.max(axis=0) + 3
+    key = ((cell[:, 0] + 1) * dims[1] + (cell[:, 1] + 1)) * dims[2] + (cell[:, 2] + 1)
+    order = np.argsort(key, kind="stable")
+    skey = key[order]
+    rows = [None] * n
+    offs = [((dx * dims[1]) + dy) * dims[2] + dz for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)]
+    uniq, start = np.unique(skey, return_index=True)
+    end = np.append(start[1:], n)
+    for u, a, b in zip(uniq, start, end):
+        q = order[a:b]                                    # the points of this cell
+        lo = np.searchsorted(skey, [u + o for o in offs], side="left")
+        hi = np.searchsorted(skey, [u + o for o in offs], side="right")
+        cand = np.concatenate([order[x:y] for x, y in zip(lo, hi) if y > x])
+        for c0 in range(0, len(q), chunk):
+            qq = q[c0:c0 + chunk]
+            dx = p[qq, None, 0] - p[None, cand, 0]
+            dy = p[qq, None, 1] - p[None, cand, 1]
+            dz = p[qq, None, 2] - p[None, cand, 2]
+            d2 = (dx * dx + dy * dy) + dz * dz
+            hit = d2 <= r2
+            for k, i in enumerate(qq):
+                rows[i] = np.sort(cand[hit[k]])
+    indptr = np.zeros(n + 1, np.int64)
+    indptr[1:] = np.cumsum([len(x) for x in rows])
+    return indptr, np.concatenate(rows).astype(np.int64)

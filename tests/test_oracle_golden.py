@@ -84,3 +84,25 @@ def test_box_oracle_union_find_chain():
     # closed intervals: touching boxes overlap
     e2 = orc.box_pairs_aabb(np.array([[0, 0, 0], [1, 0, 0]], float), np.array([[1, 1, 1], [2, 1, 1]], float), [0, 0])
     assert e2.tolist() == [[0, 1]]
+
+
+def test_radius_adjacency_matches_kdtree(scenes):
+    """The adjacency restatement (groundwork for the GPU neighbour search) against the very call the
+    reference makes: `KDTree(points).query_radius(points, r=2*ds_radius)` (`fusion.py:374-375`), on a room cloud and on a
+    lattice whose neighbour distances tie with r exactly (closed ball)."""
+    from sklearn.neighbors import KDTree
+    spec = scenes.scaled_spec("C1", npoints=6000, nframes=1, seed=17)
+    cloud = scenes.make_cloud(spec).astype(np.float64)
+    g = np.arange(6) * 0.5
+    lattice = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    for pts, r in ((cloud, 0.18), (cloud[:500], 0.05), (lattice, 0.5), (lattice, 0.5 * np.sqrt(2.0)), (lattice[:1], 1.0)):
+        indptr, indices = orc.radius_adjacency(pts, r)
+        ref = KDTree(pts).query_radius(pts, r=r)
+        assert indptr[-1] == sum(len(a) for a in ref)
+        for i in range(len(pts)):
+            assert np.array_equal(indices[indptr[i]:indptr[i + 1]], np.sort(ref[i]))
+    # the instance split consumes it unchanged
+    indptr, indices = orc.radius_adjacency(cloud, 0.18)
+    classes = (np.floor(cloud[:, 0] / 1.3).astype(np.int64) % 3) * 40 + 5
+    ids = orc.split_into_instances(classes, indptr, indices, 133, None, 1)[1]
+    assert ids.shape == (len(cloud),)

@@ -15,6 +15,7 @@ LIB_PATH = Path(os.environ.get("F3D_LIB", PKG / "libf3d.so"))   # F3D_LIB: kerne
 NSTATS = 8
 STAT_NAMES = ("candidates", "exact", "diverged", "near_edge", "seen", "audit_bad")
 DEPTH_U16_MM, DEPTH_F32_M = 0, 1
+FRAMES_U32, FRAMES_U32_T16 = 2, 3   # packed depth | class << 16 texels (f3d_pack_frames): row-major / 16x16 tiles
 
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 
@@ -22,8 +23,9 @@ _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 SIGNATURES = {
     "f3d_last_error": (C.c_char_p, []),
     "f3d_version": (C.c_int, []),
-    "f3d_fuse_timing_reset": (C.c_int, []),
-    "f3d_fuse_timing_read": (C.c_int, [_vp, _i32]),
+    "f3d_fuse_time_next_call": (C.c_int, [_vp, _vp]),
+    "f3d_packed_frame_texels": (_i64, [_i32, _i32, _i32]),
+    "f3d_pack_frames": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "f3d_frame_table_bytes": (_i64, [_i32]),
     "f3d_frames_setup": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _f64, _vp, _vp]),
     "f3d_frames_export": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),

@@ -15,11 +15,12 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libf3d.so"
-SOURCES = ["c_api.cu", "frame_setup.cu", "fuse_project_vote.cu", "vote_resolve.cu", "vote_exchange.cu", "box_merge.cu"]
-NVCC_FLAGS = [
+SOURCES = ["c_api.cu", "frame_setup.cu", "fuse_vote.cu", "fuse_aux.cu", "vote_resolve.cu", "vote_exchange.cu", "box_merge.cu"]
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off", "-Xptxas", "-v", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off", "-Xptxas", "-v",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
 
 
 def nvcc_path() -> str:
@@ -38,18 +39,38 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
-        return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    (PKG / "csrc" / "build.log").write_text(log)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log[-6000:])
+def build(force: bool = False, verbose: bool = False, extra_defs=(), out: Path | None = None) -> Path:
+    """Compile every translation unit in parallel (nvcc -c, objects under build/obj*/), then link the shared object.
+    `extra_defs` / `out`: kernel-variant experiments (tools/) only."""
+    lib = LIB if out is None else Path(out)
+    if not force and out is None and not needs_build():
+        return lib
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = PKG.parent / "build" / ("obj" if out is None else "obj_" + lib.stem)
+    objdir.mkdir(parents=True, exist_ok=True)
+    nvcc = nvcc_path()
+
+    def compile_one(src):
+        obj = objdir / (Path(src).stem + ".o")
+        cmd = [nvcc, *COMPILE_FLAGS, *extra_defs, "-c", "-o", str(obj), str(CSRC / src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, res.returncode, res.stdout + res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    log = "".join(f"==== {src}\n{out_}" for src, _, _, out_ in results)
+    bad = [src for src, _, rc, _ in results if rc != 0]
+    if not bad:
+        res = subprocess.run([nvcc, *LINK_FLAGS, "-o", str(lib), *[str(o) for _, o, _, _ in results]], capture_output=True, text=True)
+        log += "==== link\n" + res.stdout + res.stderr
+        if res.returncode != 0:
+            bad = ["link"]
+    (PKG / "csrc" / "build.log" if out is None else lib.with_suffix(".log")).write_text(log)
+    if bad:
+        raise RuntimeError(f"nvcc failed ({', '.join(bad)}):\n" + log[-6000:])
     if verbose:
         print(log)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -1,5 +1,6 @@
 // Kernel (1) fused project + z-test + mask gather + vote (+ optional fused label resolve), kernel (2) z-buffer splat
-// and the uv2pt writer.
+// (point-stationary variant) and the uv2pt writer: device code and launch templates.  The extern "C" entry points live
+// in fuse_vote.cu / fuse_aux.cu, which instantiate the modes they need (separate translation units compile in parallel).
 //
 // Replaces, for a fixed cloud, the per-frame body of Fusion.fuse (Fusion3DSeg/fusion.py:248-298:
 // point_inside_polyhedra intersections.py:146-164 -> points2pixel camera_utils.py:9-26 -> single-pixel
@@ -7,61 +8,72 @@
 // VotingSegmentation.segment (segUtils/voting.py:106-137).
 //
 // Design (point-stationary, B200):
-//   * one CTA owns a tile of BLOCK consecutive points (float4, coalesced 16 B/thread); a thread keeps its point
-//     in registers for the whole launch, so the cloud is streamed from HBM exactly once;
-//   * the tile's axis-aligned box is tested conservatively against every frame's five frustum planes (fp32 with
-//     an explicit rounding margin); surviving frame ids are compacted into shared memory.  With a spatially
-//     sorted cloud this skips ~97 % of the nominal point-views without changing any result;
-//   * candidate frames' 128-byte fp32 projection tiles are staged into shared memory with TMA bulk copies
-//     (cp.async.bulk + mbarrier, double buffered) and broadcast to the threads;
-//   * candidates are processed NB at a time: all NB projections first, then all NB depth + mask gathers are
-//     issued together (memory-level parallelism: one DRAM round trip per NB candidates instead of 2 per candidate),
-//     then the distance tests and histogram updates;
+//   * one CTA owns a tile of FUSE_BLOCK consecutive points (float4, coalesced 16 B/thread); a thread keeps its point in
+//     registers for the whole launch, so the cloud is streamed from HBM exactly once;
+//   * cull: supertile_cull_kernel lists the frames that can see each 4096-point super-tile; the CTA then tests every
+//     (listed frame, warp box) pair -- one pair per thread -- against the frame's five frustum planes (fp32 with an
+//     explicit rounding margin, conservative) and compacts the surviving frame ids with the mask of warps that keep them;
+//   * sweep: WARP-AUTONOMOUS.  Each warp walks the candidate list on its own, NB of its candidates at a time; the
+//     128-byte fp32 projection tiles of the next group are prefetched into registers (16 B per lane) while the current
+//     group is processed, then parked in the warp's own 512-byte staging block and broadcast to the lanes.  There is no
+//     CTA-wide barrier and no shared staging ring inside the sweep (round 1 staged the tiles CTA-wide through TMA +
+//     mbarriers and lost 21 % of its warp samples on those barriers);
+//   * per group: all NB projections first, then all NB frame gathers are issued together (one packed depth|mask texel
+//     per point-view with the packed frame formats, else a depth and a mask read), then the distance tests and votes;
 //   * per point-view the fp32 path carries a rigorous rounding bound; any decision (frustum, pixel floor, depth
-//     distance) that falls inside its bound is re-evaluated by `exact_eval` in fp64 in the reference's operation
-//     order, so every integer outcome is bit-exact against the numpy path.  Both the population of that band
-//     and every fp32-vs-fp64 divergence inside it are counted;
-//   * votes are accumulated in a per-CTA shared-memory histogram (uint16 [BLOCK][RS], a thread owns its point's
-//     row; RS/2 odd => conflict-free) and written to HBM exactly once with 16-byte stores -- no global atomics,
-//     no memset.  The label resolve can run straight from that histogram.
+//     distance) that falls inside its bound is re-evaluated in fp64 in the reference's operation order (`exact_eval`),
+//     so every integer outcome is bit-exact against the numpy path.  The population of that band and every
+//     fp32-vs-fp64 divergence inside it are counted;
+//   * votes are accumulated in a per-CTA shared-memory byte histogram (a thread owns its point's row) and written to
+//     HBM exactly once with 32-byte stores -- no global atomics, no memset.  Labels come from the running arg-max.
+#pragma once
 #include "f3d_common.cuh"
 #include "f3d_host.h"
-#include <cstdlib>
 
 #define MODE_VOTE 0
 #define MODE_SPLAT 1
 #define MODE_UV2PT 2
 
+#ifndef FUSE_BLOCK
 #define FUSE_BLOCK 256
-#define FUSE_FCHUNK 512   // frames culled per pass (candidate list capacity)
-#define FUSE_STAGE 16     // FrameFast tiles per staging buffer (2 KB); two buffers
+#endif
+#define FUSE_NW (FUSE_BLOCK / 32)
+#ifndef FUSE_FCHUNK
+#define FUSE_FCHUNK (2 * FUSE_BLOCK)   // candidate list capacity per cull pass
+#endif
 #ifndef FUSE_NB
-#define FUSE_NB 8         // candidates whose gathers are in flight together
+#define FUSE_NB 4         // candidates of a warp processed together (their gathers are in flight together)
 #endif
 #ifndef FUSE_MINB
-#define FUSE_MINB 2       // resident CTAs per SM the register allocation targets (128 registers: keeps all NB gathers in flight)
+#define FUSE_MINB (512 / FUSE_BLOCK)        // resident CTAs per SM of the uint16-histogram / splat / uv2pt builds (128 registers)
 #endif
-// Byte-histogram build of the vote kernel (HB = 1): uint8 counters halve the shared-memory footprint, so twice the CTAs
-// are resident and their latency-bound phases (cull, frame staging, gathers, vote write) overlap.  A counter can hold
-// 255: the sweep flushes the warp's rows to HBM (first flush overwrites, later ones add) before more than
-// FUSE_LIMIT8 candidates have been swept since the last flush, so no count is ever lost.
-#ifndef FUSE_NB8
-#define FUSE_NB8 4        // gather batch of the byte-histogram build
-#endif
+// Byte-histogram build of the vote kernel (HB = 1): uint8 counters halve the shared-memory footprint, so 24 warps are
+// resident per SM and their latency-bound phases (cull, gathers, vote write) overlap.  A counter can hold 255: a warp
+// flushes its rows to HBM (first flush overwrites, later ones add) before more than FUSE_LIMIT8 candidates have been
+// swept since its last flush, so no count is ever lost.
 #ifndef FUSE_MINB8
-#define FUSE_MINB8 3      // resident CTAs per SM of the byte-histogram build (80 registers; 64 spills and is slower)
+#define FUSE_MINB8 (768 / FUSE_BLOCK)       // 80 registers
 #endif
-#define FUSE_ST_TILES 16   // tiles per super-tile (4096 points) of the first cull level
+#define FUSE_ST_POINTS 4096                 // points per super-tile of the first cull level
+#define FUSE_ST_TILES (FUSE_ST_POINTS / FUSE_BLOCK)
 #define FUSE_ST_LCAP 1024  // candidate frames a super-tile list holds
-#define FUSE_RED_WORDS 160 // small per-CTA scalars (see the layout comment in the kernel)
+#ifndef FUSE_QWARP
 #define FUSE_QWARP 20     // deferred entries per warp (12 B each); overflow falls back to inline evaluation
-#define FUSE_LIMIT8 (255 - FUSE_QWARP)   // the warp's deferred pass can add up to FUSE_QWARP votes to one cell at the end
+#endif
+#define FUSE_LIMIT8 (255 - FUSE_QWARP)
+// compiler-level fence between the per-candidate bodies of the unrolled group loops: keeps nvcc from hoisting the ~23
+// shared-memory operands of all NB candidates at once (which costs more registers than the 80-register budget has)
+#ifndef FUSE_NO_FENCE
+#define FUSE_SCHED_FENCE() asm volatile("" ::: "memory")
+#else
+#define FUSE_SCHED_FENCE()
+#endif   // the warp's deferred pass can add up to FUSE_QWARP votes to one cell at the end
 
 // an uncertain point-view handed from the fused sweep to the fix-up kernels through the caller's workspace
 struct GEntry {
     int32_t pt;        // global point index (-1: reserved but unused slot)
     uint32_t w;        // frame (relative to f_begin) | st << 16 | seen << 24
-    int32_t pix;       // fp32 pixel guess
+    int32_t pix;       // fp32 pixel guess (linear v * W + u)
     uint32_t guess;    // fp32 decision guess (visibility / quantised depth)
 };
 
@@ -70,25 +82,25 @@ struct FuseParams {
     int64_t N;
     const void* table;
     int f_begin, f_end;
-    const void* depth;
-    const uint8_t* mask;
+    const void* depth;      // uint16 mm / float32 m images, or packed uint32 texels (depth | class << 16)
+    const uint8_t* mask;    // NULL with the packed formats
     int H, W;
+    int64_t frame_stride;   // elements per frame of `depth` (H*W, or tiles * 256 for the tiled layout)
+    int tiles_x;            // tiled layout: 16-pixel tile columns per row of tiles
     double K[9];
     float cx, cy, inv_fx, inv_fy;
     float radius;
     double radius_d, zmin, zmax;
     uint32_t d_lo, d_hi;    // uint16 depth: valid <=> d_lo <= d <= d_hi   (fusion.py:62-63 on d/1000)
     int32_t* votes;
-    uint16_t* votes16;      // alternative packed output (uint16 counters): halves the vote write and the multi-GPU exchange
+    uint16_t* votes16;      // alternative packed output (uint16 counters): halves the vote write and the dense multi-GPU exchange
     int C1, RS, accumulate;
     int32_t* uv2pt;
     uint32_t* zbuf;
     int64_t* labels;
     unsigned long long* stats;
-    int time_kernel;  // flags bit 1: CUDA events around the fused kernel (f3d_fuse_timing_*)
-    int audit, dbg;   // dbg: timing experiments only (bits: 1 drop candidates, 2 skip cull, 4 classify only)
-    // first cull level (optional, from the workspace): candidate frames of every super-tile of FUSE_ST_TILES tiles, found
-    // by supertile_cull_kernel; a tile then tests only its super-tile's list instead of every frame of the launch
+    // first cull level (optional, from the workspace): candidate frames of every super-tile, found by
+    // supertile_cull_kernel; a tile then tests only its super-tile's list instead of every frame of the launch
     const unsigned* st_count;      // [super-tiles] list length, 0xFFFFFFFF = list overflowed (scan all frames)
     const uint16_t* st_list;       // [super-tiles][FUSE_ST_LCAP] frame ids relative to f_begin
     // fused labels + deferred queue: per-point resolve state (total | best << 24 | first position << 48) written by the sweep,
@@ -104,9 +116,9 @@ struct FuseParams {
     // block's points as uint16 class | count << 8 (0 = none), L = the longest list in the block.  The block's warp reserves
     // L rows in one of F3D_XCH_NREG sub-regions of this rank's record region at the owner (an atomic on a local cursor
     // that only ~300 warps share -- a single cursor serialises at ~10 ns per warp in L2 and binds the whole kernel),
-    // writes them and the directory entry {row offset, L} straight into the owner's memory over NVLink.  A tile with more
-    // than FUSE_LIMIT8 candidate frames flushes its byte histogram several times: every flush writes its own record, the
-    // directory holds F3D_XCH_NLEVEL of them per block.
+    // writes them and the directory entry {row offset, L} straight into the owner's memory over NVLink.  A warp that sweeps
+    // more than FUSE_LIMIT8 candidate frames flushes its byte histogram several times: every flush writes its own record,
+    // the directory holds F3D_XCH_NLEVEL of them per block.
     // What cannot go into a record (sub-region full, more than F3D_XCH_NLEVEL flushes, and the deferred fp64 votes of the
     // fix-up kernel) is appended as (cell, count) to one of F3D_XCH_NSUB sub-queues:
     // fix-up block b owns sub-queue b (no global atomics at all), spills take the sub-queues above F3D_XCH_NSUB_FIX.
@@ -118,7 +130,7 @@ struct FuseParams {
     unsigned* xg_rowcur;                       // local [G][F3D_XCH_NREG] row cursors (caller zeroes them per call)
     unsigned* xg_qcur;                         // local [G][F3D_XCH_NSUB] queue cursors (ditto); published to the owners afterwards
     unsigned xg_subrows, xg_subcap;            // rows per record sub-region, entries per sub-queue
-    unsigned* xg_overflow;                     // set when a sub-queue is full (entries are then dropped: caller must check)
+    unsigned* xg_overflow;                     // set when a sub-queue is full (entries are then dropped: the owner side raises)
 };
 #define FUSE_NSLOT 32   // classes per point remembered by cast_vote; longer lists are re-read from the histogram row
 #define FUSE_STG_ROWS 8 // record rows per staging chunk (512 B per warp: shared memory taken here is L1 taken from the gathers)
@@ -128,55 +140,82 @@ __device__ __forceinline__ unsigned long long summ_pack(int total, int best, int
 }
 
 // one (cell, count) entry for owner d through sub-queue `sub`
-__device__ __forceinline__ void xg_append(const FuseParams& P, int d, unsigned sub, unsigned at, unsigned key, unsigned count) {
-    if (at < P.xg_subcap) P.xg_queue[d][(size_t)sub * P.xg_subcap + at] = (unsigned long long)key | ((unsigned long long)count << 32);
+__device__ __forceinline__ void xg_append(const FuseParams& P, int d, unsigned sub, unsigned at, unsigned long long key, unsigned count) {
+    if (at < P.xg_subcap) P.xg_queue[d][(size_t)sub * P.xg_subcap + at] = key | ((unsigned long long)count << 40);
     else atomicExch(P.xg_overflow, 1u);
 }
 
-struct ExactOut {
-    int in, pix, vis, near_edge;
-    double zcam;
-};
+// ---- frame addressing ----------------------------------------------------------------------------------------------
+// element offset of pixel (iu, iv) of frame `frel` in P.depth (and P.mask for the two-array formats)
+template <int FMT>
+__device__ __forceinline__ size_t frame_off(const FuseParams& P, int frel, int iu, int iv) {
+    if (FMT == F3D_FRAMES_U32_T16)
+        return (size_t)frel * (size_t)P.frame_stride + (size_t)((((iv >> 4) * P.tiles_x + (iu >> 4)) << 8) | ((iv & 15) << 4) | (iu & 15));
+    return (size_t)frel * (size_t)P.frame_stride + (size_t)(iv * P.W + iu);
+}
 
-// fp64 evaluation of one point-view in the oracle's operation order (oracle.fuse_frame_visibility).
+// raw depth word (uint16 mm, float32 bits) and -- vote mode only -- the class id of one pixel
 template <int MODE, int FMT>
-__device__ __noinline__ void exact_eval(const FuseParams& P, const FrameExact* __restrict__ fe, int frel, float px,
-                                        float py, float pz, ExactOut& o) {
-    o.in = 0;
-    o.pix = 0;
-    o.vis = 0;
-    o.near_edge = 0;
-    o.zcam = 0.0;
+__device__ __forceinline__ void load_pixel(const FuseParams& P, size_t off, uint32_t& draw, uint32_t& cls) {
+    cls = 0;
+    if (FMT == F3D_DEPTH_U16_MM) {
+        draw = __ldg(reinterpret_cast<const uint16_t*>(P.depth) + off);
+        if (MODE == MODE_VOTE) cls = __ldg(P.mask + off);
+    } else if (FMT == F3D_DEPTH_F32_M) {
+        draw = __float_as_uint(__ldg(reinterpret_cast<const float*>(P.depth) + off));
+        if (MODE == MODE_VOTE) cls = __ldg(P.mask + off);
+    } else {
+        const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(P.depth) + off);
+        draw = t & 0xffffu;
+        cls = (t >> 16) & 0xffu;
+    }
+}
+
+__device__ __forceinline__ uint32_t quantise_mm(double z) {
+    double q = floor(xadd(xmul(z, 1000.0), 0.5));
+    q = fmin(fmax(q, 1.0), 65535.0);
+    return (uint32_t)q;
+}
+
+// fp64 evaluation of one point-view in the oracle's operation order (oracle.fuse_frame_visibility).  Returns
+//   bit 0 in-image, bit 1 visible, bit 2 within 1e-4 px of a pixel edge, bits 8..15 class (vote mode, when visible),
+//   bits 16..31 quantised camera z (splat mode), bits 32..63 linear pixel index
+// packed into one register pair, so no local of the caller has its address taken (the call sits on a cold path of the
+// sweep and must not cost the hot path any stack traffic).
+#define EX_IN 1ull
+#define EX_VIS 2ull
+#define EX_EDGE 4ull
+template <int MODE, int FMT>
+__device__ __noinline__ unsigned long long exact_eval(const FuseParams& P, const FrameExact* __restrict__ fe, int frel, float px,
+                                                      float py, float pz) {
     D3 p = {(double)px, (double)py, (double)pz};
-    if (!dinside_planes(fe, p)) return;                              // fusion.py:260
+    if (!dinside_planes(fe, p)) return 0ull;                         // fusion.py:260
     D3 h = dproject_h(P.K, fe->qi, fe->t, p);                        // camera_utils.py:21-23
     double uf = xdiv(h.x, h.z), vf = xdiv(h.y, h.z);                 // camera_utils.py:24
     double fu = floor(uf), fv = floor(vf);                           // camera_utils.py:25
     int iu = d2i_numpy(fu), iv = d2i_numpy(fv);
-    if (iu < 0 || iu >= P.W || iv < 0 || iv >= P.H) return;
-    o.in = 1;
-    o.pix = iv * P.W + iu;
-    o.zcam = h.z;
+    if (iu < 0 || iu >= P.W || iv < 0 || iv >= P.H) return 0ull;
+    unsigned long long r = EX_IN | ((unsigned long long)(unsigned)(iv * P.W + iu) << 32);
     double fru = xsub(uf, fu), frv = xsub(vf, fv);
-    o.near_edge = (fmin(fru, xsub(1.0, fru)) < 1e-4) || (fmin(frv, xsub(1.0, frv)) < 1e-4);
-    if (MODE == MODE_SPLAT) return;
-    size_t off = (size_t)frel * (size_t)P.H * (size_t)P.W + (size_t)o.pix;
+    if ((fmin(fru, xsub(1.0, fru)) < 1e-4) || (fmin(frv, xsub(1.0, frv)) < 1e-4)) r |= EX_EDGE;
+    if (MODE == MODE_SPLAT) return r | ((unsigned long long)quantise_mm(h.z) << 16);
+    uint32_t draw, cls;
+    load_pixel<MODE, FMT>(P, frame_off<FMT>(P, frel, iu, iv), draw, cls);
     double dd;
     bool valid;
-    if (FMT == F3D_DEPTH_U16_MM) {
-        uint32_t d = __ldg(reinterpret_cast<const uint16_t*>(P.depth) + off);
-        valid = (d >= P.d_lo) && (d <= P.d_hi);
-        dd = (double)d;
+    if (FMT != F3D_DEPTH_F32_M) {
+        valid = (draw >= P.d_lo) && (draw <= P.d_hi);
+        dd = (double)draw;
     } else {
-        dd = (double)__ldg(reinterpret_cast<const float*>(P.depth) + off);
+        dd = (double)__uint_as_float(draw);
         valid = (dd > P.zmin) && (dd <= P.zmax);                     // fusion.py:62-63
     }
-    if (!valid) return;
+    if (!valid) return r;
     D3 c;                                                            // ios_rtab.py:168-173
     c.x = xmul(xsub((double)iu, P.K[2]), xdiv(dd, P.K[0]));
     c.y = xmul(xsub((double)iv, P.K[5]), xdiv(dd, P.K[4]));
     c.z = dd;
-    if (FMT == F3D_DEPTH_U16_MM) {                                   // ios_rtab.py:185
+    if (FMT != F3D_DEPTH_F32_M) {                                    // ios_rtab.py:185
         c.x = xdiv(c.x, 1000.0);
         c.y = xdiv(c.y, 1000.0);
         c.z = xdiv(c.z, 1000.0);
@@ -186,16 +225,11 @@ __device__ __noinline__ void exact_eval(const FuseParams& P, const FrameExact* _
     double d1 = xsub(xadd(m.y, fe->t[1]), p.y);
     double d2 = xsub(xadd(m.z, fe->t[2]), p.z);
     double dist = __dsqrt_rn(xadd(xadd(xmul(d0, d0), xmul(d1, d1)), xmul(d2, d2)));   // fusion.py:224
-    o.vis = dist < P.radius_d;                                       // fusion.py:225
+    if (dist < P.radius_d) r |= EX_VIS | ((unsigned long long)cls << 8);             // fusion.py:225
+    return r;
 }
 
-__device__ __forceinline__ uint32_t quantise_mm(double z) {
-    double q = floor(xadd(xmul(z, 1000.0), 0.5));
-    q = fmin(fmax(q, 1.0), 65535.0);
-    return (uint32_t)q;
-}
-
-// ---- mbarrier / TMA bulk-copy helpers (cp.async.bulk: SASS UBLKCP) -------------------------------------------------
+// ---- mbarrier / TMA bulk-copy helpers (cp.async.bulk: SASS UBLKCP), used by the fix-up kernel's frame-record staging
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -242,12 +276,8 @@ __device__ __forceinline__ Cls classify(const float4* __restrict__ s, const floa
     // rounding bound of a row: 8 u * sum |M_i| |d_i| (M rounded to fp32: 1 u; d: 2 u; product and two fused adds: 3 u; the
     // sum itself is computed to 3 u) -- two to three times tighter than 8 u * max|M_i| * sum|d_i|, which is what decides
     // how many pixel floors have to be re-evaluated in fp64.  The 1e-9 m floor covers the absolute error of d near 0.
-#ifndef FUSE_LOOSE_BOUND
     const float ad0 = fabsf(d0), ad1 = fabsf(d1), ad2 = fabsf(d2);
     const float ez = 8.0f * F3D_U24 * fmaf(fabsf(Mz.x), ad0, fmaf(fabsf(Mz.y), ad1, fmaf(fabsf(Mz.z), ad2, Mz.w * 1.0e-9f)));
-#else
-    const float ez = 8.0f * F3D_U24 * Mz.w * S;
-#endif
     c.z = z;
     if (z < -16.0f * ez) return c;
     if (z <= 16.0f * ez) {
@@ -259,12 +289,8 @@ __device__ __forceinline__ Cls classify(const float4* __restrict__ s, const floa
     const float b = fmaf(Mv.x, d0, fmaf(Mv.y, d1, Mv.z * d2));
     const float r = __frcp_rn(z);
     const float u = a * r, v = b * r;
-#ifndef FUSE_LOOSE_BOUND
     const float ea = 8.0f * F3D_U24 * fmaf(fabsf(Mu.x), ad0, fmaf(fabsf(Mu.y), ad1, fmaf(fabsf(Mu.z), ad2, Mu.w * 1.0e-9f)));
     const float eb = 8.0f * F3D_U24 * fmaf(fabsf(Mv.x), ad0, fmaf(fabsf(Mv.y), ad1, fmaf(fabsf(Mv.z), ad2, Mv.w * 1.0e-9f)));
-#else
-    const float ea = 8.0f * F3D_U24 * Mu.w * S, eb = 8.0f * F3D_U24 * Mv.w * S;
-#endif
     const float eu = 1.125f * (ea + fabsf(u) * ez) * r + 8.0f * F3D_U24 * fabsf(u) + 1.0e-4f;
     const float ev = 1.125f * (eb + fabsf(v) * ez) * r + 8.0f * F3D_U24 * fabsf(v) + 1.0e-4f;
     const float sl = fmaf(s[5].w, d0, fmaf(s[6].w, d1, s[7].w * d2));   // (p - eye) . lookat
@@ -342,34 +368,35 @@ __device__ __forceinline__ void cast_vote(CellT* hist, int row_off, int cls, con
     }
 }
 
+// fp64 decision for one point-view inside the sweep (audit mode, a full warp queue, the warp's own deferred pass when
+// there is no workspace queue) and its consequence.  `st` >= 2: the fp32 path was unsure (g_in / pix = its guess);
+// st < 2 (audit): the fp32 path certified `fast_seen` / `pix` / `fast_zq`.
 template <int MODE, int FMT, typename CellT>
 __device__ __forceinline__ void resolve_exact(const FuseParams& P, const FuseResolve& RP, const FrameRecord* __restrict__ frec,
                                               CellT* hist, int RS, int64_t tile_base, int owner_tid, int frel, float px, float py,
                                               float pz, int st, int g_in, int pix, bool fast_seen, uint32_t fast_zq,
                                               bool owner_is_self, unsigned* dirty_w, Tally& t) {
-    const int HW = P.H * P.W;
-    ExactOut eo;
-    exact_eval<MODE, FMT>(P, &frec[P.f_begin + frel].exact, frel, px, py, pz, eo);
-    const bool e_seen = (MODE == MODE_SPLAT) ? (eo.in != 0) : (eo.vis != 0);
-    const uint32_t e_zq = (MODE == MODE_SPLAT && eo.in) ? quantise_mm(eo.zcam) : 0u;
+    const unsigned long long eo = exact_eval<MODE, FMT>(P, &frec[P.f_begin + frel].exact, frel, px, py, pz);
+    const int e_in = (int)(eo & EX_IN), e_vis = (int)((eo >> 1) & 1ull), e_pix = (int)(eo >> 32);
+    const bool e_seen = (MODE == MODE_SPLAT) ? (e_in != 0) : (e_vis != 0);
+    const uint32_t e_zq = (MODE == MODE_SPLAT && e_in) ? (uint32_t)((eo >> 16) & 0xffffull) : 0u;
     if (st >= 2) {
         atomicAdd(t.rare + F3D_STAT_EXACT, 1u);
         bool diverged;
-        if (st == 2) diverged = (g_in != eo.in) || (eo.in && pix != eo.pix);
-        else if (MODE == MODE_SPLAT) diverged = (!eo.in) || (pix != eo.pix) || ((uint32_t)g_in != e_zq);
-        else diverged = (g_in != eo.vis) || (eo.in && pix != eo.pix);
+        if (st == 2) diverged = (g_in != e_in) || (e_in && pix != e_pix);
+        else if (MODE == MODE_SPLAT) diverged = (!e_in) || (pix != e_pix) || ((uint32_t)g_in != e_zq);
+        else diverged = (g_in != e_vis) || (e_in && pix != e_pix);
         if (diverged) atomicAdd(t.rare + F3D_STAT_DIVERGED, 1u);
     } else {
         // audit: a certified fp32 outcome must equal the fp64 outcome
-        const bool bad = (fast_seen != e_seen) || (fast_seen && pix != eo.pix) || (fast_seen && MODE == MODE_SPLAT && fast_zq != e_zq);
+        const bool bad = (fast_seen != e_seen) || (fast_seen && pix != e_pix) || (fast_seen && MODE == MODE_SPLAT && fast_zq != e_zq);
         if (bad) atomicAdd(t.rare + F3D_STAT_AUDIT_BAD, 1u);
     }
-    if (eo.in && eo.near_edge) atomicAdd(t.rare + F3D_STAT_NEAR_EDGE, 1u);
+    if (e_in && (eo & EX_EDGE)) atomicAdd(t.rare + F3D_STAT_NEAR_EDGE, 1u);
     if (e_seen) {
         ++t.n_seen;
-        const size_t off = (size_t)frel * (size_t)HW + (size_t)eo.pix;
         if (MODE == MODE_VOTE) {
-            const int cls = __ldg(P.mask + off);
+            const int cls = (int)((eo >> 8) & 0xffull);
             if (owner_is_self) {
                 cast_vote(hist, owner_tid * RS, cls, P, RP, t);
             } else if (cls < P.C1) {
@@ -382,9 +409,9 @@ __device__ __forceinline__ void resolve_exact(const FuseParams& P, const FuseRes
                 atomicOr(dirty_w, 1u << (owner_tid & 31));
             }
         } else if (MODE == MODE_SPLAT) {
-            atomicMin(P.zbuf + off, e_zq);
+            atomicMin(P.zbuf + (size_t)frel * (size_t)(P.H * P.W) + (size_t)e_pix, e_zq);
         } else {
-            atomicMax(P.uv2pt + off, (int)(tile_base + owner_tid));
+            atomicMax(P.uv2pt + (size_t)frel * (size_t)(P.H * P.W) + (size_t)e_pix, (int)(tile_base + owner_tid));
         }
     }
 }
@@ -392,8 +419,15 @@ __device__ __forceinline__ void resolve_exact(const FuseParams& P, const FuseRes
 template <int HB> struct HistCell { typedef uint16_t T; };
 template <> struct HistCell<1> { typedef uint8_t T; };
 
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                             uint32_t a6, uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5),
+                 "r"(a6), "r"(a7)
+                 : "memory");
+}
+
 // ---- byte-histogram flush: the warp's 32 rows (32*C1 contiguous bytes, row stride == C1) -> HBM ------------------
-// first flush of a non-accumulating launch overwrites (every cell written exactly once, 16-byte stores); later
+// first flush of a non-accumulating launch overwrites (every cell written exactly once, 32-byte stores: STG.256); later
 // flushes add their non-zero cells.  Rows are warp-private, so no CTA barrier and no atomics are involved.
 __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int warp, int lane, int64_t tile_base, bool add,
                                        bool rezero, Tally& T, uint16_t* stg, int level, bool dirty, uint2* dcache) {
@@ -401,7 +435,7 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
     const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
     const int total = nrows * P.C1;
     const int n4 = total >> 2;
-    uint32_t* __restrict__ h32 = reinterpret_cast<uint32_t*>(hist + row0 * P.C1);   // 32*C1 bytes per warp: word aligned
+    uint32_t* __restrict__ h32 = reinterpret_cast<uint32_t*>(hist + row0 * P.C1);   // 32*C1 bytes per warp: 32-byte aligned
     const uint8_t* __restrict__ h8 = hist + row0 * P.C1;
     if (P.xg_G > 0) {
         // slot records (see FuseParams)
@@ -420,7 +454,7 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
         for (int s2 = 16; s2 > 0; s2 >>= 1) L = max(L, __shfl_xor_sync(0xffffffffu, L, s2));
         unsigned off = 0;
         if (rec) {
-            const unsigned reg = (blockIdx.x * (FUSE_BLOCK / 32) + warp) & (F3D_XCH_NREG - 1);
+            const unsigned reg = (blockIdx.x * FUSE_NW + warp) & (F3D_XCH_NREG - 1);
             if (lane == 0 && L > 0) off = atomicAdd(P.xg_rowcur + d * F3D_XCH_NREG + reg, (unsigned)L);
             off = __shfl_sync(0xffffffffu, off, 0);
             if (off + (unsigned)L > P.xg_subrows) {   // sub-region full: everything of this block goes to the queue
@@ -466,7 +500,7 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
             __syncwarp();
         }
         if (spill) {
-            const unsigned key0 = (unsigned)((p0 + lane - (long long)d * P.xg_per) * C1);
+            const unsigned long long key0 = (unsigned long long)(p0 + lane - (long long)d * P.xg_per) * (unsigned long long)C1;
             const unsigned sub = F3D_XCH_NSUB_FIX + blockIdx.x % (F3D_XCH_NSUB - F3D_XCH_NSUB_FIX);
             for (int c = 0; c < C1; ++c) {
                 const unsigned v = row[c];
@@ -478,13 +512,26 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
         if (P.votes) {
             int32_t* __restrict__ out = P.votes + (tile_base + row0) * P.C1;
             if (!add) {
-                for (int i = lane; i < n4; i += 32) {
-                    const uint32_t w = h32[i];
-                    const int4 v4 = make_int4((int)__byte_perm(w, 0u, 0x4440), (int)__byte_perm(w, 0u, 0x4441),
-                                              (int)__byte_perm(w, 0u, 0x4442), (int)__byte_perm(w, 0u, 0x4443));
-                    *reinterpret_cast<int4*>(out + 4 * i) = v4;
+                if ((reinterpret_cast<uintptr_t>(out) & 31u) == 0) {
+                    // eight cells per lane and step: LDS.64 -> 8 x PRMT -> one 32-byte store (1 KB contiguous per warp instruction)
+                    const uint2* __restrict__ h64 = reinterpret_cast<const uint2*>(h8);
+                    const int n8 = total >> 3;
+                    for (int i = lane; i < n8; i += 32) {
+                        const uint2 w = h64[i];
+                        st_global_v8(out + 8 * i, __byte_perm(w.x, 0u, 0x4440), __byte_perm(w.x, 0u, 0x4441), __byte_perm(w.x, 0u, 0x4442),
+                                     __byte_perm(w.x, 0u, 0x4443), __byte_perm(w.y, 0u, 0x4440), __byte_perm(w.y, 0u, 0x4441),
+                                     __byte_perm(w.y, 0u, 0x4442), __byte_perm(w.y, 0u, 0x4443));
+                    }
+                    for (int e = (n8 << 3) + lane; e < total; e += 32) out[e] = (int)h8[e];
+                } else {
+                    for (int i = lane; i < n4; i += 32) {
+                        const uint32_t w = h32[i];
+                        const int4 v4 = make_int4((int)__byte_perm(w, 0u, 0x4440), (int)__byte_perm(w, 0u, 0x4441),
+                                                  (int)__byte_perm(w, 0u, 0x4442), (int)__byte_perm(w, 0u, 0x4443));
+                        *reinterpret_cast<int4*>(out + 4 * i) = v4;
+                    }
+                    for (int e = (n4 << 2) + lane; e < total; e += 32) out[e] = (int)h8[e];
                 }
-                for (int e = (n4 << 2) + lane; e < total; e += 32) out[e] = (int)h8[e];
             } else {
                 for (int i = lane; i < n4; i += 32) {
                     const uint32_t w = h32[i];
@@ -530,37 +577,48 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
     }
 }
 
-template <int MODE, int FMT, int HB>
+// small per-CTA scalars in shared memory
+struct __align__(16) FuseShared {
+    float wbox[FUSE_NW][8];                    // per-warp box: lo[3], hi[3], |lo| + |hi| magnitude, unused
+    uint2 dcache[FUSE_NW][F3D_XCH_NLEVEL];     // exchange mode: the warp's directory levels {row offset, L}
+    int nq[FUSE_NW];                           // per-warp deferred counts
+    unsigned dirty[FUSE_NW];                   // rows another lane's deferred pass touched
+    unsigned stat[8];                          // CTA totals of the statistics, flushed once at the end
+    int ncand;
+    int pad[3];
+};
+
+__host__ __device__ constexpr size_t fuse_align16(size_t v) { return (v + 15) & ~(size_t)15; }
+// shared-memory layout: [stage: NW x NB FrameFast][FuseShared][cand u16 x FCHUNK][cmask u8 x FCHUNK][deferred queues][hist]
+//                       [exchange mode: class lists u8 x FUSE_NSLOT x FUSE_BLOCK][record staging: NW x 512 B]
+#define FUSE_OFF_SHARED ((size_t)FUSE_NW * FUSE_NB * sizeof(FrameFast))
+#define FUSE_OFF_CAND (FUSE_OFF_SHARED + sizeof(FuseShared))
+#define FUSE_OFF_CMASK (FUSE_OFF_CAND + FUSE_FCHUNK * sizeof(uint16_t))
+#define FUSE_OFF_QUEUE fuse_align16(FUSE_OFF_CMASK + FUSE_FCHUNK)
+#define FUSE_OFF_HIST fuse_align16(FUSE_OFF_QUEUE + (size_t)FUSE_NW * FUSE_QWARP * sizeof(Deferred))
+
+template <int MODE, int FMT, int HB, bool AUDIT>
 __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? FUSE_MINB8 : FUSE_MINB)
     fuse_kernel(const __grid_constant__ FuseParams P, const __grid_constant__ FuseResolve RP) {
     typedef typename HistCell<HB>::T CellT;
-    constexpr int NB = (MODE == MODE_VOTE && HB == 1) ? FUSE_NB8 : FUSE_NB;
+    constexpr int NB = FUSE_NB;
+    static_assert(NB % 4 == 0 && FUSE_NW <= 8, "a lane prefetches NB/4 16-byte pieces; cmask holds one bit per warp");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [2 x stage FrameFast x FUSE_STAGE][cand u16 x FUSE_FCHUNK][cmask u8 x FUSE_FCHUNK]
-    //         [red: 48 floats (8 warp boxes) | ncand | 2 mbarriers | 8 nq | 8 dirty | tile box (7) | 8 stat counters | pad |
-    //               8 warps x F3D_XCH_NLEVEL directory entries]
-    //         [deferred queues: 8 warps x FUSE_QWARP][hist]
     float4* stage = reinterpret_cast<float4*>(smem_raw);
-    uint16_t* cand = reinterpret_cast<uint16_t*>(smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast));
-    uint8_t* cmask = smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * sizeof(uint16_t);   // warps that keep candidate i
-    float* red = reinterpret_cast<float*>(smem_raw + 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * (sizeof(uint16_t) + 1));
-    int* ncand_s = reinterpret_cast<int*>(red + 48);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 52);   // two barriers (16-byte aligned offset)
-    int* nq_s = reinterpret_cast<int*>(red + 56);             // per-warp deferred counts
-    unsigned* dirty_s = reinterpret_cast<unsigned*>(red + 64);
-    float* tbox = red + 72;                                   // tile box lo[3], hi[3], magnitude
-    unsigned* stat_s = reinterpret_cast<unsigned*>(red + 80); // CTA totals of the statistics, flushed once at the end
-    uint2* dcache_all = reinterpret_cast<uint2*>(red + 96);   // exchange mode: this warp's directory levels {row offset, L}
-    Deferred* queue_all = reinterpret_cast<Deferred*>(red + FUSE_RED_WORDS);
-    CellT* hist = reinterpret_cast<CellT*>(reinterpret_cast<unsigned char*>(queue_all) + (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred));
+    FuseShared& sh = *reinterpret_cast<FuseShared*>(smem_raw + FUSE_OFF_SHARED);
+    uint16_t* cand = reinterpret_cast<uint16_t*>(smem_raw + FUSE_OFF_CAND);
+    uint8_t* cmask = smem_raw + FUSE_OFF_CMASK;   // warps that keep candidate i
+    Deferred* queue_all = reinterpret_cast<Deferred*>(smem_raw + FUSE_OFF_QUEUE);
+    CellT* hist = reinterpret_cast<CellT*>(smem_raw + FUSE_OFF_HIST);
     const int RS = P.RS;
-    // exchange mode only: [class lists u8 x FUSE_NSLOT x FUSE_BLOCK][staging blocks: 8 warps x 512 B] after the histogram
-    uint8_t* clist_all = reinterpret_cast<uint8_t*>(hist) + (((size_t)FUSE_BLOCK * RS * sizeof(CellT) + 15) & ~(size_t)15);
+    // exchange mode only: [class lists u8 x FUSE_NSLOT x FUSE_BLOCK][staging blocks: NW x 512 B] after the histogram
+    uint8_t* clist_all = reinterpret_cast<uint8_t*>(hist) + fuse_align16((size_t)FUSE_BLOCK * RS * sizeof(CellT));
     uint16_t* stg_all = reinterpret_cast<uint16_t*>(clist_all + FUSE_NSLOT * FUSE_BLOCK);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     Deferred* queue = queue_all + warp * FUSE_QWARP;
+    float4* stage_w = stage + warp * (NB * 8);
     const int64_t tile_base = (int64_t)blockIdx.x * FUSE_BLOCK;
     const int64_t gi = tile_base + tid;
     const bool active = gi < P.N;
@@ -570,24 +628,19 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) pt = __ldg(P.points + gi);
 
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     if (lane == 0) {
-        nq_s[warp] = 0;
-        dirty_s[warp] = 0u;
-        stat_s[warp] = 0u;
+        sh.nq[warp] = 0;
+        sh.dirty[warp] = 0u;
+        sh.stat[warp & 7] = 0u;
     }
-    if (lane < F3D_XCH_NLEVEL) dcache_all[warp * F3D_XCH_NLEVEL + lane] = make_uint2(0u, 0u);
+    if (lane < F3D_XCH_NLEVEL) sh.dcache[warp][lane] = make_uint2(0u, 0u);
     if (MODE == MODE_VOTE) {
         uint4* h128 = reinterpret_cast<uint4*>(hist);
         const int n128 = (FUSE_BLOCK * RS * (int)sizeof(CellT) + 15) / 16;
         for (int i = tid; i < n128; i += FUSE_BLOCK) h128[i] = make_uint4(0u, 0u, 0u, 0u);
     }
 
-    // ---- tile bounding box (exact min / max of the float32 coordinates)
+    // ---- per-warp bounding box (exact min / max of the float32 coordinates of the warp's 32 points)
     {
         const float big = 3.0e38f;
         float lo[3] = {active ? pt.x : big, active ? pt.y : big, active ? pt.z : big};
@@ -603,224 +656,202 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                red[warp * 6 + k] = lo[k];
-                red[warp * 6 + 3 + k] = hi[k];
+                sh.wbox[warp][k] = lo[k];
+                sh.wbox[warp][3 + k] = hi[k];
             }
+            // an empty warp (past the end of the cloud) keeps an inverted box that no frame can keep
+            sh.wbox[warp][6] = fabsf(lo[0]) + fabsf(lo[1]) + fabsf(lo[2]) + fabsf(hi[0]) + fabsf(hi[1]) + fabsf(hi[2]);
+            sh.wbox[warp][7] = (tile_base + warp * 32 < P.N) ? 1.f : 0.f;
         }
     }
-    __syncthreads();
-    if (tid < 3) {
-        float l = red[tid], h = red[3 + tid];
-#pragma unroll
-        for (int w = 1; w < FUSE_BLOCK / 32; ++w) {
-            l = fminf(l, red[w * 6 + tid]);
-            h = fmaxf(h, red[w * 6 + 3 + tid]);
-        }
-        tbox[tid] = l;
-        tbox[3 + tid] = h;
-    }
-    // (the chunk loop starts with a barrier before the box is read)
 
     const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
 
     Tally T;
     T.n_cand = T.n_seen = 0u;
-    T.rare = stat_s;
+    T.rare = sh.stat;
     T.nlist = 0;
     T.clist = (MODE == MODE_VOTE && HB == 1 && P.xg_G > 0) ? clist_all + threadIdx.x : nullptr;
     T.total = 0;
     T.best = 0;
     T.bpos = 0x7fff;
-    unsigned phase_bits = 0;   // parity of the two staging barriers
-#ifdef FUSE_PROBE
-    unsigned probe_lane = 0, probe_warp = 0;
-#endif
-    int since_flush = 0, nflush = 0;   // byte histogram: candidates swept since the last flush, flushes so far (CTA-uniform)
+    int since_flush = 0, nflush = 0;   // byte histogram: candidates swept since the warp's last flush, its flushes so far
 
     // frames to test: the super-tile's candidate list when the first cull level ran, else every frame of the launch
     const unsigned st_n = P.st_count ? __ldg(P.st_count + blockIdx.x / FUSE_ST_TILES) : 0xffffffffu;
     const bool use_list = st_n != 0xffffffffu;
     const uint16_t* __restrict__ st_list = P.st_list + (size_t)(blockIdx.x / FUSE_ST_TILES) * FUSE_ST_LCAP;
     const int ntest = use_list ? (int)st_n : P.f_end - P.f_begin;
+    __syncthreads();       // histogram zeroed, warp boxes visible
     for (int cbase = 0; cbase < ntest; cbase += FUSE_FCHUNK) {
         if (cbase != 0) __syncthreads();   // previous chunk's candidate list fully consumed
-        if (tid == 0) *ncand_s = 0;
+        if (tid == 0) sh.ncand = 0;
         __syncthreads();
         const int cend = min(cbase + FUSE_FCHUNK, ntest);
-        // ---- conservative tile x frustum cull (fp32 + explicit rounding margin; never drops a visible pair)
-        const float blo[3] = {tbox[0], tbox[1], tbox[2]}, bhi[3] = {tbox[3], tbox[4], tbox[5]};
-        const float box_mag = fabsf(blo[0]) + fabsf(blo[1]) + fabsf(blo[2]) + fabsf(bhi[0]) + fabsf(bhi[1]) + fabsf(bhi[2]);
-        // Two levels in one pass: a frame that survives the tile box is tested against the box of each warp's 32 points
-        // while its planes are still in registers.  In a spatially sorted cloud a warp's points are a few centimetres
-        // apart, so a warp is almost always entirely inside or entirely outside a frustum: this drops ~45 % of the
-        // (warp, frame) pairs -- and every frame no warp keeps -- before any per-point work.  Same conservative rule.
-        for (int f0 = cbase; f0 < cend && !(P.dbg & 2); f0 += FUSE_BLOCK) {
-            const int fi = f0 + tid;
-            bool keep = false;
+        // ---- conservative (frame, warp box) cull, one pair per thread (fp32 + explicit rounding margin; never drops a
+        // visible pair).  In a spatially sorted cloud a warp's points are a few centimetres apart, so a warp is almost
+        // always entirely inside or entirely outside a frustum: this removes ~45 % of the (warp, frame) pairs of the
+        // frames that touch the tile -- and every frame no warp keeps -- before any per-point work.
+        const int npairs = (cend - cbase) * FUSE_NW;
+        for (int p0 = 0; p0 < npairs; p0 += FUSE_BLOCK) {
+            const int p = p0 + tid;
+            bool kw = false;
             int frel = 0;
-            unsigned wmask = 0u;
-            if (fi < cend) {
-                keep = true;
+            if (p < npairs) {
+                const int fi = cbase + p / FUSE_NW;
+                const float* wb = sh.wbox[p % FUSE_NW];
                 frel = use_list ? (int)__ldg(st_list + fi) : fi;
                 const float4* pl = frec[P.f_begin + frel].cull.pl;
-                float4 q[5];
+                const float l0 = wb[0], l1 = wb[1], l2 = wb[2], h0 = wb[3], h1 = wb[4], h2 = wb[5], mag = wb[6];
+                kw = wb[7] != 0.f;
 #pragma unroll
                 for (int m = 0; m < 5; ++m) {
-                    q[m] = __ldg(pl + m);
-                    float mx = fmaxf(q[m].x * blo[0], q[m].x * bhi[0]) + fmaxf(q[m].y * blo[1], q[m].y * bhi[1]) +
-                               fmaxf(q[m].z * blo[2], q[m].z * bhi[2]) - q[m].w;
-                    float margin = 2.0e-6f * (box_mag + fabsf(q[m].w)) + 1.0e-7f;
-                    keep = keep && (mx >= -margin);
-                }
-                if (keep) {
-                    for (int wb = 0; wb < FUSE_BLOCK / 32; ++wb) {
-                        const float* wbox = red + wb * 6;
-                        const float l0 = wbox[0], l1 = wbox[1], l2 = wbox[2], h0 = wbox[3], h1 = wbox[4], h2 = wbox[5];
-                        bool kw = true;
-#pragma unroll
-                        for (int m = 0; m < 5; ++m) {
-                            const float mx = fmaxf(q[m].x * l0, q[m].x * h0) + fmaxf(q[m].y * l1, q[m].y * h1) +
-                                             fmaxf(q[m].z * l2, q[m].z * h2) - q[m].w;
-                            const float margin = 4.0e-6f * (box_mag + fabsf(q[m].w)) + 1.0e-7f;   // a warp box lies inside the tile box
-                            kw = kw && (mx >= -margin);
-                        }
-                        wmask |= kw ? (1u << wb) : 0u;
-                    }
-                    keep = wmask != 0u;
+                    const float4 q = __ldg(pl + m);
+                    const float mx = fmaxf(q.x * l0, q.x * h0) + fmaxf(q.y * l1, q.y * h1) + fmaxf(q.z * l2, q.z * h2) - q.w;
+                    const float margin = 2.0e-6f * (mag + fabsf(q.w)) + 1.0e-7f;
+                    kw = kw && (mx >= -margin);
                 }
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            // the FUSE_NW lanes of a frame are adjacent: its warp mask is a bit field of the ballot
+            const unsigned bal = __ballot_sync(0xffffffffu, kw);
+            const unsigned wmask = (bal >> (lane & ~(FUSE_NW - 1))) & ((1u << FUSE_NW) - 1u);
+            const bool lead = ((lane & (FUSE_NW - 1)) == 0) && wmask != 0u;
+            const unsigned lb = __ballot_sync(0xffffffffu, lead);
             int base = 0;
-            if (lane == 0 && bal) base = atomicAdd(ncand_s, __popc(bal));
+            if (lane == 0 && lb) base = atomicAdd(&sh.ncand, __popc(lb));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) {
-                const int at = base + __popc(bal & ((1u << lane) - 1u));
+            if (lead) {
+                const int at = base + __popc(lb & ((1u << lane) - 1u));
                 cand[at] = (uint16_t)frel;
                 cmask[at] = (uint8_t)wmask;
             }
         }
         __syncthreads();
-        const int ncand = (P.dbg & 3) ? 0 : *ncand_s;
-        const int nbatch = (ncand + FUSE_STAGE - 1) / FUSE_STAGE;
+        const int ncand = sh.ncand;
 
-        // TMA producer (warp 0): lane 0 arms the barrier with the batch's byte count, lane k issues the 128-byte bulk
-        // copy of candidate k's projection tile
-        auto issue = [&](int batch) {
-            const int buf = batch & 1;
-            const int b0 = batch * FUSE_STAGE;
-            const int nb = min(FUSE_STAGE, ncand - b0);
-            if (lane == 0) mbar_expect_tx(&mbar[buf], (unsigned)(nb * sizeof(FrameFast)));
-            __syncwarp();
-            if (lane < nb)
-                tma_bulk_g2s(stage + (buf * FUSE_STAGE + lane) * 8, &frec[P.f_begin + cand[b0 + lane]].fast, sizeof(FrameFast),
-                             &mbar[buf]);
+        // ---- warp-autonomous sweep over this warp's candidates of the list
+        int lbase = -32;        // current 32-entry block of the candidate list (warp-uniform)
+        unsigned wm = 0u;       // this warp's candidates of that block not yet taken
+        // lane l fetches 16-byte piece (l & 7) of the projection tiles of candidates (l >> 3), (l >> 3) + 4, ... of a group:
+        // next_group leaves the list position of those candidates in mine[] (-1 = none) and returns the group's size
+        int mine[NB / 4];
+        auto next_group = [&]() -> int {
+            int n = 0;
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                while (wm == 0u && lbase + 32 < ncand) {
+                    lbase += 32;
+                    const int i = lbase + lane;
+                    wm = __ballot_sync(0xffffffffu, i < ncand && ((cmask[i] >> warp) & 1u));
+                }
+                int pos = -1;
+                if (wm) {
+                    pos = lbase + __ffs(wm) - 1;
+                    wm &= wm - 1u;
+                    ++n;
+                }
+                if ((lane >> 3) == (k & 3)) mine[k >> 2] = pos;
+            }
+            return n;
         };
-        if (warp == 0 && nbatch > 0) issue(0);
-
-        for (int batch = 0; batch < nbatch; ++batch) {
-            const int buf = batch & 1;
-            const int b0 = batch * FUSE_STAGE;
-            const int nb = min(FUSE_STAGE, ncand - b0);
-            // buffer buf^1 was released by the barrier at the end of iteration batch-1
-            if (warp == 0 && batch + 1 < nbatch) issue(batch + 1);
-            mbar_wait(&mbar[buf], (phase_bits >> buf) & 1u);
-            phase_bits ^= (1u << buf);
-            // this warp's candidates of the batch (bit k: candidate b0 + k)
-            unsigned wm = __ballot_sync(0xffffffffu, lane < nb && ((cmask[b0 + (lane & (FUSE_STAGE - 1))] >> warp) & 1u));
+        uint4 pref[NB / 4];
+        int pfr[NB / 4];        // frame ids of the prefetched tiles
+        auto prefetch = [&]() {
+#pragma unroll
+            for (int h = 0; h < NB / 4; ++h) {
+                pfr[h] = mine[h] >= 0 ? (int)cand[mine[h]] : -1;
+                pref[h] = make_uint4(0u, 0u, 0u, 0u);
+                if (pfr[h] >= 0) pref[h] = __ldg(reinterpret_cast<const uint4*>(&frec[P.f_begin + pfr[h]].fast) + (lane & 7));
+            }
+        };
+        int nn = next_group();
+        if (nn > 0) prefetch();
+        while (nn > 0) {
+            const int ncur = nn;
             if (MODE == MODE_VOTE && HB == 1) {
-                // a byte counter holds 255: flush the warp's rows before this batch could push a cell past the limit
-                const int nw = __popc(wm);
-                if (since_flush + nw > FUSE_LIMIT8) {
+                // a byte counter holds 255: flush the warp's rows before this group could push a cell past the limit
+                if (since_flush + ncur > FUSE_LIMIT8) {
                     __syncwarp();
                     flush8(P, reinterpret_cast<uint8_t*>(hist), warp, lane, tile_base, nflush > 0 || P.accumulate, true, T,
-                           stg_all + warp * (FUSE_STG_ROWS * 32), nflush, false, dcache_all + warp * F3D_XCH_NLEVEL);
+                           stg_all + warp * (FUSE_STG_ROWS * 32), nflush, false, sh.dcache[warp]);
                     ++nflush;
                     since_flush = 0;
                 }
-                since_flush += nw;
+                since_flush += ncur;
             }
+            __syncwarp();           // every lane is done with the previous group's tiles
+            int fr[NB];             // frame ids of the current group (-1 = none)
+#pragma unroll
+            for (int h = 0; h < NB / 4; ++h) {
+                reinterpret_cast<uint4*>(stage_w)[h * 32 + lane] = pref[h];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) fr[4 * h + k] = __shfl_sync(0xffffffffu, pfr[h], 8 * k);
+            }
+            __syncwarp();
+            nn = next_group();
+            if (nn > 0) prefetch();   // in flight while this group is processed
             if (active) {
-                T.n_cand += (unsigned)__popc(wm);
-                while (wm) {
-                    int kk[NB];   // positions (within the batch) of the next NB candidates of this warp; -1 = none
+                T.n_cand += (unsigned)ncur;
+                // ---- phase 1: fp32 projection + certification of NB candidates
+                uint32_t puv[NB];
+                unsigned stw = 0;   // 4 bits per candidate: st | g_in << 3
+                float zc[MODE == MODE_SPLAT ? NB : 1];
 #pragma unroll
-                    for (int k = 0; k < NB; ++k) {
-                        kk[k] = wm ? (__ffs(wm) - 1) : -1;
-                        wm &= wm - 1u;
+                for (int k = 0; k < NB; ++k) {
+                    puv[k] = 0;
+                    if (fr[k] >= 0) {
+                        const Cls c = classify(stage_w + k * 8, pt, fW, fH);
+                        puv[k] = c.puv;
+                        stw |= (unsigned)(c.st | (c.g_in << 3)) << (4 * k);
+                        if (MODE == MODE_SPLAT) zc[k] = c.z;
                     }
-                    // ---- phase 1: fp32 projection + certification of NB candidates
-                    uint32_t puv[NB];
-                    unsigned long long stw = 0;   // 4 bits per candidate: st | g_in << 3
-                    float zc[MODE == MODE_SPLAT ? NB : 1];
-#pragma unroll
-                    for (int k = 0; k < NB; ++k) {
-                        puv[k] = 0;
-                        if (kk[k] >= 0) {
-                            const Cls c = classify(stage + (buf * FUSE_STAGE + kk[k]) * 8, pt, fW, fH);
-                            puv[k] = c.puv;
-                            stw |= (unsigned long long)(c.st | (c.g_in << 3)) << (4 * k);
-                            if (MODE == MODE_SPLAT) zc[k] = c.z;
-                        }
-                    }
-#ifdef FUSE_PROBE   // experiment build: how many classified pairs are in-image, and how many (warp, candidate) pairs have any
-#pragma unroll
-                    for (int k = 0; k < NB; ++k) {
-                        const bool on = ((stw >> (4 * k)) & 7ull) != 0ull;
-                        probe_lane += on ? 1u : 0u;
-                        probe_warp += (lane == 0 && __any_sync(__activemask(), on)) ? 32u : 0u;
-                    }
-#endif
-                    if ((stw == 0 && !P.audit) || (P.dbg & 4)) continue;
+                    FUSE_SCHED_FENCE();
+                }
+                if (stw != 0u || AUDIT) {
                     // ---- phase 2: every gather of the certified candidates is issued before any is consumed
-                    uint32_t dv[MODE == MODE_SPLAT ? 1 : NB];
-                    uint32_t mk[MODE == MODE_VOTE ? NB : 1];
+                    uint32_t g0[MODE == MODE_SPLAT ? 1 : NB];                                   // depth word or packed texel
+                    uint32_t g1[(MODE == MODE_VOTE && FMT < F3D_FRAMES_U32) ? NB : 1];          // class (two-array formats)
                     if (MODE != MODE_SPLAT) {
 #pragma unroll
                         for (int k = 0; k < NB; ++k) {
-                            dv[k] = 0;
-                            if (MODE == MODE_VOTE) mk[k] = 0;
-                            if (((stw >> (4 * k)) & 7ull) == 1ull) {
-                                const size_t off = (size_t)cand[b0 + kk[k]] * (size_t)HW + (size_t)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
-                                if (FMT == F3D_DEPTH_U16_MM) dv[k] = __ldg(reinterpret_cast<const uint16_t*>(P.depth) + off);
-                                else dv[k] = __float_as_uint(__ldg(reinterpret_cast<const float*>(P.depth) + off));
-                                if (MODE == MODE_VOTE) mk[k] = __ldg(P.mask + off);
+                            g0[k] = 0;
+                            if (MODE == MODE_VOTE && FMT < F3D_FRAMES_U32) g1[k] = 0;
+                            if (((stw >> (4 * k)) & 7u) == 1u) {
+                                const size_t off = frame_off<FMT>(P, fr[k], (int)(puv[k] & 0xffffu), (int)(puv[k] >> 16));
+                                if (FMT == F3D_DEPTH_U16_MM) g0[k] = __ldg(reinterpret_cast<const uint16_t*>(P.depth) + off);
+                                else g0[k] = __ldg(reinterpret_cast<const uint32_t*>(P.depth) + off);
+                                if (MODE == MODE_VOTE && FMT < F3D_FRAMES_U32) g1[k] = __ldg(P.mask + off);
                             }
                         }
-                    }
-                    if (P.dbg & 8) {   // timing experiment: consume the gathers trivially
-                        unsigned acc = 0;
-#pragma unroll
-                        for (int k = 0; k < NB; ++k) acc ^= dv[MODE == MODE_SPLAT ? 0 : k] ^ mk[MODE == MODE_VOTE ? k : 0];
-                        if (acc == 0xdeadbeefu) T.n_seen++;
-                        continue;
                     }
                     // ---- phase 3: depth validity + distance criterion, votes; uncertain pairs are deferred
 #pragma unroll
                     for (int k = 0; k < NB; ++k) {
-                        int st = (int)((stw >> (4 * k)) & 7ull);
-                        if (st == 0 && !P.audit) continue;
-                        if (kk[k] < 0) continue;
-                        const int frel = cand[b0 + kk[k]];
-                        const float4* s = stage + (buf * FUSE_STAGE + kk[k]) * 8;
-                        int g_in = (int)((stw >> (4 * k + 3)) & 1ull);
+                        int st = (int)((stw >> (4 * k)) & 7u);
+                        if (fr[k] < 0 || (st == 0 && !AUDIT)) continue;
+                        const int frel = fr[k];
+                        const float4* s = stage_w + k * 8;
+                        int g_in = (int)((stw >> (4 * k + 3)) & 1u);
                         const int pix = (int)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
                         uint32_t zq = 0;
+                        uint32_t cls = 0;
                         if (st == 1 && MODE != MODE_SPLAT) {
                             float dm;
                             bool valid;
-                            if (FMT == F3D_DEPTH_U16_MM) {
-                                const uint32_t d = dv[k];
+                            if (FMT != F3D_DEPTH_F32_M) {
+                                const uint32_t d = g0[k] & 0xffffu;
                                 valid = (d >= P.d_lo) && (d <= P.d_hi);
                                 dm = (float)d * 0.001f;
                             } else {
-                                dm = __uint_as_float(dv[k]);
+                                dm = __uint_as_float(g0[k]);
                                 valid = ((double)dm > P.zmin) && ((double)dm <= P.zmax);
                             }
+                            if (MODE == MODE_VOTE) cls = (FMT < F3D_FRAMES_U32) ? g1[(MODE == MODE_VOTE && FMT < F3D_FRAMES_U32) ? k : 0] : ((g0[k] >> 16) & 0xffu);
                             st = valid ? distance_test(s, pt, puv[k], dm, P, g_in) : 0;
                         }
                         if (MODE == MODE_SPLAT && st == 1) {
                             // quantised camera z: floor(z*1000 + 0.5); certify the floor
-                            const float zm = fmaf(zc[k], 1000.0f, 0.5f);
+                            const float zm = fmaf(zc[MODE == MODE_SPLAT ? k : 0], 1000.0f, 0.5f);
                             const float fz = floorf(zm);
                             const float ez = 8.0f * F3D_U24 * s[4].w *
                                              (fabsf((pt.x - s[0].x) - s[1].x) + fabsf((pt.y - s[0].y) - s[1].y) +
@@ -834,38 +865,38 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
                             }
                         }
                         const bool seen = (st == 1);
-                        if ((st >= 2 && !(P.dbg & 16)) || P.audit) {
+                        if (st >= 2 || AUDIT) {
                             // defer to the warp's dense fp64 pass (queue full or audit sweep: evaluate inline)
-                            const int slot = (st >= 2 && !P.audit) ? atomicAdd(nq_s + warp, 1) : FUSE_QWARP;
+                            const int slot = (st >= 2 && !AUDIT) ? atomicAdd(sh.nq + warp, 1) : FUSE_QWARP;
                             if (slot < FUSE_QWARP) {
                                 queue[slot].w0 = (uint32_t)tid | ((uint32_t)frel << 16);
                                 queue[slot].w1 = (uint32_t)pix;
                                 queue[slot].w2 = (uint32_t)st | ((uint32_t)g_in << 8);
                             } else {
                                 resolve_exact<MODE, FMT, CellT>(P, RP, frec, hist, RS, tile_base, tid, frel, pt.x, pt.y, pt.z, st, g_in, pix,
-                                                         seen, zq, true, dirty_s + warp, T);
+                                                                seen, zq, true, sh.dirty + warp, T);
                             }
                         } else if (seen) {
                             ++T.n_seen;
                             if (MODE == MODE_VOTE) {
-                                cast_vote(hist, tid * RS, (int)mk[k], P, RP, T);
+                                cast_vote(hist, tid * RS, (int)cls, P, RP, T);
                             } else {
                                 const size_t off = (size_t)frel * (size_t)HW + (size_t)pix;
                                 if (MODE == MODE_SPLAT) atomicMin(P.zbuf + off, zq);
                                 else atomicMax(P.uv2pt + off, (int)gi);
                             }
                         }
+                        FUSE_SCHED_FENCE();
                     }
                 }
             }
-            if (batch + 1 < nbatch) __syncthreads();   // stage buffer `buf` may be refilled two iterations later
         }
     }
 
     // ---- warp-private dense fp64 pass over the deferred point-views (one entry per lane)
     __syncwarp();
     {
-        const int nq = min(nq_s[warp], FUSE_QWARP);
+        const int nq = min(sh.nq[warp], FUSE_QWARP);
         // preferred: hand the uncertain pairs to the dense fix-up kernels through the caller's workspace queue
         bool flushed = false;
         if (P.gq && nq > 0) {
@@ -888,23 +919,23 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             const int owner = (int)(d.w0 & 0xffffu), frel = (int)(d.w0 >> 16);
             const float4 op = __ldg(P.points + tile_base + owner);
             resolve_exact<MODE, FMT, CellT>(P, RP, frec, hist, RS, tile_base, owner, frel, op.x, op.y, op.z, (int)(d.w2 & 0xffu),
-                                     (int)(d.w2 >> 8), (int)d.w1, false, 0u, false, dirty_s + warp, T);
+                                            (int)(d.w2 >> 8), (int)d.w1, false, 0u, false, sh.dirty + warp, T);
         }
     }
     __syncwarp();
 
-    // ---- epilogue (warp-private rows): histogram -> HBM, written once with 16-byte stores; fused label resolve
+    // ---- epilogue (warp-private rows): histogram -> HBM, written once; fused label resolve
     if constexpr (MODE == MODE_VOTE && HB == 1) {
         uint8_t* hist8 = reinterpret_cast<uint8_t*>(hist);
         flush8(P, hist8, warp, lane, tile_base, nflush > 0 || P.accumulate, false, T, stg_all + warp * (FUSE_STG_ROWS * 32), nflush,
-               ((dirty_s[warp] >> lane) & 1u) != 0u, dcache_all + warp * F3D_XCH_NLEVEL);
+               ((sh.dirty[warp] >> lane) & 1u) != 0u, sh.dcache[warp]);
         if (RP.enabled && active) {
             // VotingSegmentation.segment (voting.py:120-135).  The running (total, best, bpos) is exact unless another
-            // lane's deferred pass added votes to this row (re-derived from the row) or the tile was flushed more than
+            // lane's deferred pass added votes to this row (re-derived from the row) or the warp flushed more than
             // once (re-derived from the complete row in HBM, which this warp has just written).
             const bool multi = nflush > 0 && (P.votes || P.votes16);
             if (multi) __syncwarp();
-            if (multi || ((dirty_s[warp] >> lane) & 1u)) {
+            if (multi || ((sh.dirty[warp] >> lane) & 1u)) {
                 T.total = 0;
                 T.best = 0;
                 T.bpos = 0x7fff;
@@ -927,55 +958,33 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             if (P.summ) P.summ[gi] = summ_pack(T.total, T.best, T.bpos);
         }
     } else if constexpr (MODE == MODE_VOTE) {
-      {
         const int row0 = warp * 32;
         const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
         if (P.votes16 && nrows > 0) {
             uint16_t* __restrict__ out = P.votes16 + (tile_base + row0) * P.C1;
-            if (RS == P.C1 && !P.accumulate) {
-                const uint4* __restrict__ h128 = reinterpret_cast<const uint4*>(hist + row0 * RS);
-                const int total = nrows * P.C1;
-                const int n8 = total >> 3;
-                for (int i = lane; i < n8; i += 32) *reinterpret_cast<uint4*>(out + 8 * i) = h128[i];
-                for (int e = (n8 << 3) + lane; e < total; e += 32) out[e] = hist[row0 * RS + e];
-            } else {
-                for (int j = 0; j < nrows; ++j) {
-                    for (int c = lane; c < P.C1; c += 32) {
-                        const uint16_t v = hist[(row0 + j) * RS + c];
-                        if (!P.accumulate) out[j * P.C1 + c] = v;
-                        else if (v) out[j * P.C1 + c] += v;
-                    }
+            for (int j = 0; j < nrows; ++j) {
+                for (int c = lane; c < P.C1; c += 32) {
+                    const uint16_t v = hist[(row0 + j) * RS + c];
+                    if (!P.accumulate) out[j * P.C1 + c] = v;
+                    else if (v) out[j * P.C1 + c] += v;
                 }
             }
         }
         if (P.votes && nrows > 0) {
             int32_t* __restrict__ out = P.votes + (tile_base + row0) * P.C1;
-            if (RS == P.C1 && !P.accumulate) {
-                // rows are dense (RS == C1): the histogram rows are the output rows, widened from uint16 to int32
-                const uint2* __restrict__ h64 = reinterpret_cast<const uint2*>(hist + row0 * RS);
-                const int total = nrows * P.C1;
-                const int n4 = total >> 2;
-                for (int i = lane; i < n4; i += 32) {
-                    const uint2 w = h64[i];
-                    *reinterpret_cast<int4*>(out + 4 * i) =
-                        make_int4((int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16));
-                }
-                for (int e = (n4 << 2) + lane; e < total; e += 32) out[e] = (int)hist[row0 * RS + e];
-            } else {
-                for (int j = 0; j < nrows; ++j) {
-                    for (int c = lane; c < P.C1; c += 32) {
-                        const int v = (int)hist[(row0 + j) * RS + c];
-                        if (!P.accumulate) out[j * P.C1 + c] = v;   // overwrite mode writes every cell exactly once
-                        else if (v) out[j * P.C1 + c] += v;         // accumulate mode touches only the sparse non-zero cells
-                    }
+            for (int j = 0; j < nrows; ++j) {
+                for (int c = lane; c < P.C1; c += 32) {
+                    const int v = (int)hist[(row0 + j) * RS + c];
+                    if (!P.accumulate) out[j * P.C1 + c] = v;   // overwrite mode writes every cell exactly once
+                    else if (v) out[j * P.C1 + c] += v;         // accumulate mode touches only the sparse non-zero cells
                 }
             }
         }
         if (RP.enabled && active) {
             // VotingSegmentation.segment (voting.py:120-135).  The running (total, best, bpos) is exact unless another
             // lane's deferred pass added votes to this row: then it is re-derived from the row itself.
-            if ((dirty_s[warp] >> lane) & 1u) {
-                const uint16_t* __restrict__ row = hist + tid * RS;
+            if ((sh.dirty[warp] >> lane) & 1u) {
+                const uint16_t* __restrict__ row = reinterpret_cast<const uint16_t*>(hist) + tid * RS;
                 T.total = 0;
                 T.best = 0;
                 T.bpos = 0x7fff;
@@ -994,42 +1003,35 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             P.labels[gi] = (int64_t)(unc ? RP.unclassified : RP.remap[T.bpos]);
             if (P.summ) P.summ[gi] = summ_pack(T.total, T.best, T.bpos);
         }
-      }
     }
 
-    // ---- statistics
-#ifdef FUSE_PROBE
-    if (P.stats) {
-        atomicAdd(P.stats + 6, (unsigned long long)probe_lane);
-        atomicAdd(P.stats + 7, (unsigned long long)probe_warp);
-    }
-#endif
+    // ---- statistics: one atomic per counter per CTA
     if (P.stats) {
         const unsigned nc = __reduce_add_sync(0xffffffffu, T.n_cand), ns = __reduce_add_sync(0xffffffffu, T.n_seen);
         if (lane == 0) {
-            if (nc) atomicAdd(stat_s + F3D_STAT_CANDIDATES, nc);
-            if (ns) atomicAdd(stat_s + F3D_STAT_SEEN, ns);
+            if (nc) atomicAdd(sh.stat + F3D_STAT_CANDIDATES, nc);
+            if (ns) atomicAdd(sh.stat + F3D_STAT_SEEN, ns);
         }
         __syncthreads();
-        if (tid < 6 && stat_s[tid]) atomicAdd(P.stats + tid, (unsigned long long)stat_s[tid]);   // one atomic per counter per CTA
+        if (tid < 6 && sh.stat[tid]) atomicAdd(P.stats + tid, (unsigned long long)sh.stat[tid]);
     }
 }
 
-// ---- first cull level: candidate frames per super-tile (FUSE_ST_TILES tiles = 4096 consecutive points) -------------------------
+// ---- first cull level: candidate frames per super-tile (4096 consecutive points) ---------------------------------------
 // One CTA per super-tile: exact box of its points, every frame of the launch tested with the same conservative rule as
-// the tile test, surviving frame ids appended to the super-tile's list.  With F frames and T tiles this replaces T*F
+// the warp-box test, surviving frame ids appended to the super-tile's list.  With F frames and T tiles this replaces T*F
 // plane tests inside the fused kernel by T*F/16 here plus (list length) per tile -- what keeps the cull from dominating
 // at thousands of frames (C3 / C4) and keeps the frame table out of the fused kernel's L1.
-__global__ void __launch_bounds__(256) supertile_cull_kernel(const __grid_constant__ FuseParams P, unsigned* __restrict__ st_count,
-                                                             uint16_t* __restrict__ st_list) {
+static __global__ void __launch_bounds__(256) supertile_cull_kernel(const __grid_constant__ FuseParams P, unsigned* __restrict__ st_count,
+                                                                    uint16_t* __restrict__ st_list) {
     __shared__ float s_box[8 * 6];
     __shared__ unsigned s_n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t p0 = (int64_t)blockIdx.x * (FUSE_ST_TILES * FUSE_BLOCK);
+    const int64_t p0 = (int64_t)blockIdx.x * FUSE_ST_POINTS;
     const float big = 3.0e38f;
     float lo[3] = {big, big, big}, hi[3] = {-big, -big, -big};
-    for (int k = 0; k < FUSE_ST_TILES; ++k) {
-        const int64_t i = p0 + (int64_t)k * FUSE_BLOCK + tid;
+    for (int k = 0; k < FUSE_ST_POINTS / 256; ++k) {
+        const int64_t i = p0 + (int64_t)k * 256 + tid;
         if (i < P.N) {
             const float4 q = __ldg(P.points + i);
             lo[0] = fminf(lo[0], q.x); hi[0] = fmaxf(hi[0], q.x);
@@ -1097,28 +1099,27 @@ __device__ __forceinline__ void fixup_entry(const FuseParams& P, const FuseResol
                                             unsigned long long i, unsigned qsub, unsigned* s_qcnt, unsigned& n_exact,
                                             unsigned& n_div, unsigned& n_edge, unsigned& n_seen) {
     const int frel = (int)(e.w & 0xffffu), st = (int)((e.w >> 16) & 0xffu);
-    const int HW = P.H * P.W;
     const float4 p = __ldg(P.points + e.pt);
-    ExactOut eo;
-    exact_eval<MODE, FMT>(P, fe, frel, p.x, p.y, p.z, eo);
-    const bool e_seen = (MODE == MODE_SPLAT) ? (eo.in != 0) : (eo.vis != 0);
-    const uint32_t e_zq = (MODE == MODE_SPLAT && eo.in) ? quantise_mm(eo.zcam) : 0u;
+    const unsigned long long eo = exact_eval<MODE, FMT>(P, fe, frel, p.x, p.y, p.z);
+    const int e_in = (int)(eo & EX_IN), e_vis = (int)((eo >> 1) & 1ull), e_pix = (int)(eo >> 32);
+    const bool e_seen = (MODE == MODE_SPLAT) ? (e_in != 0) : (e_vis != 0);
+    const uint32_t e_zq = (MODE == MODE_SPLAT && e_in) ? (uint32_t)((eo >> 16) & 0xffffull) : 0u;
     bool diverged;
-    if (st == 2) diverged = ((int)e.guess != eo.in) || (eo.in && e.pix != eo.pix);
-    else if (MODE == MODE_SPLAT) diverged = (!eo.in) || (e.pix != eo.pix) || (e.guess != e_zq);
-    else diverged = ((int)e.guess != eo.vis) || (eo.in && e.pix != eo.pix);
+    if (st == 2) diverged = ((int)e.guess != e_in) || (e_in && e.pix != e_pix);
+    else if (MODE == MODE_SPLAT) diverged = (!e_in) || (e.pix != e_pix) || (e.guess != e_zq);
+    else diverged = ((int)e.guess != e_vis) || (e_in && e.pix != e_pix);
     ++n_exact;
     n_div += diverged ? 1u : 0u;
-    n_edge += (eo.in && eo.near_edge) ? 1u : 0u;
+    n_edge += (e_in && (eo & EX_EDGE)) ? 1u : 0u;
     if (!e_seen) return;
     ++n_seen;
-    const size_t off = (size_t)frel * (size_t)HW + (size_t)eo.pix;
+    const size_t off = (size_t)frel * (size_t)(P.H * P.W) + (size_t)e_pix;
     if (MODE == MODE_VOTE) {
-        const int cls = __ldg(P.mask + off);
+        const int cls = (int)((eo >> 8) & 0xffull);
         if (cls < P.C1 && P.xg_G > 0) {
             // exchange mode: the vote goes to the owner's queue through a sub-queue this block owns (shared-memory cursor)
             const int d = (int)(e.pt / P.xg_per);
-            xg_append(P, d, qsub, atomicAdd(&s_qcnt[d], 1u), (unsigned)((e.pt - (long long)d * P.xg_per) * P.C1 + cls), 1u);
+            xg_append(P, d, qsub, atomicAdd(&s_qcnt[d], 1u), (unsigned long long)(e.pt - (long long)d * P.xg_per) * (unsigned long long)P.C1 + (unsigned)cls, 1u);
         } else if (cls < P.C1) {
             if (P.votes16) {
                 const size_t cell = (size_t)e.pt * P.C1 + cls;   // 32-bit atomic on the word of the uint16 counter
@@ -1161,8 +1162,9 @@ __device__ __forceinline__ void fixup_stats(const FuseParams& P, unsigned n_exac
 }
 
 // When the launch has few enough frames, the used part of every frame's exact record (FIXUP_REC_BYTES of 448) fits one
-// SM's shared memory: one 1024-thread block per SM keeps the whole table on chip and every thread evaluates its entries
-// against it directly -- no per-warp staging round trips, 32 warps per SM in flight.
+// SM's shared memory: one 1024-thread block per SM stages the whole table on chip with TMA bulk copies (one
+// cp.async.bulk per frame record, all completing on one mbarrier) and every thread evaluates its entries against it
+// directly -- no per-warp staging round trips, 32 warps per SM in flight.
 #define FIXUP_REC_BYTES 368   // q, qi, t, ss, plane_pt, plane_n, lookat = 360 bytes, padded to 16
 #define FIXUP_TABLE_THREADS 1024
 #define FIXUP_TABLE_QSUBS (F3D_XCH_NSUB_FIX / 148)   // sub-queues a table block owns (warps share them round-robin)
@@ -1171,15 +1173,29 @@ __global__ void __launch_bounds__(FIXUP_TABLE_THREADS, 1) fixup_apply_table_kern
                                                                                     const __grid_constant__ FuseResolve RP) {
     extern __shared__ __align__(16) unsigned char fx_smem[];
     __shared__ unsigned s_qcnt[FIXUP_TABLE_QSUBS][F3D_MAX_RANKS];
+    __shared__ __align__(8) uint64_t s_bar;
     const int nf = P.f_end - P.f_begin;
     const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
     for (int i = threadIdx.x; i < FIXUP_TABLE_QSUBS * F3D_MAX_RANKS; i += blockDim.x) (&s_qcnt[0][0])[i] = 0u;
-    for (int i = threadIdx.x; i < nf * (FIXUP_REC_BYTES / 16); i += blockDim.x) {
-        const int f = i / (FIXUP_REC_BYTES / 16), c = i % (FIXUP_REC_BYTES / 16);
-        reinterpret_cast<uint4*>(fx_smem + (size_t)f * FIXUP_REC_BYTES)[c] = __ldg(reinterpret_cast<const uint4*>(&frec[P.f_begin + f].exact) + c);
+    const unsigned long long n = min(*P.gq_count, P.gq_cap);
+    if ((unsigned long long)blockIdx.x * blockDim.x >= n) {   // nothing for this block (grid-stride start past the end)
+        if (P.xg_G > 0) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < FIXUP_TABLE_QSUBS * P.xg_G; i += blockDim.x)
+                P.xg_qcur[(i % P.xg_G) * F3D_XCH_NSUB + blockIdx.x * FIXUP_TABLE_QSUBS + i / P.xg_G] = 0u;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const unsigned long long n = min(*P.gq_count, P.gq_cap);
+    if (threadIdx.x == 0) mbar_expect_tx(&s_bar, (unsigned)(nf * FIXUP_REC_BYTES));
+    __syncthreads();
+    for (int f = threadIdx.x; f < nf; f += blockDim.x)
+        tma_bulk_g2s(fx_smem + (size_t)f * FIXUP_REC_BYTES, &frec[P.f_begin + f].exact, FIXUP_REC_BYTES, &s_bar);
+    mbar_wait(&s_bar, 0u);
     const unsigned wsub = (threadIdx.x >> 5) % FIXUP_TABLE_QSUBS;
     unsigned n_exact = 0, n_div = 0, n_edge = 0, n_seen = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -1252,7 +1268,7 @@ __global__ void __launch_bounds__(FIXUP_THREADS) fixup_apply_kernel(const __grid
 }
 
 // labels of the points whose votes changed, from their 8-byte resolve state (VotingSegmentation.segment, voting.py:120-135)
-__global__ void __launch_bounds__(256) fixup_labels_summary_kernel(const __grid_constant__ FuseParams P, const __grid_constant__ FuseResolve RP) {
+static __global__ void __launch_bounds__(256) fixup_labels_summary_kernel(const __grid_constant__ FuseParams P, const __grid_constant__ FuseResolve RP) {
     const unsigned long long n = min(*P.gq_count, P.gq_cap);
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
         const GEntry e = P.gq[i];
@@ -1267,7 +1283,7 @@ __global__ void __launch_bounds__(256) fixup_labels_summary_kernel(const __grid_
 
 // labels of the points whose votes changed in fixup_apply_kernel (VotingSegmentation.segment, voting.py:120-135);
 // eight lanes per entry stream the point's vote row, like resolve_kernel
-__global__ void __launch_bounds__(256) fixup_labels_kernel(const __grid_constant__ FuseParams P, const __grid_constant__ FuseResolve RP) {
+static __global__ void __launch_bounds__(256) fixup_labels_kernel(const __grid_constant__ FuseParams P, const __grid_constant__ FuseResolve RP) {
     __shared__ int16_t s_fpos[RES_MAXC];
     for (int c = threadIdx.x; c < RES_MAXC; c += blockDim.x) s_fpos[c] = RP.fpos[c];
     __syncthreads();
@@ -1315,119 +1331,74 @@ __global__ void __launch_bounds__(256) fixup_labels_kernel(const __grid_constant
     }
 }
 
-__global__ void zbuf_finalize_kernel(const uint32_t* __restrict__ zbuf, uint16_t* __restrict__ out, int64_t total, int H,
-                                     int W, int border) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    uint32_t z = zbuf[i];
-    int pix = (int)(i % ((int64_t)H * W));
-    int y = pix / W, x = pix - y * W;
-    bool edge = (x < border) || (y < border) || (x >= W - border) || (y >= H - border);
-    out[i] = (z == 0xffffffffu || edge) ? (uint16_t)0 : (uint16_t)z;
-}
-
 // ---- host side ----------------------------------------------------------------------------------------------------
-static int hist_row_stride(int C1) {
+static inline int hist_row_stride(int C1) {
     int rs = (C1 + 1) & ~1;            // even number of uint16
     if (((rs / 2) & 1) == 0) rs += 2;  // odd number of 32-bit words per row: lanes hit distinct banks
     return rs;
 }
 
-static size_t fuse_smem_bytes(int mode, int C1, int hb, bool slots) {
-    size_t b = 2 * FUSE_STAGE * sizeof(FrameFast) + FUSE_FCHUNK * (sizeof(uint16_t) + 1) + FUSE_RED_WORDS * sizeof(float) +
-               (FUSE_BLOCK / 32) * FUSE_QWARP * sizeof(Deferred);
-    if (mode == MODE_VOTE)
-        b += ((size_t)FUSE_BLOCK * (hb == 1 ? (size_t)C1 : hist_row_stride(C1) * sizeof(uint16_t)) + 15) & ~(size_t)15;
-    if (slots) b += (size_t)FUSE_NSLOT * FUSE_BLOCK + (size_t)(FUSE_BLOCK / 32) * FUSE_STG_ROWS * 32 * sizeof(uint16_t);
+static inline size_t fuse_smem_bytes(int mode, int C1, int hb, bool slots) {
+    size_t b = FUSE_OFF_HIST;
+    if (mode == MODE_VOTE) b += fuse_align16((size_t)FUSE_BLOCK * (hb == 1 ? (size_t)C1 : hist_row_stride(C1) * sizeof(uint16_t)));
+    if (slots) b += (size_t)FUSE_NSLOT * FUSE_BLOCK + (size_t)FUSE_NW * FUSE_STG_ROWS * 32 * sizeof(uint16_t);
     return b;
 }
 
-// ---- optional timing of the fused kernel alone (flags bit 1): event pairs recorded on the launch stream around
-// fuse_kernel, read back after the timed region -- so a benchmark reports the dominant kernel's duration measured live,
-// not the whole call (first cull level + fused kernel + fix-up kernels)
-#define F3D_TIMING_SLOTS 256
-static cudaEvent_t g_tev[F3D_TIMING_SLOTS][2];
-static int g_tev_created = 0, g_tev_used = 0;
+// Timing of the fused kernel alone: the caller hands two of ITS events to f3d_fuse_time_next_call; the next fused launch
+// of this host thread records them around fuse_kernel and forgets them (thread-local one-shot hand-over, no other state).
+struct FuseTimingSlot {
+    cudaEvent_t ev[2];
+    bool armed;
+};
+FuseTimingSlot& f3d_timing_slot();   // fuse_vote.cu
 
-extern "C" int f3d_fuse_timing_reset(void) {
-    g_tev_used = 0;
-    return F3D_OK;
-}
-
-extern "C" int f3d_fuse_timing_read(float* ms_out, int32_t max_n) {
-    if (!ms_out || max_n < 0) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_timing_read: bad argument");
-    int n = g_tev_used < max_n ? g_tev_used : max_n;
-    for (int i = 0; i < n; ++i) {
-        if (cudaEventSynchronize(g_tev[i][1]) != cudaSuccess || cudaEventElapsedTime(ms_out + i, g_tev[i][0], g_tev[i][1]) != cudaSuccess)
-            return f3d_check_launch("f3d_fuse_timing_read");
-    }
-    return n;
-}
-
-static bool timing_slot(cudaEvent_t*& pair) {
-    if (g_tev_used >= F3D_TIMING_SLOTS) return false;
-    while (g_tev_created <= g_tev_used) {
-        if (cudaEventCreate(&g_tev[g_tev_created][0]) != cudaSuccess || cudaEventCreate(&g_tev[g_tev_created][1]) != cudaSuccess) return false;
-        ++g_tev_created;
-    }
-    pair = g_tev[g_tev_used++];
-    return true;
-}
-
-template <int MODE, int FMT, int HB>
-static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stream);
-
-// the vote kernel runs on the byte histogram unless the caller wants labels without any vote output from more frames
-// than a byte counter can hold between flushes (there is then nowhere to flush to): that case keeps uint16 counters
-template <int MODE, int FMT>
-static int launch_fuse(const FuseParams& P, const FuseResolve& RP, cudaStream_t stream) {
-    if constexpr (MODE == MODE_VOTE) {
-        const bool no_sink = !P.votes && !P.votes16 && P.xg_G == 0;
-        const bool hist16 = P.xg_G == 0 && ((no_sink && P.f_end - P.f_begin > FUSE_LIMIT8) || getenv("F3D_HIST16") != nullptr);
-        if (!hist16) return launch_fuse_hb<MODE, FMT, 1>(P, RP, stream);
-    }
-    return launch_fuse_hb<MODE, FMT, 2>(P, RP, stream);
-}
-
-template <int MODE, int FMT, int HB>
+template <int MODE, int FMT, int HB, bool AUDIT>
 static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stream) {
     if (MODE == MODE_VOTE) P.RS = HB == 1 ? P.C1 : hist_row_stride(P.C1);
-    size_t smem = fuse_smem_bytes(MODE, P.C1, HB, MODE == MODE_VOTE && HB == 1 && P.xg_G > 0);
-    if (const char* ex = getenv("F3D_EXTRA_SMEM")) smem += (size_t)atoi(ex);   // occupancy experiments only
+    const size_t smem = fuse_smem_bytes(MODE, P.C1, HB, MODE == MODE_VOTE && HB == 1 && P.xg_G > 0);
     if (smem > 227 * 1024) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: nclasses+1 too large for the shared-memory histogram");
-    cudaError_t e = cudaFuncSetAttribute(fuse_kernel<MODE, FMT, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute)");
+    static thread_local size_t smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // per device: the attribute is sticky, set it when it grows
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 8 || smem > smem_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fuse_kernel<MODE, FMT, HB, AUDIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute)");
+        if (dev >= 0 && dev < 8) smem_set[dev] = smem;
+    }
     int64_t tiles = (P.N + FUSE_BLOCK - 1) / FUSE_BLOCK;
     if (tiles > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: too many points for one launch");
     const bool use_queue = P.gq != nullptr;
     if (use_queue) {
-        e = cudaMemsetAsync(P.gq_count, 0, sizeof(unsigned long long), stream);
+        cudaError_t e = cudaMemsetAsync(P.gq_count, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(memset)");
     }
     if (P.st_count) {
-        if (P.f_end - P.f_begin > 32 && !(P.dbg & 2) && !getenv("F3D_NO_SUPERTILE")) {   // env: A/B experiments only
-            const unsigned nst = (unsigned)((tiles + FUSE_ST_TILES - 1) / FUSE_ST_TILES);
+        if (P.f_end - P.f_begin > 32) {
+            const unsigned nst = (unsigned)((P.N + FUSE_ST_POINTS - 1) / FUSE_ST_POINTS);
             supertile_cull_kernel<<<nst, 256, 0, stream>>>(P, const_cast<unsigned*>(P.st_count), const_cast<uint16_t*>(P.st_list));
         } else {
             P.st_count = nullptr;   // few frames: the per-tile scan is cheaper than another launch
         }
     }
-    cudaEvent_t* tev = nullptr;
-    if (P.time_kernel && timing_slot(tev)) cudaEventRecord(tev[0], stream);
-    fuse_kernel<MODE, FMT, HB><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
-    if (tev) cudaEventRecord(tev[1], stream);
+    FuseTimingSlot& ts = f3d_timing_slot();
+    const bool timed = ts.armed;
+    ts.armed = false;
+    if (timed) cudaEventRecord(ts.ev[0], stream);
+    fuse_kernel<MODE, FMT, HB, AUDIT><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
+    if (timed) cudaEventRecord(ts.ev[1], stream);
     if (use_queue) {
         // the queue length lives on the device: fixed grids with grid-stride loops, no host synchronisation
-        const int fx_smem = (FIXUP_THREADS / 32) * 32 * (int)sizeof(FrameExact);
-        e = cudaFuncSetAttribute(fixup_apply_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem);
-        if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute fixup)");
         static_assert(F3D_XCH_NSUB_FIX == 148 * 12, "one sub-queue per fix-up block");
         const size_t table_smem = (size_t)(P.f_end - P.f_begin) * FIXUP_REC_BYTES;
-        if (table_smem <= 200 * 1024 && !getenv("F3D_FIXUP_STAGING")) {   // env: A/B experiments only
-            e = cudaFuncSetAttribute(fixup_apply_table_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_smem);
+        if (table_smem <= 200 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(fixup_apply_table_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute fixup table)");
             fixup_apply_table_kernel<MODE, FMT><<<148, FIXUP_TABLE_THREADS, table_smem, stream>>>(P, RP);
         } else {
+            const int fx_smem = (FIXUP_THREADS / 32) * 32 * (int)sizeof(FrameExact);
+            cudaError_t e = cudaFuncSetAttribute(fixup_apply_kernel<MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fx_smem);
+            if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(cudaFuncSetAttribute fixup)");
             fixup_apply_kernel<MODE, FMT><<<F3D_XCH_NSUB_FIX, FIXUP_THREADS, fx_smem, stream>>>(P, RP);
         }
         if (MODE == MODE_VOTE && RP.enabled) {
@@ -1438,16 +1409,27 @@ static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stre
     return f3d_check_launch("f3d_fuse");
 }
 
+// the vote kernel runs on the byte histogram unless the caller wants labels without any vote output from more frames
+// than a byte counter can hold between flushes (there is then nowhere to flush to): that case keeps uint16 counters
+template <int MODE, int FMT>
+static int launch_fuse(const FuseParams& P, const FuseResolve& RP, int audit, cudaStream_t stream) {
+    if constexpr (MODE == MODE_VOTE) {
+        const bool no_sink = !P.votes && !P.votes16 && P.xg_G == 0;
+        if (!(no_sink && P.f_end - P.f_begin > FUSE_LIMIT8))
+            return audit ? launch_fuse_hb<MODE, FMT, 1, true>(P, RP, stream) : launch_fuse_hb<MODE, FMT, 1, false>(P, RP, stream);
+    }
+    return audit ? launch_fuse_hb<MODE, FMT, 2, true>(P, RP, stream) : launch_fuse_hb<MODE, FMT, 2, false>(P, RP, stream);
+}
+
 // workspace = [deferred count u64][pad u64][super-tile counts u32 x S, padded to 16 B][super-tile lists u16 x S x FUSE_ST_LCAP]
-//             [resolve states u64 x N (fused labels only)][GEntry x cap]; S = super-tiles of the cloud.  The super-tile part is attached whenever it fits, the deferred
-// queue only when the caller's mode wants it; returns whether the queue was attached.
-static int64_t supertile_bytes(int64_t npoints) {
-    const int64_t tiles = (npoints + FUSE_BLOCK - 1) / FUSE_BLOCK;
-    const int64_t S = (tiles + FUSE_ST_TILES - 1) / FUSE_ST_TILES;
+//             [resolve states u64 x N (fused labels only)][GEntry x cap]; S = super-tiles of the cloud.  The super-tile part is
+// attached whenever it fits, the deferred queue only when the caller's mode wants it; returns whether the queue was attached.
+static inline int64_t supertile_bytes(int64_t npoints) {
+    const int64_t S = (npoints + FUSE_ST_POINTS - 1) / FUSE_ST_POINTS;
     return ((S * 4 + 15) & ~(int64_t)15) + S * FUSE_ST_LCAP * 2;
 }
 
-static bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_bytes, bool want_queue = true, bool want_summ = false) {
+static inline bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_bytes, bool want_queue = true, bool want_summ = false) {
     P.summ = nullptr;
     P.gq = nullptr;
     P.gq_count = nullptr;
@@ -1459,15 +1441,14 @@ static bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_b
     int64_t off = 16;
     const int64_t stb = supertile_bytes(P.N);
     if (workspace_bytes >= off + stb) {
-        const int64_t tiles = (P.N + FUSE_BLOCK - 1) / FUSE_BLOCK;
-        const int64_t S = (tiles + FUSE_ST_TILES - 1) / FUSE_ST_TILES;
+        const int64_t S = (P.N + FUSE_ST_POINTS - 1) / FUSE_ST_POINTS;
         P.st_count = reinterpret_cast<const unsigned*>(base + off);
         P.st_list = reinterpret_cast<const uint16_t*>(base + off + ((S * 4 + 15) & ~(int64_t)15));
         off += stb;
     }
     if (!want_queue) return false;
     // resolve states only when the queue still gets its share (one entry per 8 points) behind them
-    if (want_summ && !getenv("F3D_NO_SUMMARY") && workspace_bytes - off >= P.N * 8 + (P.N / 8 + 1024) * (int64_t)sizeof(GEntry)) {
+    if (want_summ && workspace_bytes - off >= P.N * 8 + (P.N / 8 + 1024) * (int64_t)sizeof(GEntry)) {
         P.summ = reinterpret_cast<unsigned long long*>(base + off);
         off += P.N * 8;
     }
@@ -1481,21 +1462,14 @@ static bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_b
     return true;
 }
 
-extern "C" int64_t f3d_fuse_workspace_bytes(int64_t npoints) {
-    // room for one uncertain point-view per 4 points (measured: ~0.08 per point on the 1920x1440 scene), at least 1 Mi entries,
-    // plus the super-tile candidate lists of the first cull level and the 8-byte per-point resolve states
-    int64_t cap = npoints / 4;
-    if (cap < (1 << 20)) cap = 1 << 20;
-    if (npoints < 0) npoints = 0;
-    return 16 + supertile_bytes(npoints) + npoints * 8 + cap * (int64_t)sizeof(GEntry);
-}
+static inline bool fmt_is_packed(int fmt) { return fmt == F3D_FRAMES_U32 || fmt == F3D_FRAMES_U32_T16; }
 
-static int fill_common(FuseParams& P, const void* points, int64_t N, const void* table, int fb, int fe, const void* depth,
-                       int fmt, int H, int W, const double* h_K9, double radius, double zmin, double zmax,
-                       uint64_t* stats, int flags) {
+static inline int fill_common(FuseParams& P, const void* points, int64_t N, const void* table, int fb, int fe, const void* depth,
+                              int fmt, int H, int W, const double* h_K9, double radius, double zmin, double zmax,
+                              uint64_t* stats) {
     if (!points || !table || !h_K9 || N < 0 || fb < 0 || fe < fb || H <= 0 || W <= 0)
         return f3d_fail(F3D_ERR_ARG, "f3d_fuse: bad argument");
-    if (fmt != F3D_DEPTH_U16_MM && fmt != F3D_DEPTH_F32_M) return f3d_fail(F3D_ERR_ARG, "f3d_fuse: unknown depth format");
+    if (fmt != F3D_DEPTH_U16_MM && fmt != F3D_DEPTH_F32_M && !fmt_is_packed(fmt)) return f3d_fail(F3D_ERR_ARG, "f3d_fuse: unknown frame format");
     if ((int64_t)H * W > 0x7fffffff || H > 65535 || W > 65535) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: image too large");
     P.points = reinterpret_cast<const float4*>(points);
     P.N = N;
@@ -1503,6 +1477,8 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.depth = depth;
     P.H = H;
     P.W = W;
+    P.tiles_x = (W + 15) / 16;
+    P.frame_stride = fmt == F3D_FRAMES_U32_T16 ? (int64_t)P.tiles_x * ((H + 15) / 16) * 256 : (int64_t)H * W;
     for (int i = 0; i < 9; ++i) P.K[i] = h_K9[i];
     P.cx = (float)h_K9[2];
     P.cy = (float)h_K9[5];
@@ -1524,9 +1500,6 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     P.d_lo = lo;
     P.d_hi = hi;
     P.stats = reinterpret_cast<unsigned long long*>(stats);
-    P.audit = flags & 1;
-    P.time_kernel = (flags >> 1) & 1;
-    P.dbg = (flags >> 8) & 0xff;
     P.votes = nullptr;
     P.votes16 = nullptr;
     P.uv2pt = nullptr;
@@ -1557,224 +1530,9 @@ static int fill_common(FuseParams& P, const void* points, int64_t N, const void*
     return F3D_OK;
 }
 
-// composed sequential remap `for i, cls in enumerate(filter): pc[pc == i] = cls` (voting.py:133-135) and the
-// column -> filter position table, shared with f3d_resolve_labels
-int f3d_build_resolve(int C1, double threshold, const int32_t* h_filter, int nfilter, int nclasses_id, FuseResolve& rp) {
-    if (C1 > RES_MAXC || nfilter > RES_MAXC) return f3d_fail(F3D_ERR_UNSUPPORTED, "label resolve: more than 256 columns / filter classes");
-    rp.enabled = 1;
-    rp.nfilter = nfilter;
-    rp.threshold = threshold;
-    for (int c = 0; c < RES_MAXC; ++c) {
-        rp.fpos[c] = nfilter > 0 ? (int16_t)-1 : (int16_t)c;
-        rp.remap[c] = c;
-    }
-    for (int k = nfilter - 1; k >= 0; --k) {
-        if (h_filter[k] < 0 || h_filter[k] >= C1) return f3d_fail(F3D_ERR_ARG, "label resolve: filter class out of range");
-        rp.fpos[h_filter[k]] = (int16_t)k;   // first position wins
-    }
-    rp.unclassified = nclasses_id;
-    for (int start = 0; start <= nfilter; ++start) {
-        int v = start < nfilter ? start : nclasses_id;
-        for (int i = 0; i < nfilter; ++i)
-            if (v == i) v = h_filter[i];
-        if (start < nfilter) rp.remap[start] = v;
-        else rp.unclassified = v;
-    }
-    return F3D_OK;
-}
-
 // frames are processed in launches of at most 65535 - FUSE_QWARP (uint16 candidate ids; a uint16 histogram counter
 // must also hold the warp's deferred votes)
 #define F3D_MAX_FRAMES_PER_LAUNCH (65535 - FUSE_QWARP)
 
-static int fuse_vote_impl(const void* points, int64_t N, const void* frame_table, int32_t frame_begin, int32_t frame_end,
-                          const void* depth, int32_t depth_fmt, const uint8_t* mask, int32_t H, int32_t W,
-                          const double* h_K9, double radius, double zmin, double zmax, int32_t* votes, uint16_t* votes16,
-                          int32_t C1, int32_t accumulate, const FuseResolve& RP, int64_t* labels, void* workspace,
-                          int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
-    FuseParams P;
-    int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
-                         zmax, stats, flags);
-    if (rc) return rc;
-    if ((!votes && !votes16 && !labels) || (votes && votes16) || C1 <= 0 || C1 > 256 || (frame_end > frame_begin && (!depth || !mask)))
-        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote: bad argument (votes/mask/depth NULL or C1 not in 1..256)");
-    if (labels && (accumulate || frame_end - frame_begin > F3D_MAX_FRAMES_PER_LAUNCH))
-        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_resolve: fused labels need all frames in one non-accumulating launch");
-    if ((votes && (reinterpret_cast<uintptr_t>(votes) & 15u)) || (votes16 && (reinterpret_cast<uintptr_t>(votes16) & 15u)))
-        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote: votes must be 16-byte aligned");
-    if (N == 0) return F3D_OK;
-    P.votes = votes;
-    P.votes16 = votes16;
-    P.labels = labels;
-    P.C1 = C1;
-    attach_workspace(P, workspace, workspace_bytes, (votes || votes16) && !P.audit && N <= 0x7fffffff,
-                     votes && labels && frame_end - frame_begin < (1 << 24));   // labels-only / audit: fp64 inside the sweep
-    P.RS = hist_row_stride(C1);
-    const size_t esz = depth_fmt == F3D_DEPTH_U16_MM ? 2 : 4;
-    int fb = frame_begin;
-    bool first = true;
-    do {
-        int fe = frame_end - fb > F3D_MAX_FRAMES_PER_LAUNCH ? fb + F3D_MAX_FRAMES_PER_LAUNCH : frame_end;
-        P.f_begin = fb;
-        P.f_end = fe;
-        P.depth = reinterpret_cast<const char*>(depth) + (size_t)(fb - frame_begin) * H * W * esz;
-        P.mask = mask + (size_t)(fb - frame_begin) * H * W;
-        P.accumulate = (first && !accumulate) ? 0 : 1;
-        rc = depth_fmt == F3D_DEPTH_U16_MM ? launch_fuse<MODE_VOTE, F3D_DEPTH_U16_MM>(P, RP, (cudaStream_t)stream)
-                                           : launch_fuse<MODE_VOTE, F3D_DEPTH_F32_M>(P, RP, (cudaStream_t)stream);
-        if (rc) return rc;
-        first = false;
-        fb = fe;
-    } while (fb < frame_end);
-    return F3D_OK;
-}
-
-extern "C" int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
-                                     int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
-                                     int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                                     int32_t* votes, int32_t C1, int32_t accumulate, void* workspace,
-                                     int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
-    if (!votes) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote: votes is NULL");
-    FuseResolve RP;
-    RP.enabled = 0;
-    return fuse_vote_impl(points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, mask, H, W, h_K9, radius, zmin,
-                          zmax, votes, nullptr, C1, accumulate, RP, nullptr, workspace, workspace_bytes, stats, flags, stream);
-}
-
-extern "C" int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
-                                         int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
-                                         int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                                         uint16_t* votes_u16, int32_t C1, int32_t accumulate, void* workspace,
-                                         int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
-    if (!votes_u16) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_u16: votes is NULL");
-    FuseResolve RP;
-    RP.enabled = 0;
-    return fuse_vote_impl(points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, mask, H, W, h_K9, radius, zmin,
-                          zmax, nullptr, votes_u16, C1, accumulate, RP, nullptr, workspace, workspace_bytes, stats, flags, stream);
-}
-
-extern "C" int f3d_fuse_project_vote_resolve(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
-                                             int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
-                                             int32_t H, int32_t W, const double* h_K9, double radius, double zmin,
-                                             double zmax, int32_t* votes, int32_t C1, double threshold,
-                                             const int32_t* h_filter, int32_t nfilter, int32_t nclasses_id, int64_t* labels,
-                                             void* workspace, int64_t workspace_bytes, uint64_t* stats, int32_t flags,
-                                             void* stream) {
-    if (!labels || nfilter < 0 || (nfilter > 0 && !h_filter))
-        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_resolve: bad argument");
-    FuseResolve RP;
-    int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
-    if (rc) return rc;
-    return fuse_vote_impl(points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, mask, H, W, h_K9, radius, zmin,
-                          zmax, votes, nullptr, C1, 0, RP, labels, workspace, workspace_bytes, stats, flags, stream);
-}
-
-extern "C" int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
-                              int32_t frame_end, const void* depth, int32_t depth_fmt, int32_t H, int32_t W,
-                              const double* h_K9, double radius, double zmin, double zmax, int32_t* uv2pt,
-                              void* workspace, int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
-    FuseParams P;
-    int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
-                         zmax, stats, flags);
-    if (rc) return rc;
-    if (!uv2pt || !depth) return f3d_fail(F3D_ERR_ARG, "f3d_fuse_uv2pt: bad argument");
-    if (N == 0 || frame_end == frame_begin) return F3D_OK;
-    if (N > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_uv2pt: point index does not fit int32");
-    attach_workspace(P, workspace, workspace_bytes, !P.audit);
-    FuseResolve RP;
-    RP.enabled = 0;
-    const size_t esz = depth_fmt == F3D_DEPTH_U16_MM ? 2 : 4;
-    for (int fb = frame_begin; fb < frame_end; fb += F3D_MAX_FRAMES_PER_LAUNCH) {
-        int fe = frame_end - fb > F3D_MAX_FRAMES_PER_LAUNCH ? fb + F3D_MAX_FRAMES_PER_LAUNCH : frame_end;
-        P.f_begin = fb;
-        P.f_end = fe;
-        P.depth = reinterpret_cast<const char*>(depth) + (size_t)(fb - frame_begin) * H * W * esz;
-        P.uv2pt = uv2pt + (size_t)(fb - frame_begin) * H * W;
-        rc = depth_fmt == F3D_DEPTH_U16_MM ? launch_fuse<MODE_UV2PT, F3D_DEPTH_U16_MM>(P, RP, (cudaStream_t)stream)
-                                           : launch_fuse<MODE_UV2PT, F3D_DEPTH_F32_M>(P, RP, (cudaStream_t)stream);
-        if (rc) return rc;
-    }
-    return F3D_OK;
-}
-
-extern "C" int f3d_zbuffer_splat(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
-                                 int32_t frame_end, int32_t H, int32_t W, const double* h_K9, uint32_t* zbuf,
-                                 uint16_t* depth_out, int32_t border, void* workspace, int64_t workspace_bytes,
-                                 uint64_t* stats, int32_t flags, void* stream) {
-    FuseParams P;
-    int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, nullptr, F3D_DEPTH_U16_MM, H, W, h_K9, 0.0,
-                         0.0, 0.0, stats, flags);
-    if (rc) return rc;
-    if (!zbuf || !depth_out || border < 0) return f3d_fail(F3D_ERR_ARG, "f3d_zbuffer_splat: bad argument");
-    attach_workspace(P, workspace, workspace_bytes, !P.audit && N <= 0x7fffffff);
-    const int nf = frame_end - frame_begin;
-    if (nf == 0) return F3D_OK;
-    const int64_t total = (int64_t)nf * H * W;
-    cudaError_t e = cudaMemsetAsync(zbuf, 0xff, (size_t)total * sizeof(uint32_t), (cudaStream_t)stream);
-    if (e != cudaSuccess) return f3d_check_launch("f3d_zbuffer_splat(memset)");
-    FuseResolve RP;
-    RP.enabled = 0;
-    if (N > 0) {
-        for (int fb = frame_begin; fb < frame_end; fb += F3D_MAX_FRAMES_PER_LAUNCH) {
-            int fe = frame_end - fb > F3D_MAX_FRAMES_PER_LAUNCH ? fb + F3D_MAX_FRAMES_PER_LAUNCH : frame_end;
-            P.f_begin = fb;
-            P.f_end = fe;
-            P.zbuf = zbuf + (size_t)(fb - frame_begin) * H * W;
-            rc = launch_fuse<MODE_SPLAT, F3D_DEPTH_U16_MM>(P, RP, (cudaStream_t)stream);
-            if (rc) return rc;
-        }
-    }
-    const int64_t blocks = (total + 255) / 256;
-    if (blocks > 0x7fffffff) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_zbuffer_splat: too many pixels for one launch");
-    zbuf_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(zbuf, depth_out, total, H, W, border);
-    return f3d_check_launch("f3d_zbuffer_splat");
-}
-
-
-// ---- vote exchange over peer memory: sender side (owner side: vote_exchange.cu) ---------------------------------------
-extern "C" int f3d_fuse_project_vote_exchange(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
-                                              int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
-                                              int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
-                                              int32_t C1, int32_t nranks, int64_t points_per_shard, const uint64_t* h_peer_slots,
-                                              const uint64_t* h_peer_dirs, const uint64_t* h_peer_queues, int64_t sub_rows,
-                                              int64_t sub_cap, uint32_t* cursors, uint32_t* overflow, void* workspace,
-                                              int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream) {
-    FuseParams P;
-    int rc = fill_common(P, points, N, frame_table, frame_begin, frame_end, depth, depth_fmt, H, W, h_K9, radius, zmin,
-                         zmax, stats, flags);
-    if (rc) return rc;
-    if (!h_peer_slots || !h_peer_dirs || !h_peer_queues || nranks < 1 || nranks > F3D_MAX_RANKS || points_per_shard <= 0 ||
-        (points_per_shard % FUSE_BLOCK) != 0 || sub_rows <= 0 || sub_cap <= 0 || sub_rows * F3D_XCH_NREG > 0xffffffffLL ||
-        sub_cap > 0x7fffffffLL || !cursors || !overflow || C1 <= 0 || C1 > 256 || (frame_end > frame_begin && (!depth || !mask)))
-        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_exchange: bad argument (points_per_shard must be a multiple of 256)");
-    if (frame_end - frame_begin > F3D_MAX_FRAMES_PER_LAUNCH)
-        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_exchange: too many frames per call (limit 65515)");
-    if ((int64_t)points_per_shard * C1 > 0xffffffffLL)
-        return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse_project_vote_exchange: shard cell index does not fit 32 bits");
-    if (points_per_shard * nranks < N)
-        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_exchange: nranks * points_per_shard does not cover the cloud");
-    if (N == 0) return F3D_OK;
-    P.C1 = C1;
-    P.f_begin = frame_begin;
-    P.f_end = frame_end;
-    P.mask = mask;
-    P.xg_G = nranks;
-    P.xg_per = points_per_shard;
-    for (int i = 0; i < nranks; ++i) {
-        P.xg_slots[i] = reinterpret_cast<uint16_t*>(h_peer_slots[i]);
-        P.xg_dir[i] = reinterpret_cast<uint2*>(h_peer_dirs[i]);
-        P.xg_queue[i] = reinterpret_cast<unsigned long long*>(h_peer_queues[i]);
-    }
-    P.xg_rowcur = cursors;
-    P.xg_qcur = cursors + (size_t)nranks * F3D_XCH_NREG;
-    P.xg_subrows = (unsigned)sub_rows;
-    P.xg_subcap = (unsigned)sub_cap;
-    P.xg_overflow = overflow;
-    // the fix-up kernel's blocks own the first F3D_XCH_NSUB_FIX sub-queues: the deferred queue is mandatory here
-    if (P.audit || N > 0x7fffffff || !attach_workspace(P, workspace, workspace_bytes))
-        return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_exchange: needs the workspace of f3d_fuse_workspace_bytes (no audit mode)");
-    FuseResolve RP;
-    RP.enabled = 0;
-    return depth_fmt == F3D_DEPTH_U16_MM ? launch_fuse<MODE_VOTE, F3D_DEPTH_U16_MM>(P, RP, (cudaStream_t)stream)
-                                         : launch_fuse<MODE_VOTE, F3D_DEPTH_F32_M>(P, RP, (cudaStream_t)stream);
-}
+// byte size of one element of the frame stack `depth` points to
+static inline size_t frame_elem_bytes(int fmt) { return fmt == F3D_DEPTH_U16_MM ? 2 : 4; }

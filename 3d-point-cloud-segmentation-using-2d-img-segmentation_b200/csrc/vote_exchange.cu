@@ -42,9 +42,9 @@ __global__ void __launch_bounds__(256) queue_accumulate_kernel(const unsigned lo
         const unsigned n = min(counts[(size_t)src * F3D_XCH_NSUB + sub], subcap);
         const unsigned long long* __restrict__ seg = rx + ((size_t)src * F3D_XCH_NSUB + sub) * subcap;
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned long long e = seg[i];
-            const unsigned key = (unsigned)(e & 0xffffffffu);
-            if (key < ncells) atomicAdd(votes + key, (int)(e >> 32));
+            const unsigned long long e = seg[i];                      // cell (40 bits) | count << 40
+            const unsigned long long key = e & 0xffffffffffull;
+            if (key < ncells) atomicAdd(votes + key, (int)(e >> 40));
         }
     }
 }
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) queue_relabel_kernel(const unsigned long 
         for (unsigned i0 = 0; i0 < n; i0 += blockDim.x >> 3) {             // block-uniform trip count
             const unsigned i = i0 + (threadIdx.x >> 3);
             long long pt = -1;
-            if (i < n) pt = (long long)((unsigned)(seg[i] & 0xffffffffu) / (unsigned)C1);
+            if (i < n) pt = (long long)((seg[i] & 0xffffffffffull) / (unsigned long long)C1);
             const bool live = pt >= 0 && pt < nrows;
             long long total = 0;
             int best = 0, bpos = 0x7fff;

@@ -58,6 +58,38 @@ __global__ void resize_nearest_kernel(const uint8_t* __restrict__ src, int sh, i
     dst[((size_t)img * dh + y) * dw + x] = __ldg(src + ((size_t)img * sh + sy) * sw + sx);
 }
 
+// ---- frame packing: uint16 depth + uint8 class image -> one uint32 texel (depth | class << 16) per pixel -------------------------
+// The fused sweep then needs ONE 32-byte sector per point-view instead of a depth sector and a mask sector (its gathers are
+// sector-count bound, not byte bound).  The mask may arrive at its own resolution: cv2.resize(mask, (w, h), INTER_NEAREST)
+// (voting.py:93, same float64 index rule as resize_nearest_kernel) is folded into the read.  Layout F3D_FRAMES_U32_T16 stores
+// 16 x 16-pixel tiles contiguously (tiles row-major, texels row-major inside a tile, partial tiles zero-padded).
+__global__ void __launch_bounds__(256) pack_frames_kernel(const uint16_t* __restrict__ depth, const uint8_t* __restrict__ mask,
+                                                          uint32_t* __restrict__ out, int H, int W, int mh, int mw, double ifx,
+                                                          double ify, int tiled, int tiles_x, long long frame_texels) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (t >= frame_texels) return;
+    int ix, iy;
+    if (tiled) {
+        const int tile = (int)(t >> 8);
+        iy = (tile / tiles_x) * 16 + (int)((t >> 4) & 15);
+        ix = (tile % tiles_x) * 16 + (int)(t & 15);
+    } else {
+        iy = (int)(t / W);
+        ix = (int)(t - (long long)iy * W);
+    }
+    uint32_t v = 0u;
+    if (ix < W && iy < H) {
+        int sx = ix, sy = iy;
+        if (mw != W || mh != H) {
+            sx = min((int)floor(xmul((double)ix, ifx)), mw - 1);
+            sy = min((int)floor(xmul((double)iy, ify)), mh - 1);
+        }
+        v = (uint32_t)__ldg(depth + ((size_t)f * H + iy) * W + ix) | ((uint32_t)__ldg(mask + ((size_t)f * mh + sy) * mw + sx) << 16);
+    }
+    out[(size_t)f * (size_t)frame_texels + (size_t)t] = v;
+}
+
 // ---- kernel (3): label resolve --------------------------------------------------------------------------------------------
 #define RES_MAX_FILTER 256
 struct ResolveParams {
@@ -193,6 +225,21 @@ extern "C" int f3d_resize_nearest_u8(const uint8_t* src, int32_t nimg, int32_t s
     dim3 grid((unsigned)((dst_w + 255) / 256), (unsigned)dst_h, (unsigned)nimg);
     resize_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_h, src_w, dst, dst_h, dst_w, ifx, ify);
     return f3d_check_launch("f3d_resize_nearest_u8");
+}
+
+extern "C" int f3d_pack_frames(const uint16_t* depth_mm, const uint8_t* mask, int32_t nframes, int32_t H, int32_t W,
+                               int32_t mask_h, int32_t mask_w, int32_t frame_fmt, uint32_t* out, void* stream) {
+    if (!depth_mm || !mask || !out || nframes < 0 || nframes > 65535 || H <= 0 || W <= 0 || mask_h <= 0 || mask_w <= 0 ||
+        (frame_fmt != F3D_FRAMES_U32 && frame_fmt != F3D_FRAMES_U32_T16))
+        return f3d_fail(F3D_ERR_ARG, "f3d_pack_frames: bad argument");
+    if (nframes == 0) return F3D_OK;
+    const int tiles_x = (W + 15) / 16;
+    const long long texels = frame_fmt == F3D_FRAMES_U32_T16 ? (long long)tiles_x * ((H + 15) / 16) * 256 : (long long)H * W;
+    volatile double isx = (double)W / (double)mask_w, isy = (double)H / (double)mask_h;   // OpenCV: inv_scale = dsize / ssize
+    dim3 grid((unsigned)((texels + 255) / 256), (unsigned)nframes);
+    pack_frames_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(depth_mm, mask, out, H, W, mask_h, mask_w, 1.0 / isx, 1.0 / isy,
+                                                               frame_fmt == F3D_FRAMES_U32_T16, tiles_x, texels);
+    return f3d_check_launch("f3d_pack_frames");
 }
 
 template <typename VT>

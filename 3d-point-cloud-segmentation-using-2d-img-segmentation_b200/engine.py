@@ -8,7 +8,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DEPTH_F32_M, DEPTH_U16_MM, NSTATS, STAT_NAMES, F3dError, check, host_f64, load, ptr, require_cuda, stream_ptr
+from ._lib import (DEPTH_F32_M, DEPTH_U16_MM, FRAMES_U32, FRAMES_U32_T16, NSTATS, STAT_NAMES, F3dError, check, host_f64, load, ptr,
+                   require_cuda, stream_ptr)
 
 
 def as_cuda(a, dtype=None) -> torch.Tensor:
@@ -69,12 +70,89 @@ class FrameTable:
         return eyes, look, nrm
 
 
+class PackedFrames:
+    """Device-resident frame stack in the fused kernel's packed format: one uint32 texel per pixel = uint16 depth mm |
+    class id << 16 (`f3d_pack_frames`), row-major or in 16x16-pixel tiles.  The on-disk contract (16-bit depth PNGs
+    `RTAB_utils/ios_rtab.py:97-113`, uint8 mask PNGs `segUtils/voting.py:66`) is unchanged: this is the device layout
+    the ingest path produces so that a point-view costs one 32-byte sector instead of two."""
+
+    def __init__(self, texels: torch.Tensor, height: int, width: int, fmt: int = FRAMES_U32_T16):
+        self.texels, self.H, self.W, self.fmt = texels, int(height), int(width), int(fmt)
+
+    @property
+    def nframes(self):
+        return int(self.texels.shape[0])
+
+    @staticmethod
+    def texels_per_frame(height, width, fmt=FRAMES_U32_T16) -> int:
+        return int(load().f3d_packed_frame_texels(int(height), int(width), int(fmt)))
+
+    @classmethod
+    def empty(cls, nframes, height, width, fmt=FRAMES_U32_T16, device=None):
+        dev = require_cuda() if device is None else device
+        t = torch.empty((int(nframes), cls.texels_per_frame(height, width, fmt)), dtype=torch.int32, device=dev)
+        return cls(t, height, width, fmt)
+
+    def slice(self, a, b):
+        return PackedFrames(self.texels[a:b], self.H, self.W, self.fmt)
+
+
+def pack_frames(depth, mask, fmt=FRAMES_U32_T16, out: PackedFrames | None = None, frame_begin=0) -> PackedFrames:
+    """depth [F,H,W] uint16 mm + mask [F,mh,mw] uint8 (any resolution: nearest-resized with OpenCV's rule, voting.py:93)
+    -> PackedFrames.  With `out`, frames are written at out[frame_begin : frame_begin + F] (streaming ingest)."""
+    if depth.dtype != torch.uint16 or mask.dtype != torch.uint8:
+        raise TypeError("pack_frames needs uint16 depth (mm) and uint8 masks")
+    F, H, W = depth.shape
+    if mask.shape[0] != F:
+        raise ValueError("depth / mask frame counts differ")
+    if out is None:
+        out = PackedFrames.empty(F, H, W, fmt, depth.device)
+        frame_begin = 0
+    if (out.H, out.W) != (H, W) or frame_begin + F > out.nframes:
+        raise ValueError("pack_frames: output stack does not match")
+    if F:
+        dst = out.texels[frame_begin:frame_begin + F]
+        check(load().f3d_pack_frames(ptr(depth), ptr(mask), F, H, W, int(mask.shape[1]), int(mask.shape[2]), out.fmt, ptr(dst),
+                                     stream_ptr()), "f3d_pack_frames")
+    return out
+
+
+def _frames_args(depth, mask, table, nf):
+    """(depth pointer, format, mask pointer) of a frame stack given either as PackedFrames or as depth + mask tensors."""
+    if isinstance(depth, PackedFrames):
+        if nf > 0 and (depth.nframes != nf or (depth.H, depth.W) != (table.H, table.W)):
+            raise ValueError("packed frames must be [frame_end-frame_begin] frames of the table's H x W")
+        return (ptr(depth.texels) if nf else None), depth.fmt, None
+    if nf > 0 and (depth.shape[0] != nf or tuple(depth.shape[1:]) != (table.H, table.W)
+                   or (mask is not None and (mask.shape[0] != nf or tuple(mask.shape[1:]) != (table.H, table.W)))):
+        raise ValueError("depth / mask must be [frame_end-frame_begin, H, W]")
+    return (ptr(depth) if nf else None), (_depth_fmt(depth) if nf else 0), (ptr(mask) if (nf and mask is not None) else None)
+
+
 def _depth_fmt(depth: torch.Tensor) -> int:
     if depth.dtype == torch.uint16:
         return DEPTH_U16_MM
     if depth.dtype == torch.float32:
         return DEPTH_F32_M
     raise TypeError("depth must be uint16 (millimetres) or float32 (metres)")
+
+
+class KernelTimer:
+    """CUDA events recorded by the library around the fused kernel alone (`f3d_fuse_time_next_call`): the events are
+    the caller's, the library keeps nothing.  `arm()` before a fused call, `ms()` after synchronising."""
+
+    def __init__(self):
+        self.pairs = []
+
+    def arm(self):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()   # torch creates the cudaEvent_t lazily: recording materialises the handle
+        e1.record()
+        check(load().f3d_fuse_time_next_call(e0.cuda_event, e1.cuda_event), "f3d_fuse_time_next_call")
+        self.pairs.append((e0, e1))
+
+    def ms(self):
+        return np.array([a.elapsed_time(b) for a, b in self.pairs], dtype=np.float64)
 
 
 _WORKSPACE = {}
@@ -102,23 +180,23 @@ def stats_dict(stats: torch.Tensor) -> dict:
 
 
 def fuse_project_vote(points4, table: FrameTable, depth, mask, nclasses1, radius=0.05, zmin=0.1, zmax=4.0, votes=None,
-                      accumulate=False, stats=None, audit=False, frame_begin=0, frame_end=None, packed_u16=False):
-    """Kernel (1).  depth / mask: [F', H, W] device tensors covering frames [frame_begin, frame_end).  `votes` may be
-    int32 (reference layout) or uint16 (packed exchange format, also selected by `packed_u16` when allocating)."""
+                      accumulate=False, stats=None, audit=False, frame_begin=0, frame_end=None, packed_u16=False, timer=None):
+    """Kernel (1).  depth / mask: [F', H, W] device tensors covering frames [frame_begin, frame_end), or depth =
+    PackedFrames (mask ignored).  `votes` may be int32 (reference layout) or uint16 (packed exchange format, also
+    selected by `packed_u16` when allocating)."""
     frame_end = table.F if frame_end is None else frame_end
     N = points4.shape[0]
     if votes is None:
         votes = torch.empty((N, nclasses1), dtype=torch.uint16 if packed_u16 else torch.int32, device=points4.device)
         accumulate = False
     nf = frame_end - frame_begin
-    if nf > 0 and (depth.shape[0] != nf or mask.shape[0] != nf or tuple(depth.shape[1:]) != (table.H, table.W)
-                   or tuple(mask.shape[1:]) != (table.H, table.W)):
-        raise ValueError("depth / mask must be [frame_end-frame_begin, H, W]")
+    dptr, fmt, mptr = _frames_args(depth, mask, table, nf)
     ws = workspace(N, points4.device)
     fn = load().f3d_fuse_project_vote_u16 if votes.dtype == torch.uint16 else load().f3d_fuse_project_vote
+    if timer is not None:
+        timer.arm()
     check(fn(
-        ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth) if nf else None,
-        _depth_fmt(depth) if nf else 0, ptr(mask) if nf else None, table.H, table.W, ptr(table.K), float(radius),
+        ptr(points4), N, ptr(table.table), frame_begin, frame_end, dptr, fmt, mptr, table.H, table.W, ptr(table.K), float(radius),
         float(zmin), float(zmax), ptr(votes), int(nclasses1), int(bool(accumulate)), ptr(ws), ws.numel(), ptr(stats),
         int(bool(audit)), stream_ptr()), "f3d_fuse_project_vote")
     return votes
@@ -126,9 +204,9 @@ def fuse_project_vote(points4, table: FrameTable, depth, mask, nclasses1, radius
 
 def fuse_project_vote_resolve(points4, table: FrameTable, depth, mask, nclasses1, nclasses_id, radius=0.05, zmin=0.1,
                               zmax=4.0, threshold=0.5, filter_classes=None, votes=None, want_votes=True, labels=None,
-                              stats=None, audit=False, frame_begin=0, frame_end=None, time_kernel=False):
+                              stats=None, audit=False, frame_begin=0, frame_end=None, timer=None):
     """Kernel (1) with the label resolve fused into its epilogue.  Returns (votes or None, labels int64 [N]).
-    `time_kernel`: record CUDA events around the fused kernel alone (read them with `fuse_timing_read`)."""
+    `timer`: a KernelTimer that gets the duration of the fused kernel alone."""
     frame_end = table.F if frame_end is None else frame_end
     N = points4.shape[0]
     if votes is None and want_votes:
@@ -137,27 +215,16 @@ def fuse_project_vote_resolve(points4, table: FrameTable, depth, mask, nclasses1
         labels = torch.empty(N, dtype=torch.int64, device=points4.device)
     filt = None if filter_classes is None else np.ascontiguousarray(np.asarray(filter_classes, dtype=np.int32))
     nf = frame_end - frame_begin
+    dptr, fmt, mptr = _frames_args(depth, mask, table, nf)
     ws = workspace(N, points4.device)
+    if timer is not None:
+        timer.arm()
     check(load().f3d_fuse_project_vote_resolve(
-        ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth) if nf else None,
-        _depth_fmt(depth) if nf else 0, ptr(mask) if nf else None, table.H, table.W, ptr(table.K), float(radius),
+        ptr(points4), N, ptr(table.table), frame_begin, frame_end, dptr, fmt, mptr, table.H, table.W, ptr(table.K), float(radius),
         float(zmin), float(zmax), ptr(votes), int(nclasses1), float(threshold), ptr(filt),
         0 if filt is None else int(filt.size), int(nclasses_id), ptr(labels), ptr(ws), ws.numel(), ptr(stats),
-        int(bool(audit)) | (2 if time_kernel else 0), stream_ptr()), "f3d_fuse_project_vote_resolve")
+        int(bool(audit)), stream_ptr()), "f3d_fuse_project_vote_resolve")
     return votes, labels
-
-
-def fuse_timing_reset():
-    check(load().f3d_fuse_timing_reset(), "f3d_fuse_timing_reset")
-
-
-def fuse_timing_read(max_n=256):
-    """Durations (ms) of the fused kernel alone for the calls made with time_kernel=True since the last reset."""
-    out = np.zeros(max_n, dtype=np.float32)
-    n = load().f3d_fuse_timing_read(ptr(out), int(max_n))
-    if n < 0:
-        check(n, "f3d_fuse_timing_read")
-    return out[:n].astype(np.float64)
 
 
 def _filter_arg(filter_classes):
@@ -177,7 +244,7 @@ def exchange_constants():
 
 def fuse_project_vote_exchange(points4, table: FrameTable, depth, mask, nclasses1, nranks, points_per_shard, peer_slot_ptrs,
                                peer_dir_ptrs, peer_queue_ptrs, sub_rows, sub_cap, cursors, overflow, radius=0.05, zmin=0.1,
-                               zmax=4.0, stats=None, frame_begin=0, frame_end=None, time_kernel=False):
+                               zmax=4.0, stats=None, frame_begin=0, frame_end=None, timer=None):
     """Kernel (1) with the multi-GPU exchange fused in: the votes of this rank's frames go straight into the owner
     ranks' memory through the peer pointers (numpy uint64 [G] each) as slot records + directory entries, and as
     (cell, count) queue entries for what does not go into a record.  `cursors` is uint32 [G * (NREG + NSUB)], zeroed
@@ -191,11 +258,14 @@ def fuse_project_vote_exchange(points4, table: FrameTable, depth, mask, nclasses
     nreg, nsub = exchange_constants()[:2]
     if cursors.dtype != torch.int32 or cursors.numel() < nranks * (nreg + nsub):
         raise ValueError("cursors must be int32 [nranks * (NREG + NSUB)]")
+    dptr, fmt, mptr = _frames_args(depth, mask, table, frame_end - frame_begin)
+    if timer is not None:
+        timer.arm()
     check(load().f3d_fuse_project_vote_exchange(
-        ptr(points4), N, ptr(table.table), frame_begin, frame_end, ptr(depth), _depth_fmt(depth), ptr(mask), table.H, table.W,
+        ptr(points4), N, ptr(table.table), frame_begin, frame_end, dptr, fmt, mptr, table.H, table.W,
         ptr(table.K), float(radius), float(zmin), float(zmax), int(nclasses1), int(nranks), int(points_per_shard), ptr(arrs[0]),
         ptr(arrs[1]), ptr(arrs[2]), int(sub_rows), int(sub_cap), ptr(cursors), ptr(overflow), ptr(ws), ws.numel(), ptr(stats),
-        2 if time_kernel else 0, stream_ptr()), "f3d_fuse_project_vote_exchange")
+        0, stream_ptr()), "f3d_fuse_project_vote_exchange")
 
 
 def exchange_publish(cursors, peer_count_ptrs, rank, sub_cap):
@@ -229,8 +299,9 @@ def fuse_uv2pt(points4, table: FrameTable, depth, radius=0.05, zmin=0.1, zmax=4.
     uv2pt = torch.full((nf, table.H * table.W), -1, dtype=torch.int32, device=points4.device)
     if nf:
         ws = workspace(points4.shape[0], points4.device)
-        check(load().f3d_fuse_uv2pt(ptr(points4), points4.shape[0], ptr(table.table), frame_begin, frame_end, ptr(depth),
-                                    _depth_fmt(depth), table.H, table.W, ptr(table.K), float(radius), float(zmin),
+        dptr, fmt, _ = _frames_args(depth, None, table, nf)
+        check(load().f3d_fuse_uv2pt(ptr(points4), points4.shape[0], ptr(table.table), frame_begin, frame_end, dptr,
+                                    fmt, table.H, table.W, ptr(table.K), float(radius), float(zmin),
                                     float(zmax), ptr(uv2pt), ptr(ws), ws.numel(), ptr(stats), int(bool(audit)),
                                     stream_ptr()), "f3d_fuse_uv2pt")
     return uv2pt

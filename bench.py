@@ -145,15 +145,15 @@ def cpu_sample(pts, K, spec, wxyz, t, depth, masks, target_pv=4.8e7):
 
 
 def run_reference_arm(args, rank, world):
-    """`--impl reference`: the CPU port of the reference path on the host cores, same workload shape, bounded sample."""
+    """`--impl reference`: the CPU port of the reference path on the host cores, same workload shape, bounded sample.
+    Pure numpy: nothing of the CUDA library is imported or mapped here (the sample's depth images are rendered by the
+    oracle's own z-buffer splat of the sample points)."""
     if rank != 0:
         return
-    import torch
-    scenes = importlib.import_module(PKG_NAME + ".scenes")
+    scenes = importlib.import_module(PKG_NAME + ".scenes")     # seeded numpy scene generator (no CUDA, no libf3d)
     cfg_key, desc = WORKLOADS[args.workload]
     spec = scenes.CONFIGS[cfg_key] if args.workload != "small" else scenes.scaled_spec("C1", 200_000, 8, 320, 240)
-    # the sample's depth images come from the oracle's own splat when no GPU is available, else from kernel (2)
-    from oracle import cpu_baseline as cb, f3d_oracle as orc
+    from oracle import cpu_baseline as cb
     K = scenes.scaled_intrinsics(spec.width, spec.height)
     wxyz, t = scenes.make_poses(spec)
     pts = scenes.make_cloud(spec)
@@ -163,31 +163,21 @@ def run_reference_arm(args, rank, world):
     stride = max(1, len(pts) // npts)
     sub = np.ascontiguousarray(pts[::stride][:npts])
     wq, tt = wxyz[fidx], t[fidx]
-    if torch.cuda.is_available():
-        engine = importlib.import_module(PKG_NAME + ".engine")
-        tab = engine.FrameTable(K, spec.width, spec.height, wq, tt, spec.zmax)
-        d = engine.zbuffer_splat(engine.pack_points(pts), tab, border=10).cpu().numpy()
-    else:
-        eyes, look, nrm = orc.frustum_data(K, spec.width, spec.height, wq, tt)
-        d = np.stack([orc.zero_border(orc.zbuffer_splat(sub.astype(np.float64), K, spec.width, spec.height, wq[f], tt[f],
-                                                        eyes[f], look[f], nrm[f], spec.zmax), 10) for f in range(len(tt))])
     m = scenes.block_masks((spec.height, spec.width), len(tt), seed=spec.seed, block=32)
-    cpu = cb.CpuFusion(sub, K, spec.width, spec.height, wq, tt, d, m, RADIUS, 0.1, spec.zmax, spec.zmax, NCLASSES + 1)
-    for _ in range(args.warmup):
-        cpu.run()
-    times = [cpu.run()[0] for _ in range(args.steps)]
-    cpu.close()
-    sec = float(np.mean(times))
-    pv = len(sub) * len(tt)
-    sample = f"every {stride}th point ({len(sub)}) x {len(tt)} evenly spaced frames of the {spec.width}x{spec.height} workload per step"
-    val = pv / sec
+    res, _, _, _ = cb.measure(sub, K, spec.width, spec.height, wq, tt, None, m, RADIUS, 0.1, spec.zmax, spec.zmax, NCLASSES + 1,
+                              warmup=args.warmup, steps=args.steps)
+    sample = (f"every {stride}th point ({len(sub)}) x {len(tt)} evenly spaced frames of the {spec.width}x{spec.height} workload per "
+              f"step; depth = oracle z-buffer splat of the sample points")
+    val, sec = res["value"], res["seconds"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "points": spec.npoints, "frames": spec.nframes, "width": spec.width,
                    "height": spec.height, "nclasses": NCLASSES},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu.workers, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": sample,
+                         "host_cores_available": res["host_cores_available"], "frames_stage_seconds": res["frames_stage_seconds"],
+                         "segment_seconds": res["segment_seconds"], "single_process": res["single_process"]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -246,6 +236,7 @@ def main():
     stats = fl.stats
 
     labels_buf = torch.empty(N, dtype=torch.int64, device="cuda")
+    ktimer = None   # engine.KernelTimer during the timed region: CUDA events around the fused kernel alone
 
     def step_single():
         # one launch: kernel (1) with the label resolve (kernel 3's arithmetic) fused into its epilogue
@@ -253,7 +244,7 @@ def main():
         e0.record()
         votes, labels = engine.fuse_project_vote_resolve(fl.points4, fl.table, depth, masks, C1, NCLASSES, RADIUS, fl.zmin,
                                                          fl.zmax, THRESHOLD, None, votes=fl.votes, labels=labels_buf,
-                                                         stats=stats, time_kernel=True)
+                                                         stats=stats, timer=ktimer)
         e1.record()
         fl.votes = votes
         return labels, (e0, e1), 4   # supertile_cull + fuse_kernel + fixup_apply + fixup_labels
@@ -281,7 +272,7 @@ def main():
     def step_records():
         def fuse(**xargs):
             engine.fuse_project_vote_exchange(fl.points4, fl.table, depth, masks, C1, radius=RADIUS, zmin=fl.zmin, zmax=fl.zmax,
-                                              stats=stats, time_kernel=True, **xargs)
+                                              stats=stats, timer=ktimer, **xargs)
 
         labels = xchg.run(fuse, NCLASSES, THRESHOLD, None)
         return labels, None, 7   # supertile_cull, fuse_kernel, fixup_apply, publish, slot_merge, queue_accumulate, queue_relabel
@@ -313,7 +304,7 @@ def main():
     t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_events, launches = [], 0
-    engine.fuse_timing_reset()
+    ktimer = engine.KernelTimer()
     ev0.record()
     for _ in range(args.steps):
         labels, kev, nl = step()
@@ -339,7 +330,7 @@ def main():
     roof = None
     if kernel_events:
         call_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))   # whole C-ABI call (4 kernels)
-        kt = engine.fuse_timing_read()                                             # the fused kernel alone, same launches
+        kt = ktimer.ms()
         kms = float(np.mean(kt)) if len(kt) else call_ms
         balg = algorithmic_bytes(N, F, H, W, 2, C1)
         peak, how = peaks()
@@ -358,7 +349,7 @@ def main():
                 pass
 
     if roof is None and xchg is not None:
-        kt = engine.fuse_timing_read()
+        kt = ktimer.ms()
         if len(kt):
             kms = float(np.mean(kt))
             balg = 16 * N + F * H * W * 3 + 64 * F + 4 * xchg.rows * C1    # per rank: the dense vote write is this rank's shard

@@ -30,6 +30,12 @@ extern "C" {
 /* depth image formats (per-frame [H,W] images, frames contiguous) */
 #define F3D_DEPTH_U16_MM 0 /* uint16 millimetres, RTAB export convention (RTAB_utils/ios_rtab.py:97-113,185) */
 #define F3D_DEPTH_F32_M 1  /* float32 metres (extension: the /1000 step of ios_rtab.py:185 is skipped)      */
+/* packed frame formats produced by f3d_pack_frames: one uint32 texel per pixel = uint16 depth mm | class id << 16, so a
+ * point-view costs one 32-byte sector instead of a depth and a mask sector.  `depth` then points to the texels and
+ * `mask` is ignored (may be NULL).  Device layout only: the on-disk contract (16-bit depth PNG ios_rtab.py:97-113, uint8
+ * mask PNG voting.py:66) is unchanged. */
+#define F3D_FRAMES_U32 2     /* texels row-major [F,H,W]                                                      */
+#define F3D_FRAMES_U32_T16 3 /* 16x16-pixel tiles contiguous, f3d_packed_frame_texels(H,W,3) texels per frame   */
 
 /* indices into the uint64 statistics block written by f3d_fuse_* (F3D_NSTATS entries, accumulated) */
 #define F3D_STAT_CANDIDATES 0 /* point-views that survived the conservative tile x frustum cull            */
@@ -43,11 +49,11 @@ extern "C" {
 const char* f3d_last_error(void);
 int f3d_version(void);
 
-/* Timing of the fused kernel alone (not the first cull level or the fix-up kernels of the same call): every f3d_fuse_*
- * call with flags bit 1 records one event pair (up to 256 since the last reset; process-wide, not thread-safe).
- * f3d_fuse_timing_read waits for the recorded pairs and writes their durations in milliseconds; returns how many. */
-int f3d_fuse_timing_reset(void);
-int f3d_fuse_timing_read(float* ms_out, int32_t max_n);
+/* Timing of the fused kernel alone (not the first cull level or the fix-up kernels of the same call): hands two of the
+ * CALLER's cudaEvent_t to the next f3d_fuse_* / f3d_zbuffer_splat call made by THIS host thread, which records them on its
+ * stream immediately before and after its fuse_kernel launch and forgets them (thread-local one-shot, like
+ * f3d_last_error; nothing else is kept).  NULL, NULL disarms. */
+int f3d_fuse_time_next_call(void* event_start, void* event_stop);
 
 
 /* ---- frame table -------------------------------------------------------------------------------------- */
@@ -81,14 +87,14 @@ int64_t f3d_fuse_workspace_bytes(int64_t npoints);
 /* Replaces, for a FIXED cloud, the per-frame body of Fusion.fuse (fusion.py:248-298: point_inside_polyhedra
  * -> points2pixel -> single-pixel criterion) composed with VotingSegmentation.vote (segUtils/voting.py:89-98).
  *   points   [N] float4 (x,y,z,unused) -- float32 values are the contract (widened exactly to fp64)
- *   depth    [F,H,W] uint16 mm or float32 m (depth_fmt); mask [F,H,W] uint8 class ids < C1
+ *   depth    [F,H,W] uint16 mm or float32 m (depth_fmt); mask [F,H,W] uint8 class ids < C1;
+ *            or depth = packed texels of f3d_pack_frames (depth_fmt F3D_FRAMES_U32 / _T16), mask NULL
  *   radius   criterion distance (fusion.py:225, strict <); zmin/zmax valid range (fusion.py:62-63: > / <=)
  *   votes    [N,C1] int32, row-major like the reference's votes[npts, nclasses+1] (voting.py:34).
  *            accumulate = 0: every cell is overwritten (no memset needed); 1: added to.  16-byte aligned.
  *   workspace optional scratch, see f3d_fuse_workspace_bytes
  *   stats    optional uint64[F3D_NSTATS], accumulated with atomics (caller zeroes)
- *   flags    bit 0: audit mode (fp64 for every candidate, counts F3D_STAT_AUDIT_BAD)
- *            bit 1: record CUDA events on `stream` around the fused kernel alone (see f3d_fuse_timing_read) */
+ *   flags    bit 0: audit mode (fp64 for every candidate, counts F3D_STAT_AUDIT_BAD) */
 int f3d_fuse_project_vote(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                           int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
                           int32_t H, int32_t W, const double* h_K9, double radius, double zmin, double zmax,
@@ -121,7 +127,7 @@ int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_t
  *     entry is rewritten on every call (no clearing needed);
  *   - (cell, count) entries for everything else (a full sub-region, more than NLEVEL flushes, the deferred fp64
  *     votes): h_peer_queues[d] = peer pointer to THIS rank's queue
- *     [NSUB][sub_cap] uint64 (cell = local_point * C1 + class in the low half, count in the high half) inside rank d's
+ *     [NSUB][sub_cap] uint64 (cell = local_point * C1 + class in the low 40 bits, count above) inside rank d's
  *     buffer; the fix-up kernel's block b owns sub-queue b < NSUB_FIX, the rest take spills.
  * cursors: local uint32 [nranks * (NREG + NSUB)] (row cursors, then queue cursors), zeroed by the caller before the call;
  * *overflow is set to 1 when a sub-queue filled up (entries dropped: the caller must check it and enlarge sub_cap or
@@ -166,6 +172,17 @@ int f3d_fuse_uv2pt(const void* points, int64_t N, const void* frame_table, int32
                    int32_t frame_end, const void* depth, int32_t depth_fmt, int32_t H, int32_t W,
                    const double* h_K9, double radius, double zmin, double zmax, int32_t* uv2pt, void* workspace,
                    int64_t workspace_bytes, uint64_t* stats, int32_t flags, void* stream);
+
+/* ---- frame packing (ingest) ---------------------------------------------------------------------------------------- */
+
+/* uint32 texels per frame of a packed frame stack (H*W, or 256 per 16x16 tile for F3D_FRAMES_U32_T16). */
+int64_t f3d_packed_frame_texels(int32_t H, int32_t W, int32_t frame_fmt);
+
+/* depth_mm [F,H,W] uint16 + mask [F,mask_h,mask_w] uint8 -> out [F, f3d_packed_frame_texels] uint32 (depth | class << 16).
+ * A mask at another resolution is nearest-resized on the fly with OpenCV's INTER_NEAREST index rule
+ * (cv2.resize(mask, (w, h), INTER_NEAREST), segUtils/voting.py:93), i.e. f3d_resize_nearest_u8 fused into the pack. */
+int f3d_pack_frames(const uint16_t* depth_mm, const uint8_t* mask, int32_t nframes, int32_t H, int32_t W, int32_t mask_h,
+                    int32_t mask_w, int32_t frame_fmt, uint32_t* out, void* stream);
 
 /* ---- kernel (2): z-buffer splat ----------------------------------------------------------------------------- */
 

@@ -16,7 +16,11 @@ open3d) on seeded scenes and stores their outputs under `tests/golden/`; `tests/
 this restatement against those vectors (`tests/golden/make_golden_ingest.py` does the same for the scan-directory
 readers, which are host code of the product and are compared with the reference's readers directly).  The box-merge part has no runnable reference in this image
 (Open3D absent) -> "parity unpinned" for OBB fitting; the pair predicate and merge drivers are restated from
-the source text only.
+the source text only.  UPDATE (round 2): the merge DRIVERS are pinned too -- `tests/golden/make_golden_merge.py` runs the
+unmodified `Fusion3DSeg/merge_intersecting_bb.py` (`merge_bb`, `check_intersection_open3d`, `update_id_info`, `cal_min_max`,
+`check_intersection`) on the stated box models of `oracle/refshim/open3d` and `tests/test_merge_golden.py` checks `fit_box`,
+`cal_min_max`, `check_intersection_as_shipped`, `merge_bb_sequential` against those outputs.  Still unpinned: Open3D's
+hull-based box FIT itself (`create_from_points`), which needs Open3D.
 """
 from __future__ import annotations
 
@@ -435,6 +439,102 @@ def obb_contains(center, R, extent, pts):
         proj = (d[:, 0] * R[0, k] + d[:, 1] * R[1, k]) + d[:, 2] * R[2, k]
         ok &= np.abs(proj) <= extent[k] / 2
     return ok
+
+
+def fit_box(points, model="pca"):
+    """The STATED box models behind the `o3d.geometry.OrientedBoundingBox.create_from_points` call sites
+    (`merge_intersecting_bb.py:18,75,86,126`, `get3DSeg.py:434`) -- identical to `oracle/refshim/open3d`, which is what
+    the unmodified reference was run on to make `tests/golden/g7_merge.json`.  Open3D's own fit (Qhull hull vertices ->
+    covariance) is NOT reproduced: parity of the FIT is unpinned, parity of everything downstream of a box is pinned.
+    -> (centre [3], R [3,3] columns = axes, extent [3])."""
+    p = np.asarray(points, dtype=np.float64)
+    if model == "aabb":
+        mn, mx = p.min(0), p.max(0)
+        return (mn + mx) * 0.5, np.eye(3), mx - mn
+    mean = p.mean(0)
+    q = p - mean
+    cov = (q.T @ q) / max(len(p) - 1, 1)
+    _, evecs = np.linalg.eigh(cov)
+    R = evecs[:, [2, 1, 0]].copy()
+    R[:, 2] = np.cross(R[:, 0], R[:, 1])
+    proj = q @ R
+    mn, mx = proj.min(0), proj.max(0)
+    return mean + R @ ((mn + mx) * 0.5), R, mx - mn
+
+
+def box_corners(center, R, extent):
+    """`OrientedBoundingBox.get_box_points` (call sites `merge_intersecting_bb.py:19,127`, `get3DSeg.py:435`):
+    the 8 corners centre +- R[:,k] * extent[k] / 2 in Open3D's corner order."""
+    x, y, z = (R[:, k] * (extent[k] * 0.5) for k in range(3))
+    c = np.asarray(center, dtype=np.float64)
+    return np.array([c - x - y - z, c + x - y - z, c - x + y - z, c - x - y + z, c + x + y + z, c - x + y + z,
+                     c + x - y + z, c + x + y - z])
+
+
+def cal_min_max(corners):
+    """`cal_min_max` (`merge_intersecting_bb.py:15-42`) from the 8 box corners: each corner is projected on the x, y
+    and z axis through the origin (`Line.project_point`, `:20-36`), the component-wise min / max of the projected
+    points is taken and its EXACT-ZERO components are dropped (`min_x[np.nonzero(min_x)]`, `:23-25`) -- so every
+    result is a 1-element array (empty if the bound is exactly 0).  -> (min_x, max_x, min_y, max_y, min_z, max_z)."""
+    c = np.asarray(corners, dtype=np.float64)
+    out = []
+    for k in range(3):
+        proj = np.zeros_like(c)
+        proj[:, k] = c[:, k]                                     # point + direction * ((p - point) . direction) / 1
+        for v in (proj.min(0), proj.max(0)):
+            out.append(v[np.nonzero(v)])
+    return tuple(out)
+
+
+def check_intersection_as_shipped(id1, id_list, ids, pts, info_sem, model="pca"):
+    """`check_intersection` (`merge_intersecting_bb.py:44-56`) as shipped: the result list is re-created inside the
+    loop (`:48`), so only the LAST id2 != id1 decides what is returned; same-category gate `:49`; closed-interval
+    AABB-of-corners overlap `:51-53`."""
+    def mm(k):
+        sel = ids == k
+        return cal_min_max(box_corners(*fit_box(pts[sel], model)))
+    a = mm(id_list[id1])
+    intersecting = []
+    for id2 in range(1, len(id_list)):
+        if id1 != id2:
+            intersecting = []
+            if info_sem[id1]["category_id"] == info_sem[id2]["category_id"]:
+                b = mm(id_list[id2])
+                if all(((a[2 * k] <= b[2 * k]) and (b[2 * k] <= a[2 * k + 1])) or ((b[2 * k] <= a[2 * k]) and (a[2 * k] <= b[2 * k + 1]))
+                       for k in range(3)):
+                    intersecting.append(id2)
+    return intersecting
+
+
+def merge_hit_fn(pts, model="pca"):
+    """`hit_fn` for merge_bb_sequential: the geometric part of `check_intersection_open3d` (`:68-91`) -- box of the
+    instance's points, membership of the WHOLE cloud (`:75-76,86-87`), non-empty intersection of the index lists (`:88-90`)."""
+    pts = np.asarray(pts, dtype=np.float64)
+
+    def inside(k, ids):
+        sel = ids == k
+        if sel.sum() < 4:
+            return None
+        return obb_contains(*fit_box(pts[sel], model), pts)
+
+    def hit(id1, id2, ids):
+        a = inside(id1, ids)
+        if id2 is None:
+            return False if a is None else True
+        b = inside(id2, ids)
+        if b is None:
+            return None
+        return bool((a & b).any())
+    return hit
+
+
+def merge_bb_final_boxes(info_sem, ids, pts, model="pca"):
+    """Tail of `merge_bb` (`merge_intersecting_bb.py:122-128`): fresh box corners for survivors with > 4 points."""
+    for k in range(1, len(info_sem)):
+        sel = ids == info_sem[k]["id"]
+        if sel.sum() > 4:
+            info_sem[k]["bbox"] = box_corners(*fit_box(pts[sel], model)).tolist()
+    return info_sem
 
 
 def merge_bb_sequential(info_sem, ids, hit_fn):

@@ -9,9 +9,12 @@ Two contracts (SURVEY a-14 / a-15):
   (`:103-137`) with all its quirks (loop index used as instance id `:70,113`; shrinking-list guards `:79`; early
   `return` on a < 4 point instance `:83-84`; `del` without index correction `:118-120`), emulated on the host
   while every geometric predicate (oriented-box membership of the whole cloud, `:75-76,86-87`) runs on the GPU.
-  Open3D's `OrientedBoundingBox.create_from_points` is not available in this image; boxes are fitted by
-  `fit_obb` (PCA axes + extents, the covariance variant of Open3D's algorithm) -- "parity unpinned" for the fit,
-  the membership rule |(p-c).axis_k| <= extent_k/2 is Open3D's.
+  Open3D's `OrientedBoundingBox.create_from_points` is not available in this image; boxes are fitted by the batched
+  kernel `f3d_obb_fit` on a STATED model (covariance of all the instance's points, or axis aligned) -- NOT Open3D's
+  hull-vertex covariance, so "parity unpinned" for the fit itself; the membership rule |(p-c).axis_k| <= extent_k/2 and
+  the corner order are Open3D's, and the driver logic is pinned against the unmodified reference run on the same box
+  models (tests/golden/make_golden_merge.py).
+* `cal_min_max`, `check_intersection`, `update_id_info`, `intersection_point_bb` -- the reference's helper signatures.
 """
 from __future__ import annotations
 
@@ -38,52 +41,130 @@ def merge_boxes(lo, hi, group, area=None):
     return labels, edges, merged
 
 
-def check_intersection(lo, hi, group):
-    """All intersecting same-group box pairs (i < j), sorted -- `check_intersection` (`:44-56`) for every id1 at once."""
+def intersecting_pairs(lo, hi, group):
+    """All intersecting same-group box pairs (i < j), sorted -- the pair predicate of `check_intersection` (`:49-53`) for
+    every id1 at once (sort-and-sweep broad phase on the GPU)."""
     e = engine.box_pairs_aabb(lo, hi, group).cpu().numpy().astype(np.int64)
     return np.unique(e, axis=0) if len(e) else e.reshape(0, 2)
 
 
-def fit_obb(points_dev: torch.Tensor):
-    """Oriented box of a point set on the GPU: centre, rotation (columns = axes, sorted by decreasing variance,
-    right-handed) and extents.  Returns a float64 [15] device tensor (centre, R row-major, extent)."""
-    p = points_dev.to(torch.float64)
-    mean = p.mean(0)
-    q = p - mean
-    cov = (q.T @ q) / max(len(p) - 1, 1)
-    evals, evecs = torch.linalg.eigh(cov)
-    R = evecs[:, [2, 1, 0]].clone()
-    R[:, 2] = torch.linalg.cross(R[:, 0], R[:, 1])
-    proj = q @ R
-    mn, mx = proj.min(0).values, proj.max(0).values
-    centre = mean + R @ ((mn + mx) * 0.5)
-    return torch.cat([centre, R.reshape(-1), mx - mn])
+def fit_obb(points_dev: torch.Tensor, box_model="pca"):
+    """Oriented box of ONE point set on the GPU (`f3d_obb_fit`, hand-written segmented covariance + 3x3 Jacobi): centre,
+    rotation (columns = axes by decreasing variance, right-handed) and extents as a float64 [15] device tensor (centre,
+    R row-major, extent).  The box MODEL is the stated one of `oracle.fit_box` ("pca": covariance of all points; "aabb"):
+    Open3D's `create_from_points` fits the covariance of the convex-hull vertices instead, which is not reproduced here
+    (merged ids / final_info.json can therefore differ from an Open3D run on real data; the DRIVER logic is pinned against
+    the unmodified reference on these box models, tests/test_merge_golden.py)."""
+    p = points_dev.to(torch.float64).contiguous()
+    boxes, _ = engine.obb_fit(p, torch.zeros(len(p), dtype=torch.int64, device=p.device), [0], box_model)
+    return boxes[0]
+
+
+def _corners_o3d(box15: np.ndarray):
+    """`OrientedBoundingBox.get_box_points` corner order (call sites `:19,127`, `get3DSeg.py:435`)."""
+    c, R, e = box15[:3], box15[3:12].reshape(3, 3), box15[12:]
+    x, y, z = (R[:, k] * (e[k] * 0.5) for k in range(3))
+    return np.array([c - x - y - z, c + x - y - z, c - x + y - z, c - x - y + z, c + x + y + z, c - x + y + z,
+                     c + x - y + z, c + x + y - z])
 
 
 def _box_corners(box15: np.ndarray):
-    c, R, e = box15[:3], box15[3:12].reshape(3, 3), box15[12:]
-    s = np.array([[sx, sy, sz] for sx in (-0.5, 0.5) for sy in (-0.5, 0.5) for sz in (-0.5, 0.5)])
-    return (c[None, :] + (s * e[None, :]) @ R.T).tolist()
+    return _corners_o3d(box15).tolist()
 
 
-def merge_bb(dir_name, info_sem, id_info_per_point, pcd):
+def _instance_boxes(pts, ids, instance_ids, box_model):
+    boxes, counts = engine.obb_fit(pts, ids, instance_ids, box_model)
+    return boxes, counts.cpu().numpy()
+
+
+def cal_min_max(id, id_info_per_point, pcd_points, box_model="pca"):
+    """Reference `cal_min_max` (`merge_intersecting_bb.py:15-42`), same call and return shape: the box of instance `id` is
+    fitted on the GPU, its 8 corners are projected on the three axes through the origin (`Line.project_point`, `:20-36`)
+    and the component-wise min / max with their exact-zero components dropped (`:23-25`) are returned as six arrays."""
+    dev = require_cuda()
+    pts = torch.as_tensor(np.ascontiguousarray(np.asarray(pcd_points, dtype=np.float64))).to(dev)
+    ids = torch.as_tensor(np.ascontiguousarray(np.asarray(id_info_per_point)).astype(np.int64)).to(dev)
+    boxes, _ = _instance_boxes(pts, ids, [int(id)], box_model)
+    c = _corners_o3d(boxes[0].cpu().numpy())
+    out = []
+    for k in range(3):
+        proj = np.zeros_like(c)
+        proj[:, k] = c[:, k]
+        for v in (proj.min(0), proj.max(0)):
+            out.append(v[np.nonzero(v)])
+    return tuple(out)
+
+
+def check_intersection(id1, id_list, id_info_per_point, pcd_points, info_sem, box_model="pca"):
+    """Reference `check_intersection` (`merge_intersecting_bb.py:44-56`) with its behaviour as shipped: the result list is
+    re-created inside the loop (`:48`), so the LAST id2 != id1 decides; same-category gate `:49`; closed-interval overlap
+    of the corner AABBs `:51-53`.  All boxes are fitted in one GPU pass."""
+    dev = require_cuda()
+    pts = torch.as_tensor(np.ascontiguousarray(np.asarray(pcd_points, dtype=np.float64))).to(dev)
+    ids = torch.as_tensor(np.ascontiguousarray(np.asarray(id_info_per_point)).astype(np.int64)).to(dev)
+    need = [id1] + [j for j in range(1, len(id_list)) if j != id1 and info_sem[id1]["category_id"] == info_sem[j]["category_id"]]
+    boxes, _ = _instance_boxes(pts, ids, [int(id_list[j]) for j in need], box_model)
+    boxes = boxes.cpu().numpy()
+    mm = {}
+    for j, b in zip(need, boxes):
+        c = _corners_o3d(b)
+        mm[j] = (c.min(0), c.max(0))
+    intersecting_id = []
+    for id2 in range(1, len(id_list)):
+        if id1 != id2:
+            intersecting_id = []
+            if info_sem[id1]["category_id"] == info_sem[id2]["category_id"]:
+                (lo1, hi1), (lo2, hi2) = mm[id1], mm[id2]
+                if all((lo1[k] <= lo2[k] <= hi1[k]) or (lo2[k] <= lo1[k] <= hi2[k]) for k in range(3)):
+                    intersecting_id.append(id2)
+    return intersecting_id
+
+
+def update_id_info(id1, int_bb, info_sem, id_info_per_point):
+    """Reference `update_id_info` (`:58-62`): area credited to list POSITION id1, points of id value int_bb relabelled."""
+    info_sem[id1]["area"] += info_sem[int_bb]["area"]
+    id_info_per_point[id_info_per_point == int_bb] = id1
+    return info_sem, id_info_per_point
+
+
+def intersection_point_bb(lst1, lst2):
+    """Reference `intersection_point_bb` (`:64-66`) -- order-preserving list intersection (set lookup instead of the
+    reference's O(|A||B|) scan; same result)."""
+    s2 = set(int(v) for v in lst2)
+    return [value for value in lst1 if int(value) in s2]
+
+
+def merge_bb(dir_name, info_sem, id_info_per_point, pcd, box_model="pca"):
     """Same call and side effects as the reference `merge_bb` (`merge_intersecting_bb.py:103-137`): mutates
-    `info_sem` and `id_info_per_point`, writes panoptic_segmentation/{final_info.json, ids.npy}."""
+    `info_sem` and `id_info_per_point`, writes panoptic_segmentation/{final_info.json, ids.npy}.
+
+    The sequential, order-dependent driver is replayed on the host; the geometry runs on the GPU: all instance boxes are
+    fitted in ONE pass (`f3d_obb_fit`), the whole-cloud membership of a box (`:75-76,86-87`) is computed by
+    `f3d_obb_contains` and CACHED per instance until a relabel changes that instance's point set -- the reference re-fits
+    `id2` inside the inner loop, O(L^2 N); here a box is fitted once per point-set version."""
     dev = require_cuda()
     len_info_sem = len(info_sem)
     pts_np = np.ascontiguousarray(np.asarray(pcd.points if hasattr(pcd, "points") else pcd, dtype=np.float64))
     pts = torch.as_tensor(pts_np).to(dev)
-    ids = torch.as_tensor(np.ascontiguousarray(id_info_per_point)).to(dev)
+    ids = torch.as_tensor(np.ascontiguousarray(id_info_per_point).astype(np.int64)).to(dev)
     start_time = time.perf_counter()
+
+    L = len(info_sem)
+    boxes, counts = _instance_boxes(pts, ids, list(range(L)), box_model)       # loop index == instance id value (:70,113)
+    cache = {}                                                                # id value -> uint8 [N] membership or None
 
     def inside_of(instance_id):
         """None if the instance has < 4 points (`:72,83`), else the uint8 [N] membership of the whole cloud (`:75-76`)."""
-        sel = ids == instance_id
-        if int(sel.sum()) < 4:
-            return None
-        return engine.obb_contains(pts, fit_obb(pts[sel])[None, :])[0]
+        if instance_id not in cache:
+            cache[instance_id] = None if counts[instance_id] < 4 else engine.obb_contains(pts, boxes[instance_id][None, :])[0]
+        return cache[instance_id]
 
-    L = len(info_sem)
+    def refit(instance_id):
+        b, c = _instance_boxes(pts, ids, [instance_id], box_model)
+        boxes[instance_id] = b[0]
+        counts[instance_id] = c[0]
+        cache.pop(instance_id, None)
+
     for id1 in range(1, L):                                               # :113
         hits = []
         a = inside_of(id1)
@@ -100,14 +181,20 @@ def merge_bb(dir_name, info_sem, id_info_per_point, pcd):
             for hb in hits:                                               # update_id_info, :58-62
                 info_sem[id1]["area"] += info_sem[hb]["area"]
                 ids[ids == hb] = id1
+            for hb in hits:                                               # point sets changed: id1 grew, the hits are empty
+                refit(hb)
+            refit(id1)
             for i in hits:                                                # :118-120
                 if i < len(info_sem):
                     del info_sem[i]
 
-    for k in range(1, len(info_sem)):                                     # :122-128
-        sel = ids == info_sem[k]["id"]
-        if int(sel.sum()) > 4:
-            info_sem[k]["bbox"] = _box_corners(fit_obb(pts[sel]).cpu().numpy())
+    final_ids = [int(info_sem[k]["id"]) for k in range(1, len(info_sem))]      # :122-128
+    if final_ids:
+        fboxes, fcounts = _instance_boxes(pts, ids, final_ids, box_model)
+        fboxes = fboxes.cpu().numpy()
+        for k, (b, c) in enumerate(zip(fboxes, fcounts), start=1):
+            if c > 4:
+                info_sem[k]["bbox"] = _box_corners(b)
 
     id_info_per_point[...] = ids.cpu().numpy()
     end_time = time.perf_counter()

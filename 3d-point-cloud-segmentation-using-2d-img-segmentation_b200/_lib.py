@@ -54,7 +54,12 @@ SIGNATURES = {
     "f3d_project_pixels": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "f3d_frustum_mask": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp, _vp]),
     "f3d_box_pairs_aabb": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "f3d_box_pairs_sweep": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "f3d_union_find": (C.c_int, [_i32, _vp, _i64, _vp, _vp]),
+    "f3d_obb_fit_workspace_bytes": (_i64, [_i32]),
+    "f3d_obb_fit": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "f3d_radius_grid_keys": (C.c_int, [_vp, _i64, _vp, _vp, _f64, _vp, _vp]),
+    "f3d_radius_adjacency": (C.c_int, [_vp, _i64, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "f3d_obb_contains": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp]),
 }
 

@@ -15,7 +15,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libf3d.so"
-SOURCES = ["c_api.cu", "frame_setup.cu", "fuse_vote.cu", "fuse_aux.cu", "vote_resolve.cu", "vote_exchange.cu", "box_merge.cu"]
+SOURCES = ["c_api.cu", "frame_setup.cu", "fuse_vote.cu", "fuse_aux.cu", "vote_resolve.cu", "vote_exchange.cu", "box_merge.cu", "geometry.cu"]
 COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off", "-Xptxas", "-v",

@@ -13,13 +13,12 @@
 //   * cull: supertile_cull_kernel lists the frames that can see each 4096-point super-tile; the CTA then tests every
 //     (listed frame, warp box) pair -- one pair per thread -- against the frame's five frustum planes (fp32 with an
 //     explicit rounding margin, conservative) and compacts the surviving frame ids with the mask of warps that keep them;
-//   * sweep: WARP-AUTONOMOUS.  Each warp walks the candidate list on its own, NB of its candidates at a time; the
-//     128-byte fp32 projection tiles of the next group are prefetched into registers (16 B per lane) while the current
-//     group is processed, then parked in the warp's own 512-byte staging block and broadcast to the lanes.  There is no
-//     CTA-wide barrier and no shared staging ring inside the sweep (round 1 staged the tiles CTA-wide through TMA +
-//     mbarriers and lost 21 % of its warp samples on those barriers);
-//   * per group: all NB projections first, then all NB frame gathers are issued together (one packed depth|mask texel
-//     per point-view with the packed frame formats, else a depth and a mask read), then the distance tests and votes;
+//   * sweep: WARP-AUTONOMOUS and software pipelined.  Each warp walks the candidate list on its own, one candidate per
+//     iteration: the 128-byte fp32 projection tile of candidate i+2 and the packed depth|mask texel of candidate i travel
+//     to the warp's own shared-memory rings as cp.async copies (LDGSTS, no registers held), candidate i is projected in
+//     fp32 and candidate i-2 is depth-tested and voted from its landed texel.  There is no CTA-wide barrier and no shared
+//     staging ring inside the sweep (round 1 staged the tiles CTA-wide through TMA + mbarriers and lost 21 % of its warp
+//     samples on those barriers), and the loop body is a few hundred instructions (it must live in the instruction cache);
 //   * per point-view the fp32 path carries a rigorous rounding bound; any decision (frustum, pixel floor, depth
 //     distance) that falls inside its bound is re-evaluated in fp64 in the reference's operation order (`exact_eval`),
 //     so every integer outcome is bit-exact against the numpy path.  The population of that band and every
@@ -35,14 +34,11 @@
 #define MODE_UV2PT 2
 
 #ifndef FUSE_BLOCK
-#define FUSE_BLOCK 256
+#define FUSE_BLOCK 128
 #endif
 #define FUSE_NW (FUSE_BLOCK / 32)
 #ifndef FUSE_FCHUNK
 #define FUSE_FCHUNK (2 * FUSE_BLOCK)   // candidate list capacity per cull pass
-#endif
-#ifndef FUSE_NB
-#define FUSE_NB 4         // candidates of a warp processed together (their gathers are in flight together)
 #endif
 #ifndef FUSE_MINB
 #define FUSE_MINB (512 / FUSE_BLOCK)        // resident CTAs per SM of the uint16-histogram / splat / uv2pt builds (128 registers)
@@ -52,7 +48,7 @@
 // flushes its rows to HBM (first flush overwrites, later ones add) before more than FUSE_LIMIT8 candidates have been
 // swept since its last flush, so no count is ever lost.
 #ifndef FUSE_MINB8
-#define FUSE_MINB8 (768 / FUSE_BLOCK)       // 80 registers
+#define FUSE_MINB8 (FUSE_BLOCK == 128 ? 5 : 2)   // 128-point tiles: 5 CTAs = 20 warps per SM at 96 registers (6 would need 80: spills)
 #endif
 #define FUSE_ST_POINTS 4096                 // points per super-tile of the first cull level
 #define FUSE_ST_TILES (FUSE_ST_POINTS / FUSE_BLOCK)
@@ -153,6 +149,32 @@ __device__ __forceinline__ size_t frame_off(const FuseParams& P, int frel, int i
         return (size_t)frel * (size_t)P.frame_stride + (size_t)((((iv >> 4) * P.tiles_x + (iu >> 4)) << 8) | ((iv & 15) << 4) | (iu & 15));
     return (size_t)frel * (size_t)P.frame_stride + (size_t)(iv * P.W + iu);
 }
+
+// Frame gathers.  A plain global load that misses L1 makes this GPU fill the WHOLE 128-byte line from HBM (measured:
+// tools/micro/gather_fetch.cu, 3.9 DRAM sectors per 4-byte gather; cudaLimitMaxL2FetchGranularity changes nothing), i.e. four
+// times the bytes a random gather needs.  The .L2::64B qualifier is the smallest fill the ISA offers: 2.2 sectors per gather
+// and 27 % less time in the micro-benchmark.
+#ifndef FUSE_PLAIN_GATHER
+__device__ __forceinline__ uint32_t gather_u32(const uint32_t* p) {
+    uint32_t v;
+    asm("ld.global.nc.L2::64B.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t gather_u16(const uint16_t* p) {
+    uint16_t v;
+    asm("ld.global.nc.L2::64B.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t gather_u8(const uint8_t* p) {
+    uint32_t v;
+    asm("ld.global.nc.L2::64B.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+#else
+__device__ __forceinline__ uint32_t gather_u32(const uint32_t* p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t gather_u16(const uint16_t* p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t gather_u8(const uint8_t* p) { return __ldg(p); }
+#endif
 
 // raw depth word (uint16 mm, float32 bits) and -- vote mode only -- the class id of one pixel
 template <int MODE, int FMT>
@@ -287,7 +309,10 @@ __device__ __forceinline__ Cls classify(const float4* __restrict__ s, const floa
     const float4 Mu = s[2], Mv = s[3];
     const float a = fmaf(Mu.x, d0, fmaf(Mu.y, d1, Mu.z * d2));
     const float b = fmaf(Mv.x, d0, fmaf(Mv.y, d1, Mv.z * d2));
-    const float r = __frcp_rn(z);
+    // rcp.approx: relative error <= 2^-23 = 2 u (PTX ISA); with the rounding of a * r that is 3 u of the 8 u the bounds below
+    // allow for u and v.  z > 16 ez > 0 is a normal number here.
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z));
     const float u = a * r, v = b * r;
     const float ea = 8.0f * F3D_U24 * fmaf(fabsf(Mu.x), ad0, fmaf(fabsf(Mu.y), ad1, fmaf(fabsf(Mu.z), ad2, Mu.w * 1.0e-9f)));
     const float eb = 8.0f * F3D_U24 * fmaf(fabsf(Mv.x), ad0, fmaf(fabsf(Mv.y), ad1, fmaf(fabsf(Mv.z), ad2, Mv.w * 1.0e-9f)));
@@ -429,8 +454,11 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, 
 // ---- byte-histogram flush: the warp's 32 rows (32*C1 contiguous bytes, row stride == C1) -> HBM ------------------
 // first flush of a non-accumulating launch overwrites (every cell written exactly once, 32-byte stores: STG.256); later
 // flushes add their non-zero cells.  Rows are warp-private, so no CTA barrier and no atomics are involved.
+// V8: 32-byte stores.  Only the inlined epilogue instance uses them: inside a non-inlined (ABI) function ptxas 12.9 was seen
+// to lower the st.global.v8 of some kernel instantiations to a single 32-bit store.
+template <bool V8>
 __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int warp, int lane, int64_t tile_base, bool add,
-                                       bool rezero, Tally& T, uint16_t* stg, int level, bool dirty, uint2* dcache) {
+                                       bool rezero, int nlist, const uint8_t* clist, uint16_t* stg, int level, bool dirty, uint2* dcache) {
     const int row0 = warp * 32;
     const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
     const int total = nrows * P.C1;
@@ -448,7 +476,7 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
         bool spill = live && (!rec || dirty);
         const int C1 = P.C1;
         const uint8_t* __restrict__ row = h8 + lane * C1;
-        int n = (live && !spill) ? min(T.nlist, C1) : 0;      // classes of this lane's point
+        int n = (live && !spill) ? min(nlist, C1) : 0;        // classes of this lane's point
         int L = n;
 #pragma unroll
         for (int s2 = 16; s2 > 0; s2 >>= 1) L = max(L, __shfl_xor_sync(0xffffffffu, L, s2));
@@ -481,7 +509,7 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
             if (n <= FUSE_NSLOT) {
                 const int j1 = min(n, j0 + FUSE_STG_ROWS);
                 for (int j = j0; j < j1; ++j) {                   // the classes cast_vote remembered
-                    const unsigned cls = T.clist[j * FUSE_BLOCK];
+                    const unsigned cls = clist[j * FUSE_BLOCK];
                     stg[(j - j0) * 32 + lane] = (uint16_t)(cls | ((unsigned)row[cls] << 8));
                 }
             } else {
@@ -507,12 +535,11 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
                 if (v) xg_append(P, d, sub, atomicAdd(P.xg_qcur + d * F3D_XCH_NSUB + sub, 1u), key0 + c, v);
             }
         }
-        T.nlist = 0;
     } else if (nrows > 0) {
         if (P.votes) {
             int32_t* __restrict__ out = P.votes + (tile_base + row0) * P.C1;
             if (!add) {
-                if ((reinterpret_cast<uintptr_t>(out) & 31u) == 0) {
+                if (V8 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0) {
                     // eight cells per lane and step: LDS.64 -> 8 x PRMT -> one 32-byte store (1 KB contiguous per warp instruction)
                     const uint2* __restrict__ h64 = reinterpret_cast<const uint2*>(h8);
                     const int n8 = total >> 3;
@@ -577,6 +604,13 @@ __device__ __forceinline__ void flush8(const FuseParams& P, uint8_t* hist, int w
     }
 }
 
+// The sweep's own flush (a warp passed FUSE_LIMIT8 candidates): rare, so NOT inlined -- the hot loop must stay small enough
+// for the instruction cache (inlined there it made `no_instruction` the third largest stall reason).
+static __device__ __noinline__ void flush8_mid(const FuseParams& P, uint8_t* hist, int warp, int lane, int64_t tile_base, bool add,
+                                               int nlist, const uint8_t* clist, uint16_t* stg, int level, uint2* dcache) {
+    flush8<false>(P, hist, warp, lane, tile_base, add, true, nlist, clist, stg, level, false, dcache);
+}
+
 // small per-CTA scalars in shared memory
 struct __align__(16) FuseShared {
     float wbox[FUSE_NW][8];                    // per-warp box: lo[3], hi[3], |lo| + |hi| magnitude, unused
@@ -584,14 +618,31 @@ struct __align__(16) FuseShared {
     int nq[FUSE_NW];                           // per-warp deferred counts
     unsigned dirty[FUSE_NW];                   // rows another lane's deferred pass touched
     unsigned stat[8];                          // CTA totals of the statistics, flushed once at the end
+    int wfr[FUSE_NW][8];                       // frame ids of the warp's staged tiles (ring of FUSE_TR, -1 = none)
     int ncand;
     int pad[3];
 };
 
+// 16-byte asynchronous global -> shared copy (LDGSTS): the projection tiles of the NEXT group land in the warp's other
+// staging buffer while the current group is processed; no registers are tied up and nobody but the warp itself waits
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+// 4-byte asynchronous gather with the 64-byte L2 fill (see gather_u32)
+__device__ __forceinline__ void cp_async4_l2_64(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global.L2::64B [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
 __host__ __device__ constexpr size_t fuse_align16(size_t v) { return (v + 15) & ~(size_t)15; }
-// shared-memory layout: [stage: NW x NB FrameFast][FuseShared][cand u16 x FCHUNK][cmask u8 x FCHUNK][deferred queues][hist]
+// shared-memory layout: [stage: NW x FUSE_TR FrameFast][texel rings: NW x FUSE_GR x 32 u32][FuseShared][cand u16 x FCHUNK][cmask u8 x FCHUNK][deferred queues][hist]
 //                       [exchange mode: class lists u8 x FUSE_NSLOT x FUSE_BLOCK][record staging: NW x 512 B]
-#define FUSE_OFF_SHARED ((size_t)FUSE_NW * FUSE_NB * sizeof(FrameFast))
+#define FUSE_TR 8   // per-warp ring of staged projection tiles (candidates it-2 .. it+2 are live)
+#define FUSE_GR 4   // per-lane ring of gathered texels (candidates it-2 .. it)
+#define FUSE_OFF_TEXR ((size_t)FUSE_NW * FUSE_TR * sizeof(FrameFast))
+#define FUSE_OFF_SHARED (FUSE_OFF_TEXR + (size_t)FUSE_NW * FUSE_GR * 32 * sizeof(uint32_t))
 #define FUSE_OFF_CAND (FUSE_OFF_SHARED + sizeof(FuseShared))
 #define FUSE_OFF_CMASK (FUSE_OFF_CAND + FUSE_FCHUNK * sizeof(uint16_t))
 #define FUSE_OFF_QUEUE fuse_align16(FUSE_OFF_CMASK + FUSE_FCHUNK)
@@ -601,8 +652,7 @@ template <int MODE, int FMT, int HB, bool AUDIT>
 __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? FUSE_MINB8 : FUSE_MINB)
     fuse_kernel(const __grid_constant__ FuseParams P, const __grid_constant__ FuseResolve RP) {
     typedef typename HistCell<HB>::T CellT;
-    constexpr int NB = FUSE_NB;
-    static_assert(NB % 4 == 0 && FUSE_NW <= 8, "a lane prefetches NB/4 16-byte pieces; cmask holds one bit per warp");
+    static_assert(FUSE_NW <= 8, "cmask holds one bit per warp");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* stage = reinterpret_cast<float4*>(smem_raw);
     FuseShared& sh = *reinterpret_cast<FuseShared*>(smem_raw + FUSE_OFF_SHARED);
@@ -618,7 +668,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     Deferred* queue = queue_all + warp * FUSE_QWARP;
-    float4* stage_w = stage + warp * (NB * 8);
+    uint32_t* texring = reinterpret_cast<uint32_t*>(smem_raw + FUSE_OFF_TEXR);
     const int64_t tile_base = (int64_t)blockIdx.x * FUSE_BLOCK;
     const int64_t gi = tile_base + tid;
     const bool active = gi < P.N;
@@ -631,8 +681,8 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     if (lane == 0) {
         sh.nq[warp] = 0;
         sh.dirty[warp] = 0u;
-        sh.stat[warp & 7] = 0u;
     }
+    if (tid < 8) sh.stat[tid] = 0u;
     if (lane < F3D_XCH_NLEVEL) sh.dcache[warp][lane] = make_uint2(0u, 0u);
     if (MODE == MODE_VOTE) {
         uint4* h128 = reinterpret_cast<uint4*>(hist);
@@ -729,168 +779,159 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         __syncthreads();
         const int ncand = sh.ncand;
 
-        // ---- warp-autonomous sweep over this warp's candidates of the list
+        // ---- warp-autonomous sweep over this warp's candidates of the list: ONE candidate per iteration, software pipelined
+        // through shared memory so that the loop body stays a few hundred instructions (the L0 instruction cache holds
+        // ~380; the NB-times unrolled body of the first version spent more cycles on instruction fetch than on gathers):
+        //   iteration i:  wait until tile i and texel i-2 have landed | start the async copy of tile i+2 |
+        //                 project candidate i in fp32, start the async 4-byte copy of its texel into this lane's ring slot |
+        //                 depth test + vote of candidate i-2 from its landed texel.
+        // All copies are cp.async (LDGSTS): no registers are tied up while they are in flight, two gathers per lane are
+        // outstanding across iterations, and nobody but the warp itself ever waits.  The two-array frame formats (a 2-byte
+        // depth sample cannot be a cp.async) and the splat consume their candidate in the same iteration instead.
+        constexpr bool PIPE = (MODE != MODE_SPLAT) && (FMT >= F3D_FRAMES_U32);
         int lbase = -32;        // current 32-entry block of the candidate list (warp-uniform)
         unsigned wm = 0u;       // this warp's candidates of that block not yet taken
-        // lane l fetches 16-byte piece (l & 7) of the projection tiles of candidates (l >> 3), (l >> 3) + 4, ... of a group:
-        // next_group leaves the list position of those candidates in mine[] (-1 = none) and returns the group's size
-        int mine[NB / 4];
-        auto next_group = [&]() -> int {
-            int n = 0;
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                while (wm == 0u && lbase + 32 < ncand) {
-                    lbase += 32;
-                    const int i = lbase + lane;
-                    wm = __ballot_sync(0xffffffffu, i < ncand && ((cmask[i] >> warp) & 1u));
-                }
-                int pos = -1;
-                if (wm) {
-                    pos = lbase + __ffs(wm) - 1;
-                    wm &= wm - 1u;
-                    ++n;
-                }
-                if ((lane >> 3) == (k & 3)) mine[k >> 2] = pos;
+        float4* tiles = stage + warp * (FUSE_TR * 8);
+        uint32_t* texr = texring + warp * (FUSE_GR * 32) + lane;
+        int* wfr = sh.wfr[warp];
+        auto pop = [&]() -> int {   // next candidate frame of this warp, -1 = none (warp-uniform)
+            while (wm == 0u && lbase + 32 < ncand) {
+                lbase += 32;
+                const int i = lbase + lane;
+                wm = __ballot_sync(0xffffffffu, i < ncand && ((cmask[i] >> warp) & 1u));
             }
-            return n;
+            if (!wm) return -1;
+            const int pos = lbase + __ffs(wm) - 1;
+            wm &= wm - 1u;
+            return (int)cand[pos];
         };
-        uint4 pref[NB / 4];
-        int pfr[NB / 4];        // frame ids of the prefetched tiles
-        auto prefetch = [&]() {
-#pragma unroll
-            for (int h = 0; h < NB / 4; ++h) {
-                pfr[h] = mine[h] >= 0 ? (int)cand[mine[h]] : -1;
-                pref[h] = make_uint4(0u, 0u, 0u, 0u);
-                if (pfr[h] >= 0) pref[h] = __ldg(reinterpret_cast<const uint4*>(&frec[P.f_begin + pfr[h]].fast) + (lane & 7));
+        auto stage_tile = [&](int slot, int f) {   // lanes 0..7 copy the 8 x 16 bytes of the frame's projection tile
+            if (f >= 0 && lane < 8) cp_async16(tiles + slot * 8 + lane, reinterpret_cast<const uint4*>(&frec[P.f_begin + f].fast) + lane);
+            if (lane == 0) wfr[slot] = f;
+        };
+        // depth validity + distance criterion + vote (or splat / uv2pt write) of one classified candidate
+        auto consume = [&](const int frel, const float4* __restrict__ s, const uint32_t puv, const unsigned sg, const uint32_t g0,
+                           const uint32_t g1, const float zc) {
+            int st = (int)(sg & 7u);
+            int g_in = (int)((sg >> 3) & 1u);
+            const int pix = (int)((puv >> 16) * P.W + (puv & 0xffffu));
+            uint32_t zq = 0, cls = 0;
+            if (st == 1 && MODE != MODE_SPLAT) {
+                float dm;
+                bool valid;
+                if (FMT != F3D_DEPTH_F32_M) {
+                    const uint32_t d = g0 & 0xffffu;
+                    valid = (d >= P.d_lo) && (d <= P.d_hi);
+                    dm = (float)d * 0.001f;
+                } else {
+                    dm = __uint_as_float(g0);
+                    valid = ((double)dm > P.zmin) && ((double)dm <= P.zmax);
+                }
+                if (MODE == MODE_VOTE) cls = (FMT < F3D_FRAMES_U32) ? g1 : ((g0 >> 16) & 0xffu);
+                st = valid ? distance_test(s, pt, puv, dm, P, g_in) : 0;
+            }
+            if (MODE == MODE_SPLAT && st == 1) {
+                // quantised camera z: floor(z*1000 + 0.5); certify the floor
+                const float zm = fmaf(zc, 1000.0f, 0.5f);
+                const float fz = floorf(zm);
+                const float ez = 8.0f * F3D_U24 * s[4].w *
+                                 (fabsf((pt.x - s[0].x) - s[1].x) + fabsf((pt.y - s[0].y) - s[1].y) + fabsf((pt.z - s[0].z) - s[1].z) + 1.0e-9f);
+                const float eq = 1010.0f * ez + 8.0f * F3D_U24 * zm;
+                if ((zm - fz >= eq) && (fz + 1.0f - zm > eq)) {
+                    zq = (uint32_t)fminf(fmaxf(fz, 1.0f), 65535.0f);
+                } else {
+                    st = 3;
+                    g_in = (int)fminf(fmaxf(fz, 1.0f), 65535.0f);
+                }
+            }
+            const bool seen = (st == 1);
+            if (st >= 2 || AUDIT) {
+                // defer to the warp's dense fp64 pass (queue full or audit sweep: evaluate inline)
+                const int slot = (st >= 2 && !AUDIT) ? atomicAdd(sh.nq + warp, 1) : FUSE_QWARP;
+                if (slot < FUSE_QWARP) {
+                    queue[slot].w0 = (uint32_t)tid | ((uint32_t)frel << 16);
+                    queue[slot].w1 = (uint32_t)pix;
+                    queue[slot].w2 = (uint32_t)st | ((uint32_t)g_in << 8);
+                } else {
+                    resolve_exact<MODE, FMT, CellT>(P, RP, frec, hist, RS, tile_base, tid, frel, pt.x, pt.y, pt.z, st, g_in, pix, seen, zq,
+                                                    true, sh.dirty + warp, T);
+                }
+            } else if (seen) {
+                ++T.n_seen;
+                if (MODE == MODE_VOTE) {
+                    cast_vote(hist, tid * RS, (int)cls, P, RP, T);
+                } else {
+                    const size_t off = (size_t)frel * (size_t)HW + (size_t)pix;
+                    if (MODE == MODE_SPLAT) atomicMin(P.zbuf + off, zq);
+                    else atomicMax(P.uv2pt + off, (int)gi);
+                }
             }
         };
-        int nn = next_group();
-        if (nn > 0) prefetch();
-        while (nn > 0) {
-            const int ncur = nn;
-            if (MODE == MODE_VOTE && HB == 1) {
-                // a byte counter holds 255: flush the warp's rows before this group could push a cell past the limit
-                if (since_flush + ncur > FUSE_LIMIT8) {
-                    __syncwarp();
-                    flush8(P, reinterpret_cast<uint8_t*>(hist), warp, lane, tile_base, nflush > 0 || P.accumulate, true, T,
-                           stg_all + warp * (FUSE_STG_ROWS * 32), nflush, false, sh.dcache[warp]);
+
+        if (lane < FUSE_TR) wfr[lane] = -1;
+        __syncwarp();
+        stage_tile(0, pop());
+        cp_async_commit();
+        stage_tile(1, pop());
+        cp_async_commit();
+        uint32_t puv1 = 0, puv2 = 0;   // pixel of candidates i-1 / i-2
+        unsigned sg1 = 0, sg2 = 0;     // their st | g_in << 3
+#pragma unroll 1
+        for (int it = 0;; ++it) {
+            cp_async_wait_but_one();   // every copy of this lane except the newest group: tile `it`, texel `it - 2` have landed
+            __syncwarp();              // ... everybody else's too; every lane is done with iteration it - 1
+            const int f0 = wfr[it & (FUSE_TR - 1)];
+            const int f2 = PIPE ? wfr[(it + FUSE_TR - 2) & (FUSE_TR - 1)] : -1;
+            if (f0 < 0 && (!PIPE || (f2 < 0 && wfr[(it + FUSE_TR - 1) & (FUSE_TR - 1)] < 0))) break;
+            stage_tile((it + 2) & (FUSE_TR - 1), pop());
+            if (MODE == MODE_VOTE && HB == 1 && f0 >= 0) {
+                // a byte counter holds 255: flush the warp's rows before this candidate could push a cell past the limit
+                if (since_flush + 1 > FUSE_LIMIT8) {
+                    flush8_mid(P, reinterpret_cast<uint8_t*>(hist), warp, lane, tile_base, nflush > 0 || P.accumulate, T.nlist, T.clist,
+                               stg_all + warp * (FUSE_STG_ROWS * 32), nflush, sh.dcache[warp]);
+                    T.nlist = 0;
                     ++nflush;
-                    since_flush = 0;
+                    since_flush = 2;   // the two candidates still in the pipeline vote after this flush
                 }
-                since_flush += ncur;
+                ++since_flush;
             }
-            __syncwarp();           // every lane is done with the previous group's tiles
-            int fr[NB];             // frame ids of the current group (-1 = none)
-#pragma unroll
-            for (int h = 0; h < NB / 4; ++h) {
-                reinterpret_cast<uint4*>(stage_w)[h * 32 + lane] = pref[h];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) fr[4 * h + k] = __shfl_sync(0xffffffffu, pfr[h], 8 * k);
+            // ---- candidate `it`: fp32 projection + certification; its frame gather starts
+            uint32_t puv0 = 0;
+            unsigned sg0 = 0;
+            if (f0 >= 0 && active) {
+                ++T.n_cand;
+                const float4* s = tiles + (it & (FUSE_TR - 1)) * 8;
+                const Cls c = classify(s, pt, fW, fH);
+                puv0 = c.puv;
+                sg0 = (unsigned)(c.st | (c.g_in << 3));
+                if (PIPE) {
+                    if (c.st == 1)
+                        cp_async4_l2_64(texr + (it & (FUSE_GR - 1)) * 32,
+                                        reinterpret_cast<const uint32_t*>(P.depth) + frame_off<FMT>(P, f0, (int)(puv0 & 0xffffu), (int)(puv0 >> 16)));
+                } else if (c.st != 0 || AUDIT) {
+                    uint32_t g0 = 0, g1 = 0;
+                    if (MODE != MODE_SPLAT && c.st == 1) {
+                        const size_t off = frame_off<FMT>(P, f0, (int)(puv0 & 0xffffu), (int)(puv0 >> 16));
+                        if (FMT == F3D_DEPTH_U16_MM) g0 = gather_u16(reinterpret_cast<const uint16_t*>(P.depth) + off);
+                        else g0 = gather_u32(reinterpret_cast<const uint32_t*>(P.depth) + off);
+                        if (MODE == MODE_VOTE && FMT < F3D_FRAMES_U32) g1 = gather_u8(P.mask + off);
+                    }
+                    consume(f0, s, puv0, sg0, g0, g1, c.z);
+                }
             }
-            __syncwarp();
-            nn = next_group();
-            if (nn > 0) prefetch();   // in flight while this group is processed
-            if (active) {
-                T.n_cand += (unsigned)ncur;
-                // ---- phase 1: fp32 projection + certification of NB candidates
-                uint32_t puv[NB];
-                unsigned stw = 0;   // 4 bits per candidate: st | g_in << 3
-                float zc[MODE == MODE_SPLAT ? NB : 1];
-#pragma unroll
-                for (int k = 0; k < NB; ++k) {
-                    puv[k] = 0;
-                    if (fr[k] >= 0) {
-                        const Cls c = classify(stage_w + k * 8, pt, fW, fH);
-                        puv[k] = c.puv;
-                        stw |= (unsigned)(c.st | (c.g_in << 3)) << (4 * k);
-                        if (MODE == MODE_SPLAT) zc[k] = c.z;
-                    }
-                    FUSE_SCHED_FENCE();
-                }
-                if (stw != 0u || AUDIT) {
-                    // ---- phase 2: every gather of the certified candidates is issued before any is consumed
-                    uint32_t g0[MODE == MODE_SPLAT ? 1 : NB];                                   // depth word or packed texel
-                    uint32_t g1[(MODE == MODE_VOTE && FMT < F3D_FRAMES_U32) ? NB : 1];          // class (two-array formats)
-                    if (MODE != MODE_SPLAT) {
-#pragma unroll
-                        for (int k = 0; k < NB; ++k) {
-                            g0[k] = 0;
-                            if (MODE == MODE_VOTE && FMT < F3D_FRAMES_U32) g1[k] = 0;
-                            if (((stw >> (4 * k)) & 7u) == 1u) {
-                                const size_t off = frame_off<FMT>(P, fr[k], (int)(puv[k] & 0xffffu), (int)(puv[k] >> 16));
-                                if (FMT == F3D_DEPTH_U16_MM) g0[k] = __ldg(reinterpret_cast<const uint16_t*>(P.depth) + off);
-                                else g0[k] = __ldg(reinterpret_cast<const uint32_t*>(P.depth) + off);
-                                if (MODE == MODE_VOTE && FMT < F3D_FRAMES_U32) g1[k] = __ldg(P.mask + off);
-                            }
-                        }
-                    }
-                    // ---- phase 3: depth validity + distance criterion, votes; uncertain pairs are deferred
-#pragma unroll
-                    for (int k = 0; k < NB; ++k) {
-                        int st = (int)((stw >> (4 * k)) & 7u);
-                        if (fr[k] < 0 || (st == 0 && !AUDIT)) continue;
-                        const int frel = fr[k];
-                        const float4* s = stage_w + k * 8;
-                        int g_in = (int)((stw >> (4 * k + 3)) & 1u);
-                        const int pix = (int)((puv[k] >> 16) * P.W + (puv[k] & 0xffffu));
-                        uint32_t zq = 0;
-                        uint32_t cls = 0;
-                        if (st == 1 && MODE != MODE_SPLAT) {
-                            float dm;
-                            bool valid;
-                            if (FMT != F3D_DEPTH_F32_M) {
-                                const uint32_t d = g0[k] & 0xffffu;
-                                valid = (d >= P.d_lo) && (d <= P.d_hi);
-                                dm = (float)d * 0.001f;
-                            } else {
-                                dm = __uint_as_float(g0[k]);
-                                valid = ((double)dm > P.zmin) && ((double)dm <= P.zmax);
-                            }
-                            if (MODE == MODE_VOTE) cls = (FMT < F3D_FRAMES_U32) ? g1[(MODE == MODE_VOTE && FMT < F3D_FRAMES_U32) ? k : 0] : ((g0[k] >> 16) & 0xffu);
-                            st = valid ? distance_test(s, pt, puv[k], dm, P, g_in) : 0;
-                        }
-                        if (MODE == MODE_SPLAT && st == 1) {
-                            // quantised camera z: floor(z*1000 + 0.5); certify the floor
-                            const float zm = fmaf(zc[MODE == MODE_SPLAT ? k : 0], 1000.0f, 0.5f);
-                            const float fz = floorf(zm);
-                            const float ez = 8.0f * F3D_U24 * s[4].w *
-                                             (fabsf((pt.x - s[0].x) - s[1].x) + fabsf((pt.y - s[0].y) - s[1].y) +
-                                              fabsf((pt.z - s[0].z) - s[1].z) + 1.0e-9f);
-                            const float eq = 1010.0f * ez + 8.0f * F3D_U24 * zm;
-                            if ((zm - fz >= eq) && (fz + 1.0f - zm > eq)) {
-                                zq = (uint32_t)fminf(fmaxf(fz, 1.0f), 65535.0f);
-                            } else {
-                                st = 3;
-                                g_in = (int)fminf(fmaxf(fz, 1.0f), 65535.0f);
-                            }
-                        }
-                        const bool seen = (st == 1);
-                        if (st >= 2 || AUDIT) {
-                            // defer to the warp's dense fp64 pass (queue full or audit sweep: evaluate inline)
-                            const int slot = (st >= 2 && !AUDIT) ? atomicAdd(sh.nq + warp, 1) : FUSE_QWARP;
-                            if (slot < FUSE_QWARP) {
-                                queue[slot].w0 = (uint32_t)tid | ((uint32_t)frel << 16);
-                                queue[slot].w1 = (uint32_t)pix;
-                                queue[slot].w2 = (uint32_t)st | ((uint32_t)g_in << 8);
-                            } else {
-                                resolve_exact<MODE, FMT, CellT>(P, RP, frec, hist, RS, tile_base, tid, frel, pt.x, pt.y, pt.z, st, g_in, pix,
-                                                                seen, zq, true, sh.dirty + warp, T);
-                            }
-                        } else if (seen) {
-                            ++T.n_seen;
-                            if (MODE == MODE_VOTE) {
-                                cast_vote(hist, tid * RS, (int)cls, P, RP, T);
-                            } else {
-                                const size_t off = (size_t)frel * (size_t)HW + (size_t)pix;
-                                if (MODE == MODE_SPLAT) atomicMin(P.zbuf + off, zq);
-                                else atomicMax(P.uv2pt + off, (int)gi);
-                            }
-                        }
-                        FUSE_SCHED_FENCE();
-                    }
-                }
+            cp_async_commit();   // tile it + 2 and texel it travel as one group
+            // ---- candidate `it - 2`: its texel has landed
+            if (PIPE) {
+                if (f2 >= 0 && active && ((sg2 & 7u) != 0u || AUDIT))
+                    consume(f2, tiles + ((it + FUSE_TR - 2) & (FUSE_TR - 1)) * 8, puv2, sg2, texr[((it + FUSE_GR - 2) & (FUSE_GR - 1)) * 32], 0u, 0.f);
+                puv2 = puv1;
+                sg2 = sg1;
+                puv1 = puv0;
+                sg1 = sg0;
             }
         }
+        cp_async_wait_all();
+        __syncwarp();
     }
 
     // ---- warp-private dense fp64 pass over the deferred point-views (one entry per lane)
@@ -927,8 +968,8 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     // ---- epilogue (warp-private rows): histogram -> HBM, written once; fused label resolve
     if constexpr (MODE == MODE_VOTE && HB == 1) {
         uint8_t* hist8 = reinterpret_cast<uint8_t*>(hist);
-        flush8(P, hist8, warp, lane, tile_base, nflush > 0 || P.accumulate, false, T, stg_all + warp * (FUSE_STG_ROWS * 32), nflush,
-               ((sh.dirty[warp] >> lane) & 1u) != 0u, sh.dcache[warp]);
+        flush8<true>(P, hist8, warp, lane, tile_base, nflush > 0 || P.accumulate, false, T.nlist, T.clist, stg_all + warp * (FUSE_STG_ROWS * 32),
+               nflush, ((sh.dirty[warp] >> lane) & 1u) != 0u, sh.dcache[warp]);
         if (RP.enabled && active) {
             // VotingSegmentation.segment (voting.py:120-135).  The running (total, best, bpos) is exact unless another
             // lane's deferred pass added votes to this row (re-derived from the row) or the warp flushed more than

@@ -382,21 +382,83 @@ def frustum_mask(points64, plane_points, normals):
     return out
 
 
-def box_pairs_aabb(lo, hi, group, cap=None):
-    """All i<j pairs of equal group whose closed AABBs overlap.  -> int32 [E,2] (unordered)."""
+def box_pairs_aabb(lo, hi, group, cap=None, brute_force=False):
+    """All i<j pairs of equal group whose closed AABBs overlap (`merge_intersecting_bb.py:49-53`).  -> int32 [E,2]
+    (unordered).  Default: sort-and-sweep broad phase over the boxes ordered by (group, lo.x); `brute_force=True` runs the
+    all-pairs tile kernel (kept as the cross-check)."""
     lo, hi = as_cuda(lo, torch.float64), as_cuda(hi, torch.float64)
     group = as_cuda(group, torch.int32)
     B = lo.shape[0]
     cap = max(1024, 8 * B) if cap is None else cap
+    order = None
+    if not brute_force and B:
+        o1 = torch.sort(lo[:, 0].contiguous(), stable=True).indices            # by lo.x ...
+        order = o1[torch.sort(group[o1], stable=True).indices].to(torch.int32).contiguous()   # ... then (stable) by group
     while True:
         edges = torch.empty((cap, 2), dtype=torch.int32, device=lo.device)
         count = torch.zeros(1, dtype=torch.int64, device=lo.device)
-        check(load().f3d_box_pairs_aabb(ptr(lo), ptr(hi), ptr(group), B, ptr(edges), cap, ptr(count), stream_ptr()),
-              "f3d_box_pairs_aabb")
+        if order is None:
+            check(load().f3d_box_pairs_aabb(ptr(lo), ptr(hi), ptr(group), B, ptr(edges), cap, ptr(count), stream_ptr()),
+                  "f3d_box_pairs_aabb")
+        else:
+            check(load().f3d_box_pairs_sweep(ptr(lo), ptr(hi), ptr(group), ptr(order), B, ptr(edges), cap, ptr(count), stream_ptr()),
+                  "f3d_box_pairs_sweep")
         n = int(count.item())
         if n <= cap:
             return edges[:n]
         cap = n
+
+
+OBB_MODELS = {"pca": 0, "aabb": 1}
+
+
+def obb_fit(points64, ids, instance_ids, model="pca"):
+    """Boxes of the listed instances in ONE pass over the cloud (`f3d_obb_fit`).  points64 [N,3] float64 device tensor,
+    ids [N] int64 device tensor, instance_ids: sequence of id values.  -> (boxes [L,15] float64: centre, R row major,
+    extent; counts [L] int64), device tensors."""
+    inst = np.asarray(instance_ids, dtype=np.int64).reshape(-1)
+    L = int(inst.size)
+    dev = points64.device
+    boxes = torch.zeros((L, 15), dtype=torch.float64, device=dev)
+    counts = torch.zeros(L, dtype=torch.int64, device=dev)
+    if L == 0:
+        return boxes, counts
+    if inst.min() < 0:
+        raise ValueError("instance ids must be non-negative")
+    nslot = int(inst.max()) + 1
+    table = np.full(nslot, -1, dtype=np.int32)
+    table[inst[::-1]] = np.arange(L - 1, -1, -1, dtype=np.int32)           # first occurrence wins
+    slot = torch.as_tensor(table).to(dev)
+    ws = torch.empty(int(load().f3d_obb_fit_workspace_bytes(L)), dtype=torch.uint8, device=dev)
+    check(load().f3d_obb_fit(ptr(points64), ptr(ids), int(points64.shape[0]), ptr(slot), nslot, L, OBB_MODELS[model], ptr(boxes),
+                             ptr(counts), ptr(ws), stream_ptr()), "f3d_obb_fit")
+    return boxes, counts
+
+
+def radius_adjacency(points64, r):
+    """`KDTree(points).query_radius(points, r)` (`fusion.py:374-375`) as a CSR pair of device tensors
+    (indptr int64 [N+1], indices int64), rows sorted ascending.  Uniform grid of cell size r; torch provides the key sort
+    and the exclusive scan (plumbing), the kernels of csrc/geometry.cu the cell keys, the counting and the fill."""
+    p = as_cuda(points64, torch.float64)
+    N = int(p.shape[0])
+    dev = p.device
+    if N == 0:
+        return torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.int64, device=dev)
+    r = float(r)
+    mn = host_f64(p.min(0).values.cpu().numpy(), 3)
+    mx = host_f64(p.max(0).values.cpu().numpy(), 3)
+    keys = torch.empty(N, dtype=torch.int64, device=dev)
+    check(load().f3d_radius_grid_keys(ptr(p), N, ptr(mn), ptr(mx), r, ptr(keys), stream_ptr()), "f3d_radius_grid_keys")
+    skeys, order = torch.sort(keys, stable=True)
+    counts = torch.empty(N, dtype=torch.int64, device=dev)
+    check(load().f3d_radius_adjacency(ptr(p), N, ptr(mn), ptr(mx), r, ptr(skeys), ptr(order), ptr(counts), None, None, stream_ptr()),
+          "f3d_radius_adjacency(count)")
+    indptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=indptr[1:])
+    indices = torch.empty(int(indptr[-1].item()), dtype=torch.int64, device=dev)
+    check(load().f3d_radius_adjacency(ptr(p), N, ptr(mn), ptr(mx), r, ptr(skeys), ptr(order), None, ptr(indptr), ptr(indices), stream_ptr()),
+          "f3d_radius_adjacency(fill)")
+    return indptr, indices
 
 
 def union_find(nboxes, edges):

@@ -238,6 +238,13 @@ int f3d_frustum_mask(const double* points, int64_t N, const double* h_plane_poin
 int f3d_box_pairs_aabb(const double* lo, const double* hi, const int32_t* group, int32_t B, int32_t* edges,
                        int64_t cap, unsigned long long* count, void* stream);
 
+/* Same pair set as f3d_box_pairs_aabb through a sort-and-sweep broad phase: `order` [B] int32 lists the boxes sorted by
+ * (group, lo.x) (the caller sorts, e.g. torch); a box is tested only against the later boxes of its group whose lo.x does
+ * not exceed its hi.x (or ties its lo.x), with the exact float64 closed-interval predicate (merge_intersecting_bb.py:51-53).
+ * Edges are written as (min, max) box indices, unordered. */
+int f3d_box_pairs_sweep(const double* lo, const double* hi, const int32_t* group, const int32_t* order, int32_t B,
+                        int32_t* edges, int64_t cap, unsigned long long* count, void* stream);
+
 /* Union-find closure: labels[i] = smallest box index of i's connected component. */
 int f3d_union_find(int32_t B, const int32_t* edges, int64_t E, int32_t* labels, void* stream);
 
@@ -246,6 +253,35 @@ int f3d_union_find(int32_t B, const int32_t* edges, int64_t E, int32_t* labels, 
  * extent[3] (device). */
 int f3d_obb_contains(const double* points, int64_t N, const double* boxes15, int32_t nboxes,
                      uint8_t* inside, void* stream);
+
+/* Batched oriented-box fit (the box behind the o3d.geometry.OrientedBoundingBox.create_from_points call sites
+ * merge_intersecting_bb.py:18,75,86,126 and get3DSeg.py:434-436), every requested instance in one pass over the cloud:
+ *   points [N,3] float64, ids [N] int64 instance id per point, slot_of_id [nslot] int32: output slot of instance id
+ *   (-1 = not requested; ids outside [0, nslot) are ignored), ninst output slots.
+ *   model 0: centre / axes from the mean and covariance of ALL the instance's points (3x3 Jacobi, axes by descending
+ *            eigenvalue, third = first x second), extent = range of the projections, centre = mean + R @ mid-range;
+ *   model 1: axis-aligned box of the points (R = I).
+ * Open3D's own fit (Qhull hull vertices first) is NOT reproduced -- see oracle.fit_box for the stated models.
+ *   boxes15 [ninst,15] float64 = centre[3], R[9] row major (columns = axes), extent[3]; counts [ninst] int64 points per slot;
+ *   workspace: f3d_obb_fit_workspace_bytes(ninst) bytes of device scratch. */
+int64_t f3d_obb_fit_workspace_bytes(int32_t ninst);
+int f3d_obb_fit(const double* points, const int64_t* ids, int64_t N, const int32_t* slot_of_id, int64_t nslot, int32_t ninst,
+                int32_t model, double* boxes15, int64_t* counts, void* workspace, void* stream);
+
+/* ---- radius adjacency ------------------------------------------------------------------------- */
+
+/* KDTree(points).query_radius(points, r) (Fusion3DSeg/fusion.py:374-375) on a uniform grid of cell size r:
+ * membership = scikit-learn's Euclidean leaf test, reduced distance (dx*dx + dy*dy) + dz*dz <= r*r in float64 (a point is
+ * its own neighbour).  h_min3 / h_max3: host, component-wise minimum / maximum of the cloud.
+ *   f3d_radius_grid_keys   keys [N] int64 = cell key of every point; the caller sorts them (stable) and passes the sorted
+ *                          keys and the sorting permutation `order` [N] int64 to
+ *   f3d_radius_adjacency   pass 1 (indices NULL): counts [N] int64 = row lengths; the caller builds indptr [N+1] by an
+ *                          exclusive scan; pass 2 (indices given): rows written at indptr[i] and sorted ascending. */
+int f3d_radius_grid_keys(const double* points, int64_t N, const double* h_min3, const double* h_max3, double r, int64_t* keys,
+                         void* stream);
+int f3d_radius_adjacency(const double* points, int64_t N, const double* h_min3, const double* h_max3, double r,
+                         const int64_t* sorted_keys, const int64_t* order, int64_t* counts, const int64_t* indptr,
+                         int64_t* indices, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,59 @@ def parse_rts(rts):
 
 
 class FrameData:
+    """Reference `FrameData` (`fusion.py:17-64`): per-frame pickle loader of an RTAB cache
+    (`PointcloudMergeResults/tofsegment_*.pkl` lists the per-frame files) with the valid-range test and the decimation
+    lattice.  `__getitem__` returns the reference's 5-tuple; `depth_mm` gives the frame as the fused kernel wants it."""
+
+    def __init__(self, tof, point_range=None, decimation=1, depth_hw=(256, 192)):
+        self.point_range = point_range
+        self.decimation = decimation
+        self.depth_hw = depth_hw
+        self.mask = np.ones(depth_hw, bool)
+        dirname = Path(str(tof).split('PointcloudMergeResults')[0])
+        with open(tof, 'rb') as fp:
+            tofdata = pickle.load(fp)
+            self.tofcamedata = [dirname / data['fileName'].strip() for data in tofdata]
+
+    def __len__(self):
+        return len(self.tofcamedata)
+
+    def _load(self, i):
+        with open(self.tofcamedata[i], 'rb') as fp:
+            return pickle.load(fp)
+
+    def _valids(self, orgpts):
+        if self.point_range is not None:
+            valids = self.get_valid(orgpts, self.point_range[0], self.point_range[1])
+        else:
+            valids = np.ones(len(orgpts), bool)
+        if self.decimation > 1:                                   # fusion.py:43-46: only the ::decimation lattice stays valid
+            mask = self.mask.copy()
+            mask[::self.decimation, ::self.decimation] = False
+            valids[mask.reshape(-1)] = False
+        return valids
+
+    def __getitem__(self, i):
+        data = self._load(i)
+        frame_name = str(data['frameNumber'])
+        orgpts = np.array(data['orgPoints'])
+        return frame_name, np.array(data['modPoints']), np.array(data['modSurfaceNormals']), np.array(data['orgColorPoints']), \
+            self._valids(orgpts)
+
+    def depth_mm(self, i):
+        """(frame name, uint16 [h,w] depth in millimetres with every pixel `__getitem__` calls invalid set to 0).
+        `orgPoints[:, 2]` is depth_png / 1000 in float64 (`ios_rtab.py:185`), so rounding z * 1000 recovers the sensor's
+        integer exactly; a cache whose z is not a millimetre multiple is rejected (the kernel contract is integer mm)."""
+        data = self._load(i)
+        org = np.array(data['orgPoints'])
+        z = org[:, 2] * 1000.0
+        d = np.rint(z)
+        if np.abs(z - d).max(initial=0.0) > 1e-6 or d.min(initial=0) < 0 or d.max(initial=0) > 65535:
+            raise ValueError(f"frame {data['frameNumber']}: orgPoints z is not a uint16 millimetre depth")
+        d = d.astype(np.uint16)
+        d[~self._valids(org)] = 0
+        return str(data['frameNumber']), d.reshape(self.depth_hw)
+
     @staticmethod
     def get_valid(points, mindist, maxdist):
         """Reference `FrameData.get_valid` (`fusion.py:50-64`): camera-space z in (mindist, maxdist]."""
@@ -73,14 +126,28 @@ class Fusion:
         return out
 
     @staticmethod
-    def dump_data(dirname, points, normals=None, colors=None, nmerges=None, occurences=None, nframes=0, depth_hw=None):
-        """Writes `fusion/fusion_data.pkl` with the reference's keys (`fusion.py:360-368`); no adjacency, no PLY."""
+    def dump_data(dirname, points, normals=None, colors=None, nmerges=None, occurences=None, nframes=0, depth_hw=None,
+                  compute_adjacency=False, ds_radius=None):
+        """Writes `fusion/fusion_data.pkl` with the reference's keys (`fusion.py:360-368`) and, when asked, `fusion/adj.pkl`
+        = `KDTree(points).query_radius(points, r=2*ds_radius)` (`fusion.py:369-377`) from the GPU uniform-grid search
+        (`f3d_radius_adjacency`; rows sorted ascending, the reference's are in tree order).  No PLY, no GUI."""
         dirname = Path(dirname)
         (dirname / 'fusion').mkdir(exist_ok=True, parents=True)
         data = {'points': points, 'normals': normals, 'colors': colors, 'nmerges': nmerges, 'occurences': occurences,
                 'nframes': nframes, 'depth_hw': depth_hw}
         with (dirname / 'fusion' / 'fusion_data.pkl').open('wb') as fp:
             pickle.dump(data, fp)
+        if compute_adjacency:
+            if ds_radius is None:
+                adj = None
+            else:
+                indptr, indices = engine.radius_adjacency(engine.as_cuda(np.asarray(points, dtype=np.float64)), 2 * ds_radius)
+                ip, ix = indptr.cpu().numpy(), indices.cpu().numpy()
+                adj = np.empty(len(ip) - 1, dtype=object)
+                for i in range(len(ip) - 1):
+                    adj[i] = ix[ip[i]:ip[i + 1]]
+            with (dirname / 'fusion' / 'adj.pkl').open('wb') as fp:
+                pickle.dump(np.array(adj, dtype=object) if adj is None else adj, fp)
 
     # ---- fixed-cloud GPU drivers -------------------------------------------------------------------------------------
     @staticmethod

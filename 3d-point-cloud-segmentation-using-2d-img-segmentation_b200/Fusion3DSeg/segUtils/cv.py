@@ -17,25 +17,35 @@ from ..._lib import require_cuda
 
 
 def adjacency_to_csr(adj):
-    """list / object array of neighbour-index arrays (`fusion.py:374-377`) or an (indptr, indices) pair -> CSR int64."""
+    """list / object array of neighbour-index arrays (`fusion.py:374-377`) or an (indptr, indices) pair (numpy arrays or
+    device tensors, e.g. straight from `engine.radius_adjacency`) -> CSR int64 device tensors."""
+    dev = require_cuda()
     if isinstance(adj, tuple) and len(adj) == 2:
-        return np.asarray(adj[0], dtype=np.int64), np.asarray(adj[1], dtype=np.int64)
+        ip, ix = adj
+        if isinstance(ip, torch.Tensor):
+            return ip.to(dev, torch.int64), ix.to(dev, torch.int64)
+        return torch.as_tensor(np.asarray(ip, dtype=np.int64)).to(dev), torch.as_tensor(np.asarray(ix, dtype=np.int64)).to(dev)
     counts = np.fromiter((len(a) for a in adj), dtype=np.int64, count=len(adj))
     indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     indices = np.concatenate([np.asarray(a, dtype=np.int64) for a in adj]) if len(adj) else np.zeros(0, np.int64)
-    return indptr, indices
+    return torch.as_tensor(indptr).to(dev), torch.as_tensor(indices).to(dev)
 
 
 def connected_components(classes, adj):
-    """labels int64 [N] (device): smallest point index of the point's equal-class connected component."""
+    """labels int64 [N] (device): smallest point index of the point's equal-class connected component.
+
+    The adjacency is treated as an UNDIRECTED graph: every listed pair (i, j), i != j, links i and j whichever row lists
+    it.  For the symmetric lists the reference produces (`KDTree.query_radius`, `fusion.py:374-375`) this is exactly what
+    its BFS (`cv.py:425-440`) computes; a hand-made one-directional list is closed symmetrically here, whereas the
+    reference BFS would follow it as directed."""
     dev = require_cuda()
-    indptr, indices = adjacency_to_csr(adj)
-    n = len(indptr) - 1
+    indptr, dst = adjacency_to_csr(adj)
+    n = int(indptr.shape[0]) - 1
     cls = torch.as_tensor(np.ascontiguousarray(classes)).to(dev)
-    dst = torch.as_tensor(indices).to(dev)
-    src = torch.repeat_interleave(torch.arange(n, device=dev), torch.as_tensor(np.diff(indptr)).to(dev))
-    keep = (cls[src] == cls[dst]) & (src < dst)
-    edges = torch.stack([src[keep], dst[keep]], dim=1).to(torch.int32).contiguous()
+    src = torch.repeat_interleave(torch.arange(n, device=dev), indptr[1:] - indptr[:-1])
+    keep = (cls[src] == cls[dst]) & (src != dst)
+    a, b = src[keep], dst[keep]
+    edges = torch.stack([torch.minimum(a, b), torch.maximum(a, b)], dim=1).to(torch.int32).contiguous()
     return engine.union_find(n, edges).to(torch.int64)
 
 

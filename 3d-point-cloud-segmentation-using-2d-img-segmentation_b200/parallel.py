@@ -187,6 +187,10 @@ class VoteExchange:
         self.rx_dir, self.rx_slots = self.rx[o_d:o_s], self.rx[o_s:]
         self.cursors = torch.zeros(G * (self.nreg + self.nsub), dtype=torch.int32, device=self.device)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.ovf_any = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.ovf_event = torch.cuda.Event()
+        self._ovf_pending = False
         self.shard = torch.zeros((max(self.per, 1), c1), dtype=torch.int32, device=self.device)
         self.lab = torch.zeros(max(self.per, 1), dtype=torch.int64, device=self.device)
         self.full = torch.zeros(max(self.per, 1) * G, dtype=torch.int64, device=self.device)
@@ -199,12 +203,19 @@ class VoteExchange:
                     peer_dir_ptrs=self.peer_dir_ptrs, peer_queue_ptrs=self.peer_queue_ptrs, sub_rows=self.sub_rows,
                     sub_cap=self.sub_cap, cursors=self.cursors, overflow=self.overflow)
 
-    def run(self, fuse, nclasses_id, threshold=0.5, filter_classes=None) -> torch.Tensor:
+    def run(self, fuse, nclasses_id, threshold=0.5, filter_classes=None, check=True) -> torch.Tensor:
         """`fuse(**self.fuse_args())` enqueues the exchange-mode fused kernel over this rank's frames.  Returns labels
-        [npoints]; `self.shard[:self.rows]` holds this rank's reduced votes."""
+        [npoints]; `self.shard[:self.rows]` holds this rank's reduced votes.
+
+        A sub-queue that fills up DROPS entries (`xg_append`): the sender's flag is max-reduced over the ranks on the
+        device right after the exchange and copied to pinned host memory.  `check=True` (default) waits for it and raises
+        -- wrong labels never leave this call silently.  `check="deferred"` keeps the step free of host synchronisation
+        (benchmark loops): the flag of step k is examined at the start of step k+1 and by `finish()`."""
         eng = self.engine
+        self._raise_if_overflowed(wait=False)          # deferred flag of the previous step
         self.hdl.barrier(channel=0)
         self.cursors.zero_()
+        self.overflow.zero_()
         fuse(**self.fuse_args())
         eng.exchange_publish(self.cursors, self.peer_count_ptrs, self.rank, self.sub_cap)
         self.hdl.barrier(channel=1)
@@ -222,14 +233,37 @@ class VoteExchange:
             self.full.copy_(self.full16)
         else:
             _all_gather(self.full, self.lab, grp)
+        # overflow: any rank's dropped entry invalidates every rank's result
+        self.ovf_any.copy_(self.overflow)
+        if self.world > 1:
+            dist.all_reduce(self.ovf_any, op=dist.ReduceOp.MAX, group=grp)
+        self.ovf_host.copy_(self.ovf_any, non_blocking=True)
+        self.ovf_event.record()
+        self._ovf_pending = True
+        if check is True:
+            self._raise_if_overflowed(wait=True)
         return self.full[:self.npoints]
 
+    def _raise_if_overflowed(self, wait: bool):
+        if not getattr(self, "_ovf_pending", False):
+            return
+        if wait:
+            self.ovf_event.synchronize()
+        elif not self.ovf_event.query():
+            self.ovf_event.synchronize()   # the previous step has long finished when the next one starts
+        self._ovf_pending = False
+        if int(self.ovf_host[0]):
+            raise RuntimeError("vote exchange: a (cell, count) sub-queue overflowed on some rank and votes were dropped; "
+                               "the labels of this step are invalid -- enlarge sub_cap (VoteExchange(..., sub_cap=...)) or "
+                               "use ShardedPipeline (dense reduce-scatter)")
+
+    def finish(self):
+        """Examine the overflow flag of the last `run(check="deferred")` step (synchronises)."""
+        self._raise_if_overflowed(wait=True)
+
     def check_overflow(self):
-        """Host check (synchronises): raises if any sub-queue filled up during the steps so far."""
-        t = self.overflow.clone()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if int(t.item()):
-            raise RuntimeError("vote exchange: a sub-queue overflowed; enlarge sub_cap or use ShardedPipeline")
+        """Kept for callers of round 1: same as finish()."""
+        self.finish()
 
 
 def fuse_sharded(fuse_chunk, resolve, npoints: int, nchunks: int, device, group=None):

@@ -1,18 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of the fused label-fusion hot path (BASELINE.json metric: point-view projections / s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C1|C4|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C1|C3|C4|small] [--configs C1,C4,C5,micro]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over the whole synthetic scene: kernel (1) fused project + z-test + mask
-gather + vote over every frame, then kernel (3) label resolve (N = 1), or per point-chunk fuse -> NCCL
-reduce-scatter -> resolve -> all-gather with frames sharded across ranks (N > 1, weak scaling: every rank brings
-its own `frames_per_gpu` frames of the same cloud).  A point-view is one (point, frame) pair of the nominal
-N_points x N_frames product.  Rank 0 prints ONE JSON line.
+One "step" = one pass of the hot path over the whole synthetic scene.
+
+N = 1 (default workload C2, BASELINE configs[1]): ONE launch of kernel (1) -- fused project + z-test + frame gather + vote over
+every frame with the label resolve (kernel 3's arithmetic) in its epilogue -- on frames resident in HBM in the ingest
+path's packed device layout (uint32 texel = depth mm | class << 16, `f3d_pack_frames`).  The same line also reports the step
+on the two-array inputs (uint16 depth + uint8 mask stacks) and with the re-pack inside the step, the end-to-end step from
+pinned HOST buffers through the public API, the CPU port of the reference on the host cores (both figures), and nested
+lines for the other BASELINE configs (C1 compared cell for cell with the CPU port, C4, C5) and the other kernels.
+
+N > 1 (default workload C3, configs[2]: 100 M points x 5000 frames = a FIXED problem split over the ranks, strong scaling):
+frames sharded over the ranks (interleaved and contiguous are both timed), the vote exchange fused into the kernel
+(slot records written straight into the owner rank's memory over NVLink), owner-side merge + label resolve, all-gather of the
+labels.  Rank 0 additionally runs the whole frame set on its single GPU and the CPU port on a sample, and the line says
+whether the N-rank result equals both.
+
+A point-view is one (point, frame) pair of the nominal N_points x N_frames product.  Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import importlib
 import json
 import os
@@ -32,15 +44,18 @@ PKG_NAME = "3d-point-cloud-segmentation-using-2d-img-segmentation_b200"
 METRIC = "point_view_projections_per_sec"
 UNIT = "point-views/s"
 NCLASSES = 133
+C1 = NCLASSES + 1
 RADIUS, THRESHOLD = 0.05, 0.5
 
 WORKLOADS = {
     # name: (config key in scenes.CONFIGS, description)
     "C2": ("C2", "configs[1] iOS RTAB-style scan: 10M points x 500 frames 1920x1440 uint16-mm depth + uint8 masks"),
     "C1": ("C1", "configs[0] CPU-reference scene: 1M points x 50 frames 640x480"),
+    "C3": ("C3", "configs[2] large building scan: 100M points x 5000 frames 1920x1440, frames sharded over the GPUs"),
     "C4": ("C4", "configs[3] dense 4K: 20M points x 1000 frames 3840x2160"),
     "small": ("C1", "debug scene: 200k points x 8 frames 320x240"),
 }
+T_START = time.time()
 
 
 def peaks():
@@ -90,58 +105,130 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
 
 
-def algorithmic_bytes(N, F, H, W, depth_bytes, C1):
-    """SURVEY 8(d) designated figure for kernel (1): every input read once, every output written once."""
-    return 16 * N + F * H * W * (1 + depth_bytes) + 64 * F + 4 * N * C1
+def algorithmic_bytes(N, F, H, W, depth_bytes, c1, rows=None):
+    """SURVEY 8(d) designated figure for kernel (1): every input read once, every output written once (`rows`: vote rows this
+    launch writes, default all N)."""
+    return 16 * N + F * H * W * (1 + depth_bytes) + 64 * F + 4 * (N if rows is None else rows) * c1
+
+
+def kernel_source_hash():
+    h = hashlib.sha1()
+    for f in ("fuse_kernel.cuh", "f3d_common.cuh"):
+        h.update((ROOT / PKG_NAME / "csrc" / f).read_bytes())
+    return h.hexdigest()[:12]
+
+
+def profile_figures(workload):
+    """ncu-derived figures of the fused kernel committed under profiles/ (DRAM traffic per launch, fp32 pipe utilisation).
+    They are stamped with the hash of the kernel source they were captured on and dropped when the source has changed."""
+    tj = ROOT / "profiles" / "fuse_kernel_traffic.json"
+    if not tj.exists():
+        return None
+    try:
+        d = json.loads(tj.read_text())
+    except Exception:   # noqa: BLE001
+        return None
+    if d.get("kernel_source_hash") != kernel_source_hash() or d.get("workload") != workload:
+        return None
+    return d
+
+
+def frame_masks(torch, frame_ids, H, W, seed, device="cuda", block=32):
+    """uint8 [F,H,W] block-constant label images, a pure function of (seed, global frame id, block): every rank -- and the
+    single-GPU reference run of the multi-GPU parity check -- produces identical masks for the same frame id.  Labels
+    0..132, 5 % of the blocks = 133 (unclassified, `get2DSeg.py:118`)."""
+    bh, bw = -(-H // block), -(-W // block)
+    fid = torch.as_tensor(np.asarray(frame_ids, dtype=np.int64), device=device)[:, None, None]
+    by = torch.arange(bh, device=device, dtype=torch.int64)[None, :, None]
+    bx = torch.arange(bw, device=device, dtype=torch.int64)[None, None, :]
+    h = (fid * 73856093 + by * 19349663 + bx * 83492791 + int(seed) * 2654435761) & 0x7fffffff
+    h = ((h ^ (h >> 15)) * 0x2c1b3c6d) & 0x7fffffff
+    h = ((h ^ (h >> 12)) * 0x297a2d39) & 0x7fffffff
+    h = h ^ (h >> 15)
+    lab = (h % NCLASSES).to(torch.uint8)
+    lab[((h >> 8) % 20) == 0] = NCLASSES
+    return lab.repeat_interleave(block, dim=1).repeat_interleave(block, dim=2)[:, :H, :W].contiguous()
+
+
+def build_frames(torch, engine, fl, spec, frame_ids, keep_unpacked=False):
+    """Depth = GPU z-buffer splat of the cloud (kernel 2) for the labeler's frames, masks = `frame_masks`; both are packed
+    chunk by chunk into the labeler's resident packed stack.  Returns (depth, masks) stacks when `keep_unpacked`."""
+    F, H, W = fl.nframes, spec.height, spec.width
+    step = max(1, min(F, (1 << 30) // (H * W * 4)))
+    zbuf = torch.empty((step, H * W), dtype=torch.int32, device="cuda")
+    depth = torch.empty((F if keep_unpacked else step, H, W), dtype=torch.uint16, device="cuda")
+    masks = torch.empty((F, H, W), dtype=torch.uint8, device="cuda") if keep_unpacked else None
+    for a in range(0, F, step):
+        b = min(a + step, F)
+        d = depth[a:b] if keep_unpacked else depth[: b - a]
+        engine.zbuffer_splat(fl.points4, fl.table, border=10, frame_begin=a, frame_end=b, zbuf=zbuf, out=d)
+        for a2 in range(a, b, 32):
+            b2 = min(a2 + 32, b)
+            m = frame_masks(torch, frame_ids[a2:b2], H, W, spec.seed)
+            if keep_unpacked:
+                masks[a2:b2] = m
+            fl.pack(d[a2 - a:b2 - a], m, frame_begin=a2)
+    torch.cuda.synchronize()
+    del zbuf
+    return (depth, masks) if keep_unpacked else (None, None)
+
+
+def make_labeler(fused, scenes, spec, frame_ids, pts):
+    K = scenes.scaled_intrinsics(spec.width, spec.height)
+    wxyz, t = scenes.make_poses(spec)
+    ids = np.asarray(frame_ids, dtype=np.int64)
+    fl = fused.FusedLabeler(pts, K, spec.width, spec.height, np.ascontiguousarray(wxyz[ids]), np.ascontiguousarray(t[ids]),
+                            point_range=(0.1, spec.zmax), radius=RADIUS, nclasses=NCLASSES)
+    return fl, K, wxyz, t
 
 
 def build_scene(scenes, engine, fused, spec, frame_lo, frame_hi, torch, frame_ids=None):
-    """Cloud + poses on the host (seeded numpy), depth = GPU z-buffer splat of the cloud (kernel 2), block masks on
-    the GPU.  Returns the FusedLabeler (cloud + frame table for frames [frame_lo, frame_hi), or the global frame indices
-    `frame_ids`) and device depth / masks."""
-    K = scenes.scaled_intrinsics(spec.width, spec.height)
-    wxyz, t = scenes.make_poses(spec)
-    if frame_ids is None:
-        frame_ids = list(range(frame_lo, frame_hi))
-    frame_lo = frame_ids[0] if len(frame_ids) else 0
-    wxyz, t = np.ascontiguousarray(wxyz[frame_ids]), np.ascontiguousarray(t[frame_ids])
+    """Whole synthetic scene on the device (tests / tools): labeler with its packed frame stack plus the two-array stacks."""
+    ids = list(range(frame_lo, frame_hi)) if frame_ids is None else list(frame_ids)
     pts = scenes.make_cloud(spec)
-    fl = fused.FusedLabeler(pts, K, spec.width, spec.height, wxyz, t, point_range=(0.1, spec.zmax), radius=RADIUS,
-                            nclasses=NCLASSES)
-    F, H, W = len(t), spec.height, spec.width
-    depth = torch.empty((F, H, W), dtype=torch.uint16, device="cuda")
-    step = max(1, min(F, (1 << 30) // (H * W * 4)))
-    zbuf = torch.empty((step, H * W), dtype=torch.int32, device="cuda")
-    for a in range(0, F, step):
-        b = min(a + step, F)
-        engine.zbuffer_splat(fl.points4, fl.table, border=10, frame_begin=a, frame_end=b, zbuf=zbuf, out=depth[a:b])
-    del zbuf
-    g = torch.Generator(device="cuda")
-    g.manual_seed(spec.seed + 104729 + frame_lo)
-    masks = torch.empty((F, H, W), dtype=torch.uint8, device="cuda")
-    bh, bw = -(-H // 32), -(-W // 32)
-    for a in range(0, F, 32):
-        b = min(a + 32, F)
-        lab = torch.randint(0, NCLASSES, (b - a, bh, bw), generator=g, device="cuda", dtype=torch.int16)
-        lab[torch.rand((b - a, bh, bw), generator=g, device="cuda") < 0.05] = NCLASSES
-        m = lab.to(torch.uint8).repeat_interleave(32, dim=1).repeat_interleave(32, dim=2)[:, :H, :W]
-        masks[a:b] = m
+    fl, K, wxyz, t = make_labeler(fused, scenes, spec, ids, pts)
+    depth, masks = build_frames(torch, engine, fl, spec, ids, keep_unpacked=True)
+    return fl, pts, K, np.ascontiguousarray(wxyz[ids]), np.ascontiguousarray(t[ids]), depth, masks
+
+
+def timed(torch, fn, steps, warmup=1):
+    for _ in range(warmup):
+        fn()
     torch.cuda.synchronize()
-    return fl, pts, K, wxyz, t, depth, masks
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
 
-def cpu_sample(pts, K, spec, wxyz, t, depth, masks, target_pv=4.8e7):
-    """Bounded CPU sample of the same workload: every k-th point x evenly spaced frames (about 10-30 s of CPU work)."""
-    F = len(t)
-    nf = min(F, 64)
-    fidx = np.unique(np.linspace(0, F - 1, nf).astype(int))
-    npts = int(min(len(pts), max(1000, target_pv // len(fidx))))
-    stride = max(1, len(pts) // npts)
-    sub = np.ascontiguousarray(pts[::stride][:npts])
-    d = np.stack([depth[int(f)].cpu().numpy() for f in fidx])
-    m = np.stack([masks[int(f)].cpu().numpy() for f in fidx])
-    desc = f"every {stride}th point ({len(sub)}) x {len(fidx)} evenly spaced frames of the {spec.width}x{spec.height} workload"
-    return sub, wxyz[fidx], t[fidx], d, m, desc
+def sample_indices(npts, nframes, target_pv=4.8e7, max_frames=64):
+    nf = min(nframes, max_frames)
+    fidx = np.unique(np.linspace(0, nframes - 1, nf).astype(int))
+    n = int(min(npts, max(1000, target_pv // len(fidx))))
+    stride = max(1, npts // n)
+    return fidx, stride, n
+
+
+def cpu_vs_gpu_sample(torch, engine, pts, K, spec, wxyz, t, depth_of, masks_of, target_pv=4.8e7, warmup=0, steps=1):
+    """Bounded CPU sample of the same workload (every k-th point x evenly spaced frames, about 10-30 s of CPU work) through
+    the numpy port, both CPU figures, and the same sample through the CUDA path: must agree bit for bit."""
+    from oracle import cpu_baseline as cb
+    fidx, stride, n = sample_indices(len(pts), len(t), target_pv)
+    sub = np.ascontiguousarray(pts[::stride][:n])
+    d = np.stack([depth_of(int(f)) for f in fidx])
+    m = np.stack([masks_of(int(f)) for f in fidx])
+    wq, tq = wxyz[fidx], t[fidx]
+    res, cv, cl, _ = cb.measure(sub, K, spec.width, spec.height, wq, tq, d, m, RADIUS, 0.1, spec.zmax, spec.zmax, C1, warmup, steps)
+    tab = engine.FrameTable(K, spec.width, spec.height, wq, tq, spec.zmax)
+    pk = engine.pack_frames(torch.as_tensor(d).cuda(), torch.as_tensor(m).cuda())
+    gv, gl = engine.fuse_project_vote_resolve(engine.pack_points(sub), tab, pk, None, C1, NCLASSES, RADIUS, 0.1, spec.zmax, THRESHOLD, None)
+    ok = bool(np.array_equal(gv.cpu().numpy(), cv) and np.array_equal(gl.cpu().numpy(), cl))
+    res.update({"unit": UNIT, "kind": "port", "gpu_matches_bit_exact": ok,
+                "sample": f"every {stride}th point ({len(sub)}) x {len(fidx)} evenly spaced frames of the {spec.width}x{spec.height} workload"})
+    return res, (sub, wq, tq, d, m, cv, cl)
 
 
 def run_reference_arm(args, rank, world):
@@ -151,20 +238,20 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     scenes = importlib.import_module(PKG_NAME + ".scenes")     # seeded numpy scene generator (no CUDA, no libf3d)
-    cfg_key, desc = WORKLOADS[args.workload]
-    spec = scenes.CONFIGS[cfg_key] if args.workload != "small" else scenes.scaled_spec("C1", 200_000, 8, 320, 240)
+    wl = args.workload or ("C2" if args.gpus == 1 else "C3")    # the same config the B200 arm runs at this --gpus
+    cfg_key, desc = WORKLOADS[wl]
+    spec = scenes.CONFIGS[cfg_key] if wl != "small" else scenes.scaled_spec("C1", 200_000, 8, 320, 240)
+    if wl == "C3":   # the sample below strides the cloud: do not generate 100 M points for it
+        spec = scenes.scaled_spec("C3", npoints=10_000_000)
     from oracle import cpu_baseline as cb
     K = scenes.scaled_intrinsics(spec.width, spec.height)
     wxyz, t = scenes.make_poses(spec)
     pts = scenes.make_cloud(spec)
-    nf = min(len(t), 64)
-    fidx = np.unique(np.linspace(0, len(t) - 1, nf).astype(int))
-    npts = int(min(len(pts), max(1000, 4.8e7 // len(fidx))))
-    stride = max(1, len(pts) // npts)
-    sub = np.ascontiguousarray(pts[::stride][:npts])
+    fidx, stride, n = sample_indices(len(pts), len(t))
+    sub = np.ascontiguousarray(pts[::stride][:n])
     wq, tt = wxyz[fidx], t[fidx]
     m = scenes.block_masks((spec.height, spec.width), len(tt), seed=spec.seed, block=32)
-    res, _, _, _ = cb.measure(sub, K, spec.width, spec.height, wq, tt, None, m, RADIUS, 0.1, spec.zmax, spec.zmax, NCLASSES + 1,
+    res, _, _, _ = cb.measure(sub, K, spec.width, spec.height, wq, tt, None, m, RADIUS, 0.1, spec.zmax, spec.zmax, C1,
                               warmup=args.warmup, steps=args.steps)
     sample = (f"every {stride}th point ({len(sub)}) x {len(tt)} evenly spaced frames of the {spec.width}x{spec.height} workload per "
               f"step; depth = oracle z-buffer splat of the sample points")
@@ -183,21 +270,556 @@ def run_reference_arm(args, rank, world):
     }))
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# nested configs (N = 1): every BASELINE config in the one driver-run line
+# ---------------------------------------------------------------------------------------------------------------------------
+
+def nested_fused_config(torch, mods, key, steps, full_oracle):
+    """C1 / C4: resident packed frames, fused step timed with the kernel-only events, parity flag.  `full_oracle`: the CPU
+    port runs on the WHOLE scene and votes + labels are compared cell for cell; else a bounded CPU sample + properties."""
+    engine, scenes, fused = mods
+    spec = scenes.CONFIGS[key]
+    pts = scenes.make_cloud(spec)
+    ids = list(range(spec.nframes))
+    fl, K, wxyz, t = make_labeler(fused, scenes, spec, ids, pts)
+    depth, masks = build_frames(torch, engine, fl, spec, ids, keep_unpacked=True)
+    N, F, H, W = fl.N, fl.nframes, spec.height, spec.width
+    kt = engine.KernelTimer()
+    for _ in range(3):
+        fl.label()
+    fl.stats.zero_()
+    ms = timed(torch, lambda: fl.label(timer=kt), steps, warmup=0)
+    kms = float(np.mean(kt.ms()))
+    st = fl.stats_dict()
+    peak, _ = peaks()
+    balg = algorithmic_bytes(N, F, H, W, 2, C1)
+    out = {"workload": WORKLOADS[key][1], "points": N, "frames": F, "width": W, "height": H, "steps": steps, "ms_per_step": ms,
+           "value": float(N) * F / (ms * 1e-3), "unit": UNIT, "kernel_ms": kms, "algorithmic_bytes": balg,
+           "roofline_frac": balg / (kms * 1e-3) / 1e9 / peak, "call_frac": balg / (ms * 1e-3) / 1e9 / peak,
+           "candidates_per_step": st["candidates"] / steps, "votes_per_step": st["seen"] / steps}
+    votes, labels = fl.votes, fl.labels
+    props = bool(int(votes.sum()) * steps == st["seen"] and torch.equal(labels, engine.resolve_labels(votes, NCLASSES, THRESHOLD, None)))
+    if full_oracle:
+        from oracle import cpu_baseline as cb
+        d_np, m_np = depth.cpu().numpy(), masks.cpu().numpy()
+        cpu = cb.CpuFusion(pts, K, W, H, wxyz, t, d_np, m_np, RADIUS, 0.1, spec.zmax, spec.zmax, C1)
+        sec, cv, cl = cpu.run()
+        cpu.close()
+        same = bool(np.array_equal(votes.cpu().numpy(), cv) and np.array_equal(labels.cpu().numpy(), cl))
+        out.update({"parity": same and props, "parity_how": "CPU port on the WHOLE scene: votes [N,134] and labels compared cell for cell",
+                    "cpu_port_seconds": sec, "cpu_port_value": float(N) * F / sec, "cpu_port_cores": cpu.workers})
+    else:
+        res, _ = cpu_vs_gpu_sample(torch, engine, pts, K, spec, wxyz, t, lambda f: depth[f].cpu().numpy(), lambda f: masks[f].cpu().numpy(),
+                                   target_pv=1.6e7)
+        out.update({"parity": bool(res["gpu_matches_bit_exact"]) and props,
+                    "parity_how": "CPU port on a sample (" + res["sample"] + ") bit-exact + sum(votes) == votes cast + fused labels == "
+                                  "resolve(votes) at full size", "cpu_sample_value": res["value"], "cpu_sample_cores": res["cores"]})
+    del fl, depth, masks
+    torch.cuda.empty_cache()
+    return out
+
+
+def nested_c5(torch, mods, steps):
+    """C5: 200 k boxes through kernel (4): sweep broad phase + exact pair predicate, union-find closure."""
+    engine, scenes, _ = mods
+    from oracle import f3d_oracle as orc
+    lo, hi, group, area = scenes.make_boxes()
+    B = len(lo)
+    dlo, dhi, dg = engine.as_cuda(lo, torch.float64), engine.as_cuda(hi, torch.float64), engine.as_cuda(group, torch.int32)
+    edges = engine.box_pairs_aabb(dlo, dhi, dg)
+    E = int(edges.shape[0])
+    ms_pairs = timed(torch, lambda: engine.box_pairs_aabb(dlo, dhi, dg, cap=E + 1024), steps)
+    ms_brute = timed(torch, lambda: engine.box_pairs_aabb(dlo, dhi, dg, cap=E + 1024, brute_force=True), max(1, steps // 4))
+    labels = engine.union_find(B, edges)
+    ms_uf = timed(torch, lambda: engine.union_find(B, edges), steps)
+    t0 = time.perf_counter()
+    oe = orc.box_pairs_aabb(lo, hi, group)
+    ol = orc.union_find_labels(B, oe)
+    cpu_s = time.perf_counter() - t0
+    ge = np.unique(np.sort(edges.cpu().numpy().astype(np.int64), axis=1), axis=0)
+    same = bool(np.array_equal(ge, oe) and np.array_equal(labels.cpu().numpy().astype(np.int64), ol))
+    peak, _ = peaks()
+    balg = 24 * 2 * B + 4 * B + 8 * E    # lo + hi (2 x 24 B per box), group, edges written
+    return {"workload": "configs[4] instance merge stress: 200k boxes, closed-interval AABB pairs + union-find", "boxes": B, "edges": E,
+            "components": int(len(np.unique(ol))), "pairs_ms": ms_pairs, "pairs_ms_brute_force_kernel": ms_brute, "union_find_ms": ms_uf,
+            "ms_per_step": ms_pairs + ms_uf, "value": B / ((ms_pairs + ms_uf) * 1e-3), "unit": "boxes/s", "algorithmic_bytes": balg,
+            "roofline_frac": balg / ((ms_pairs + ms_uf) * 1e-3) / 1e9 / peak,
+            "roofline_note": "24*B+4*B+8*E bytes (SURVEY 8(d)) over pairs + union-find time; the sweep is latency / compare bound, not HBM bound",
+            "parity": same, "parity_how": "edge set and component labels equal the CPU restatement (sort-and-sweep + union-find) on all boxes",
+            "cpu_seconds": cpu_s}
+
+
+def micro_lines(torch, mods, fl, depth, masks, steps):
+    """Kernels (2), (3) and level V standalone on the resident C2 scene, each with its own HBM roofline."""
+    engine, scenes, _ = mods
+    peak, _ = peaks()
+    N, F, H, W = fl.N, fl.nframes, fl.H, fl.W
+    out = {}
+    # kernel (3): label resolve, 4*C1 + 8 bytes per point
+    lab = torch.empty(N, dtype=torch.int64, device="cuda")
+    ms = timed(torch, lambda: engine.resolve_labels(fl.votes, NCLASSES, THRESHOLD, None, out=lab), steps)
+    out["resolve_kernel"] = {"ms": ms, "bytes": (4 * C1 + 8) * N, "roofline_frac": (4 * C1 + 8) * N / (ms * 1e-3) / 1e9 / peak,
+                             "unit_bytes": "544 B/point", "parity": bool(torch.equal(lab, fl.labels))}
+    # kernel (2): z-buffer splat of 32 frames, 16*N + 4*H*W per frame
+    nf = min(32, F)
+    zbuf = torch.empty((nf, H * W), dtype=torch.int32, device="cuda")
+    dout = torch.empty((nf, H, W), dtype=torch.uint16, device="cuda")
+    ms = timed(torch, lambda: engine.zbuffer_splat(fl.points4, fl.table, border=10, frame_begin=0, frame_end=nf, zbuf=zbuf, out=dout), max(2, steps // 4))
+    b = nf * (16 * N + 4 * H * W)
+    out["zbuffer_splat"] = {"ms": ms, "frames": nf, "bytes": b, "roofline_frac": b / (ms * 1e-3) / 1e9 / peak,
+                            "unit_bytes": "16*N + 4*H*W per frame (SURVEY 8(d)); the point-stationary sweep reads the cloud once for all frames",
+                            "parity": bool(torch.equal(dout, depth[:nf]))}
+    del zbuf, dout
+    # level V: uv2pt + mask -> votes (VotingSegmentation.vote), 5*H*W bytes per frame
+    uv = engine.fuse_uv2pt(fl.points4, fl.table, fl.frames.slice(0, nf), RADIUS, fl.zmin, fl.zmax, frame_begin=0, frame_end=nf)
+    vp = torch.zeros((N, C1), dtype=torch.int32, device="cuda")
+    mflat = masks[:nf].reshape(nf, H * W)
+
+    def level_v():
+        vp.zero_()
+        engine.vote_uv2pt(vp, uv, mflat, 1)
+        engine.vote_finalize(vp)
+    ms = timed(torch, level_v, max(2, steps // 4))
+    ref = engine.fuse_project_vote(fl.points4, fl.table, fl.frames.slice(0, nf), None, C1, RADIUS, fl.zmin, fl.zmax, frame_begin=0, frame_end=nf)
+    # uv2pt keeps ONE point per pixel (the highest index): level V can only be compared on pixels whose winner voted
+    out["level_v_vote"] = {"ms": ms, "frames": nf, "bytes": nf * 5 * H * W, "roofline_frac": nf * 5 * H * W / (ms * 1e-3) / 1e9 / peak,
+                           "unit_bytes": "5*H*W per frame + touched vote sectors; includes the 5.4 GB memset of the vote tensor and one "
+                                         "launch per frame", "votes": int(vp.sum()), "votes_level_p_same_frames": int(ref.sum())}
+    del uv, vp, ref
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def run_single(args, torch, mods):
+    engine, scenes, fused = mods
+    wl = args.workload or "C2"
+    cfg_key, desc = WORKLOADS[wl]
+    spec = scenes.CONFIGS[cfg_key] if wl != "small" else scenes.scaled_spec("C1", 200_000, 8, 320, 240)
+    pts = scenes.make_cloud(spec)
+    ids = list(range(spec.nframes))
+    fl, K, wxyz, t = make_labeler(fused, scenes, spec, ids, pts)
+    depth, masks = build_frames(torch, engine, fl, spec, ids, keep_unpacked=True)
+    N, F, H, W = fl.N, fl.nframes, spec.height, spec.width
+
+    # ---- headline: resident packed frames, one fused launch per step
+    for _ in range(args.warmup):
+        labels = fl.label()
+    torch.cuda.synchronize()
+    fl.stats.zero_()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    kt = engine.KernelTimer()
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        labels = fl.label(timer=kt)
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    clocks = sampler.stop(t_wall0, t_wall1)
+    pv_step = float(N) * float(F)
+    st = fl.stats_dict()
+    per_step = {k: v / args.steps for k, v in st.items()}
+    launches = 4 * args.steps   # supertile_cull + fuse_kernel + fixup_apply_table + fixup_labels_summary per step
+    dev_labels = labels.cpu().numpy()
+
+    kms = float(np.mean(kt.ms()))
+    balg = algorithmic_bytes(N, F, H, W, 2, C1)
+    peak, how = peaks()
+    roof = {"bound": "hbm", "achieved": balg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": balg / (kms * 1e-3) / 1e9 / peak,
+            "traffic": None,
+            "kernel": "fuse_kernel<VOTE,U32_T16,HB1> (warp-box cull + project + z-test + packed-texel gather + vote + dense vote write + fused "
+                      "label resolve)", "kernel_ms": kms, "kernel_launches_timed": int(len(kt.pairs)),
+            "call_ms": ms_step, "call_frac": balg / (ms_step * 1e-3) / 1e9 / peak,
+            "call": "f3d_fuse_project_vote_resolve = supertile_cull + fuse_kernel + fixup_apply_table + fixup_labels_summary",
+            "algorithmic_bytes": balg, "algorithmic_bytes_formula": "16*N + F*H*W*(1+2) + 64*F + 4*N*134 (SURVEY 8(d), s_d = 2: uint16 depth + "
+            "uint8 mask; the packed texel the kernel actually reads is 4 B/pixel, i.e. the figure is conservative)",
+            "peak_source": how, "bytes_per_point_view": balg / pv_step}
+    prof = profile_figures(wl)
+    if prof:
+        roof["traffic"] = float(prof["dram_bytes_per_launch"])
+        roof["fp32_pipe_pct"] = prof.get("fp32_pipe_pct")
+        roof["dram_frac"] = float(prof["dram_bytes_per_launch"]) / (kms * 1e-3) / 1e9 / peak
+        roof["profile"] = prof.get("source")
+
+    # ---- the same step on the two-array inputs and with the re-pack inside the step
+    alt = {}
+    n_alt = max(3, args.steps // 5)
+    v2 = torch.empty_like(fl.votes)
+    l2 = torch.empty_like(fl.labels)
+    kt2 = engine.KernelTimer()
+    ms2 = timed(torch, lambda: engine.fuse_project_vote_resolve(fl.points4, fl.table, depth, masks, C1, NCLASSES, RADIUS, fl.zmin, fl.zmax,
+                                                                THRESHOLD, None, votes=v2, labels=l2, timer=kt2), n_alt)
+    same2 = bool(torch.equal(v2, fl.votes) and torch.equal(l2, fl.labels))
+    alt["two_array_inputs"] = {"ms_per_step": ms2, "value": pv_step / (ms2 * 1e-3), "kernel_ms": float(np.mean(kt2.ms()[1:])),
+                               "roofline_frac": balg / (float(np.mean(kt2.ms()[1:])) * 1e-3) / 1e9 / peak, "same_result": same2,
+                               "what": "uint16 depth [F,H,W] + uint8 mask [F,H,W] stacks gathered separately (round-1 layout)"}
+    del v2, l2
+
+    def repack_step():
+        fl.pack(depth, masks)
+        fl.label()
+    ms3 = timed(torch, repack_step, n_alt)
+    alt["with_repack_in_step"] = {"ms_per_step": ms3, "value": pv_step / (ms3 * 1e-3),
+                                  "what": "f3d_pack_frames of all frames (reads 3, writes 4 B/pixel) + the fused launch, every step"}
+
+    # ---- end to end through the public API: pinned host buffers in, host labels out (persistent labeler: no allocation in the step)
+    e2e = None
+    if not args.no_e2e:
+        h_depth = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True)
+        h_masks = torch.empty(masks.shape, dtype=masks.dtype, pin_memory=True)
+        h_depth.copy_(depth)
+        h_masks.copy_(masks)
+        h_pts = torch.as_tensor(np.ascontiguousarray(fl.points4.cpu().numpy())).pin_memory()
+        torch.cuda.synchronize()
+        n_e2e = max(2, min(args.steps, 5))
+        out = None
+        for i in range(1 + n_e2e):
+            if i == 1:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            out, _ = fused.fuse_labels_from_host(h_pts, K, W, H, wxyz, t, h_depth, h_masks, (0.1, spec.zmax), RADIUS, NCLASSES, THRESHOLD,
+                                                 None, chunk_frames=64, labeler=fl)
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / n_e2e
+        assert np.array_equal(out, dev_labels), "end-to-end labels differ from the device-resident run"
+        h2d = int(h_pts.numel() * 4 + h_depth.numel() * 2 + h_masks.numel())
+        e2e = {"value": pv_step / sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(N * 8),
+               "ms_per_step": sec * 1e3, "steps": n_e2e, "h2d_gb_per_s": h2d / sec / 1e9, "labels_match_device_run": True,
+               "api": "fused.fuse_labels_from_host(labeler=persistent): pinned host cloud + uint16 depth + uint8 masks -> device in 64-frame "
+                      "chunks on a copy stream, packed on the fly, one fused launch, labels -> pinned host"}
+        launches_e2e = (F + 63) // 64 + 4
+        e2e["gpu_launches_per_step"] = launches_e2e
+        del h_depth, h_masks
+
+    # ---- CPU baseline: the numpy port of the reference path on this box's host cores (bounded sample), both figures
+    cpu_b = None
+    if not args.no_cpu_baseline:
+        cpu_b, _ = cpu_vs_gpu_sample(torch, engine, pts, K, spec, wxyz, t, lambda f: depth[f].cpu().numpy(), lambda f: masks[f].cpu().numpy())
+
+    # ---- the other BASELINE configs and kernels, nested in the same line (bounded: skipped with a note past the time budget)
+    configs = {}
+    want = [c for c in (args.configs.split(",") if args.configs else []) if c]
+    nsteps = max(3, args.steps // 5)
+    if wl == "C2" and "micro" in want:
+        try:
+            configs["micro"] = micro_lines(torch, mods, fl, depth, masks, nsteps)
+        except Exception as ex:   # noqa: BLE001
+            configs["micro"] = {"error": repr(ex)}
+    del depth, masks
+    fl.frames = None
+    fl.votes = None
+    torch.cuda.empty_cache()
+    for key in want:
+        if key == "micro" or key == wl:
+            continue
+        if time.time() - T_START > args.budget_s:
+            configs[key] = {"skipped": f"time budget of {args.budget_s} s for the whole bench.py run reached"}
+            continue
+        try:
+            if key == "C5":
+                configs[key] = nested_c5(torch, mods, nsteps)
+            elif key in ("C1", "C4"):
+                configs[key] = nested_fused_config(torch, mods, key, nsteps, full_oracle=(key == "C1"))
+            else:
+                configs[key] = {"skipped": "C3 is the multi-GPU workload: run bench.py --gpus N (N > 1)" if key == "C3" else "unknown config"}
+        except Exception as ex:   # noqa: BLE001
+            configs[key] = {"error": repr(ex)}
+
+    line = {
+        "metric": METRIC, "value": pv_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+        "data": "synthetic",
+        "config": {"workload": desc, "points": N, "frames": F, "width": W, "height": H, "nclasses": NCLASSES,
+                   "frames_layout": "resident in HBM as packed uint32 texels (uint16 depth mm | class << 16, 16x16 tiles) produced by the "
+                                    "ingest path's f3d_pack_frames; on-disk contract unchanged", "radius": RADIUS,
+                   "cache": "inputs larger than L2 (packed frames + votes = %.1f GB per step)" % ((F * H * W * 4 + 4 * N * C1) / 1e9),
+                   "parallelism": "single GPU"},
+        "roofline": roof, "cpu_baseline": cpu_b, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "per_step_counts": per_step, "alternatives": alt, "configs": configs, "bench_seconds": time.time() - T_START,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank (and, through first touch, its pinned host buffers) to the CPU cores nearest to its GPU."""
+    info = {}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        info = {"gpu_cpu_affinity": f"{min(cpus)}-{max(cpus)}" if cpus else None, "bound_cores": len(allowed)}
+        try:
+            info["numa_node"] = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:   # noqa: BLE001
+            pass
+    except Exception as ex:   # noqa: BLE001
+        info = {"error": repr(ex)}
+    return info
+
+
+def run_multi(args, torch, mods, rank, world, local_rank):
+    import torch.distributed as dist
+    engine, scenes, fused = mods
+    parallel = importlib.import_module(PKG_NAME + ".parallel")
+    numa = bind_to_gpu_numa(local_rank)
+    parallel.init_process_group(local_rank)
+    wl = args.workload or "C3"
+    cfg_key, desc = WORKLOADS[wl]
+    base = scenes.CONFIGS[cfg_key] if wl != "small" else scenes.scaled_spec("C1", 200_000, 16, 320, 240)
+    strong = wl in ("C3", "small") or args.scaling == "strong"
+    if args.points:
+        base = scenes.scaled_spec(cfg_key, npoints=args.points, nframes=args.frames or base.nframes, width=base.width, height=base.height)
+    spec = base if strong else scenes.scaled_spec(cfg_key, npoints=base.npoints, nframes=base.nframes * world, width=base.width, height=base.height)
+    F_total, H, W = spec.nframes, spec.height, spec.width
+
+    # the cloud: generated once (rank 0), broadcast over NCCL
+    N = spec.npoints
+    p4 = torch.empty((N, 4), dtype=torch.float32, device="cuda")
+    pts = None
+    if rank == 0:
+        pts = scenes.make_cloud(spec)
+        p4[:, :3] = torch.as_tensor(pts).cuda()
+        p4[:, 3] = 0
+    dist.broadcast(p4, 0)
+    torch.cuda.synchronize()
+
+    xchg = parallel.VoteExchange(N, C1, torch.device("cuda", local_rank))
+    stats_total = {}
+
+    def run_shard(mode, steps, warmup):
+        ids = parallel.frame_shard_ids(F_total, rank, world, mode)
+        fl, K, wxyz, t = make_labeler(fused, scenes, spec, ids, p4)
+        build_frames(torch, engine, fl, spec, ids)
+        kt = engine.KernelTimer()
+
+        def step(timer=None):
+            def fuse(**xargs):
+                engine.fuse_project_vote_exchange(fl.points4, fl.table, fl.frames, None, C1, radius=RADIUS, zmin=fl.zmin, zmax=fl.zmax,
+                                                  stats=fl.stats, timer=timer, **xargs)
+            return xchg.run(fuse, NCLASSES, THRESHOLD, None, check="deferred")
+        for _ in range(warmup):
+            labels = step()
+        xchg.finish()
+        torch.cuda.synchronize()
+        fl.stats.zero_()
+        dist.barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        torch.cuda.synchronize()
+        t0w = time.time()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            labels = step(kt)
+        ev1.record()
+        torch.cuda.synchronize()
+        t1w = time.time()
+        xchg.finish()
+        ms_total = ev0.elapsed_time(ev1)
+        dist.barrier()
+        tt = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop(t0w, t1w) if sampler else None
+        st = fl.stats_dict()
+        return {"ms_per_step": float(tt.item()) / steps, "labels": labels.clone(), "fl": fl, "K": K, "wxyz": wxyz, "t": t, "ids": ids,
+                "kernel_ms": float(np.mean(kt.ms())), "clocks": clocks, "stats": {k: v / steps for k, v in st.items()}}
+
+    primary = run_shard(args.shard, args.steps, args.warmup)
+    pv_step = float(N) * float(F_total)
+    ms_step = primary["ms_per_step"]
+    fl = primary["fl"]
+    labels = primary["labels"]
+
+    # ---- parity (a): the N-rank labels against ONE GPU running the whole frame set (rank 0), labels only
+    parity = {}
+    if not args.no_verify:
+        ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        if rank == 0:
+            try:
+                ids_all = list(range(F_total))
+                fl1, _, _, _ = make_labeler(fused, scenes, spec, ids_all, p4)
+                build_frames(torch, engine, fl1, spec, ids_all)
+                t0 = time.perf_counter()
+                l1 = fl1.label(want_votes=False)
+                torch.cuda.synchronize()
+                parity["single_gpu_seconds_first_call"] = time.perf_counter() - t0
+                ms1 = timed(torch, lambda: fl1.label(want_votes=False), 2, warmup=0)
+                parity["single_gpu_labels_only_ms"] = ms1
+                same = bool(torch.equal(l1, labels))
+                parity["multi_gpu_matches_single_gpu"] = same
+                parity["single_gpu_how"] = (f"rank 0 renders all {F_total} frames and runs f3d_fuse_project_vote_resolve (labels only) on its "
+                                            f"one GPU; the {world}-rank labels [N] must be identical")
+                ok[0] = 1 if same else 0
+                del fl1, l1
+                torch.cuda.empty_cache()
+            except Exception as ex:   # noqa: BLE001
+                parity["single_gpu_error"] = repr(ex)
+        # ---- parity (b): a CPU-sized sample through the SAME N-rank exchange path against the numpy port
+        try:
+            sub_n = min(N, 750_000)
+            stride = max(1, N // sub_n)
+            fidx = np.unique(np.linspace(0, F_total - 1, min(F_total, 64)).astype(int))
+            sub4 = fl.points4[::stride][:sub_n].contiguous()
+            sN = int(sub4.shape[0])
+            mine = [int(f) for i, f in enumerate(fidx) if i % world == rank]
+            spec_s = scenes.scaled_spec(cfg_key, npoints=sN, nframes=spec.nframes, width=W, height=H)
+            flr, Kr, wxyz_r, t_r = make_labeler(fused, scenes, spec, mine if mine else [int(fidx[0])], p4)   # full cloud: depth of the real scene
+            build_frames(torch, engine, flr, spec, mine if mine else [int(fidx[0])])
+            fls = fused.FusedLabeler(sub4, Kr, W, H, wxyz_r[mine if mine else [int(fidx[0])]], t_r[mine if mine else [int(fidx[0])]],
+                                     point_range=(0.1, spec.zmax), radius=RADIUS, nclasses=NCLASSES)
+            xs = parallel.VoteExchange(sN, C1, torch.device("cuda", local_rank))
+            nfr = len(mine)
+
+            def fuse_s(**xargs):
+                engine.fuse_project_vote_exchange(fls.points4, fls.table, flr.frames.slice(0, max(nfr, 1)), None, C1, radius=RADIUS, zmin=fls.zmin,
+                                                  zmax=fls.zmax, frame_begin=0, frame_end=nfr, **xargs)
+            ls = xs.run(fuse_s, NCLASSES, THRESHOLD, None)
+            shard_votes = xs.shard[:xs.rows].clone()
+            gathered = [torch.empty((xs.per, C1), dtype=torch.int32, device="cuda") for _ in range(world)]
+            pad = torch.zeros((xs.per, C1), dtype=torch.int32, device="cuda")
+            pad[:xs.rows] = shard_votes
+            dist.all_gather(gathered, pad)
+            if rank == 0:
+                from oracle import cpu_baseline as cb
+                # depth / masks of the sample frames come from the ranks' own packed stacks: re-render them here for the CPU side
+                fla, _, wq_all, t_all = make_labeler(fused, scenes, spec, [int(f) for f in fidx], p4)
+                d_all, m_all = build_frames(torch, engine, fla, spec, [int(f) for f in fidx], keep_unpacked=True)
+                res, cv, cl, _ = cb.measure(sub4[:, :3].cpu().numpy(), Kr, W, H, wq_all[fidx], t_all[fidx], d_all.cpu().numpy(), m_all.cpu().numpy(),
+                                            RADIUS, 0.1, spec.zmax, spec.zmax, C1)
+                gv = torch.cat(gathered)[:sN].cpu().numpy()
+                same = bool(np.array_equal(gv, cv) and np.array_equal(ls.cpu().numpy(), cl))
+                parity["multi_gpu_matches_cpu_bit_exact"] = same
+                parity["cpu_sample"] = f"every {stride}th point ({sN}) x {len(fidx)} evenly spaced frames dealt to the {world} ranks, votes + labels"
+                parity["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "seconds": res["seconds"],
+                                          "single_process": res["single_process"], "host_cores_available": res["host_cores_available"]}
+                if not same:
+                    ok[0] = 0
+                del fla, d_all, m_all
+            del xs, flr, fls
+            torch.cuda.empty_cache()
+        except Exception as ex:   # noqa: BLE001
+            parity["cpu_sample_error"] = repr(ex)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity["multi_gpu_matches_bit_exact"] = bool(int(ok.item())) and "single_gpu_error" not in parity and "cpu_sample_error" not in parity
+
+    # ---- the other sharding (a real scan arrives contiguous)
+    other = None
+    if not args.no_other_shard:
+        other_mode = "contiguous" if args.shard == "interleaved" else "interleaved"
+        del primary["fl"]
+        fl_frames_bytes = None
+        fl.frames = None
+        torch.cuda.empty_cache()
+        sec = run_shard(other_mode, max(3, args.steps // 4), 2)
+        other = {"shard": other_mode, "ms_per_step": sec["ms_per_step"], "value": pv_step / (sec["ms_per_step"] * 1e-3),
+                 "kernel_ms_rank0": sec["kernel_ms"], "labels_equal_primary": bool(torch.equal(sec["labels"], labels))}
+        fl = sec["fl"]
+
+    # ---- end to end: every rank copies ITS frames from pinned host memory, packs, runs the exchange step, labels land on the host
+    e2e = None
+    if not args.no_e2e:
+        ok = 1
+        try:
+            ids = other and parallel.frame_shard_ids(F_total, rank, world, other["shard"]) or primary["ids"]
+            dd, mm = build_frames(torch, engine, fl, spec, ids, keep_unpacked=True)
+            h_depth = torch.empty(dd.shape, dtype=dd.dtype, pin_memory=True)
+            h_masks = torch.empty(mm.shape, dtype=mm.dtype, pin_memory=True)
+            h_depth.copy_(dd)
+            h_masks.copy_(mm)
+            del dd, mm
+            h_out = torch.empty(N, dtype=torch.int64, pin_memory=True)
+        except Exception as ex:   # noqa: BLE001
+            ok = 0
+            print(f"bench.py: rank {rank}: no pinned host memory for the end-to-end arm ({ex})", file=sys.stderr)
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()):
+            def fuse_e(**xargs):
+                engine.fuse_project_vote_exchange(fl.points4, fl.table, fl.frames, None, C1, radius=RADIUS, zmin=fl.zmin, zmax=fl.zmax, **xargs)
+            n_e2e = max(2, min(args.steps, 4))
+            torch.cuda.synchronize()
+            dist.barrier()
+            for i in range(1 + n_e2e):
+                if i == 1:
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    t0 = time.perf_counter()
+                fl.ingest(h_depth, h_masks, 64)
+                lab = xchg.run(fuse_e, NCLASSES, THRESHOLD, None, check="deferred")
+                h_out.copy_(lab, non_blocking=True)
+            torch.cuda.synchronize()
+            xchg.finish()
+            dist.barrier()
+            sec = (time.perf_counter() - t0) / n_e2e
+            tt = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sec = float(tt.item())
+            same = bool(torch.equal(torch.as_tensor(h_out.numpy()).cuda(), labels))
+            h2d = int(h_depth.numel() * 2 + h_masks.numel())
+            tot = torch.tensor([h2d], device="cuda", dtype=torch.int64)
+            dist.all_reduce(tot)
+            e2e = {"value": pv_step / sec, "unit": UNIT, "h2d_bytes_per_step": int(tot.item()), "d2h_bytes_per_step": int(N * 8) * world,
+                   "ms_per_step": sec * 1e3, "steps": n_e2e, "labels_match_device_run": same, "h2d_gb_per_s_per_rank": h2d / sec / 1e9,
+                   "api": "per rank: pinned host uint16 depth + uint8 masks of its frames -> FusedLabeler.ingest (copy stream + pack) -> "
+                          "parallel.VoteExchange.run -> labels -> pinned host"}
+            del h_depth, h_masks
+
+    if rank == 0:
+        peak, how = peaks()
+        kms = primary["kernel_ms"]
+        Fr = len(primary["ids"])
+        balg = algorithmic_bytes(N, Fr, H, W, 2, C1, rows=xchg.rows)
+        roof = {"bound": "hbm", "achieved": balg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": balg / (kms * 1e-3) / 1e9 / peak,
+                "traffic": None, "kernel": "fuse_kernel<VOTE,U32_T16,HB1> in exchange mode on rank 0 (sweep + slot records written to the owners); "
+                "the dense shard write happens in slot_merge_kernel", "kernel_ms": kms, "algorithmic_bytes": balg, "peak_source": how,
+                "note": "per-rank bytes: cloud + this rank's frames + this rank's shard of the vote tensor"}
+        line = {
+            "metric": METRIC, "value": pv_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": desc, "points": N, "frames_total": F_total, "frames_per_gpu": len(primary["ids"]), "width": W, "height": H,
+                       "nclasses": NCLASSES, "radius": RADIUS, "shard": args.shard,
+                       "frames_layout": "packed uint32 texels resident in HBM (see N = 1)",
+                       "cache": "inputs larger than L2 (packed frames per GPU %.1f GB + exchange buffers)" % (len(primary["ids"]) * H * W * 4 / 1e9),
+                       "parallelism": f"frames sharded over {world} GPUs ({args.shard}); cloud replicated; vote exchange fused into the kernel: "
+                                      "slot records written into the owner rank's memory over NVLink (symmetric memory), owner-side merge into "
+                                      "the dense int32 shard + label resolve, all-gather of int16 labels over NCCL"},
+            "roofline": roof, "cpu_baseline": parity.get("cpu_baseline"), "e2e": e2e, "gpu_launches": 7 * args.steps, "clocks": primary["clocks"],
+            "per_step_counts_rank0": primary["stats"], "parity": parity, "other_shard": other, "numa": numa,
+            "bench_seconds": time.time() - T_START,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--chunks", type=int, default=4, help="point chunks of the multi-GPU pipeline")
-    ap.add_argument("--exchange", default="records", choices=["records", "dense"],
-                    help="multi-GPU vote exchange: slot records written by the fused kernel into the owner's memory over "
-                         "NVLink (default), or dense packed-uint16 reduce-scatter through NCCL")
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="default: C2 on one GPU, C3 on several")
+    ap.add_argument("--configs", default="micro,C1,C5,C4", help="N = 1: other BASELINE configs / kernels nested in the line")
+    ap.add_argument("--budget-s", type=float, default=420.0, help="nested configs are skipped once the run is this old")
     ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
-                    help="how the frames of the N-GPU job are dealt to the ranks (same results either way)")
+                    help="how the frames of the N-GPU job are dealt to the ranks (same results either way; the other one is timed too)")
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"], help="N > 1 with --workload C2: weak = N x 500 frames")
+    ap.add_argument("--points", type=int, default=None, help="N > 1: override the cloud size (experiments)")
+    ap.add_argument("--frames", type=int, default=None, help="N > 1: override the total frame count (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the single-GPU / CPU parity runs")
+    ap.add_argument("--no-other-shard", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,11 +829,10 @@ def main():
         args.warmup = 1 if args.warmup is None else args.warmup
         run_reference_arm(args, rank, world)
         return
-    args.steps = 100 if args.steps is None else args.steps   # 0.25 s timed at C2: enough for several clock samples
+    args.steps = (100 if world == 1 else 20) if args.steps is None else args.steps
     args.warmup = 3 if args.warmup is None else max(args.warmup, 3)
 
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -219,259 +840,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     pkg = importlib.import_module(PKG_NAME)
     pkg.load()
-    engine = importlib.import_module(PKG_NAME + ".engine")
-    scenes = importlib.import_module(PKG_NAME + ".scenes")
-    fused = importlib.import_module(PKG_NAME + ".fused")
-    parallel = importlib.import_module(PKG_NAME + ".parallel")
-    if world > 1:
-        parallel.init_process_group(local_rank)
-
-    cfg_key, desc = WORKLOADS[args.workload]
-    base = scenes.CONFIGS[cfg_key] if args.workload != "small" else scenes.scaled_spec("C1", 200_000, 8, 320, 240)
-    fpg = base.nframes                                   # frames per GPU (weak scaling in frames)
-    spec = scenes.scaled_spec(cfg_key, npoints=base.npoints, nframes=fpg * world, width=base.width, height=base.height)
-    fl, pts, K, wxyz, t, depth, masks = build_scene(scenes, engine, fused, spec, 0, 0, torch,
-                                                    frame_ids=parallel.frame_shard_ids(spec.nframes, rank, world, args.shard))
-    N, F, H, W, C1 = fl.N, fl.table.F, spec.height, spec.width, NCLASSES + 1
-    stats = fl.stats
-
-    labels_buf = torch.empty(N, dtype=torch.int64, device="cuda")
-    ktimer = None   # engine.KernelTimer during the timed region: CUDA events around the fused kernel alone
-
-    def step_single():
-        # one launch: kernel (1) with the label resolve (kernel 3's arithmetic) fused into its epilogue
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        votes, labels = engine.fuse_project_vote_resolve(fl.points4, fl.table, depth, masks, C1, NCLASSES, RADIUS, fl.zmin,
-                                                         fl.zmax, THRESHOLD, None, votes=fl.votes, labels=labels_buf,
-                                                         stats=stats, timer=ktimer)
-        e1.record()
-        fl.votes = votes
-        return labels, (e0, e1), 4   # supertile_cull + fuse_kernel + fixup_apply + fixup_labels
-
-    pipe = xchg = None
-    if world > 1 and args.exchange == "dense":
-        pipe = parallel.ShardedPipeline(N, C1, args.chunks, torch.device("cuda", local_rank))
-    elif world > 1:
-        # the record exchange needs peer-mapped symmetric memory (NVLink / NVSwitch P2P); every rank must take the same
-        # path, so a failure anywhere falls back to the NCCL reduce-scatter pipeline everywhere
-        err = None
-        try:
-            xchg = parallel.VoteExchange(N, C1, torch.device("cuda", local_rank))
-        except Exception as ex:   # noqa: BLE001
-            err = ex
-        bad = torch.tensor([1 if err is not None else 0], device="cuda")
-        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-        if int(bad.item()):
-            if rank == 0:
-                print(f"bench.py: symmetric-memory vote exchange unavailable ({err}); using the NCCL reduce-scatter pipeline", file=sys.stderr)
-            xchg = None
-            args.exchange = "dense"
-            pipe = parallel.ShardedPipeline(N, C1, args.chunks, torch.device("cuda", local_rank))
-
-    def step_records():
-        def fuse(**xargs):
-            engine.fuse_project_vote_exchange(fl.points4, fl.table, depth, masks, C1, radius=RADIUS, zmin=fl.zmin, zmax=fl.zmax,
-                                              stats=stats, timer=ktimer, **xargs)
-
-        labels = xchg.run(fuse, NCLASSES, THRESHOLD, None)
-        return labels, None, 7   # supertile_cull, fuse_kernel, fixup_apply, publish, slot_merge, queue_accumulate, queue_relabel
-
-    def step_multi():
-        launches = [0]
-
-        def fuse_into(a, b, out):
-            launches[0] += 3   # supertile_cull + fuse_kernel + fixup_apply
-            engine.fuse_project_vote(fl.points4[a:b], fl.table, depth, masks, C1, RADIUS, fl.zmin, fl.zmax, votes=out[:b - a],
-                                     stats=stats)
-
-        def resolve(v, out):
-            launches[0] += 1
-            engine.resolve_labels(v, NCLASSES, THRESHOLD, None, out=out)
-
-        labels = pipe.run(fuse_into, resolve)
-        return labels, None, launches[0]
-
-    step = step_single if world == 1 else (step_multi if pipe is not None else step_records)
-    for _ in range(args.warmup):
-        labels, _, _ = step()
-    torch.cuda.synchronize()
-    stats.zero_()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    torch.cuda.synchronize()
-    t_wall0 = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_events, launches = [], 0
-    ktimer = engine.KernelTimer()
-    ev0.record()
-    for _ in range(args.steps):
-        labels, kev, nl = step()
-        launches += nl
-        if kev:
-            kernel_events.append(kev)
-    ev1.record()
-    torch.cuda.synchronize()
-    t_wall1 = time.time()
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        dist.barrier()
-        tt = torch.tensor([ms_total], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total = float(tt.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    ms_step = ms_total / args.steps
-    pv_step = float(N) * float(F) * world
-    value = pv_step / (ms_step * 1e-3)
-    st = engine.stats_dict(stats)
-    per_step = {k: v / args.steps for k, v in st.items()}
-
-    roof = None
-    if kernel_events:
-        call_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))   # whole C-ABI call (4 kernels)
-        kt = ktimer.ms()
-        kms = float(np.mean(kt)) if len(kt) else call_ms
-        balg = algorithmic_bytes(N, F, H, W, 2, C1)
-        peak, how = peaks()
-        ach = balg / (kms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "kernel": "fuse_kernel<VOTE,U16MM,HB1> (cull level 2 + project + z-test + gather + vote + dense vote write + "
-                          "fused label resolve)", "kernel_ms": kms, "kernel_launches_timed": int(len(kt)),
-                "call_ms": call_ms, "call_frac": balg / (call_ms * 1e-3) / 1e9 / peak,
-                "call": "f3d_fuse_project_vote_resolve = supertile_cull + fuse_kernel + fixup_apply + fixup_labels",
-                "algorithmic_bytes": balg, "peak_source": how, "bytes_per_point_view": balg / (float(N) * float(F))}
-        tj = ROOT / "profiles" / "fuse_kernel_traffic.json"
-        if tj.exists() and args.workload == "C2":
-            try:
-                roof["traffic"] = float(json.loads(tj.read_text())["dram_bytes_per_launch"])
-            except Exception:
-                pass
-
-    if roof is None and xchg is not None:
-        kt = ktimer.ms()
-        if len(kt):
-            kms = float(np.mean(kt))
-            balg = 16 * N + F * H * W * 3 + 64 * F + 4 * xchg.rows * C1    # per rank: the dense vote write is this rank's shard
-            peak, how = peaks()
-            roof = {"bound": "hbm", "achieved": balg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": balg / (kms * 1e-3) / 1e9 / peak, "traffic": None,
-                    "kernel": "fuse_kernel<VOTE,U16MM,HB1> in exchange mode on rank 0 (sweep + slot records written to the owners); "
-                              "the dense shard write happens in slot_merge_kernel", "kernel_ms": kms,
-                    "kernel_launches_timed": int(len(kt)), "algorithmic_bytes": balg, "peak_source": how,
-                    "note": "per-rank bytes: cloud + this rank's frames + this rank's shard of the vote tensor"}
-
-    # ---- end to end through the public API: host (pinned) buffers in, host labels out ------------------------------------
-    e2e = None
-    if not args.no_e2e and world > 1:
-        # every rank copies its frames from pinned host memory, the exchange step runs, labels land on the host.  The
-        # pinned allocation (4 GB per rank) is the only step that can fail on one rank alone: agree on it first.
-        ok = 1
-        try:
-            h_depth = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True)
-            h_masks = torch.empty(masks.shape, dtype=masks.dtype, pin_memory=True)
-            h_depth.copy_(depth)
-            h_masks.copy_(masks)
-            h_pts = torch.as_tensor(np.ascontiguousarray(fl.points4.cpu().numpy())).pin_memory()
-            h_out = torch.empty(N, dtype=torch.int64, pin_memory=True)
-        except Exception as ex:   # noqa: BLE001
-            ok = 0
-            print(f"bench.py: rank {rank}: no pinned host memory for the end-to-end arm ({ex})", file=sys.stderr)
-        flag = torch.tensor([ok], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()):
-            ref_labels = labels.clone()
-            n_e2e = max(2, min(args.steps, 5))
-            torch.cuda.synchronize()
-            dist.barrier()
-            for i in range(1 + n_e2e):
-                if i == 1:
-                    torch.cuda.synchronize()
-                    dist.barrier()
-                    t0 = time.perf_counter()
-                fl.points4.copy_(h_pts, non_blocking=True)
-                depth.copy_(h_depth, non_blocking=True)
-                masks.copy_(h_masks, non_blocking=True)
-                lab = step()[0]
-                h_out.copy_(lab, non_blocking=True)
-            torch.cuda.synchronize()
-            dist.barrier()
-            sec = (time.perf_counter() - t0) / n_e2e
-            tt = torch.tensor([sec], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            sec = float(tt.item())
-            same = bool(torch.equal(torch.as_tensor(h_out.numpy()).cuda(), ref_labels))
-            h2d = int(h_pts.numel() * 4 + h_depth.numel() * 2 + h_masks.numel())
-            e2e = {"value": pv_step / sec, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(N * 8) * world,
-                   "ms_per_step": sec * 1e3, "steps": n_e2e, "labels_match_device_run": same,
-                   "api": "per rank: pinned host cloud + frames -> device, parallel.VoteExchange.run, labels -> pinned host"}
-            del h_depth, h_masks
-    if not args.no_e2e and world == 1:
-        h_depth = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True)
-        h_masks = torch.empty(masks.shape, dtype=masks.dtype, pin_memory=True)
-        h_depth.copy_(depth)
-        h_masks.copy_(masks)
-        h_pts = torch.as_tensor(pts).pin_memory()
-        dev_labels = labels.cpu().numpy()
-        del fl.votes
-        fl.votes = None
-        torch.cuda.synchronize()
-        n_e2e = max(2, min(args.steps, 5))
-        out = None
-        for i in range(1 + n_e2e):
-            if i == 1:
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-            out, fl2 = fused.fuse_labels_from_host(h_pts, K, W, H, wxyz, t, h_depth, h_masks, (0.1, spec.zmax), RADIUS,
-                                                   NCLASSES, THRESHOLD, None)
-            del fl2
-        torch.cuda.synchronize()
-        sec = (time.perf_counter() - t0) / n_e2e
-        assert np.array_equal(out, dev_labels), "end-to-end labels differ from the device-resident run"
-        h2d = int(h_pts.numel() * 4 + h_depth.numel() * 2 + h_masks.numel() + len(t) * 7 * 8)
-        e2e = {"value": pv_step / sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(N * 8),
-               "ms_per_step": sec * 1e3, "steps": n_e2e,
-               "api": "fused.fuse_labels_from_host (pinned host frames streamed in 64-frame chunks)"}
-        del h_depth, h_masks
-
-    # ---- CPU baseline: the numpy port of the reference path on this box's host cores (bounded sample) ------------------
-    cpu_b = None
-    if not args.no_cpu_baseline and world == 1 and rank == 0:
-        from oracle import cpu_baseline as cb
-        sub, wq, tq, d, m, sdesc = cpu_sample(pts, K, spec, wxyz, t, depth, masks)
-        cpu = cb.CpuFusion(sub, K, W, H, wq, tq, d, m, RADIUS, 0.1, spec.zmax, spec.zmax, C1)
-        sec, cv, cl = cpu.run()
-        cpu.close()
-        # the same sample on the GPU must agree bit for bit (the oracle stays the checker, never the product)
-        tab = engine.FrameTable(K, W, H, wq, tq, spec.zmax)
-        gv = engine.fuse_project_vote(engine.pack_points(sub), tab, torch.as_tensor(d).cuda(), torch.as_tensor(m).cuda(), C1,
-                                      RADIUS, 0.1, spec.zmax)
-        gl = engine.resolve_labels(gv, NCLASSES, THRESHOLD, None)
-        ok = bool(np.array_equal(gv.cpu().numpy(), cv) and np.array_equal(gl.cpu().numpy(), cl))
-        cpu_b = {"value": len(sub) * len(tq) / sec, "unit": UNIT, "cores": cpu.workers, "kind": "port", "sample": sdesc,
-                 "seconds": sec, "host_cores_available": cpu.cores, "gpu_matches_bit_exact": ok}
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
-            "data": "synthetic",
-            "config": {"workload": desc, "points": N, "frames_per_gpu": F, "frames_total": F * world, "width": W, "height": H,
-                       "nclasses": NCLASSES, "depth": "uint16 mm", "radius": RADIUS, "cache": "inputs larger than L2 "
-                       "(depth+masks+votes = %.1f GB per GPU)" % ((F * H * W * 3 + 4 * N * C1) / 1e9),
-                       "parallelism": "single GPU" if world == 1 else f"frames sharded over {world} GPUs ({args.shard}), "
-                       + ("vote exchange fused into the kernel: slot records written into the owner's memory over NVLink, "
-                          "owner-side merge into the dense shard + labels, all-gather of labels" if args.exchange == "records" else
-                          f"{args.chunks}-chunk pipeline: fuse -> NCCL reduce-scatter of packed uint16 votes -> resolve -> "
-                          "all-gather")},
-            "roofline": roof, "cpu_baseline": cpu_b, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "per_step_counts": per_step,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        if xchg is not None:
-            xchg.check_overflow()
-        dist.destroy_process_group()
+    mods = (importlib.import_module(PKG_NAME + ".engine"), importlib.import_module(PKG_NAME + ".scenes"),
+            importlib.import_module(PKG_NAME + ".fused"))
+    if world == 1:
+        run_single(args, torch, mods)
+    else:
+        run_multi(args, torch, mods, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -46,3 +46,7 @@ def test_c2_full_size_properties(engine, scenes):
     votes_b, labels_b = engine.fuse_project_vote_resolve(fl.points4, fl.table, depth, masks, C1, 133, 0.05, 0.1, spec.zmax, 0.5,
                                                          None)
     assert torch.equal(votes_b, votes) and torch.equal(labels_b, labels)
+    del votes_b, labels_b
+    # the ingest path's packed device layout (one uint32 texel per pixel, 16x16 tiles) gives the same bytes
+    votes_p, labels_p = engine.fuse_project_vote_resolve(fl.points4, fl.table, fl.frames, None, C1, 133, 0.05, 0.1, spec.zmax, 0.5, None)
+    assert torch.equal(votes_p, votes) and torch.equal(labels_p, labels)

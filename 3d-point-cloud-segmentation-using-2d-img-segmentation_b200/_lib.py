@@ -52,6 +52,7 @@ SIGNATURES = {
     "f3d_resize_nearest_u8": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
     "f3d_resolve_labels": (C.c_int, [_vp, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp]),
     "f3d_project_pixels": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "f3d_quat_rotate": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "f3d_frustum_mask": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp, _vp]),
     "f3d_box_pairs_aabb": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "f3d_box_pairs_sweep": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),

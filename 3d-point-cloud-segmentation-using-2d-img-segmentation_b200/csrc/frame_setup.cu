@@ -181,6 +181,20 @@ __global__ void project_pixels_kernel(const double* __restrict__ pts, int64_t N,
     uv[N + i] = d2i_numpy(floor(xdiv(h.y, h.z)));
 }
 
+// ---- SpatQuadranion.rotate, whole array, fp64 (RTAB_utils/spatQuad.py:6-28) -------------------------------------
+struct QuatParam {
+    double q[4];
+};
+__global__ void quat_rotate_kernel(const double* __restrict__ pts, int64_t N, QuatParam qp, double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    D3 p = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    D3 r = dquat_rotate(qp.q, p);
+    out[3 * i] = r.x;
+    out[3 * i + 1] = r.y;
+    out[3 * i + 2] = r.z;
+}
+
 // ---- point_inside_polyhedra, whole array, fp64 (intersections.py:146-164) ----------------------------------
 #define F3D_MAX_PLANES 16
 struct PlaneParams {
@@ -257,6 +271,15 @@ extern "C" int f3d_project_pixels(const double* points, int64_t N, const double*
     unsigned blocks = (unsigned)((N + 255) / 256);
     project_pixels_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(points, N, pp, uv);
     return f3d_check_launch("f3d_project_pixels");
+}
+
+extern "C" int f3d_quat_rotate(const double* points, int64_t N, const double* h_wxyz, double* out, void* stream) {
+    if (!points || !h_wxyz || !out || N < 0) return f3d_fail(F3D_ERR_ARG, "f3d_quat_rotate: bad argument");
+    if (N == 0) return F3D_OK;
+    QuatParam qp;
+    for (int i = 0; i < 4; ++i) qp.q[i] = h_wxyz[i];
+    quat_rotate_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(points, N, qp, out);
+    return f3d_check_launch("f3d_quat_rotate");
 }
 
 extern "C" int f3d_frustum_mask(const double* points, int64_t N, const double* h_plane_points, const double* h_normals,

@@ -371,6 +371,14 @@ def project_pixels(points64, K, quat, translation):
     return uv
 
 
+def quat_rotate(points64, wxyz):
+    """`SpatQuadranion(wxyz).rotate(points)` (`RTAB_utils/spatQuad.py:6-28`) -> float64 [N,3] device tensor."""
+    p = as_cuda(points64, torch.float64)
+    out = torch.empty_like(p)
+    check(load().f3d_quat_rotate(ptr(p), p.shape[0], ptr(host_f64(wxyz, 4)), ptr(out), stream_ptr()), "f3d_quat_rotate")
+    return out
+
+
 def frustum_mask(points64, plane_points, normals):
     p = as_cuda(points64, torch.float64)
     N = p.shape[0]

@@ -365,10 +365,22 @@ def micro_lines(torch, mods, fl, depth, masks, steps):
     zbuf = torch.empty((nf, H * W), dtype=torch.int32, device="cuda")
     dout = torch.empty((nf, H, W), dtype=torch.uint16, device="cuda")
     ms = timed(torch, lambda: engine.zbuffer_splat(fl.points4, fl.table, border=10, frame_begin=0, frame_end=nf, zbuf=zbuf, out=dout), max(2, steps // 4))
-    b = nf * (16 * N + 4 * H * W)
+    b_survey = nf * (16 * N + 4 * H * W)
+    b = 16 * N + nf * H * W * (4 + 4 + 2)     # cloud once for all frames; z-buffer initialised (4) + finalised (4 read, 2 written) per pixel
+    views = engine.new_stats()
+    engine.zbuffer_splat(fl.points4, fl.table, border=0, frame_begin=0, frame_end=nf, zbuf=zbuf, out=dout, stats=views)
+    touched = int((dout.view(torch.int16) != 0).sum())
+    seen = engine.stats_dict(views)["seen"]
     out["zbuffer_splat"] = {"ms": ms, "frames": nf, "bytes": b, "roofline_frac": b / (ms * 1e-3) / 1e9 / peak,
-                            "unit_bytes": "16*N + 4*H*W per frame (SURVEY 8(d)); the point-stationary sweep reads the cloud once for all frames",
-                            "parity": bool(torch.equal(dout, depth[:nf]))}
+                            "unit_bytes": "16*N once (the point-stationary sweep reads the cloud once for all frames) + 10*H*W per frame "
+                                          "(uint32 z-buffer initialised, read back, uint16 depth written)",
+                            "survey_bytes_16N_plus_4HW_per_frame": b_survey, "parity": bool(torch.equal(engine.zbuffer_splat(
+                                fl.points4, fl.table, border=10, frame_begin=0, frame_end=nf, zbuf=zbuf, out=dout), depth[:nf])),
+                            "point_views_splatted": seen, "texels_touched": touched, "point_views_per_touched_texel": seen / max(touched, 1),
+                            "shared_memory_tile_variant": "not built: a shared-memory z-tile can only save global atomics when several point-views "
+                            "of a tile fall on the SAME pixel; here %.3f point-views per touched texel (1.3 mm pixels vs ~1 cm point spacing), so "
+                            "there is nothing for an on-chip tile to merge and the frame-tile-stationary variant would add a binning pass of "
+                            "16 B per point-view for no saved atomics" % (seen / max(touched, 1))}
     del zbuf, dout
     # level V: uv2pt + mask -> votes (VotingSegmentation.vote), 5*H*W bytes per frame
     uv = engine.fuse_uv2pt(fl.points4, fl.table, fl.frames.slice(0, nf), RADIUS, fl.zmin, fl.zmax, frame_begin=0, frame_end=nf)
@@ -376,15 +388,17 @@ def micro_lines(torch, mods, fl, depth, masks, steps):
     mflat = masks[:nf].reshape(nf, H * W)
 
     def level_v():
-        vp.zero_()
         engine.vote_uv2pt(vp, uv, mflat, 1)
-        engine.vote_finalize(vp)
-    ms = timed(torch, level_v, max(2, steps // 4))
+    vp.zero_()
+    ms = timed(torch, level_v, 1, warmup=0)          # tags must increase across calls: one timed pass over fresh counters
+    engine.vote_finalize(vp)
     ref = engine.fuse_project_vote(fl.points4, fl.table, fl.frames.slice(0, nf), None, C1, RADIUS, fl.zmin, fl.zmax, frame_begin=0, frame_end=nf)
-    # uv2pt keeps ONE point per pixel (the highest index): level V can only be compared on pixels whose winner voted
-    out["level_v_vote"] = {"ms": ms, "frames": nf, "bytes": nf * 5 * H * W, "roofline_frac": nf * 5 * H * W / (ms * 1e-3) / 1e9 / peak,
-                           "unit_bytes": "5*H*W per frame + touched vote sectors; includes the 5.4 GB memset of the vote tensor and one "
-                                         "launch per frame", "votes": int(vp.sum()), "votes_level_p_same_frames": int(ref.sum())}
+    # uv2pt keeps ONE point per pixel (the highest index), so level V casts at most the level-P votes of the same frames
+    out["level_v_vote"] = {"ms": ms, "frames": nf, "ms_per_frame": ms / nf, "bytes": nf * 5 * H * W,
+                           "roofline_frac": nf * 5 * H * W / (ms * 1e-3) / 1e9 / peak,
+                           "unit_bytes": "5*H*W per frame (int32 uv2pt + uint8 mask) + touched vote sectors; one launch per frame (the "
+                                         "per-frame de-dup epoch of votes[idx, cls] += 1, voting.py:98), memset / tag strip not included",
+                           "votes": int(vp.sum()), "votes_level_p_same_frames": int(ref.sum())}
     del uv, vp, ref
     return out
 

@@ -227,6 +227,10 @@ int f3d_resolve_labels_u16(const uint16_t* votes_u16, int64_t N, int32_t C1, dou
 int f3d_project_pixels(const double* points, int64_t N, const double* h_K9, const double* h_wxyz,
                        const double* h_t, int32_t* uv, void* stream);
 
+/* SpatQuadranion.rotate (RTAB_utils/spatQuad.py:6-28): raw Hamilton sandwich q p q* on the UN-normalised h_wxyz, fp64 in the
+ * reference's operation order.  points, out [N,3] float64 (may alias). */
+int f3d_quat_rotate(const double* points, int64_t N, const double* h_wxyz, double* out, void* stream);
+
 /* point_inside_polyhedra (Fusion3DSeg/intersections.py:146-164): inside [N] uint8. */
 int f3d_frustum_mask(const double* points, int64_t N, const double* h_plane_points, const double* h_normals,
                      int32_t nplanes, uint8_t* inside, void* stream);

@@ -70,9 +70,9 @@ def test_fused_packed_formats_match_oracle(engine, scenes, fmt, wh):
 
 
 def test_many_views_flush_paths_on_packed_frames(engine, scenes):
-    """600 frames looking at the same points: byte counters flush mid-sweep (several flushes per warp), cells pass 255."""
+    """900 frames looking at the same points: byte counters flush mid-sweep (several flushes per warp), cells pass 255."""
     s = small_scene(scenes, orc, npoints=3000, nframes=3, width=96, height=72, seed=2)
-    reps = 200
+    reps = 300
     wxyz, t = np.tile(s["wxyz"], (reps, 1)), np.tile(s["t"], (reps, 1))
     depths, masks = np.tile(s["depths"], (reps, 1, 1)), np.tile(s["masks"], (reps, 1, 1))
     ov1 = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0, 0.05, 0.1, 4.0, 4.0)
@@ -219,3 +219,15 @@ def test_vote_exchange_overflow_is_caught(engine, scenes):
             tiny.finish()
     finally:
         dist.destroy_process_group()
+
+
+def test_spatquadranion_rotate_matches_oracle(engine):
+    sq = importlib.import_module(PKG_NAME + ".RTAB_utils.spatQuad")
+    rng = np.random.default_rng(1)
+    p = rng.normal(size=(5000, 3)) * 3
+    for q in ([0.9, 0.1, -0.3, 0.2], ["0.707107", "0", "0.707107", "0"], [2.0, 0.0, 0.0, 0.0]):
+        Q = sq.SpatQuadranion(*q) if len(q) == 4 and isinstance(q[0], str) else sq.SpatQuadranion(q)
+        qa = np.asarray([float(v) for v in q])
+        assert np.array_equal(Q.rotate(p), orc.quat_rotate(qa, p))                   # un-normalised sandwich, bit for bit
+        assert np.array_equal(Q.inverse.elements, orc.quat_inverse(qa))
+        assert np.array_equal(Q.inverse.rotate(p), orc.quat_rotate(orc.quat_inverse(qa), p))

@@ -50,7 +50,9 @@
 #ifndef FUSE_MINB8
 #define FUSE_MINB8 (FUSE_BLOCK == 128 ? 5 : 2)   // 128-point tiles: 5 CTAs = 20 warps per SM at 96 registers (6 would need 80: spills)
 #endif
+#ifndef FUSE_ST_POINTS
 #define FUSE_ST_POINTS 4096                 // points per super-tile of the first cull level
+#endif
 #define FUSE_ST_TILES (FUSE_ST_POINTS / FUSE_BLOCK)
 #define FUSE_ST_LCAP 1024  // candidate frames a super-tile list holds
 #ifndef FUSE_QWARP
@@ -618,7 +620,6 @@ struct __align__(16) FuseShared {
     int nq[FUSE_NW];                           // per-warp deferred counts
     unsigned dirty[FUSE_NW];                   // rows another lane's deferred pass touched
     unsigned stat[8];                          // CTA totals of the statistics, flushed once at the end
-    int wfr[FUSE_NW][8];                       // frame ids of the warp's staged tiles (ring of FUSE_TR, -1 = none)
     int ncand;
     int pad[3];
 };
@@ -793,7 +794,6 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         unsigned wm = 0u;       // this warp's candidates of that block not yet taken
         float4* tiles = stage + warp * (FUSE_TR * 8);
         uint32_t* texr = texring + warp * (FUSE_GR * 32) + lane;
-        int* wfr = sh.wfr[warp];
         auto pop = [&]() -> int {   // next candidate frame of this warp, -1 = none (warp-uniform)
             while (wm == 0u && lbase + 32 < ncand) {
                 lbase += 32;
@@ -807,7 +807,6 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         };
         auto stage_tile = [&](int slot, int f) {   // lanes 0..7 copy the 8 x 16 bytes of the frame's projection tile
             if (f >= 0 && lane < 8) cp_async16(tiles + slot * 8 + lane, reinterpret_cast<const uint4*>(&frec[P.f_begin + f].fast) + lane);
-            if (lane == 0) wfr[slot] = f;
         };
         // depth validity + distance criterion + vote (or splat / uv2pt write) of one classified candidate
         auto consume = [&](const int frel, const float4* __restrict__ s, const uint32_t puv, const unsigned sg, const uint32_t g0,
@@ -868,22 +867,30 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             }
         };
 
-        if (lane < FUSE_TR) wfr[lane] = -1;
-        __syncwarp();
-        stage_tile(0, pop());
+        // frame ids of the candidates in the pipeline (warp-uniform registers): fa = candidate `it`, fb = `it + 1` (tile in
+        // flight), fp1 / fp2 = candidates `it - 1` / `it - 2` (texels in flight / landed); -1 = none
+        int fa = pop();
+        stage_tile(0, fa);
         cp_async_commit();
-        stage_tile(1, pop());
+        int fb = pop();
+        stage_tile(1, fb);
         cp_async_commit();
+        int fp1 = -1, fp2 = -1;
         uint32_t puv1 = 0, puv2 = 0;   // pixel of candidates i-1 / i-2
         unsigned sg1 = 0, sg2 = 0;     // their st | g_in << 3
 #pragma unroll 1
         for (int it = 0;; ++it) {
             cp_async_wait_but_one();   // every copy of this lane except the newest group: tile `it`, texel `it - 2` have landed
             __syncwarp();              // ... everybody else's too; every lane is done with iteration it - 1
-            const int f0 = wfr[it & (FUSE_TR - 1)];
-            const int f2 = PIPE ? wfr[(it + FUSE_TR - 2) & (FUSE_TR - 1)] : -1;
-            if (f0 < 0 && (!PIPE || (f2 < 0 && wfr[(it + FUSE_TR - 1) & (FUSE_TR - 1)] < 0))) break;
-            stage_tile((it + 2) & (FUSE_TR - 1), pop());
+            const int f0 = fa;
+            const int f2 = PIPE ? fp2 : -1;
+            if (f0 < 0 && (!PIPE || (f2 < 0 && fp1 < 0))) break;
+            const int fc = pop();
+            stage_tile((it + 2) & (FUSE_TR - 1), fc);
+            fp2 = fp1;
+            fp1 = fa;
+            fa = fb;
+            fb = fc;
             if (MODE == MODE_VOTE && HB == 1 && f0 >= 0) {
                 // a byte counter holds 255: flush the warp's rows before this candidate could push a cell past the limit
                 if (since_flush + 1 > FUSE_LIMIT8) {

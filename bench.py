@@ -275,14 +275,16 @@ def run_reference_arm(args, rank, world):
 # ---------------------------------------------------------------------------------------------------------------------------
 
 def nested_fused_config(torch, mods, key, steps, full_oracle):
-    """C1 / C4: resident packed frames, fused step timed with the kernel-only events, parity flag.  `full_oracle`: the CPU
-    port runs on the WHOLE scene and votes + labels are compared cell for cell; else a bounded CPU sample + properties."""
+    """C1 / C4 / C3 on ONE GPU: resident packed frames, fused step timed with the kernel-only events, parity flag.
+    `full_oracle`: the CPU port runs on the WHOLE scene and votes + labels are compared cell for cell; else a bounded CPU
+    sample + properties (C3: properties only -- its CPU sample runs in the multi-GPU line, bench.py --gpus N)."""
     engine, scenes, fused = mods
     spec = scenes.CONFIGS[key]
     pts = scenes.make_cloud(spec)
     ids = list(range(spec.nframes))
     fl, K, wxyz, t = make_labeler(fused, scenes, spec, ids, pts)
-    depth, masks = build_frames(torch, engine, fl, spec, ids, keep_unpacked=True)
+    big = key == "C3"          # 100 M x 5000: the two-array stacks (41 GB) are not kept next to the packed frames + 54 GB of votes
+    depth, masks = build_frames(torch, engine, fl, spec, ids, keep_unpacked=not big)
     N, F, H, W = fl.N, fl.nframes, spec.height, spec.width
     kt = engine.KernelTimer()
     for _ in range(3):
@@ -308,6 +310,11 @@ def nested_fused_config(torch, mods, key, steps, full_oracle):
         same = bool(np.array_equal(votes.cpu().numpy(), cv) and np.array_equal(labels.cpu().numpy(), cl))
         out.update({"parity": same and props, "parity_how": "CPU port on the WHOLE scene: votes [N,134] and labels compared cell for cell",
                     "cpu_port_seconds": sec, "cpu_port_value": float(N) * F / sec, "cpu_port_cores": cpu.workers})
+    elif big:
+        ms_lab = timed(torch, lambda: fl.label(want_votes=False), max(2, steps // 2))
+        out.update({"parity": props, "parity_how": "sum(votes) == votes cast + fused labels == resolve(votes) at full size; the CPU sample and "
+                    "the N-rank == 1-rank comparison of this scene run in the multi-GPU line (bench.py --gpus N)", "labels_only_ms": ms_lab,
+                    "note": "single-GPU time of the strong-scaling scene: T(1) for the efficiency of the --gpus 2/4/8 lines"})
     else:
         res, _ = cpu_vs_gpu_sample(torch, engine, pts, K, spec, wxyz, t, lambda f: depth[f].cpu().numpy(), lambda f: masks[f].cpu().numpy(),
                                    target_pv=1.6e7)
@@ -535,10 +542,10 @@ def run_single(args, torch, mods):
         try:
             if key == "C5":
                 configs[key] = nested_c5(torch, mods, nsteps)
-            elif key in ("C1", "C4"):
-                configs[key] = nested_fused_config(torch, mods, key, nsteps, full_oracle=(key == "C1"))
+            elif key in ("C1", "C4", "C3"):
+                configs[key] = nested_fused_config(torch, mods, key, nsteps if key != "C3" else 5, full_oracle=(key == "C1"))
             else:
-                configs[key] = {"skipped": "C3 is the multi-GPU workload: run bench.py --gpus N (N > 1)" if key == "C3" else "unknown config"}
+                configs[key] = {"skipped": "unknown config"}
         except Exception as ex:   # noqa: BLE001
             configs[key] = {"error": repr(ex)}
 
@@ -668,6 +675,9 @@ def run_multi(args, torch, mods, rank, world, local_rank):
                 parity["single_gpu_seconds_first_call"] = time.perf_counter() - t0
                 ms1 = timed(torch, lambda: fl1.label(want_votes=False), 2, warmup=0)
                 parity["single_gpu_labels_only_ms"] = ms1
+                parity["strong_scaling_efficiency_vs_single_gpu_labels_only"] = ms1 / (world * ms_step)
+                parity["strong_scaling_note"] = ("T(1) here is the single-GPU LABELS-ONLY time of the same scene (no 4*N*134-byte vote write), a "
+                                                 "conservative T(1); the full single-GPU step is configs.C3 of the --gpus 1 line")
                 same = bool(torch.equal(l1, labels))
                 parity["multi_gpu_matches_single_gpu"] = same
                 parity["single_gpu_how"] = (f"rank 0 renders all {F_total} frames and runs f3d_fuse_project_vote_resolve (labels only) on its "
@@ -823,7 +833,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="default: C2 on one GPU, C3 on several")
-    ap.add_argument("--configs", default="micro,C1,C5,C4", help="N = 1: other BASELINE configs / kernels nested in the line")
+    ap.add_argument("--configs", default="micro,C1,C5,C4,C3", help="N = 1: other BASELINE configs / kernels nested in the line")
     ap.add_argument("--budget-s", type=float, default=420.0, help="nested configs are skipped once the run is this old")
     ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
                     help="how the frames of the N-GPU job are dealt to the ranks (same results either way; the other one is timed too)")

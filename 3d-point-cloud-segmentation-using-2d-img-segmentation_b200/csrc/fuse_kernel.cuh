@@ -37,8 +37,8 @@
 #define FUSE_BLOCK 128
 #endif
 #define FUSE_NW (FUSE_BLOCK / 32)
-#ifndef FUSE_FCHUNK
-#define FUSE_FCHUNK (2 * FUSE_BLOCK)   // candidate list capacity per cull pass
+#ifndef FUSE_WCAP
+#define FUSE_WCAP 128     // candidate frames a warp's own list holds per cull pass (longer frame lists are swept in several passes)
 #endif
 #ifndef FUSE_MINB
 #define FUSE_MINB (512 / FUSE_BLOCK)        // resident CTAs per SM of the uint16-histogram / splat / uv2pt builds (128 registers)
@@ -615,13 +615,10 @@ static __device__ __noinline__ void flush8_mid(const FuseParams& P, uint8_t* his
 
 // small per-CTA scalars in shared memory
 struct __align__(16) FuseShared {
-    float wbox[FUSE_NW][8];                    // per-warp box: lo[3], hi[3], |lo| + |hi| magnitude, unused
     uint2 dcache[FUSE_NW][F3D_XCH_NLEVEL];     // exchange mode: the warp's directory levels {row offset, L}
     int nq[FUSE_NW];                           // per-warp deferred counts
     unsigned dirty[FUSE_NW];                   // rows another lane's deferred pass touched
     unsigned stat[8];                          // CTA totals of the statistics, flushed once at the end
-    int ncand;
-    int pad[3];
 };
 
 // 16-byte asynchronous global -> shared copy (LDGSTS): the projection tiles of the NEXT group land in the warp's other
@@ -638,15 +635,14 @@ __device__ __forceinline__ void cp_async4_l2_64(void* smem_dst, const void* gsrc
 }
 
 __host__ __device__ constexpr size_t fuse_align16(size_t v) { return (v + 15) & ~(size_t)15; }
-// shared-memory layout: [stage: NW x FUSE_TR FrameFast][texel rings: NW x FUSE_GR x 32 u32][FuseShared][cand u16 x FCHUNK][cmask u8 x FCHUNK][deferred queues][hist]
+// shared-memory layout: [stage: NW x FUSE_TR FrameFast][texel rings: NW x FUSE_GR x 32 u32][FuseShared][per-warp candidate lists: NW x FUSE_WCAP u16][deferred queues][hist]
 //                       [exchange mode: class lists u8 x FUSE_NSLOT x FUSE_BLOCK][record staging: NW x 512 B]
 #define FUSE_TR 8   // per-warp ring of staged projection tiles (candidates it-2 .. it+2 are live)
 #define FUSE_GR 4   // per-lane ring of gathered texels (candidates it-2 .. it)
 #define FUSE_OFF_TEXR ((size_t)FUSE_NW * FUSE_TR * sizeof(FrameFast))
 #define FUSE_OFF_SHARED (FUSE_OFF_TEXR + (size_t)FUSE_NW * FUSE_GR * 32 * sizeof(uint32_t))
-#define FUSE_OFF_CAND (FUSE_OFF_SHARED + sizeof(FuseShared))
-#define FUSE_OFF_CMASK (FUSE_OFF_CAND + FUSE_FCHUNK * sizeof(uint16_t))
-#define FUSE_OFF_QUEUE fuse_align16(FUSE_OFF_CMASK + FUSE_FCHUNK)
+#define FUSE_OFF_WLIST (FUSE_OFF_SHARED + sizeof(FuseShared))
+#define FUSE_OFF_QUEUE fuse_align16(FUSE_OFF_WLIST + (size_t)FUSE_NW * FUSE_WCAP * sizeof(uint16_t))
 #define FUSE_OFF_HIST fuse_align16(FUSE_OFF_QUEUE + (size_t)FUSE_NW * FUSE_QWARP * sizeof(Deferred))
 
 template <int MODE, int FMT, int HB, bool AUDIT>
@@ -657,8 +653,6 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* stage = reinterpret_cast<float4*>(smem_raw);
     FuseShared& sh = *reinterpret_cast<FuseShared*>(smem_raw + FUSE_OFF_SHARED);
-    uint16_t* cand = reinterpret_cast<uint16_t*>(smem_raw + FUSE_OFF_CAND);
-    uint8_t* cmask = smem_raw + FUSE_OFF_CMASK;   // warps that keep candidate i
     Deferred* queue_all = reinterpret_cast<Deferred*>(smem_raw + FUSE_OFF_QUEUE);
     CellT* hist = reinterpret_cast<CellT*>(smem_raw + FUSE_OFF_HIST);
     const int RS = P.RS;
@@ -685,36 +679,27 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     }
     if (tid < 8) sh.stat[tid] = 0u;
     if (lane < F3D_XCH_NLEVEL) sh.dcache[warp][lane] = make_uint2(0u, 0u);
-    if (MODE == MODE_VOTE) {
-        uint4* h128 = reinterpret_cast<uint4*>(hist);
-        const int n128 = (FUSE_BLOCK * RS * (int)sizeof(CellT) + 15) / 16;
-        for (int i = tid; i < n128; i += FUSE_BLOCK) h128[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (MODE == MODE_VOTE) {   // every warp clears its own 32 rows (contiguous: a thread's row is tid * RS)
+        uint4* h128 = reinterpret_cast<uint4*>(hist + (size_t)warp * 32 * RS);
+        const int n128 = 32 * RS * (int)sizeof(CellT) / 16;
+        for (int i = lane; i < n128; i += 32) h128[i] = make_uint4(0u, 0u, 0u, 0u);
     }
 
-    // ---- per-warp bounding box (exact min / max of the float32 coordinates of the warp's 32 points)
-    {
-        const float big = 3.0e38f;
-        float lo[3] = {active ? pt.x : big, active ? pt.y : big, active ? pt.z : big};
-        float hi[3] = {active ? pt.x : -big, active ? pt.y : -big, active ? pt.z : -big};
+    // ---- per-warp bounding box (exact min / max of the float32 coordinates of the warp's 32 points), in every lane
+    const float big = 3.0e38f;
+    float blo0 = active ? pt.x : big, blo1 = active ? pt.y : big, blo2 = active ? pt.z : big;
+    float bhi0 = active ? pt.x : -big, bhi1 = active ? pt.y : -big, bhi2 = active ? pt.z : -big;
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], s));
-                hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], s));
-            }
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                sh.wbox[warp][k] = lo[k];
-                sh.wbox[warp][3 + k] = hi[k];
-            }
-            // an empty warp (past the end of the cloud) keeps an inverted box that no frame can keep
-            sh.wbox[warp][6] = fabsf(lo[0]) + fabsf(lo[1]) + fabsf(lo[2]) + fabsf(hi[0]) + fabsf(hi[1]) + fabsf(hi[2]);
-            sh.wbox[warp][7] = (tile_base + warp * 32 < P.N) ? 1.f : 0.f;
-        }
+    for (int s = 16; s > 0; s >>= 1) {
+        blo0 = fminf(blo0, __shfl_xor_sync(0xffffffffu, blo0, s));
+        blo1 = fminf(blo1, __shfl_xor_sync(0xffffffffu, blo1, s));
+        blo2 = fminf(blo2, __shfl_xor_sync(0xffffffffu, blo2, s));
+        bhi0 = fmaxf(bhi0, __shfl_xor_sync(0xffffffffu, bhi0, s));
+        bhi1 = fmaxf(bhi1, __shfl_xor_sync(0xffffffffu, bhi1, s));
+        bhi2 = fmaxf(bhi2, __shfl_xor_sync(0xffffffffu, bhi2, s));
     }
+    const float bmag = fabsf(blo0) + fabsf(blo1) + fabsf(blo2) + fabsf(bhi0) + fabsf(bhi1) + fabsf(bhi2);
+    const bool warp_live = tile_base + warp * 32 < P.N;
 
     const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
 
@@ -733,52 +718,37 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     const bool use_list = st_n != 0xffffffffu;
     const uint16_t* __restrict__ st_list = P.st_list + (size_t)(blockIdx.x / FUSE_ST_TILES) * FUSE_ST_LCAP;
     const int ntest = use_list ? (int)st_n : P.f_end - P.f_begin;
-    __syncthreads();       // histogram zeroed, warp boxes visible
-    for (int cbase = 0; cbase < ntest; cbase += FUSE_FCHUNK) {
-        if (cbase != 0) __syncthreads();   // previous chunk's candidate list fully consumed
-        if (tid == 0) sh.ncand = 0;
-        __syncthreads();
-        const int cend = min(cbase + FUSE_FCHUNK, ntest);
-        // ---- conservative (frame, warp box) cull, one pair per thread (fp32 + explicit rounding margin; never drops a
-        // visible pair).  In a spatially sorted cloud a warp's points are a few centimetres apart, so a warp is almost
-        // always entirely inside or entirely outside a frustum: this removes ~45 % of the (warp, frame) pairs of the
-        // frames that touch the tile -- and every frame no warp keeps -- before any per-point work.
-        const int npairs = (cend - cbase) * FUSE_NW;
-        for (int p0 = 0; p0 < npairs; p0 += FUSE_BLOCK) {
-            const int p = p0 + tid;
-            bool kw = false;
+    __syncthreads();       // the CTA's statistics counters are zeroed; from here on every warp is on its own
+    // The warps of a CTA never meet again before the final statistics flush: each one culls the listed frames against
+    // ITS OWN box (one frame per lane), keeps the survivors in its own list and sweeps them.  In a spatially sorted cloud a
+    // warp's points are a few centimetres apart, so a warp is almost always entirely inside or entirely outside a frustum:
+    // the warp-box test removes ~45 % of the (warp, frame) pairs of the frames that touch the tile before any per-point work.
+    uint16_t* wlist = reinterpret_cast<uint16_t*>(smem_raw + FUSE_OFF_WLIST) + warp * FUSE_WCAP;
+    int tbase = 0;         // next entry of the frame list to cull (warp-uniform)
+    while (warp_live && tbase < ntest) {
+        // ---- conservative (frame, warp box) cull (fp32 + explicit rounding margin; never drops a visible pair)
+        int ncand = 0;
+        while (tbase < ntest && ncand <= FUSE_WCAP - 32) {
+            const int fi = tbase + lane;
+            bool kw = fi < ntest;
             int frel = 0;
-            if (p < npairs) {
-                const int fi = cbase + p / FUSE_NW;
-                const float* wb = sh.wbox[p % FUSE_NW];
+            if (kw) {
                 frel = use_list ? (int)__ldg(st_list + fi) : fi;
                 const float4* pl = frec[P.f_begin + frel].cull.pl;
-                const float l0 = wb[0], l1 = wb[1], l2 = wb[2], h0 = wb[3], h1 = wb[4], h2 = wb[5], mag = wb[6];
-                kw = wb[7] != 0.f;
 #pragma unroll
                 for (int m = 0; m < 5; ++m) {
                     const float4 q = __ldg(pl + m);
-                    const float mx = fmaxf(q.x * l0, q.x * h0) + fmaxf(q.y * l1, q.y * h1) + fmaxf(q.z * l2, q.z * h2) - q.w;
-                    const float margin = 2.0e-6f * (mag + fabsf(q.w)) + 1.0e-7f;
+                    const float mx = fmaxf(q.x * blo0, q.x * bhi0) + fmaxf(q.y * blo1, q.y * bhi1) + fmaxf(q.z * blo2, q.z * bhi2) - q.w;
+                    const float margin = 2.0e-6f * (bmag + fabsf(q.w)) + 1.0e-7f;
                     kw = kw && (mx >= -margin);
                 }
             }
-            // the FUSE_NW lanes of a frame are adjacent: its warp mask is a bit field of the ballot
             const unsigned bal = __ballot_sync(0xffffffffu, kw);
-            const unsigned wmask = (bal >> (lane & ~(FUSE_NW - 1))) & ((1u << FUSE_NW) - 1u);
-            const bool lead = ((lane & (FUSE_NW - 1)) == 0) && wmask != 0u;
-            const unsigned lb = __ballot_sync(0xffffffffu, lead);
-            int base = 0;
-            if (lane == 0 && lb) base = atomicAdd(&sh.ncand, __popc(lb));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (lead) {
-                const int at = base + __popc(lb & ((1u << lane) - 1u));
-                cand[at] = (uint16_t)frel;
-                cmask[at] = (uint8_t)wmask;
-            }
+            if (kw) wlist[ncand + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)frel;
+            ncand += __popc(bal);
+            tbase += 32;
         }
-        __syncthreads();
-        const int ncand = sh.ncand;
+        __syncwarp();
 
         // ---- warp-autonomous sweep over this warp's candidates of the list: ONE candidate per iteration, software pipelined
         // through shared memory so that the loop body stays a few hundred instructions (the L0 instruction cache holds
@@ -790,20 +760,12 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         // outstanding across iterations, and nobody but the warp itself ever waits.  The two-array frame formats (a 2-byte
         // depth sample cannot be a cp.async) and the splat consume their candidate in the same iteration instead.
         constexpr bool PIPE = (MODE != MODE_SPLAT) && (FMT >= F3D_FRAMES_U32);
-        int lbase = -32;        // current 32-entry block of the candidate list (warp-uniform)
-        unsigned wm = 0u;       // this warp's candidates of that block not yet taken
+        int li = 0;             // next entry of the warp's candidate list (warp-uniform)
         float4* tiles = stage + warp * (FUSE_TR * 8);
         uint32_t* texr = texring + warp * (FUSE_GR * 32) + lane;
         auto pop = [&]() -> int {   // next candidate frame of this warp, -1 = none (warp-uniform)
-            while (wm == 0u && lbase + 32 < ncand) {
-                lbase += 32;
-                const int i = lbase + lane;
-                wm = __ballot_sync(0xffffffffu, i < ncand && ((cmask[i] >> warp) & 1u));
-            }
-            if (!wm) return -1;
-            const int pos = lbase + __ffs(wm) - 1;
-            wm &= wm - 1u;
-            return (int)cand[pos];
+            if (li >= ncand) return -1;
+            return (int)wlist[li++];
         };
         auto stage_tile = [&](int slot, int f) {   // lanes 0..7 copy the 8 x 16 bytes of the frame's projection tile
             if (f >= 0 && lane < 8) cp_async16(tiles + slot * 8 + lane, reinterpret_cast<const uint4*>(&frec[P.f_begin + f].fast) + lane);
@@ -938,7 +900,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             }
         }
         cp_async_wait_all();
-        __syncwarp();
+        __syncwarp();          // every lane is done with the list before the next cull pass overwrites it
     }
 
     // ---- warp-private dense fp64 pass over the deferred point-views (one entry per lane)

@@ -125,7 +125,7 @@ def test_split_into_instances_from_device_adjacency(engine, scenes):
     want = orc.split_into_instances(classes, oip, oix, 133, None, 20)
     adj = engine.radius_adjacency(dev(p), 0.12)                       # stays on the device: no host CSR round trip
     got = cv.split_into_instances(classes, adj, 133, None, 20)
-    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2] == want[2] and np.array_equal(got[3], want[3])
+    assert len(got[0]) == want[0] and np.array_equal(got[1], want[1]) and got[2] == want[2] and np.array_equal(got[3], want[3])
     # one-directional adjacency lists (not the symmetric KDTree output): the reference BFS follows adj[point] as given
     keep = oix > np.repeat(np.arange(len(p)), np.diff(oip))           # only smaller -> larger entries
     ip2 = np.concatenate([[0], np.cumsum(np.add.reduceat(keep.astype(np.int64), oip[:-1]))])

@@ -190,6 +190,8 @@ def fuse_project_vote(points4, table: FrameTable, depth, mask, nclasses1, radius
         votes = torch.empty((N, nclasses1), dtype=torch.uint16 if packed_u16 else torch.int32, device=points4.device)
         accumulate = False
     nf = frame_end - frame_begin
+    if votes.dtype == torch.uint16 and table.F >= 65536:
+        raise ValueError("uint16 vote counters hold at most 65 535 frames per tensor: use int32 votes for this scan")
     dptr, fmt, mptr = _frames_args(depth, mask, table, nf)
     ws = workspace(N, points4.device)
     fn = load().f3d_fuse_project_vote_u16 if votes.dtype == torch.uint16 else load().f3d_fuse_project_vote

@@ -69,7 +69,10 @@ class ShardedPipeline:
     [a, b) into `out[:b-a]` (shape [rows, c1], dtype `vote_dtype`); `resolve(votes, out_labels)` must enqueue the label
     resolve of `votes` [rows, c1] into `out_labels` [rows] int64."""
 
-    def __init__(self, npoints: int, c1: int, nchunks: int, device, group=None, packed=True):
+    def __init__(self, npoints: int, c1: int, nchunks: int, device, group=None, packed=True, total_frames=None):
+        """`total_frames`: frames of ALL ranks (and all accumulate calls) that can vote into one tensor.  The packed uint16
+        exchange is exact only while no cell can reach 65 536, so it is used only when total_frames is given and < 65 536;
+        otherwise votes travel as int32."""
         self.group, self.device = group, torch.device(device)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.npoints, self.c1 = npoints, c1
@@ -79,7 +82,7 @@ class ShardedPipeline:
         big = max([b - a for a, b in self.bounds], default=0)
         self.per = -(-big // self.world) if big else 0
         self.cuda = self.device.type == "cuda"
-        self.packed = bool(packed and self.cuda and c1 % 2 == 0)
+        self.packed = bool(packed and self.cuda and c1 % 2 == 0 and total_frames is not None and 0 <= int(total_frames) < 65536)
         self.vote_dtype = torch.uint16 if self.packed else torch.int32
         rows = self.per * self.world
         self.part = [torch.zeros((rows, c1), dtype=self.vote_dtype, device=self.device) for _ in range(2)]

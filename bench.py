@@ -191,6 +191,11 @@ def build_scene(scenes, engine, fused, spec, frame_lo, frame_hi, torch, frame_id
     return fl, pts, K, np.ascontiguousarray(wxyz[ids]), np.ascontiguousarray(t[ids]), depth, masks
 
 
+def tensor_sum(t, rows=4_000_000):
+    """Exact integer sum of a big int32 tensor without torch's full-size int64 temporary."""
+    return sum(int(t[a:a + rows].sum()) for a in range(0, t.shape[0], rows))
+
+
 def timed(torch, fn, steps, warmup=1):
     for _ in range(warmup):
         fn()
@@ -300,7 +305,7 @@ def nested_fused_config(torch, mods, key, steps, full_oracle):
            "roofline_frac": balg / (kms * 1e-3) / 1e9 / peak, "call_frac": balg / (ms * 1e-3) / 1e9 / peak,
            "candidates_per_step": st["candidates"] / steps, "votes_per_step": st["seen"] / steps}
     votes, labels = fl.votes, fl.labels
-    props = bool(int(votes.sum()) * steps == st["seen"] and torch.equal(labels, engine.resolve_labels(votes, NCLASSES, THRESHOLD, None)))
+    props = bool(tensor_sum(votes) * steps == st["seen"] and torch.equal(labels, engine.resolve_labels(votes, NCLASSES, THRESHOLD, None)))
     if full_oracle:
         from oracle import cpu_baseline as cb
         d_np, m_np = depth.cpu().numpy(), masks.cpu().numpy()

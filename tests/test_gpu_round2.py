@@ -161,7 +161,7 @@ def test_batched_obb_fit_matches_stated_box_model(engine, model):
         got, ref = got[np.lexsort(np.round(got, 6).T)], ref[np.lexsort(np.round(ref, 6).T)]
         np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)       # same box (axis signs may differ: compare corner sets)
         inside = engine.obb_contains(dev(pts), dev(b[None, :]))[0].cpu().numpy().astype(bool)
-        assert inside[sel].mean() > 0.95                              # closed box of its own points (boundary points are ulp-fragile)
+        assert (~inside[sel]).sum() <= 6                              # closed box of its own points; only the <= 6 face-defining points are ulp-fragile
 
 
 def test_box_pairs_sweep_equals_brute_force_and_oracle(engine, scenes):

@@ -670,6 +670,40 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     const int HW = P.H * P.W;
     const float fW = (float)P.W, fH = (float)P.H;
 
+    // frames to test: the super-tile's candidate list when the first cull level ran, else every frame of the launch
+    const unsigned st_n = P.st_count ? __ldg(P.st_count + blockIdx.x / FUSE_ST_TILES) : 0xffffffffu;
+    const bool use_list = st_n != 0xffffffffu;
+    const uint16_t* __restrict__ st_list = P.st_list + (size_t)(blockIdx.x / FUSE_ST_TILES) * FUSE_ST_LCAP;
+    const int ntest = use_list ? (int)st_n : P.f_end - P.f_begin;
+    if (ntest == 0) {
+        // No frame of this launch can see the tile's super-tile (the common case of a rank whose frames look at another part
+        // of the building): nothing is loaded or cleared, the outputs of "no votes" are written straight away.
+        if (MODE == MODE_VOTE) {
+            const int row0 = warp * 32;
+            const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
+            if (P.xg_G > 0) {
+                if (nrows > 0 && lane < F3D_XCH_NLEVEL) {
+                    const long long p0 = tile_base + row0;
+                    const int d = (int)(p0 / P.xg_per);
+                    P.xg_dir[d][((p0 - (long long)d * P.xg_per) >> 5) * F3D_XCH_NLEVEL + lane] = make_uint2(0u, 0u);
+                }
+            } else if (!P.accumulate && nrows > 0) {
+                if (P.votes) {
+                    uint4* out = reinterpret_cast<uint4*>(P.votes + (tile_base + row0) * P.C1);   // 128 * C1 bytes per warp: 16-byte multiple
+                    for (int i = lane; i < nrows * P.C1 / 4; i += 32) out[i] = make_uint4(0u, 0u, 0u, 0u);
+                    for (int e = (nrows * P.C1 / 4) * 4 + lane; e < nrows * P.C1; e += 32) P.votes[(tile_base + row0) * P.C1 + e] = 0;
+                }
+                if (P.votes16)
+                    for (int e = lane; e < nrows * P.C1; e += 32) P.votes16[(tile_base + row0) * P.C1 + e] = 0;
+            }
+            if (RP.enabled && active) {
+                P.labels[gi] = (int64_t)RP.unclassified;                                  // voting.py:126 (total == 0)
+                if (P.summ) P.summ[gi] = summ_pack(0, 0, 0x7fff);
+            }
+        }
+        return;
+    }
+
     float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) pt = __ldg(P.points + gi);
 
@@ -713,11 +747,6 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     T.bpos = 0x7fff;
     int since_flush = 0, nflush = 0;   // byte histogram: candidates swept since the warp's last flush, its flushes so far
 
-    // frames to test: the super-tile's candidate list when the first cull level ran, else every frame of the launch
-    const unsigned st_n = P.st_count ? __ldg(P.st_count + blockIdx.x / FUSE_ST_TILES) : 0xffffffffu;
-    const bool use_list = st_n != 0xffffffffu;
-    const uint16_t* __restrict__ st_list = P.st_list + (size_t)(blockIdx.x / FUSE_ST_TILES) * FUSE_ST_LCAP;
-    const int ntest = use_list ? (int)st_n : P.f_end - P.f_begin;
     __syncthreads();       // the CTA's statistics counters are zeroed; from here on every warp is on its own
     // The warps of a CTA never meet again before the final statistics flush: each one culls the listed frames against
     // ITS OWN box (one frame per lane), keeps the survivors in its own list and sweeps them.  In a spatially sorted cloud a

@@ -231,3 +231,27 @@ def test_spatquadranion_rotate_matches_oracle(engine):
         assert np.array_equal(Q.rotate(p), orc.quat_rotate(qa, p))                   # un-normalised sandwich, bit for bit
         assert np.array_equal(Q.inverse.elements, orc.quat_inverse(qa))
         assert np.array_equal(Q.inverse.rotate(p), orc.quat_rotate(orc.quat_inverse(qa), p))
+
+
+def test_unseen_supertiles_fast_path(engine, scenes):
+    """Super-tiles no frame of the launch can see take the kernel's early exit: their vote rows must still be written
+    (zeros over whatever the buffer held), labels = unclassified, and accumulation must leave them untouched."""
+    s = small_scene(scenes, orc, npoints=9000, nframes=40, width=96, height=72, seed=13)     # > 32 frames: the first cull level runs
+    far = np.random.default_rng(0).uniform(-1, 1, (3 * 4096, 3)).astype(np.float32) + np.float32(500.0)
+    pts = np.concatenate([far[:4096], s["points"], far[4096:]])                              # unseen super-tiles before and after
+    ov = orc.fuse_project_vote(pts, s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0, 0.05, 0.1, 4.0, 4.0)
+    assert ov[:4096].sum() == 0 and ov[4096 + 9000:].sum() == 0 and ov.sum() > 1000
+    tab = engine.FrameTable(s["K"], s["W"], s["H"], s["wxyz"], s["t"], 4.0)
+    p4 = engine.pack_points(pts)
+    pk = engine.pack_frames(dev(s["depths"]), dev(s["masks"]))
+    for frames, m in ((pk, None), (dev(s["depths"]), dev(s["masks"]))):
+        votes = torch.full((len(pts), 134), 77, dtype=torch.int32, device="cuda")
+        labels = torch.full((len(pts),), -5, dtype=torch.int64, device="cuda")
+        engine.fuse_project_vote_resolve(p4, tab, frames, m, 134, 133, 0.05, 0.1, 4.0, 0.5, None, votes=votes, labels=labels)
+        assert np.array_equal(votes.cpu().numpy(), ov)
+        assert np.array_equal(labels.cpu().numpy(), orc.segment(ov, 133, 0.5, None))
+        engine.fuse_project_vote(p4, tab, frames, m, 134, 0.05, 0.1, 4.0, votes=votes, accumulate=True)
+        assert np.array_equal(votes.cpu().numpy(), 2 * ov)
+        v16 = torch.full((len(pts), 134), 9, dtype=torch.uint16, device="cuda")
+        engine.fuse_project_vote(p4, tab, frames, m, 134, 0.05, 0.1, 4.0, votes=v16)
+        assert np.array_equal(v16.cpu().numpy().astype(np.int64), ov)

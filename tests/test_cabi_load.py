@@ -62,3 +62,29 @@ def test_scene_generator_is_deterministic(scenes):
     assert K[0, 0] == scenes.CALIB_FX * (1920 / 720) and K[1, 2] == scenes.CALIB_CY * (1440 / 960)
     m = scenes.block_masks((48, 64), 3, seed=1, block=8)
     assert m.shape == (3, 48, 64) and m.max() <= 133
+
+
+def test_vote_epilogue_keeps_its_32_byte_stores(pkg):
+    """ptxas 12.9 was seen to lower `st.global.v8.b32` to ONE 32-bit store when the vote flush was a non-inlined function
+    (7 of 8 vote cells never written); the epilogue instance is inlined for that reason.  Every byte-histogram
+    instantiation of the fused kernel must still contain the 32-byte store, and the in-tree library must hold sm_100a code
+    for the production kernel."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    lib = ROOT / PKG_NAME / "libf3d.so"
+    if not Path(cuobjdump).exists() or not lib.exists():
+        pytest.skip("cuobjdump or libf3d.so not available")
+    sass = subprocess.run([cuobjdump, "-sass", str(lib)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    funcs = re.split(r"\n\s*Function : ", sass)
+    seen = 0
+    for f in funcs:
+        m = re.match(r"_Z11fuse_kernelILi0ELi(\d)ELi1ELb([01])E", f)
+        if m:
+            seen += 1
+            assert "STG.E.ENL2.256" in f, f"fuse_kernel<VOTE,{m.group(1)},HB1,{m.group(2)}> lost its 32-byte vote stores"
+            assert "LDGSTS" in f                      # cp.async staging of the pose tiles (and texels for the packed formats)
+    assert seen == 8
+    assert "UBLKCP" in sass                           # TMA bulk copies stage the fix-up kernel's frame records
+    assert "LTC64B" in sass                           # 64-byte L2 fills for the frame gathers

@@ -665,33 +665,78 @@ def run_multi(args, torch, mods, rank, world, local_rank):
     fl = primary["fl"]
     labels = primary["labels"]
 
-    # ---- parity (a): the N-rank labels against ONE GPU running the whole frame set (rank 0), labels only
+    # ---- the whole frame set on every rank: (i) the point-sharded alternative (SURVEY 8(e) "alternative worth measuring": each rank
+    # fuses ITS N/G points against ALL frames, no vote exchange at all, labels all-gathered) and (ii) parity (a): rank 0 runs the
+    # whole cloud x whole frame set on its ONE GPU (labels only) and the N-rank labels must be identical
     parity = {}
-    if not args.no_verify:
-        ok = torch.ones(1, dtype=torch.int32, device="cuda")
-        if rank == 0:
+    point_sharded = None
+    ok = torch.ones(1, dtype=torch.int32, device="cuda")
+    if not (args.no_verify and args.no_point_sharded):
+        ids_all = list(range(F_total))
+        fl_all, _, _, _ = make_labeler(fused, scenes, spec, ids_all, p4)
+        if rank == 0 or not args.no_point_sharded:
+            build_frames(torch, engine, fl_all, spec, ids_all)
+        if not args.no_point_sharded:
+            per_ps = parallel.shard_points(N, world)
+            a, b = min(rank * per_ps, N), min((rank + 1) * per_ps, N)
+            fl_ps, _, _, _ = make_labeler(fused, scenes, spec, ids_all, p4[a:b] if b > a else p4[:1])
+            fl_ps.frames = fl_all.frames
+            lab16 = torch.zeros(per_ps, dtype=torch.int16, device="cuda")
+            full16 = torch.zeros(per_ps * world, dtype=torch.int16, device="cuda")
+            kt_ps = engine.KernelTimer()
+
+            def step_ps(timer=None):
+                lab = fl_ps.label(timer=timer)
+                if b > a:
+                    lab16[:b - a].copy_(lab)
+                dist.all_gather_into_tensor(full16.view(torch.uint8), lab16.view(torch.uint8))
+                return full16
+            for _ in range(3):
+                step_ps()
+            torch.cuda.synchronize()
+            dist.barrier()
+            n_ps = max(3, args.steps // 2)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(n_ps):
+                step_ps(kt_ps)
+            ev1.record()
+            torch.cuda.synchronize()
+            dist.barrier()
+            tt = torch.tensor([ev0.elapsed_time(ev1) / n_ps], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            same_ps = bool(torch.equal(full16[:N].to(torch.int64), labels))
+            point_sharded = {"ms_per_step": float(tt.item()), "value": pv_step / (float(tt.item()) * 1e-3), "unit": UNIT, "steps": n_ps,
+                             "kernel_ms_rank0": float(np.mean(kt_ps.ms())), "labels_equal_frame_sharded": same_ps,
+                             "what": f"every rank holds ALL {F_total} packed frames ({F_total * H * W * 4 / 1e9:.1f} GB) and fuses its N/{world} "
+                                     "points with the single-GPU fused kernel (dense vote shard + labels), then an int16 label all-gather: no vote "
+                                     "exchange, but G x the frame ingest; frames-sharded (the headline) is what the north star prescribes"}
+            if not same_ps:
+                ok[0] = 0
+            del fl_ps, lab16, full16
+        if rank == 0 and not args.no_verify:
             try:
-                ids_all = list(range(F_total))
-                fl1, _, _, _ = make_labeler(fused, scenes, spec, ids_all, p4)
-                build_frames(torch, engine, fl1, spec, ids_all)
                 t0 = time.perf_counter()
-                l1 = fl1.label(want_votes=False)
+                l1 = fl_all.label(want_votes=False)
                 torch.cuda.synchronize()
                 parity["single_gpu_seconds_first_call"] = time.perf_counter() - t0
-                ms1 = timed(torch, lambda: fl1.label(want_votes=False), 2, warmup=0)
+                ms1 = timed(torch, lambda: fl_all.label(want_votes=False), 2, warmup=0)
                 parity["single_gpu_labels_only_ms"] = ms1
                 parity["strong_scaling_efficiency_vs_single_gpu_labels_only"] = ms1 / (world * ms_step)
                 parity["strong_scaling_note"] = ("T(1) here is the single-GPU LABELS-ONLY time of the same scene (no 4*N*134-byte vote write), a "
                                                  "conservative T(1); the full single-GPU step is configs.C3 of the --gpus 1 line")
                 same = bool(torch.equal(l1, labels))
                 parity["multi_gpu_matches_single_gpu"] = same
-                parity["single_gpu_how"] = (f"rank 0 renders all {F_total} frames and runs f3d_fuse_project_vote_resolve (labels only) on its "
-                                            f"one GPU; the {world}-rank labels [N] must be identical")
-                ok[0] = 1 if same else 0
-                del fl1, l1
-                torch.cuda.empty_cache()
+                parity["single_gpu_how"] = (f"rank 0 runs f3d_fuse_project_vote_resolve (labels only) over the whole cloud and all {F_total} "
+                                            f"frames on its one GPU; the {world}-rank labels [N] must be identical")
+                if not same:
+                    ok[0] = 0
+                del l1
             except Exception as ex:   # noqa: BLE001
                 parity["single_gpu_error"] = repr(ex)
+        del fl_all
+        torch.cuda.empty_cache()
+    if not args.no_verify:
         # ---- parity (b): a CPU-sized sample through the SAME N-rank exchange path against the numpy port
         try:
             sub_n = min(N, 750_000)
@@ -823,7 +868,7 @@ def run_multi(args, torch, mods, rank, world, local_rank):
                                       "slot records written into the owner rank's memory over NVLink (symmetric memory), owner-side merge into "
                                       "the dense int32 shard + label resolve, all-gather of int16 labels over NCCL"},
             "roofline": roof, "cpu_baseline": parity.get("cpu_baseline"), "e2e": e2e, "gpu_launches": 7 * args.steps, "clocks": primary["clocks"],
-            "per_step_counts_rank0": primary["stats"], "parity": parity, "other_shard": other, "numa": numa,
+            "per_step_counts_rank0": primary["stats"], "parity": parity, "other_shard": other, "point_sharded": point_sharded, "numa": numa,
             "bench_seconds": time.time() - T_START,
         }
         print(json.dumps(line))
@@ -840,7 +885,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="default: C2 on one GPU, C3 on several")
     ap.add_argument("--configs", default="micro,C1,C5,C4,C3", help="N = 1: other BASELINE configs / kernels nested in the line")
     ap.add_argument("--budget-s", type=float, default=420.0, help="nested configs are skipped once the run is this old")
-    ap.add_argument("--shard", default="interleaved", choices=["interleaved", "contiguous"],
+    ap.add_argument("--shard", default="contiguous", choices=["interleaved", "contiguous"],
                     help="how the frames of the N-GPU job are dealt to the ranks (same results either way; the other one is timed too)")
     ap.add_argument("--scaling", default=None, choices=["strong", "weak"], help="N > 1 with --workload C2: weak = N x 500 frames")
     ap.add_argument("--points", type=int, default=None, help="N > 1: override the cloud size (experiments)")
@@ -849,6 +894,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the single-GPU / CPU parity runs")
     ap.add_argument("--no-other-shard", action="store_true")
+    ap.add_argument("--no-point-sharded", action="store_true", help="N > 1: skip the point-sharded alternative (all frames on every rank)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

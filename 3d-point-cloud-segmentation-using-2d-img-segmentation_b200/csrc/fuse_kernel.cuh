@@ -613,6 +613,33 @@ static __device__ __noinline__ void flush8_mid(const FuseParams& P, uint8_t* his
     flush8<false>(P, hist, warp, lane, tile_base, add, true, nlist, clist, stg, level, false, dcache);
 }
 
+// Outputs of a warp whose 32 points received no vote in this launch, written without touching the histogram: zero rows (or
+// zero directory entries in exchange mode; nothing when accumulating), label = unclassified (voting.py:126, total == 0).
+__device__ __forceinline__ void write_no_votes(const FuseParams& P, const FuseResolve& RP, int warp, int lane, int64_t tile_base, int64_t gi,
+                                               bool active) {
+    const int row0 = warp * 32;
+    const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
+    if (P.xg_G > 0) {
+        if (nrows > 0 && lane < F3D_XCH_NLEVEL) {
+            const long long p0 = tile_base + row0;
+            const int d = (int)(p0 / P.xg_per);
+            P.xg_dir[d][((p0 - (long long)d * P.xg_per) >> 5) * F3D_XCH_NLEVEL + lane] = make_uint2(0u, 0u);
+        }
+    } else if (!P.accumulate && nrows > 0) {
+        if (P.votes) {
+            uint4* out = reinterpret_cast<uint4*>(P.votes + (tile_base + row0) * P.C1);   // 128 * C1 bytes per warp: 16-byte multiple
+            for (int i = lane; i < nrows * P.C1 / 4; i += 32) out[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int e = (nrows * P.C1 / 4) * 4 + lane; e < nrows * P.C1; e += 32) P.votes[(tile_base + row0) * P.C1 + e] = 0;
+        }
+        if (P.votes16)
+            for (int e = lane; e < nrows * P.C1; e += 32) P.votes16[(tile_base + row0) * P.C1 + e] = 0;
+    }
+    if (RP.enabled && active) {
+        P.labels[gi] = (int64_t)RP.unclassified;
+        if (P.summ) P.summ[gi] = summ_pack(0, 0, 0x7fff);
+    }
+}
+
 // small per-CTA scalars in shared memory
 struct __align__(16) FuseShared {
     uint2 dcache[FUSE_NW][F3D_XCH_NLEVEL];     // exchange mode: the warp's directory levels {row offset, L}
@@ -678,29 +705,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     if (ntest == 0) {
         // No frame of this launch can see the tile's super-tile (the common case of a rank whose frames look at another part
         // of the building): nothing is loaded or cleared, the outputs of "no votes" are written straight away.
-        if (MODE == MODE_VOTE) {
-            const int row0 = warp * 32;
-            const int nrows = (int)max((int64_t)0, min((int64_t)32, P.N - tile_base - row0));
-            if (P.xg_G > 0) {
-                if (nrows > 0 && lane < F3D_XCH_NLEVEL) {
-                    const long long p0 = tile_base + row0;
-                    const int d = (int)(p0 / P.xg_per);
-                    P.xg_dir[d][((p0 - (long long)d * P.xg_per) >> 5) * F3D_XCH_NLEVEL + lane] = make_uint2(0u, 0u);
-                }
-            } else if (!P.accumulate && nrows > 0) {
-                if (P.votes) {
-                    uint4* out = reinterpret_cast<uint4*>(P.votes + (tile_base + row0) * P.C1);   // 128 * C1 bytes per warp: 16-byte multiple
-                    for (int i = lane; i < nrows * P.C1 / 4; i += 32) out[i] = make_uint4(0u, 0u, 0u, 0u);
-                    for (int e = (nrows * P.C1 / 4) * 4 + lane; e < nrows * P.C1; e += 32) P.votes[(tile_base + row0) * P.C1 + e] = 0;
-                }
-                if (P.votes16)
-                    for (int e = lane; e < nrows * P.C1; e += 32) P.votes16[(tile_base + row0) * P.C1 + e] = 0;
-            }
-            if (RP.enabled && active) {
-                P.labels[gi] = (int64_t)RP.unclassified;                                  // voting.py:126 (total == 0)
-                if (P.summ) P.summ[gi] = summ_pack(0, 0, 0x7fff);
-            }
-        }
+        if (MODE == MODE_VOTE) write_no_votes(P, RP, warp, lane, tile_base, gi, active);
         return;
     }
 
@@ -713,11 +718,6 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     }
     if (tid < 8) sh.stat[tid] = 0u;
     if (lane < F3D_XCH_NLEVEL) sh.dcache[warp][lane] = make_uint2(0u, 0u);
-    if (MODE == MODE_VOTE) {   // every warp clears its own 32 rows (contiguous: a thread's row is tid * RS)
-        uint4* h128 = reinterpret_cast<uint4*>(hist + (size_t)warp * 32 * RS);
-        const int n128 = 32 * RS * (int)sizeof(CellT) / 16;
-        for (int i = lane; i < n128; i += 32) h128[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
 
     // ---- per-warp bounding box (exact min / max of the float32 coordinates of the warp's 32 points), in every lane
     const float big = 3.0e38f;
@@ -754,6 +754,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     // the warp-box test removes ~45 % of the (warp, frame) pairs of the frames that touch the tile before any per-point work.
     uint16_t* wlist = reinterpret_cast<uint16_t*>(smem_raw + FUSE_OFF_WLIST) + warp * FUSE_WCAP;
     int tbase = 0;         // next entry of the frame list to cull (warp-uniform)
+    bool hist_live = false;   // the warp's histogram rows are cleared lazily: a warp no listed frame can see never touches them
     while (warp_live && tbase < ntest) {
         // ---- conservative (frame, warp box) cull (fp32 + explicit rounding margin; never drops a visible pair)
         int ncand = 0;
@@ -776,6 +777,12 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             if (kw) wlist[ncand + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)frel;
             ncand += __popc(bal);
             tbase += 32;
+        }
+        if (MODE == MODE_VOTE && ncand > 0 && !hist_live) {   // first candidates of this warp: clear its 32 rows (a thread's row is tid * RS)
+            uint4* h128 = reinterpret_cast<uint4*>(hist + (size_t)warp * 32 * RS);
+            const int n128 = 32 * RS * (int)sizeof(CellT) / 16;
+            for (int i = lane; i < n128; i += 32) h128[i] = make_uint4(0u, 0u, 0u, 0u);
+            hist_live = true;
         }
         __syncwarp();
 
@@ -932,6 +939,10 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
         __syncwarp();          // every lane is done with the list before the next cull pass overwrites it
     }
 
+    if (MODE == MODE_VOTE && !hist_live) {
+        // no listed frame reaches this warp's box: no candidate, no deferred pair, no vote
+        if (warp_live) write_no_votes(P, RP, warp, lane, tile_base, gi, active);
+    } else {
     // ---- warp-private dense fp64 pass over the deferred point-views (one entry per lane)
     __syncwarp();
     {
@@ -1043,6 +1054,8 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             if (P.summ) P.summ[gi] = summ_pack(T.total, T.best, T.bpos);
         }
     }
+
+    }   // hist_live
 
     // ---- statistics: one atomic per counter per CTA
     if (P.stats) {

@@ -656,8 +656,12 @@ def run_multi(args, torch, mods, rank, world, local_rank):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         clocks = sampler.stop(t0w, t1w) if sampler else None
         st = fl.stats_dict()
+        kall = torch.zeros(world, device="cuda")
+        kall[rank] = float(np.mean(kt.ms()))
+        dist.all_reduce(kall)
         return {"ms_per_step": float(tt.item()) / steps, "labels": labels.clone(), "fl": fl, "K": K, "wxyz": wxyz, "t": t, "ids": ids,
-                "kernel_ms": float(np.mean(kt.ms())), "clocks": clocks, "stats": {k: v / steps for k, v in st.items()}}
+                "kernel_ms": float(np.mean(kt.ms())), "kernel_ms_per_rank": [round(v, 3) for v in kall.tolist()], "clocks": clocks,
+                "stats": {k: v / steps for k, v in st.items()}}
 
     primary = run_shard(args.shard, args.steps, args.warmup)
     pv_step = float(N) * float(F_total)
@@ -677,12 +681,24 @@ def run_multi(args, torch, mods, rank, world, local_rank):
         if rank == 0 or not args.no_point_sharded:
             build_frames(torch, engine, fl_all, spec, ids_all)
         if not args.no_point_sharded:
-            per_ps = parallel.shard_points(N, world)
-            a, b = min(rank * per_ps, N), min((rank + 1) * per_ps, N)
-            fl_ps, _, _, _ = make_labeler(fused, scenes, spec, ids_all, p4[a:b] if b > a else p4[:1])
+            # points dealt to the ranks in 4096-point super-tiles, round robin: every rank gets the same mix of the scene
+            # (a contiguous 1/G of a Morton-sorted building is an octant whose visibility differs from rank to rank)
+            ST = 4096
+            nsup = -(-N // ST)
+            per_ps = -(-nsup // world) * ST
+            sup_of = [torch.arange(r, nsup, world, device="cuda") for r in range(world)]
+            idx_of = [(su[:, None] * ST + torch.arange(ST, device="cuda")[None, :]).reshape(-1) for su in sup_of]
+            idx_of = [ix[ix < N] for ix in idx_of]
+            perm = torch.full((world, per_ps), N, dtype=torch.int64, device="cuda")          # slot N = dummy for the padding
+            for r in range(world):
+                perm[r, :len(idx_of[r])] = idx_of[r]
+            mine_idx = idx_of[rank]
+            a, b = 0, int(len(mine_idx))
+            fl_ps, _, _, _ = make_labeler(fused, scenes, spec, ids_all, p4[mine_idx].contiguous() if b > a else p4[:1])
             fl_ps.frames = fl_all.frames
             lab16 = torch.zeros(per_ps, dtype=torch.int16, device="cuda")
             full16 = torch.zeros(per_ps * world, dtype=torch.int16, device="cuda")
+            out16 = torch.zeros(N + 1, dtype=torch.int16, device="cuda")
             kt_ps = engine.KernelTimer()
 
             def step_ps(timer=None):
@@ -690,7 +706,8 @@ def run_multi(args, torch, mods, rank, world, local_rank):
                 if b > a:
                     lab16[:b - a].copy_(lab)
                 dist.all_gather_into_tensor(full16.view(torch.uint8), lab16.view(torch.uint8))
-                return full16
+                out16[perm.view(-1)] = full16                                                # back to cloud order
+                return out16
             for _ in range(3):
                 step_ps()
             torch.cuda.synchronize()
@@ -705,15 +722,16 @@ def run_multi(args, torch, mods, rank, world, local_rank):
             dist.barrier()
             tt = torch.tensor([ev0.elapsed_time(ev1) / n_ps], device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            same_ps = bool(torch.equal(full16[:N].to(torch.int64), labels))
+            same_ps = bool(torch.equal(out16[:N].to(torch.int64), labels))
             point_sharded = {"ms_per_step": float(tt.item()), "value": pv_step / (float(tt.item()) * 1e-3), "unit": UNIT, "steps": n_ps,
                              "kernel_ms_rank0": float(np.mean(kt_ps.ms())), "labels_equal_frame_sharded": same_ps,
                              "what": f"every rank holds ALL {F_total} packed frames ({F_total * H * W * 4 / 1e9:.1f} GB) and fuses its N/{world} "
-                                     "points with the single-GPU fused kernel (dense vote shard + labels), then an int16 label all-gather: no vote "
+                                     "points (4096-point super-tiles dealt round robin) with the single-GPU fused kernel (dense vote shard + "
+                                     "labels), then an int16 label all-gather + un-permute: no vote "
                                      "exchange, but G x the frame ingest; frames-sharded (the headline) is what the north star prescribes"}
             if not same_ps:
                 ok[0] = 0
-            del fl_ps, lab16, full16
+            del fl_ps, lab16, full16, out16, perm, idx_of
         if rank == 0 and not args.no_verify:
             try:
                 t0 = time.perf_counter()
@@ -795,7 +813,8 @@ def run_multi(args, torch, mods, rank, world, local_rank):
         torch.cuda.empty_cache()
         sec = run_shard(other_mode, max(3, args.steps // 4), 2)
         other = {"shard": other_mode, "ms_per_step": sec["ms_per_step"], "value": pv_step / (sec["ms_per_step"] * 1e-3),
-                 "kernel_ms_rank0": sec["kernel_ms"], "labels_equal_primary": bool(torch.equal(sec["labels"], labels))}
+                 "kernel_ms_rank0": sec["kernel_ms"], "kernel_ms_per_rank": sec["kernel_ms_per_rank"],
+                 "labels_equal_primary": bool(torch.equal(sec["labels"], labels))}
         fl = sec["fl"]
 
     # ---- end to end: every rank copies ITS frames from pinned host memory, packs, runs the exchange step, labels land on the host
@@ -854,7 +873,8 @@ def run_multi(args, torch, mods, rank, world, local_rank):
         balg = algorithmic_bytes(N, Fr, H, W, 2, C1, rows=xchg.rows)
         roof = {"bound": "hbm", "achieved": balg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": balg / (kms * 1e-3) / 1e9 / peak,
                 "traffic": None, "kernel": "fuse_kernel<VOTE,U32_T16,HB1> in exchange mode on rank 0 (sweep + slot records written to the owners); "
-                "the dense shard write happens in slot_merge_kernel", "kernel_ms": kms, "algorithmic_bytes": balg, "peak_source": how,
+                "the dense shard write happens in slot_merge_kernel", "kernel_ms": kms, "kernel_ms_per_rank": primary["kernel_ms_per_rank"],
+                "algorithmic_bytes": balg, "peak_source": how,
                 "note": "per-rank bytes: cloud + this rank's frames + this rank's shard of the vote tensor"}
         line = {
             "metric": METRIC, "value": pv_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -719,6 +719,12 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     if (tid < 8) sh.stat[tid] = 0u;
     if (lane < F3D_XCH_NLEVEL) sh.dcache[warp][lane] = make_uint2(0u, 0u);
 
+    if (MODE == MODE_VOTE) {   // every warp clears its own 32 rows (a thread's row is tid * RS) while its points are in flight
+        uint4* h128 = reinterpret_cast<uint4*>(hist + (size_t)warp * 32 * RS);
+        const int n128 = 32 * RS * (int)sizeof(CellT) / 16;
+        for (int i = lane; i < n128; i += 32) h128[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+
     // ---- per-warp bounding box (exact min / max of the float32 coordinates of the warp's 32 points), in every lane
     const float big = 3.0e38f;
     float blo0 = active ? pt.x : big, blo1 = active ? pt.y : big, blo2 = active ? pt.z : big;
@@ -754,7 +760,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     // the warp-box test removes ~45 % of the (warp, frame) pairs of the frames that touch the tile before any per-point work.
     uint16_t* wlist = reinterpret_cast<uint16_t*>(smem_raw + FUSE_OFF_WLIST) + warp * FUSE_WCAP;
     int tbase = 0;         // next entry of the frame list to cull (warp-uniform)
-    bool hist_live = false;   // the warp's histogram rows are cleared lazily: a warp no listed frame can see never touches them
+    bool hist_live = false;   // did any listed frame reach this warp's box?  (if not, its outputs are written without the histogram)
     while (warp_live && tbase < ntest) {
         // ---- conservative (frame, warp box) cull (fp32 + explicit rounding margin; never drops a visible pair)
         int ncand = 0;
@@ -778,12 +784,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             ncand += __popc(bal);
             tbase += 32;
         }
-        if (MODE == MODE_VOTE && ncand > 0 && !hist_live) {   // first candidates of this warp: clear its 32 rows (a thread's row is tid * RS)
-            uint4* h128 = reinterpret_cast<uint4*>(hist + (size_t)warp * 32 * RS);
-            const int n128 = 32 * RS * (int)sizeof(CellT) / 16;
-            for (int i = lane; i < n128; i += 32) h128[i] = make_uint4(0u, 0u, 0u, 0u);
-            hist_live = true;
-        }
+        hist_live = hist_live || ncand > 0;
         __syncwarp();
 
         // ---- warp-autonomous sweep over this warp's candidates of the list: ONE candidate per iteration, software pipelined

@@ -702,6 +702,9 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     const bool use_list = st_n != 0xffffffffu;
     const uint16_t* __restrict__ st_list = P.st_list + (size_t)(blockIdx.x / FUSE_ST_TILES) * FUSE_ST_LCAP;
     const int ntest = use_list ? (int)st_n : P.f_end - P.f_begin;
+    // the first 32 list entries are fetched before the count is known (the list storage always exists): one dependent
+    // memory round trip less on the way to the first vote, which matters for short sweeps (C1: 3.8 candidates per point)
+    const int first_frel = P.st_count ? (int)__ldg(st_list + lane) : lane;
     if (ntest == 0) {
         // No frame of this launch can see the tile's super-tile (the common case of a rank whose frames look at another part
         // of the building): nothing is loaded or cleared, the outputs of "no votes" are written straight away.
@@ -769,7 +772,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             bool kw = fi < ntest;
             int frel = 0;
             if (kw) {
-                frel = use_list ? (int)__ldg(st_list + fi) : fi;
+                frel = use_list ? (tbase == 0 ? first_frel : (int)__ldg(st_list + fi)) : fi;
                 const float4* pl = frec[P.f_begin + frel].cull.pl;
 #pragma unroll
                 for (int m = 0; m < 5; ++m) {

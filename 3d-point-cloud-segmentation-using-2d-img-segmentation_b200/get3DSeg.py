@@ -184,7 +184,9 @@ def panoptic_viz(points, ids, idinfo, outdir, coco_data=None, colors=None, alpha
 def master_classes(dirname):
     """Reference `master_classes` (`get3DSeg.py:369-475`): attaches parent ids / names / box corners from `classes.csv`
     + `classes_meta.json`, rewrites both info.json files and segmentation/final_pcd.ply, then merges intersecting
-    instance boxes (`merge_bb`, `:475`).  Oriented boxes come from `fit_obb` (GPU PCA; Open3D's fit is unpinned)."""
+    instance boxes (`merge_bb`, `:475`).  Oriented boxes come from `fit_obb` (batched GPU fit on the stated box model, see
+    `oracle.fit_box`; Open3D's hull-based fit is unpinned); everything else is pinned against the files the unmodified reference
+    writes for the same inputs (tests/golden/make_golden_master.py)."""
     import torch
     dirname = Path(dirname)
     class_id, parent_name, parent_id, flag_infojson, _ = load_csv(CLASSES_CSV)

@@ -68,3 +68,44 @@ class PointCloud:
 
 geometry = types.SimpleNamespace(OrientedBoundingBox=_Box, PointCloud=PointCloud)
 utility = types.SimpleNamespace(Vector3dVector=lambda a: np.asarray(a, dtype=np.float64))
+
+
+# ---- file I/O and GUI calls of `get3DSeg.master_classes` (`get3DSeg.py:379,465-466`): a binary little-endian PLY reader / writer for
+# x y z (double) [+ uchar colours], and a no-op window -----------------------------------------------------------------------------
+def _read_point_cloud(path):
+    with open(path, "rb") as fp:
+        props, n = [], 0
+        while True:
+            line = fp.readline().decode("ascii").strip()
+            if line.startswith("element vertex"):
+                n = int(line.split()[-1])
+            elif line.startswith("property"):
+                _, typ, name = line.split()
+                props.append((name, {"double": "<f8", "float": "<f4", "uchar": "u1"}[typ]))
+            elif line == "end_header":
+                break
+        rec = np.frombuffer(fp.read(), dtype=props, count=n)
+    return PointCloud(np.stack([rec["x"], rec["y"], rec["z"]], axis=1))
+
+
+def _write_point_cloud(path, pcd):
+    pts = np.asarray(pcd.points, dtype=np.float64)
+    cols = getattr(pcd, "colors", None)
+    fields = [("x", "<f8"), ("y", "<f8"), ("z", "<f8")]
+    header = ["ply", "format binary_little_endian 1.0", f"element vertex {len(pts)}", "property double x", "property double y", "property double z"]
+    if cols is not None:
+        fields += [("red", "u1"), ("green", "u1"), ("blue", "u1")]
+        header += ["property uchar red", "property uchar green", "property uchar blue"]
+    rec = np.zeros(len(pts), dtype=fields)
+    rec["x"], rec["y"], rec["z"] = pts[:, 0], pts[:, 1], pts[:, 2]
+    if cols is not None:
+        c = np.clip(np.asarray(cols, dtype=np.float64) * 255.0, 0, 255).astype(np.uint8)
+        rec["red"], rec["green"], rec["blue"] = c[:, 0], c[:, 1], c[:, 2]
+    with open(path, "wb") as fp:
+        fp.write(("\n".join(header + ["end_header"]) + "\n").encode("ascii"))
+        fp.write(rec.tobytes())
+    return True
+
+
+io = types.SimpleNamespace(read_point_cloud=_read_point_cloud, write_point_cloud=_write_point_cloud)
+visualization = types.SimpleNamespace(draw_geometries=lambda *a, **k: None)

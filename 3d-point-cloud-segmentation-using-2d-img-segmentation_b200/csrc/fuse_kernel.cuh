@@ -655,7 +655,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 // 4-byte asynchronous gather with the 64-byte L2 fill (see gather_u32)
 __device__ __forceinline__ void cp_async4_l2_64(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global.L2::64B [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -664,8 +664,11 @@ __device__ __forceinline__ void cp_async4_l2_64(void* smem_dst, const void* gsrc
 __host__ __device__ constexpr size_t fuse_align16(size_t v) { return (v + 15) & ~(size_t)15; }
 // shared-memory layout: [stage: NW x FUSE_TR FrameFast][texel rings: NW x FUSE_GR x 32 u32][FuseShared][per-warp candidate lists: NW x FUSE_WCAP u16][deferred queues][hist]
 //                       [exchange mode: class lists u8 x FUSE_NSLOT x FUSE_BLOCK][record staging: NW x 512 B]
-#define FUSE_TR 8   // per-warp ring of staged projection tiles (candidates it-2 .. it+2 are live)
-#define FUSE_GR 4   // per-lane ring of gathered texels (candidates it-2 .. it)
+#ifndef FUSE_PD
+#define FUSE_PD 2   // pipeline depth of the sweep: candidate it - PD is consumed while tile it + PD and texel it are started
+#endif
+#define FUSE_TR 8   // per-warp ring of staged projection tiles (candidates it-PD .. it+PD are live)
+#define FUSE_GR 4   // per-lane ring of gathered texels (candidates it-PD .. it)
 #define FUSE_OFF_TEXR ((size_t)FUSE_NW * FUSE_TR * sizeof(FrameFast))
 #define FUSE_OFF_SHARED (FUSE_OFF_TEXR + (size_t)FUSE_NW * FUSE_GR * 32 * sizeof(uint32_t))
 #define FUSE_OFF_WLIST (FUSE_OFF_SHARED + sizeof(FuseShared))
@@ -869,30 +872,43 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
             }
         };
 
-        // frame ids of the candidates in the pipeline (warp-uniform registers): fa = candidate `it`, fb = `it + 1` (tile in
-        // flight), fp1 / fp2 = candidates `it - 1` / `it - 2` (texels in flight / landed); -1 = none
-        int fa = pop();
-        stage_tile(0, fa);
-        cp_async_commit();
-        int fb = pop();
-        stage_tile(1, fb);
-        cp_async_commit();
-        int fp1 = -1, fp2 = -1;
-        uint32_t puv1 = 0, puv2 = 0;   // pixel of candidates i-1 / i-2
-        unsigned sg1 = 0, sg2 = 0;     // their st | g_in << 3
+        // Pipeline depth PD (FUSE_PD): tile `it + PD` and texel `it` are started in iteration `it`, candidate `it - PD` is consumed.
+        // Frame ids of the candidates in the pipeline live in warp-uniform registers: ahead[k] = candidate `it + k` (k < PD, tiles
+        // staged), behind[k] = candidate `it - 1 - k` (texels in flight / landed); -1 = none.
+        constexpr int PD = FUSE_PD;
+        static_assert(PD >= 1 && 2 * PD + 1 <= FUSE_TR && PD + 1 <= FUSE_GR, "rings too small for this pipeline depth");
+        int ahead[PD], behind[PD];
+        uint32_t puvq[PD];      // pixel of candidates it-1 .. it-PD
+        unsigned sgq[PD];       // their st | g_in << 3
+#pragma unroll
+        for (int k = 0; k < PD; ++k) {
+            ahead[k] = pop();
+            stage_tile(k, ahead[k]);
+            cp_async_commit();
+            behind[k] = -1;
+            puvq[k] = 0;
+            sgq[k] = 0;
+        }
 #pragma unroll 1
         for (int it = 0;; ++it) {
-            cp_async_wait_but_one();   // every copy of this lane except the newest group: tile `it`, texel `it - 2` have landed
-            __syncwarp();              // ... everybody else's too; every lane is done with iteration it - 1
-            const int f0 = fa;
-            const int f2 = PIPE ? fp2 : -1;
-            if (f0 < 0 && (!PIPE || (f2 < 0 && fp1 < 0))) break;
-            const int fc = pop();
-            stage_tile((it + 2) & (FUSE_TR - 1), fc);
-            fp2 = fp1;
-            fp1 = fa;
-            fa = fb;
-            fb = fc;
+            cp_async_wait_pending<PD - 1>();   // every copy of this lane except the newest PD-1 groups: tile `it`, texel `it - PD` have landed
+            __syncwarp();                      // ... everybody else's too; every lane is done with iteration it - 1
+            const int f0 = ahead[0];
+            const int fl = PIPE ? behind[PD - 1] : -1;
+            bool drained = f0 < 0;
+            if (PIPE) {
+#pragma unroll
+                for (int k = 0; k < PD; ++k) drained = drained && behind[k] < 0;
+            }
+            if (drained) break;
+            const int fn = pop();
+            stage_tile((it + PD) & (FUSE_TR - 1), fn);
+#pragma unroll
+            for (int k = PD - 1; k > 0; --k) behind[k] = behind[k - 1];
+            behind[0] = f0;
+#pragma unroll
+            for (int k = 0; k + 1 < PD; ++k) ahead[k] = ahead[k + 1];
+            ahead[PD - 1] = fn;
             if (MODE == MODE_VOTE && HB == 1 && f0 >= 0) {
                 // a byte counter holds 255: flush the warp's rows before this candidate could push a cell past the limit
                 if (since_flush + 1 > FUSE_LIMIT8) {
@@ -900,7 +916,7 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
                                stg_all + warp * (FUSE_STG_ROWS * 32), nflush, sh.dcache[warp]);
                     T.nlist = 0;
                     ++nflush;
-                    since_flush = 2;   // the two candidates still in the pipeline vote after this flush
+                    since_flush = PD;   // the candidates still in the pipeline vote after this flush
                 }
                 ++since_flush;
             }
@@ -928,15 +944,19 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
                     consume(f0, s, puv0, sg0, g0, g1, c.z);
                 }
             }
-            cp_async_commit();   // tile it + 2 and texel it travel as one group
-            // ---- candidate `it - 2`: its texel has landed
+            cp_async_commit();   // tile it + PD and texel it travel as one group
+            // ---- candidate `it - PD`: its texel has landed
             if (PIPE) {
-                if (f2 >= 0 && active && ((sg2 & 7u) != 0u || AUDIT))
-                    consume(f2, tiles + ((it + FUSE_TR - 2) & (FUSE_TR - 1)) * 8, puv2, sg2, texr[((it + FUSE_GR - 2) & (FUSE_GR - 1)) * 32], 0u, 0.f);
-                puv2 = puv1;
-                sg2 = sg1;
-                puv1 = puv0;
-                sg1 = sg0;
+                if (fl >= 0 && active && ((sgq[PD - 1] & 7u) != 0u || AUDIT))
+                    consume(fl, tiles + ((it + FUSE_TR - PD) & (FUSE_TR - 1)) * 8, puvq[PD - 1], sgq[PD - 1],
+                            texr[((it + FUSE_GR - PD) & (FUSE_GR - 1)) * 32], 0u, 0.f);
+#pragma unroll
+                for (int k = PD - 1; k > 0; --k) {
+                    puvq[k] = puvq[k - 1];
+                    sgq[k] = sgq[k - 1];
+                }
+                puvq[0] = puv0;
+                sgq[0] = sg0;
             }
         }
         cp_async_wait_all();
@@ -1145,6 +1165,87 @@ static __global__ void __launch_bounds__(256) supertile_cull_kernel(const __grid
     }
     __syncthreads();
     if (tid == 0) st_count[blockIdx.x] = s_n > FUSE_ST_LCAP ? 0xffffffffu : s_n;
+}
+
+// Large scenes (thousands of super-tiles x thousands of frames, C3): the kernel above re-reads the 80-byte plane block
+// of every frame once per super-tile and is bound by that L2 traffic (24.4 K x 5000 x 80 B = 9.8 GB at C3).  Here one
+// CTA owns FUSE_ST_GROUP consecutive super-tiles -- warp w builds the box of super-tile w -- and a thread tests its
+// frame's planes, loaded once, against all of them.  Same rule, same list contents (order within a list is not part of
+// the contract: votes commute).
+#define FUSE_ST_GROUP 8
+static __global__ void __launch_bounds__(256) supertile_cull_group_kernel(const __grid_constant__ FuseParams P, unsigned nst,
+                                                                          unsigned* __restrict__ st_count, uint16_t* __restrict__ st_list) {
+    __shared__ float s_box[FUSE_ST_GROUP][8];
+    __shared__ unsigned s_n[FUSE_ST_GROUP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned st0 = blockIdx.x * FUSE_ST_GROUP;
+    {
+        const int64_t p0 = (int64_t)(st0 + warp) * FUSE_ST_POINTS;
+        const float big = 3.0e38f;
+        float lo[3] = {big, big, big}, hi[3] = {-big, -big, -big};
+#pragma unroll 4
+        for (int k = 0; k < FUSE_ST_POINTS / 32; ++k) {
+            const int64_t i = p0 + (int64_t)k * 32 + lane;
+            if (i < P.N) {
+                const float4 q = __ldg(P.points + i);
+                lo[0] = fminf(lo[0], q.x); hi[0] = fmaxf(hi[0], q.x);
+                lo[1] = fminf(lo[1], q.y); hi[1] = fmaxf(hi[1], q.y);
+                lo[2] = fminf(lo[2], q.z); hi[2] = fmaxf(hi[2], q.z);
+            }
+        }
+#pragma unroll
+        for (int s2 = 16; s2 > 0; s2 >>= 1)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], s2));
+                hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], s2));
+            }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                s_box[warp][k] = lo[k];
+                s_box[warp][3 + k] = hi[k];
+            }
+            s_box[warp][6] = fabsf(lo[0]) + fabsf(lo[1]) + fabsf(lo[2]) + fabsf(hi[0]) + fabsf(hi[1]) + fabsf(hi[2]);
+            s_n[warp] = 0u;
+        }
+    }
+    __syncthreads();
+    const FrameRecord* __restrict__ frec = reinterpret_cast<const FrameRecord*>(P.table);
+    const int nf = P.f_end - P.f_begin;
+    const int ns = min((unsigned)FUSE_ST_GROUP, nst - st0);
+    for (int f0 = 0; f0 < nf; f0 += 256) {
+        const int fi = f0 + tid;
+        float4 pl[5];
+        if (fi < nf) {
+            const float4* src = frec[P.f_begin + fi].cull.pl;
+#pragma unroll
+            for (int m = 0; m < 5; ++m) pl[m] = __ldg(src + m);
+        }
+        for (int s = 0; s < ns; ++s) {
+            bool keep = fi < nf;
+            if (keep) {
+                const float l0 = s_box[s][0], l1 = s_box[s][1], l2 = s_box[s][2], h0 = s_box[s][3], h1 = s_box[s][4], h2 = s_box[s][5];
+                const float box_mag = s_box[s][6];
+#pragma unroll
+                for (int m = 0; m < 5; ++m) {
+                    const float4 q = pl[m];
+                    const float mx = fmaxf(q.x * l0, q.x * h0) + fmaxf(q.y * l1, q.y * h1) + fmaxf(q.z * l2, q.z * h2) - q.w;
+                    const float margin = 2.0e-6f * (box_mag + fabsf(q.w)) + 1.0e-7f;
+                    keep = keep && (mx >= -margin);
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (bal == 0u) continue;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&s_n[s], (unsigned)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned at = base + __popc(bal & ((1u << lane) - 1u));
+            if (keep && at < FUSE_ST_LCAP) st_list[(size_t)(st0 + s) * FUSE_ST_LCAP + at] = (uint16_t)fi;
+        }
+    }
+    __syncthreads();
+    if (tid < ns) st_count[st0 + tid] = s_n[tid] > FUSE_ST_LCAP ? 0xffffffffu : s_n[tid];
 }
 
 // ---- fix-up kernels: the deferred point-views, one per thread, in fp64 ------------------------------------------------
@@ -1432,7 +1533,13 @@ static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stre
     if (P.st_count) {
         if (P.f_end - P.f_begin > 32) {
             const unsigned nst = (unsigned)((P.N + FUSE_ST_POINTS - 1) / FUSE_ST_POINTS);
-            supertile_cull_kernel<<<nst, 256, 0, stream>>>(P, const_cast<unsigned*>(P.st_count), const_cast<uint16_t*>(P.st_list));
+            // grouped variant once there are enough super-tiles to fill the GPU with groups and enough frames for the
+            // plane re-reads to matter
+            if (nst >= 148u * 2u * FUSE_ST_GROUP && P.f_end - P.f_begin >= 256)
+                supertile_cull_group_kernel<<<(nst + FUSE_ST_GROUP - 1) / FUSE_ST_GROUP, 256, 0, stream>>>(
+                    P, nst, const_cast<unsigned*>(P.st_count), const_cast<uint16_t*>(P.st_list));
+            else
+                supertile_cull_kernel<<<nst, 256, 0, stream>>>(P, const_cast<unsigned*>(P.st_count), const_cast<uint16_t*>(P.st_list));
         } else {
             P.st_count = nullptr;   // few frames: the per-tile scan is cheaper than another launch
         }

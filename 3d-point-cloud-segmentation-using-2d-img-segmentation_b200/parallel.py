@@ -206,9 +206,11 @@ class VoteExchange:
                     peer_dir_ptrs=self.peer_dir_ptrs, peer_queue_ptrs=self.peer_queue_ptrs, sub_rows=self.sub_rows,
                     sub_cap=self.sub_cap, cursors=self.cursors, overflow=self.overflow)
 
-    def run(self, fuse, nclasses_id, threshold=0.5, filter_classes=None, check=True) -> torch.Tensor:
+    def run(self, fuse, nclasses_id, threshold=0.5, filter_classes=None, check=True, gather=True) -> torch.Tensor:
         """`fuse(**self.fuse_args())` enqueues the exchange-mode fused kernel over this rank's frames.  Returns labels
-        [npoints]; `self.shard[:self.rows]` holds this rank's reduced votes.
+        [npoints]; `self.shard[:self.rows]` holds this rank's reduced votes.  `gather=False` skips the all-gather and
+        returns only the labels of the points this rank owns, [rank*per, rank*per + rows) -- for callers that deliver
+        each shard themselves (e.g. every rank copies its slice into one shared host array).
 
         A sub-queue that fills up DROPS entries (`xg_append`): the sender's flag is max-reduced over the ranks on the
         device right after the exchange and copied to pinned host memory.  `check=True` (default) waits for it and raises
@@ -230,7 +232,9 @@ class VoteExchange:
         # labels are class ids < 2^15 (C1 <= 256 columns, filter values are columns): gather them as int16 (a quarter of
         # the int64 bytes over the fabric) and widen once
         grp = self.group if self.group is not dist.group.WORLD else None
-        if 0 <= int(nclasses_id) < 32768:
+        if not gather:
+            pass
+        elif 0 <= int(nclasses_id) < 32768:
             self.lab16.copy_(self.lab)
             _all_gather(self.full16.view(torch.uint8), self.lab16.view(torch.uint8), grp)   # NCCL has no int16: move bytes
             self.full.copy_(self.full16)
@@ -245,6 +249,8 @@ class VoteExchange:
         self._ovf_pending = True
         if check is True:
             self._raise_if_overflowed(wait=True)
+        if not gather:
+            return self.lab[:self.rows]
         return self.full[:self.npoints]
 
     def _raise_if_overflowed(self, wait: bool):

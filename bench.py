@@ -473,16 +473,19 @@ def run_single(args, torch, mods):
     # ---- the same step on the two-array inputs and with the re-pack inside the step
     alt = {}
     n_alt = max(3, args.steps // 5)
-    v2 = torch.empty_like(fl.votes)
-    l2 = torch.empty_like(fl.labels)
-    kt2 = engine.KernelTimer()
-    ms2 = timed(torch, lambda: engine.fuse_project_vote_resolve(fl.points4, fl.table, depth, masks, C1, NCLASSES, RADIUS, fl.zmin, fl.zmax,
-                                                                THRESHOLD, None, votes=v2, labels=l2, timer=kt2), n_alt)
-    same2 = bool(torch.equal(v2, fl.votes) and torch.equal(l2, fl.labels))
-    alt["two_array_inputs"] = {"ms_per_step": ms2, "value": pv_step / (ms2 * 1e-3), "kernel_ms": float(np.mean(kt2.ms()[1:])),
-                               "roofline_frac": balg / (float(np.mean(kt2.ms()[1:])) * 1e-3) / 1e9 / peak, "same_result": same2,
-                               "what": "uint16 depth [F,H,W] + uint8 mask [F,H,W] stacks gathered separately (round-1 layout)"}
-    del v2, l2
+    if torch.cuda.mem_get_info()[0] < fl.votes.numel() * 4 * 1.1 + (2 << 30):
+        alt["two_array_inputs"] = {"skipped": "a second vote tensor does not fit beside this workload"}
+    else:
+        v2 = torch.empty_like(fl.votes)
+        l2 = torch.empty_like(fl.labels)
+        kt2 = engine.KernelTimer()
+        ms2 = timed(torch, lambda: engine.fuse_project_vote_resolve(fl.points4, fl.table, depth, masks, C1, NCLASSES, RADIUS, fl.zmin, fl.zmax,
+                                                                    THRESHOLD, None, votes=v2, labels=l2, timer=kt2), n_alt)
+        same2 = bool(torch.equal(v2, fl.votes) and torch.equal(l2, fl.labels))
+        alt["two_array_inputs"] = {"ms_per_step": ms2, "value": pv_step / (ms2 * 1e-3), "kernel_ms": float(np.mean(kt2.ms()[1:])),
+                                   "roofline_frac": balg / (float(np.mean(kt2.ms()[1:])) * 1e-3) / 1e9 / peak, "same_result": same2,
+                                   "what": "uint16 depth [F,H,W] + uint8 mask [F,H,W] stacks gathered separately (round-1 layout)"}
+        del v2, l2
 
     def repack_step():
         fl.pack(depth, masks)
@@ -820,7 +823,20 @@ def run_multi(args, torch, mods, rank, world, local_rank):
     # ---- end to end: every rank copies ITS frames from pinned host memory, packs, runs the exchange step, labels land on the host
     e2e = None
     if not args.no_e2e:
-        ok = 1
+        # one host label array for the whole job: a /dev/shm file every rank maps; each rank page-locks and fills the slice
+        # of the points it owns (gathering first would only make `world` redundant 0.8 GB device->host copies)
+        path = [None]
+        if rank == 0:
+            try:
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize > N * 8 + (1 << 30):          # a short tmpfs would SIGBUS on first touch
+                    path = [f"/dev/shm/f3d_bench_labels_{os.getpid()}"]
+                    np.memmap(path[0], dtype=np.int64, mode="w+", shape=(N,)).flush()
+            except OSError:
+                path = [None]
+        dist.broadcast_object_list(path, src=0)
+        ok, shared_out = 1, path[0] is not None
+        own_a = rank * xchg.per
         try:
             ids = other and parallel.frame_shard_ids(F_total, rank, world, other["shard"]) or primary["ids"]
             dd, mm = build_frames(torch, engine, fl, spec, ids, keep_unpacked=True)
@@ -829,7 +845,15 @@ def run_multi(args, torch, mods, rank, world, local_rank):
             h_depth.copy_(dd)
             h_masks.copy_(mm)
             del dd, mm
-            h_out = torch.empty(N, dtype=torch.int64, pin_memory=True)
+            h_all = None
+            if shared_out:
+                h_all = torch.from_numpy(np.memmap(path[0], dtype=np.int64, mode="r+", shape=(N,)))
+                h_out = h_all[own_a:own_a + xchg.rows]
+                h_out.zero_()                                  # first touch on this rank's NUMA node
+                if xchg.rows and int(torch.cuda.cudart().cudaHostRegister(h_out.data_ptr(), h_out.numel() * 8, 0)) != 0:
+                    shared_out = False                         # cannot page-lock the mapping
+            if not shared_out:                                 # private pinned slice instead
+                h_out = torch.empty(xchg.rows, dtype=torch.int64, pin_memory=True)
         except Exception as ex:   # noqa: BLE001
             ok = 0
             print(f"bench.py: rank {rank}: no pinned host memory for the end-to-end arm ({ex})", file=sys.stderr)
@@ -847,7 +871,7 @@ def run_multi(args, torch, mods, rank, world, local_rank):
                     dist.barrier()
                     t0 = time.perf_counter()
                 fl.ingest(h_depth, h_masks, 64)
-                lab = xchg.run(fuse_e, NCLASSES, THRESHOLD, None, check="deferred")
+                lab = xchg.run(fuse_e, NCLASSES, THRESHOLD, None, check="deferred", gather=False)
                 h_out.copy_(lab, non_blocking=True)
             torch.cuda.synchronize()
             xchg.finish()
@@ -856,15 +880,32 @@ def run_multi(args, torch, mods, rank, world, local_rank):
             tt = torch.tensor([sec], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             sec = float(tt.item())
-            same = bool(torch.equal(torch.as_tensor(h_out.numpy()).cuda(), labels))
+            sh = torch.tensor([int(shared_out)], device="cuda")
+            dist.all_reduce(sh, op=dist.ReduceOp.MIN)
+            shared_all = bool(sh.item())
+            if shared_all:                                      # rank 0 reads the WHOLE shared array
+                same_i = int(torch.equal(h_all.cuda(), labels)) if rank == 0 else 1
+            else:
+                same_i = int(torch.equal(h_out.cuda(), labels[own_a:own_a + xchg.rows]))
+            sm = torch.tensor([same_i], device="cuda")
+            dist.all_reduce(sm, op=dist.ReduceOp.MIN)
+            same = bool(sm.item())
+            if shared_out and xchg.rows:
+                torch.cuda.cudart().cudaHostUnregister(h_out.data_ptr())
+            del h_out, h_all
             h2d = int(h_depth.numel() * 2 + h_masks.numel())
             tot = torch.tensor([h2d], device="cuda", dtype=torch.int64)
             dist.all_reduce(tot)
-            e2e = {"value": pv_step / sec, "unit": UNIT, "h2d_bytes_per_step": int(tot.item()), "d2h_bytes_per_step": int(N * 8) * world,
+            e2e = {"value": pv_step / sec, "unit": UNIT, "h2d_bytes_per_step": int(tot.item()), "d2h_bytes_per_step": int(N * 8),
                    "ms_per_step": sec * 1e3, "steps": n_e2e, "labels_match_device_run": same, "h2d_gb_per_s_per_rank": h2d / sec / 1e9,
                    "api": "per rank: pinned host uint16 depth + uint8 masks of its frames -> FusedLabeler.ingest (copy stream + pack) -> "
-                          "parallel.VoteExchange.run -> labels -> pinned host"}
+                          "parallel.VoteExchange.run(gather=False) -> every rank copies the labels of the points it owns into its slice of ONE "
+                          "page-locked host array shared by the ranks (/dev/shm); rank 0 checks the whole array against the device run"}
+            e2e["host_labels"] = "one shared page-locked array" if shared_all else "per-rank pinned slices"
             del h_depth, h_masks
+        dist.barrier()
+        if rank == 0 and path[0] and os.path.exists(path[0]):
+            os.unlink(path[0])
 
     if rank == 0:
         peak, how = peaks()

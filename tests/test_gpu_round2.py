@@ -255,3 +255,31 @@ def test_unseen_supertiles_fast_path(engine, scenes):
         v16 = torch.full((len(pts), 134), 9, dtype=torch.uint16, device="cuda")
         engine.fuse_project_vote(p4, tab, frames, m, 134, 0.05, 0.1, 4.0, votes=v16)
         assert np.array_equal(v16.cpu().numpy().astype(np.int64), ov)
+
+
+def test_grouped_supertile_cull_keeps_every_contributing_frame(engine, scenes):
+    """Large clouds take the grouped first-level cull (one CTA per 8 super-tiles).  A frame missing from a list would
+    lose its votes; launches of <= 32 frames skip the first level altogether, so the chunked sum is the reference."""
+    npts, nframes, W, H = 2368 * 4096 + 1234, 288, 64, 48          # just past the switch-over, ragged last super-tile
+    spec = scenes.scaled_spec("C1", npoints=npts, nframes=nframes, width=W, height=H, seed=21)
+    K = scenes.scaled_intrinsics(W, H)
+    wxyz, t = scenes.make_poses(spec)
+    pts = scenes.make_cloud(spec)
+    rng = np.random.default_rng(5)
+    depths = np.repeat(np.repeat(rng.integers(800, 3500, (nframes, H // 8, W // 8)), 8, axis=1), 8, axis=2).astype(np.uint16)
+    masks = scenes.block_masks((H, W), nframes, seed=3, block=8)
+    tab = engine.FrameTable(K, W, H, wxyz, t, 4.0)
+    p4 = engine.pack_points(pts)
+    pk = engine.pack_frames(dev(depths), dev(masks))
+    one = engine.fuse_project_vote(p4, tab, pk, None, 134, 0.05, 0.1, 4.0)
+    acc = None
+    for a in range(0, nframes, 32):
+        b = min(a + 32, nframes)
+        acc = engine.fuse_project_vote(p4, tab, pk.slice(a, b), None, 134, 0.05, 0.1, 4.0, votes=acc, accumulate=acc is not None,
+                                       frame_begin=a, frame_end=b)
+    assert int(one.sum()) > 100000
+    assert torch.equal(one, acc)
+    # and against the oracle on a strided sample of the points
+    idx = np.arange(0, npts, 4099)
+    ov = orc.fuse_project_vote(pts[idx], K, W, H, wxyz, t, depths, masks, 134, 0, 0.05, 0.1, 4.0, 4.0)
+    assert np.array_equal(one[torch.as_tensor(idx, device="cuda")].cpu().numpy(), ov)

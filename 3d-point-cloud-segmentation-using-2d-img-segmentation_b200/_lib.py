@@ -39,8 +39,8 @@ SIGNATURES = {
     "f3d_fuse_project_vote_exchange": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64, _f64,
                                                  _i32, _i32, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _vp]),
     "f3d_exchange_publish": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp]),
-    "f3d_exchange_merge": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _vp]),
-    "f3d_exchange_queue_apply": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp]),
+    "f3d_exchange_merge": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "f3d_exchange_queue_apply": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _i64, _vp]),
     "f3d_fuse_project_vote_resolve": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _f64,
                                                 _f64, _vp, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _i32, _vp]),
     "f3d_fuse_uv2pt": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _f64, _f64, _f64, _vp, _vp,

@@ -25,6 +25,19 @@ struct PeerPtrs {
     unsigned* p[F3D_MAX_RANKS];
 };
 
+// all-gather of the labels fused into the kernels that produce them: every rank keeps an int16 array of ALL points in
+// symmetric memory and the owner stores each label it resolves into the G copies (2 B per point and peer, coalesced
+// 64-byte segments per warp) -- the NVLink traffic rides under the HBM-bound merge instead of following it as a collective
+struct PeerLabels {
+    int16_t* p[F3D_MAX_RANKS];
+    int G;              // 0: no broadcast
+    long long first;    // global index of this rank's first point
+};
+
+__device__ __forceinline__ void bcast_label(const PeerLabels& PL, long long row, int64_t label) {
+    for (int d = 0; d < PL.G; ++d) PL.p[d][PL.first + row] = (int16_t)label;
+}
+
 // this rank's queue cursors [G][F3D_XCH_NSUB] -> row [rank] of every owner's count table [G][F3D_XCH_NSUB]
 __global__ void exchange_publish_kernel(const unsigned* __restrict__ qcur, PeerPtrs counts, int rank, int G, unsigned subcap) {
     const int d = blockIdx.y;
@@ -54,7 +67,8 @@ __global__ void __launch_bounds__(256) queue_accumulate_kernel(const unsigned lo
 __global__ void __launch_bounds__(256) queue_relabel_kernel(const unsigned long long* __restrict__ rx,
                                                             const unsigned* __restrict__ counts, unsigned subcap,
                                                             const int32_t* __restrict__ votes, long long nrows, int C1,
-                                                            const __grid_constant__ FuseResolve RP, int64_t* __restrict__ labels) {
+                                                            const __grid_constant__ FuseResolve RP, int64_t* __restrict__ labels,
+                                                            const __grid_constant__ PeerLabels PL) {
     __shared__ int16_t s_fpos[RES_MAXC];
     for (int c = threadIdx.x; c < RES_MAXC; c += blockDim.x) s_fpos[c] = RP.fpos[c];
     __syncthreads();
@@ -84,7 +98,9 @@ __global__ void __launch_bounds__(256) queue_relabel_kernel(const unsigned long 
             if (live && sub8 == 0) {
                 bool unc = (total <= 0) || (best <= 0);                                    // voting.py:126,131
                 if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;          // voting.py:128-130
-                labels[pt] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
+                const int64_t lab = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
+                labels[pt] = lab;
+                bcast_label(PL, pt, lab);
             }
         }
     }
@@ -97,7 +113,8 @@ __global__ void __launch_bounds__(XCH_BLOCK, 3) slot_merge_kernel(const uint16_t
                                                                   int G, long long rows_cap, long long blocks_per_src,
                                                                   long long nrows, int C1, int RS,
                                                                   const __grid_constant__ FuseResolve RP,
-                                                                  int32_t* __restrict__ votes, int64_t* __restrict__ labels) {
+                                                                  int32_t* __restrict__ votes, int64_t* __restrict__ labels,
+                                                                  const __grid_constant__ PeerLabels PL) {
     extern __shared__ __align__(16) unsigned char xs[];
     int16_t* s_fpos = reinterpret_cast<int16_t*>(xs);
     uint16_t* hist = reinterpret_cast<uint16_t*>(xs + RES_MAXC * sizeof(int16_t));
@@ -191,8 +208,25 @@ __global__ void __launch_bounds__(XCH_BLOCK, 3) slot_merge_kernel(const uint16_t
     if (labels && p < nrows) {
         bool unc = (total <= 0) || (best <= 0);                                    // voting.py:126,131
         if (!unc) unc = xdiv((double)best, (double)total) < RP.threshold;          // voting.py:128-130
-        labels[p] = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
+        const int64_t lab = (int64_t)(unc ? RP.unclassified : RP.remap[bpos]);
+        labels[p] = lab;
+        bcast_label(PL, p, lab);
     }
+}
+
+static int fill_peer_labels(PeerLabels& PL, const uint64_t* h_peer_labels16, int32_t nranks, int64_t first_point, const char* who) {
+    PL.G = 0;
+    PL.first = 0;
+    for (int i = 0; i < F3D_MAX_RANKS; ++i) PL.p[i] = nullptr;
+    if (!h_peer_labels16) return F3D_OK;
+    if (first_point < 0) return f3d_fail(F3D_ERR_ARG, who);
+    for (int i = 0; i < nranks; ++i) {
+        if (!h_peer_labels16[i]) return f3d_fail(F3D_ERR_ARG, who);
+        PL.p[i] = reinterpret_cast<int16_t*>(h_peer_labels16[i]);
+    }
+    PL.G = nranks;
+    PL.first = first_point;
+    return F3D_OK;
 }
 
 static int xch_row_stride(int C1) {
@@ -225,7 +259,8 @@ extern "C" int f3d_exchange_publish(const uint32_t* cursors, const uint64_t* h_p
 
 extern "C" int f3d_exchange_queue_apply(const uint64_t* queue, const uint32_t* counts, int32_t nranks, int64_t sub_cap,
                                         int32_t* votes, int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter,
-                                        int32_t nfilter, int32_t nclasses_id, int64_t* labels, void* stream) {
+                                        int32_t nfilter, int32_t nclasses_id, int64_t* labels, const uint64_t* h_peer_labels16,
+                                        int64_t first_point, void* stream) {
     if (!queue || !counts || !votes || nranks < 1 || nranks > F3D_MAX_RANKS || sub_cap <= 0 || nrows < 0 || C1 <= 0 || C1 > 256 ||
         nfilter < 0 || (nfilter > 0 && !h_filter))
         return f3d_fail(F3D_ERR_ARG, "f3d_exchange_queue_apply: bad argument");
@@ -238,15 +273,19 @@ extern "C" int f3d_exchange_queue_apply(const uint64_t* queue, const uint32_t* c
         FuseResolve RP;
         int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
         if (rc) return rc;
+        PeerLabels PL;
+        rc = fill_peer_labels(PL, h_peer_labels16, nranks, first_point, "f3d_exchange_queue_apply: bad peer label table");
+        if (rc) return rc;
         queue_relabel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(queue), counts,
-                                                                    (unsigned)sub_cap, votes, (long long)nrows, C1, RP, labels);
+                                                                    (unsigned)sub_cap, votes, (long long)nrows, C1, RP, labels, PL);
     }
     return f3d_check_launch("f3d_exchange_queue_apply");
 }
 
 extern "C" int f3d_exchange_merge(const uint16_t* slots, const void* dir, int32_t nranks, int64_t sub_rows,
                                   int64_t points_per_shard, int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter,
-                                  int32_t nfilter, int32_t nclasses_id, int32_t* votes, int64_t* labels, void* stream) {
+                                  int32_t nfilter, int32_t nclasses_id, int32_t* votes, int64_t* labels,
+                                  const uint64_t* h_peer_labels16, int64_t first_point, void* stream) {
     if (!slots || !dir || nranks < 1 || nranks > F3D_MAX_RANKS || sub_rows <= 0 || points_per_shard <= 0 ||
         (points_per_shard % XCH_BLOCK) != 0 || nrows < 0 || nrows > points_per_shard || C1 <= 0 || C1 > 256 || (!votes && !labels) ||
         nfilter < 0 || (nfilter > 0 && !h_filter) || (votes && (reinterpret_cast<uintptr_t>(votes) & 15u)))
@@ -254,6 +293,9 @@ extern "C" int f3d_exchange_merge(const uint16_t* slots, const void* dir, int32_
     if (nrows == 0) return F3D_OK;
     FuseResolve RP;
     int rc = f3d_build_resolve(C1, threshold, h_filter, nfilter, nclasses_id, RP);
+    if (rc) return rc;
+    PeerLabels PL;
+    rc = fill_peer_labels(PL, labels ? h_peer_labels16 : nullptr, nranks, first_point, "f3d_exchange_merge: bad peer label table");
     if (rc) return rc;
     const int RS = xch_row_stride(C1);
     const size_t smem = RES_MAXC * sizeof(int16_t) + (((size_t)XCH_BLOCK * RS * 2 + 15) & ~(size_t)15);
@@ -263,6 +305,6 @@ extern "C" int f3d_exchange_merge(const uint16_t* slots, const void* dir, int32_
     slot_merge_kernel<<<(unsigned)tiles, XCH_BLOCK, smem, (cudaStream_t)stream>>>(slots, reinterpret_cast<const uint2*>(dir), nranks,
                                                                                 (long long)sub_rows * F3D_XCH_NREG,
                                                                                 points_per_shard / 32, (long long)nrows, C1, RS, RP,
-                                                                                votes, labels);
+                                                                                votes, labels, PL);
     return f3d_check_launch("f3d_exchange_merge");
 }

@@ -277,21 +277,26 @@ def exchange_publish(cursors, peer_count_ptrs, rank, sub_cap):
 
 
 def exchange_merge(slots, dirs, nranks, sub_rows, points_per_shard, nrows, nclasses1, nclasses_id, threshold=0.5,
-                   filter_classes=None, votes=None, labels=None):
-    """Owner side: merge the slot records of all source ranks into the dense int32 shard rows and the labels."""
+                   filter_classes=None, votes=None, labels=None, peer_labels16=None, first_point=0):
+    """Owner side: merge the slot records of all source ranks into the dense int32 shard rows and the labels.
+    `peer_labels16` (numpy uint64 [nranks] of device pointers to every rank's int16 label array of all points) makes the
+    kernel store each label at `first_point + row` of all of them -- the label all-gather rides inside the merge."""
     filt, nf = _filter_arg(filter_classes)
+    pl = None if peer_labels16 is None else peer_labels16.ctypes.data
     check(load().f3d_exchange_merge(ptr(slots), ptr(dirs), int(nranks), int(sub_rows), int(points_per_shard), int(nrows),
                                     int(nclasses1), float(threshold), ptr(filt), nf, int(nclasses_id), ptr(votes), ptr(labels),
-                                    stream_ptr()), "f3d_exchange_merge")
+                                    pl, int(first_point), stream_ptr()), "f3d_exchange_merge")
 
 
 def exchange_queue_apply(queue, counts, nranks, sub_cap, votes, nrows, nclasses_id, labels=None, threshold=0.5,
-                         filter_classes=None):
-    """Owner side: scatter-add the received (cell, count) entries into the shard and re-resolve the touched points."""
+                         filter_classes=None, peer_labels16=None, first_point=0):
+    """Owner side: scatter-add the received (cell, count) entries into the shard and re-resolve the touched points
+    (`peer_labels16` / `first_point` as in exchange_merge)."""
     filt, nf = _filter_arg(filter_classes)
+    pl = None if peer_labels16 is None else peer_labels16.ctypes.data
     check(load().f3d_exchange_queue_apply(ptr(queue), ptr(counts), int(nranks), int(sub_cap), ptr(votes), int(nrows),
                                           votes.shape[1], float(threshold), ptr(filt), nf, int(nclasses_id), ptr(labels),
-                                          stream_ptr()), "f3d_exchange_queue_apply")
+                                          pl, int(first_point), stream_ptr()), "f3d_exchange_queue_apply")
 
 
 def fuse_uv2pt(points4, table: FrameTable, depth, radius=0.05, zmin=0.1, zmax=4.0, stats=None, audit=False,

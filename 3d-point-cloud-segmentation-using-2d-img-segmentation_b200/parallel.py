@@ -197,8 +197,13 @@ class VoteExchange:
         self.shard = torch.zeros((max(self.per, 1), c1), dtype=torch.int32, device=self.device)
         self.lab = torch.zeros(max(self.per, 1), dtype=torch.int64, device=self.device)
         self.full = torch.zeros(max(self.per, 1) * G, dtype=torch.int64, device=self.device)
-        self.lab16 = torch.zeros(max(self.per, 1), dtype=torch.int16, device=self.device)
-        self.full16 = torch.zeros(max(self.per, 1) * G, dtype=torch.int16, device=self.device)
+        # every rank's int16 copy of ALL labels, in symmetric memory: the owners store into the G copies from inside the
+        # merge / queue-apply kernels (the label all-gather as peer stores under an HBM-bound kernel)
+        self.full16 = symm.empty(max(self.per, 1) * G, dtype=torch.int16, device=self.device)
+        self.full16.zero_()
+        self.hdl16 = symm.rendezvous(self.full16, self.group)
+        self.peer_label_ptrs = np.array([self.hdl16.get_buffer(d, (max(self.per, 1) * G,), torch.int16).data_ptr() for d in range(G)],
+                                        dtype=np.uint64)
 
     def fuse_args(self):
         """Keyword arguments of engine.fuse_project_vote_exchange that describe this exchange."""
@@ -224,21 +229,20 @@ class VoteExchange:
         fuse(**self.fuse_args())
         eng.exchange_publish(self.cursors, self.peer_count_ptrs, self.rank, self.sub_cap)
         self.hdl.barrier(channel=1)
+        # labels are class ids < 2^15 (C1 <= 256 columns, filter values are columns): they travel as int16, stored by the
+        # owner straight into every rank's copy while it merges; wider ids fall back to an int64 all-gather
+        grp = self.group if self.group is not dist.group.WORLD else None
+        narrow = gather and 0 <= int(nclasses_id) < 32768 and all(0 <= int(c) < 32768 for c in (filter_classes or ()))
+        bc = dict(peer_labels16=self.peer_label_ptrs, first_point=self.rank * self.per) if narrow else {}
         if self.rows > 0:
             eng.exchange_merge(self.rx_slots, self.rx_dir, self.world, self.sub_rows, self.per, self.rows, self.c1, nclasses_id,
-                               threshold, filter_classes, votes=self.shard, labels=self.lab)
+                               threshold, filter_classes, votes=self.shard, labels=self.lab, **bc)
             eng.exchange_queue_apply(self.rx_queue, self.rx_count, self.world, self.sub_cap, self.shard, self.rows, nclasses_id,
-                                     self.lab, threshold, filter_classes)
-        # labels are class ids < 2^15 (C1 <= 256 columns, filter values are columns): gather them as int16 (a quarter of
-        # the int64 bytes over the fabric) and widen once
-        grp = self.group if self.group is not dist.group.WORLD else None
-        if not gather:
-            pass
-        elif 0 <= int(nclasses_id) < 32768:
-            self.lab16.copy_(self.lab)
-            _all_gather(self.full16.view(torch.uint8), self.lab16.view(torch.uint8), grp)   # NCCL has no int16: move bytes
+                                     self.lab, threshold, filter_classes, **bc)
+        if narrow:
+            self.hdl.barrier(channel=2)          # every owner's label stores have landed
             self.full.copy_(self.full16)
-        else:
+        elif gather:
             _all_gather(self.full, self.lab, grp)
         # overflow: any rank's dropped entry invalidates every rank's result
         self.ovf_any.copy_(self.overflow)

@@ -883,15 +883,16 @@ def run_multi(args, torch, mods, rank, world, local_rank):
             sh = torch.tensor([int(shared_out)], device="cuda")
             dist.all_reduce(sh, op=dist.ReduceOp.MIN)
             shared_all = bool(sh.item())
-            if shared_all:                                      # rank 0 reads the WHOLE shared array
-                same_i = int(torch.equal(h_all.cuda(), labels)) if rank == 0 else 1
+            if shared_out and xchg.rows:
+                torch.cuda.cudart().cudaHostUnregister(h_out.data_ptr())
+            dist.barrier()
+            if shared_all:                                      # rank 0 reads the WHOLE shared array (as plain pageable memory)
+                same_i = int(torch.equal(h_all.clone().cuda(), labels)) if rank == 0 else 1
             else:
-                same_i = int(torch.equal(h_out.cuda(), labels[own_a:own_a + xchg.rows]))
+                same_i = int(torch.equal(h_out.clone().cuda(), labels[own_a:own_a + xchg.rows]))
             sm = torch.tensor([same_i], device="cuda")
             dist.all_reduce(sm, op=dist.ReduceOp.MIN)
             same = bool(sm.item())
-            if shared_out and xchg.rows:
-                torch.cuda.cudart().cudaHostUnregister(h_out.data_ptr())
             del h_out, h_all
             h2d = int(h_depth.numel() * 2 + h_masks.numel())
             tot = torch.tensor([h2d], device="cuda", dtype=torch.int64)

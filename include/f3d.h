@@ -136,7 +136,10 @@ int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_t
  * pointer to rank d's uint32 [nranks][NSUB] table; row [rank] is written).  After a cross-rank barrier the owner runs
  *   f3d_exchange_merge       (records of all sources -> dense int32 shard rows [nrows, C1], every cell written once, and
  *                             labels: VotingSegmentation.segment, voting.py:106-137), then
- *   f3d_exchange_queue_apply (queue entries scatter-added into the shard, labels of the touched points re-resolved). */
+ *   f3d_exchange_queue_apply (queue entries scatter-added into the shard, labels of the touched points re-resolved).
+ * The label all-gather can ride inside these two kernels: h_peer_labels16 (host array of nranks device pointers, one per
+ * rank, each an int16 array of nranks * points_per_shard labels in peer-mapped memory; NULL = off) makes the owner store
+ * every label it resolves at index first_point + row of all nranks arrays (labels must fit int16). */
 int f3d_exchange_constants(int32_t* out4);
 int f3d_fuse_project_vote_exchange(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                                    int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,
@@ -149,10 +152,12 @@ int f3d_exchange_publish(const uint32_t* cursors, const uint64_t* h_peer_counts,
                          int64_t sub_cap, void* stream);
 int f3d_exchange_merge(const uint16_t* slots, const void* dir, int32_t nranks, int64_t sub_rows, int64_t points_per_shard,
                        int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter, int32_t nfilter,
-                       int32_t nclasses_id, int32_t* votes, int64_t* labels, void* stream);
+                       int32_t nclasses_id, int32_t* votes, int64_t* labels, const uint64_t* h_peer_labels16,
+                       int64_t first_point, void* stream);
 int f3d_exchange_queue_apply(const uint64_t* queue, const uint32_t* counts, int32_t nranks, int64_t sub_cap, int32_t* votes,
                              int64_t nrows, int32_t C1, double threshold, const int32_t* h_filter, int32_t nfilter,
-                             int32_t nclasses_id, int64_t* labels, void* stream);
+                             int32_t nclasses_id, int64_t* labels, const uint64_t* h_peer_labels16, int64_t first_point,
+                             void* stream);
 
 /* f3d_fuse_project_vote with VotingSegmentation.segment (segUtils/voting.py:106-137, see f3d_resolve_labels) fused
  * into the epilogue: labels [N] int64 are resolved straight from the on-chip histograms, so the vote tensor is

@@ -414,16 +414,24 @@ def _emulated_exchange(engine, s, world, nclasses_id=133, thr=0.5, fc=None, sub_
     torch.cuda.synchronize()
     assert int(overflow.item()) == 0
     votes, labels = [], []
+    # the label all-gather rides inside the owner kernels: every "rank" keeps an int16 copy of all labels
+    full16 = [torch.full((per * world,), -7, dtype=torch.int16, device="cuda") for _ in range(world)]
+    lptrs = np.array([t.data_ptr() for t in full16], dtype=np.uint64)
     for o in range(world):                                              # owner ranks
         rows = max(0, min(per, N - o * per))
         shard = torch.full((per, C1), 77, dtype=torch.int32, device="cuda")       # garbage: every cell must be written
         lab = torch.zeros(per, dtype=torch.int64, device="cuda")
         if rows:
-            engine.exchange_merge(slots[o], dirs[o], world, sub_rows, per, rows, C1, nclasses_id, thr, fc, votes=shard, labels=lab)
-            engine.exchange_queue_apply(queues[o], counts[o], world, sub_cap, shard, rows, nclasses_id, lab, thr, fc)
+            engine.exchange_merge(slots[o], dirs[o], world, sub_rows, per, rows, C1, nclasses_id, thr, fc, votes=shard, labels=lab,
+                                  peer_labels16=lptrs, first_point=o * per)
+            engine.exchange_queue_apply(queues[o], counts[o], world, sub_cap, shard, rows, nclasses_id, lab, thr, fc,
+                                        peer_labels16=lptrs, first_point=o * per)
         votes.append(shard[:rows])
         labels.append(lab[:rows])
     torch.cuda.synchronize()
+    for t in full16:                                                    # every copy holds every owner's labels
+        assert torch.equal(t[:N].to(torch.int64), torch.cat(labels))
+        assert bool((t[N:] == -7).all())
     return torch.cat(votes).cpu().numpy(), torch.cat(labels).cpu().numpy(), engine.stats_dict(st), [int(c.sum()) for c in counts], nrec
 
 

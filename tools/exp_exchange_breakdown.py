@@ -24,7 +24,7 @@ ids = parallel.frame_shard_ids(nfr, rank, world, mode)
 fl, K, wxyz, t = bench.make_labeler(fused, scenes, spec, ids, p4)
 bench.build_frames(torch, engine, fl, spec, ids)
 x = parallel.VoteExchange(npts, 134, torch.device("cuda", lr))
-names = ["barrier0+zero", "supertile+fuse+fixup", "publish", "barrier1", "merge", "queue_apply", "lab16+all_gather+widen", "overflow"]
+names = ["barrier0+zero", "supertile+fuse+fixup", "publish", "barrier1", "merge+label stores", "queue_apply", "barrier2+widen", "overflow"]
 acc = np.zeros(len(names))
 def step(record):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
@@ -33,9 +33,9 @@ def step(record):
     engine.fuse_project_vote_exchange(fl.points4, fl.table, fl.frames, None, 134, radius=0.05, zmin=fl.zmin, zmax=fl.zmax, **x.fuse_args()); ev[2].record()
     engine.exchange_publish(x.cursors, x.peer_count_ptrs, x.rank, x.sub_cap); ev[3].record()
     x.hdl.barrier(channel=1); ev[4].record()
-    engine.exchange_merge(x.rx_slots, x.rx_dir, x.world, x.sub_rows, x.per, x.rows, x.c1, 133, 0.5, None, votes=x.shard, labels=x.lab); ev[5].record()
-    engine.exchange_queue_apply(x.rx_queue, x.rx_count, x.world, x.sub_cap, x.shard, x.rows, 133, x.lab, 0.5, None); ev[6].record()
-    x.lab16.copy_(x.lab); dist.all_gather_into_tensor(x.full16.view(torch.uint8), x.lab16.view(torch.uint8)); x.full.copy_(x.full16); ev[7].record()
+    engine.exchange_merge(x.rx_slots, x.rx_dir, x.world, x.sub_rows, x.per, x.rows, x.c1, 133, 0.5, None, votes=x.shard, labels=x.lab, peer_labels16=x.peer_label_ptrs, first_point=x.rank * x.per); ev[5].record()
+    engine.exchange_queue_apply(x.rx_queue, x.rx_count, x.world, x.sub_cap, x.shard, x.rows, 133, x.lab, 0.5, None, peer_labels16=x.peer_label_ptrs, first_point=x.rank * x.per); ev[6].record()
+    x.hdl.barrier(channel=2); x.full.copy_(x.full16); ev[7].record()
     x.ovf_any.copy_(x.overflow); dist.all_reduce(x.ovf_any, op=dist.ReduceOp.MAX); ev[8].record()
     torch.cuda.synchronize()
     if record:

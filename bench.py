@@ -236,6 +236,26 @@ def cpu_vs_gpu_sample(torch, engine, pts, K, spec, wxyz, t, depth_of, masks_of, 
     return res, (sub, wq, tq, d, m, cv, cl)
 
 
+def workload_config(desc, N, F, W, H, world, shard="contiguous"):
+    """The `config` object of the JSON line -- ONE function for the B200 arm and the `--impl reference` arm, so the two lines of a
+    driver run carry the same workload description (the residency / cache notes describe the B200 arm's timed region)."""
+    if world == 1:
+        return {"workload": desc, "points": N, "frames": F, "width": W, "height": H, "nclasses": NCLASSES,
+                "frames_layout": "resident in HBM as packed uint32 texels (uint16 depth mm | class << 16, 16x16 tiles) produced by the "
+                                 "ingest path's f3d_pack_frames; on-disk contract unchanged", "radius": RADIUS,
+                "cache": "inputs larger than L2 (packed frames + votes = %.1f GB per step)" % ((F * H * W * 4 + 4 * N * C1) / 1e9),
+                "parallelism": "single GPU"}
+    per_gpu = -(-F // world)
+    return {"workload": desc, "points": N, "frames_total": F, "frames_per_gpu": per_gpu, "width": W, "height": H,
+            "nclasses": NCLASSES, "radius": RADIUS, "shard": shard,
+            "frames_layout": "packed uint32 texels resident in HBM (see N = 1)",
+            "cache": "inputs larger than L2 (packed frames per GPU %.1f GB + exchange buffers)" % (per_gpu * H * W * 4 / 1e9),
+            "parallelism": f"frames sharded over {world} GPUs ({shard}); cloud replicated; vote exchange fused into the kernel: "
+                           "slot records written into the owner rank's memory over NVLink (symmetric memory), owner-side merge into "
+                           "the dense int32 shard + label resolve; the owners store their int16 labels into every rank's copy from "
+                           "inside the merge (peer stores), no collective on the data path"}
+
+
 def run_reference_arm(args, rank, world):
     """`--impl reference`: the CPU port of the reference path on the host cores, same workload shape, bounded sample.
     Pure numpy: nothing of the CUDA library is imported or mapped here (the sample's depth images are rendered by the
@@ -245,7 +265,9 @@ def run_reference_arm(args, rank, world):
     scenes = importlib.import_module(PKG_NAME + ".scenes")     # seeded numpy scene generator (no CUDA, no libf3d)
     wl = args.workload or ("C2" if args.gpus == 1 else "C3")    # the same config the B200 arm runs at this --gpus
     cfg_key, desc = WORKLOADS[wl]
-    spec = scenes.CONFIGS[cfg_key] if wl != "small" else scenes.scaled_spec("C1", 200_000, 8, 320, 240)
+    spec = scenes.CONFIGS[cfg_key] if wl != "small" else scenes.scaled_spec("C1", 200_000, 8 if args.gpus == 1 else 16, 320, 240)
+    full = spec                                                # the workload the line is about (what the B200 arm runs)
+    strong = args.gpus == 1 or wl in ("C3", "small") or args.scaling == "strong"
     if wl == "C3":   # the sample below strides the cloud: do not generate 100 M points for it
         spec = scenes.scaled_spec("C3", npoints=10_000_000)
     from oracle import cpu_baseline as cb
@@ -263,10 +285,9 @@ def run_reference_arm(args, rank, world):
     val, sec = res["value"], res["seconds"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "points": spec.npoints, "frames": spec.nframes, "width": spec.width,
-                   "height": spec.height, "nclasses": NCLASSES},
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak" if args.gpus == 1 or not strong else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(desc, full.npoints, full.nframes * (1 if strong else args.gpus), full.width, full.height, args.gpus, args.shard),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": sample,
                          "host_cores_available": res["host_cores_available"], "frames_stage_seconds": res["frames_stage_seconds"],
                          "segment_seconds": res["segment_seconds"], "single_process": res["single_process"]},
@@ -561,11 +582,7 @@ def run_single(args, torch, mods):
         "metric": METRIC, "value": pv_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
         "data": "synthetic",
-        "config": {"workload": desc, "points": N, "frames": F, "width": W, "height": H, "nclasses": NCLASSES,
-                   "frames_layout": "resident in HBM as packed uint32 texels (uint16 depth mm | class << 16, 16x16 tiles) produced by the "
-                                    "ingest path's f3d_pack_frames; on-disk contract unchanged", "radius": RADIUS,
-                   "cache": "inputs larger than L2 (packed frames + votes = %.1f GB per step)" % ((F * H * W * 4 + 4 * N * C1) / 1e9),
-                   "parallelism": "single GPU"},
+        "config": workload_config(desc, N, F, W, H, 1),
         "roofline": roof, "cpu_baseline": cpu_b, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "per_step_counts": per_step, "alternatives": alt, "configs": configs, "bench_seconds": time.time() - T_START,
     }
@@ -922,13 +939,7 @@ def run_multi(args, torch, mods, rank, world, local_rank):
             "metric": METRIC, "value": pv_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": desc, "points": N, "frames_total": F_total, "frames_per_gpu": len(primary["ids"]), "width": W, "height": H,
-                       "nclasses": NCLASSES, "radius": RADIUS, "shard": args.shard,
-                       "frames_layout": "packed uint32 texels resident in HBM (see N = 1)",
-                       "cache": "inputs larger than L2 (packed frames per GPU %.1f GB + exchange buffers)" % (len(primary["ids"]) * H * W * 4 / 1e9),
-                       "parallelism": f"frames sharded over {world} GPUs ({args.shard}); cloud replicated; vote exchange fused into the kernel: "
-                                      "slot records written into the owner rank's memory over NVLink (symmetric memory), owner-side merge into "
-                                      "the dense int32 shard + label resolve, all-gather of int16 labels over NCCL"},
+            "config": workload_config(desc, N, F_total, W, H, world, args.shard),
             "roofline": roof, "cpu_baseline": parity.get("cpu_baseline"), "e2e": e2e, "gpu_launches": 7 * args.steps, "clocks": primary["clocks"],
             "per_step_counts_rank0": primary["stats"], "parity": parity, "other_shard": other, "point_sharded": point_sharded, "numa": numa,
             "bench_seconds": time.time() - T_START,

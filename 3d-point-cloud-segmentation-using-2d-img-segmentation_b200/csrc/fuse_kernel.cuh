@@ -101,6 +101,12 @@ struct FuseParams {
     // supertile_cull_kernel; a tile then tests only its super-tile's list instead of every frame of the launch
     const unsigned* st_count;      // [super-tiles] list length, 0xFFFFFFFF = list overflowed (scan all frames)
     const uint16_t* st_list;       // [super-tiles][FUSE_ST_LCAP] frame ids relative to f_begin
+    // compacted launch (exchange mode, optional): the grid covers only the super-tiles some frame of the launch can see;
+    // block b works on tile live_list[b / FUSE_ST_TILES] * FUSE_ST_TILES + b % FUSE_ST_TILES (NULL: tile b)
+    const unsigned* live_list;
+    unsigned* live_scratch;        // [super-tiles] storage of the list + its length at live_count (host side only)
+    unsigned* live_count;
+    int compact;                   // host side: build the list and launch the compacted grid (one stream synchronisation)
     // fused labels + deferred queue: per-point resolve state (total | best << 24 | first position << 48) written by the sweep,
     // advanced by the fix-up kernel with a compare-and-swap per deferred vote, so the labels of the touched points are
     // re-resolved from 8 bytes instead of re-reading their 4*C1-byte vote rows (NULL: re-read the rows)
@@ -694,16 +700,19 @@ __global__ void __launch_bounds__(FUSE_BLOCK, (MODE == MODE_VOTE && HB == 1) ? F
     const int lane = tid & 31, warp = tid >> 5;
     Deferred* queue = queue_all + warp * FUSE_QWARP;
     uint32_t* texring = reinterpret_cast<uint32_t*>(smem_raw + FUSE_OFF_TEXR);
-    const int64_t tile_base = (int64_t)blockIdx.x * FUSE_BLOCK;
+    unsigned tile_id = blockIdx.x;
+    if (P.live_list) tile_id = __ldg(P.live_list + blockIdx.x / FUSE_ST_TILES) * FUSE_ST_TILES + blockIdx.x % FUSE_ST_TILES;
+    const int64_t tile_base = (int64_t)tile_id * FUSE_BLOCK;
+    if (tile_base >= P.N) return;              // tail tiles of the cloud's last (partial) super-tile in a compacted launch
     const int64_t gi = tile_base + tid;
     const bool active = gi < P.N;
     const int HW = P.H * P.W;
     const float fW = (float)P.W, fH = (float)P.H;
 
     // frames to test: the super-tile's candidate list when the first cull level ran, else every frame of the launch
-    const unsigned st_n = P.st_count ? __ldg(P.st_count + blockIdx.x / FUSE_ST_TILES) : 0xffffffffu;
+    const unsigned st_n = P.st_count ? __ldg(P.st_count + tile_id / FUSE_ST_TILES) : 0xffffffffu;
     const bool use_list = st_n != 0xffffffffu;
-    const uint16_t* __restrict__ st_list = P.st_list + (size_t)(blockIdx.x / FUSE_ST_TILES) * FUSE_ST_LCAP;
+    const uint16_t* __restrict__ st_list = P.st_list + (size_t)(tile_id / FUSE_ST_TILES) * FUSE_ST_LCAP;
     const int ntest = use_list ? (int)st_n : P.f_end - P.f_begin;
     // the first 32 list entries are fetched before the count is known (the list storage always exists): one dependent
     // memory round trip less on the way to the first vote, which matters for short sweeps (C1: 3.8 candidates per point)
@@ -1248,6 +1257,57 @@ static __global__ void __launch_bounds__(256) supertile_cull_group_kernel(const 
     if (tid < ns) st_count[st0 + tid] = s_n[tid] > FUSE_ST_LCAP ? 0xffffffffu : s_n[tid];
 }
 
+// ---- compacted launch (exchange mode) ------------------------------------------------------------------------------------
+// A rank of a frame-sharded job sees a fraction of the building: at 8 ranks 7 of 8 super-tiles have an empty frame list,
+// and a CTA that only finds that out holds one of the SM's five slots for a memory round trip (measured: the eight 1/8
+// shards of C3 cost 40 ms of kernel time in total, the one 5000-frame launch 25 ms).  One block lists the super-tiles with
+// a non-empty list in ascending order; the host reads the count (the one synchronisation of the step) and launches the
+// fused kernel over those only.  The directory entries the skipped tiles would have cleared in the owners' memory are
+// cleared by dead_directory_kernel with coalesced stores.
+static __global__ void __launch_bounds__(1024) supertile_compact_kernel(const unsigned* __restrict__ st_count, unsigned nst,
+                                                                        unsigned* __restrict__ live_list, unsigned* __restrict__ live_count) {
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned base_out = 0;
+    for (unsigned base = 0; base < nst; base += 1024) {
+        const unsigned s = base + tid;
+        const bool live = s < nst && st_count[s] != 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) s_warp[warp] = (unsigned)__popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned v = s_warp[lane];
+            unsigned inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            s_warp[lane] = inc - v;
+            if (lane == 31) s_total = inc;
+        }
+        __syncthreads();
+        if (live) live_list[base_out + s_warp[warp] + (unsigned)__popc(bal & ((1u << lane) - 1u))] = s;
+        base_out += s_total;
+        __syncthreads();
+    }
+    if (tid == 0) *live_count = base_out;
+}
+
+static __global__ void __launch_bounds__(256) dead_directory_kernel(const __grid_constant__ FuseParams P, unsigned nst) {
+    constexpr unsigned PER_ST = (FUSE_ST_POINTS / 32) * F3D_XCH_NLEVEL;        // directory entries of one super-tile
+    const unsigned long long total = (unsigned long long)nst * PER_ST;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned s = (unsigned)(e / PER_ST), r = (unsigned)(e % PER_ST);
+        if (__ldg(P.st_count + s) != 0u) continue;
+        const long long p0 = (long long)s * FUSE_ST_POINTS + (long long)(r / F3D_XCH_NLEVEL) * 32;
+        if (p0 >= P.N) continue;
+        const int d = (int)(p0 / P.xg_per);
+        P.xg_dir[d][((p0 - (long long)d * P.xg_per) >> 5) * F3D_XCH_NLEVEL + (r % F3D_XCH_NLEVEL)] = make_uint2(0u, 0u);
+    }
+}
+
 // ---- fix-up kernels: the deferred point-views, one per thread, in fp64 ------------------------------------------------
 // one deferred point-view: fp64 evaluation against its frame's exact record `fe`, then the vote / depth sample / index goes
 // where the mode wants it (dense votes by atomics, the owner's sub-queue `qsub` in exchange mode, z-buffer, uv2pt)
@@ -1544,11 +1604,24 @@ static int launch_fuse_hb(FuseParams P, const FuseResolve& RP, cudaStream_t stre
             P.st_count = nullptr;   // few frames: the per-tile scan is cheaper than another launch
         }
     }
+    P.live_list = nullptr;
+    if (MODE == MODE_VOTE && P.compact && P.st_count && P.xg_G > 0 && P.live_scratch) {
+        const unsigned nst = (unsigned)((P.N + FUSE_ST_POINTS - 1) / FUSE_ST_POINTS);
+        supertile_compact_kernel<<<1, 1024, 0, stream>>>(P.st_count, nst, P.live_scratch, P.live_count);
+        dead_directory_kernel<<<148 * 8, 256, 0, stream>>>(P, nst);
+        unsigned h_live = 0;
+        cudaError_t e = cudaMemcpyAsync(&h_live, P.live_count, sizeof(unsigned), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return f3d_check_launch("f3d_fuse(compacted launch)");
+        if (h_live > nst) return f3d_fail(F3D_ERR_CUDA, "f3d_fuse: corrupt live super-tile count");
+        P.live_list = P.live_scratch;
+        tiles = (int64_t)h_live * FUSE_ST_TILES;
+    }
     FuseTimingSlot& ts = f3d_timing_slot();
     const bool timed = ts.armed;
     ts.armed = false;
     if (timed) cudaEventRecord(ts.ev[0], stream);
-    fuse_kernel<MODE, FMT, HB, AUDIT><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
+    if (tiles > 0) fuse_kernel<MODE, FMT, HB, AUDIT><<<(unsigned)tiles, FUSE_BLOCK, smem, stream>>>(P, RP);
     if (timed) cudaEventRecord(ts.ev[1], stream);
     if (use_queue) {
         // the queue length lives on the device: fixed grids with grid-stride loops, no host synchronisation
@@ -1589,7 +1662,7 @@ static int launch_fuse(const FuseParams& P, const FuseResolve& RP, int audit, cu
 // attached whenever it fits, the deferred queue only when the caller's mode wants it; returns whether the queue was attached.
 static inline int64_t supertile_bytes(int64_t npoints) {
     const int64_t S = (npoints + FUSE_ST_POINTS - 1) / FUSE_ST_POINTS;
-    return ((S * 4 + 15) & ~(int64_t)15) + S * FUSE_ST_LCAP * 2;
+    return 2 * ((S * 4 + 15) & ~(int64_t)15) + S * FUSE_ST_LCAP * 2;      // counts, live list, frame lists
 }
 
 static inline bool attach_workspace(FuseParams& P, void* workspace, int64_t workspace_bytes, bool want_queue = true, bool want_summ = false) {
@@ -1599,14 +1672,20 @@ static inline bool attach_workspace(FuseParams& P, void* workspace, int64_t work
     P.gq_cap = 0;
     P.st_count = nullptr;
     P.st_list = nullptr;
+    P.live_list = nullptr;
+    P.live_scratch = nullptr;
+    P.live_count = nullptr;
     if (!workspace || workspace_bytes < 16 || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return false;
     char* base = reinterpret_cast<char*>(workspace);
     int64_t off = 16;
     const int64_t stb = supertile_bytes(P.N);
     if (workspace_bytes >= off + stb) {
         const int64_t S = (P.N + FUSE_ST_POINTS - 1) / FUSE_ST_POINTS;
+        const int64_t cb = (S * 4 + 15) & ~(int64_t)15;
         P.st_count = reinterpret_cast<const unsigned*>(base + off);
-        P.st_list = reinterpret_cast<const uint16_t*>(base + off + ((S * 4 + 15) & ~(int64_t)15));
+        P.live_scratch = reinterpret_cast<unsigned*>(base + off + cb);
+        P.live_count = reinterpret_cast<unsigned*>(base + 8);              // second half of the 16-byte header
+        P.st_list = reinterpret_cast<const uint16_t*>(base + off + 2 * cb);
         off += stb;
     }
     if (!want_queue) return false;
@@ -1635,6 +1714,10 @@ static inline int fill_common(FuseParams& P, const void* points, int64_t N, cons
     if (fmt != F3D_DEPTH_U16_MM && fmt != F3D_DEPTH_F32_M && !fmt_is_packed(fmt)) return f3d_fail(F3D_ERR_ARG, "f3d_fuse: unknown frame format");
     if ((int64_t)H * W > 0x7fffffff || H > 65535 || W > 65535) return f3d_fail(F3D_ERR_UNSUPPORTED, "f3d_fuse: image too large");
     P.points = reinterpret_cast<const float4*>(points);
+    P.live_list = nullptr;
+    P.live_scratch = nullptr;
+    P.live_count = nullptr;
+    P.compact = 0;
     P.N = N;
     P.table = table;
     P.depth = depth;

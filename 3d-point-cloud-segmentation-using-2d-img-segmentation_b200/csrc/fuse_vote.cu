@@ -196,6 +196,7 @@ extern "C" int f3d_fuse_project_vote_exchange(const void* points, int64_t N, con
     // the fix-up kernel's blocks own the first F3D_XCH_NSUB_FIX sub-queues: the deferred queue is mandatory here
     if ((flags & 1) || N > 0x7fffffff || !attach_workspace(P, workspace, workspace_bytes))
         return f3d_fail(F3D_ERR_ARG, "f3d_fuse_project_vote_exchange: needs the workspace of f3d_fuse_workspace_bytes (no audit mode)");
+    P.compact = (flags & F3D_FUSE_COMPACT) ? 1 : 0;
     FuseResolve RP;
     RP.enabled = 0;
     return launch_vote(depth_fmt, P, RP, 0, (cudaStream_t)stream);

@@ -246,11 +246,12 @@ def exchange_constants():
 
 def fuse_project_vote_exchange(points4, table: FrameTable, depth, mask, nclasses1, nranks, points_per_shard, peer_slot_ptrs,
                                peer_dir_ptrs, peer_queue_ptrs, sub_rows, sub_cap, cursors, overflow, radius=0.05, zmin=0.1,
-                               zmax=4.0, stats=None, frame_begin=0, frame_end=None, timer=None):
+                               zmax=4.0, stats=None, frame_begin=0, frame_end=None, timer=None, compact=False):
     """Kernel (1) with the multi-GPU exchange fused in: the votes of this rank's frames go straight into the owner
     ranks' memory through the peer pointers (numpy uint64 [G] each) as slot records + directory entries, and as
     (cell, count) queue entries for what does not go into a record.  `cursors` is uint32 [G * (NREG + NSUB)], zeroed
-    by the caller.  No dense vote tensor is written."""
+    by the caller.  No dense vote tensor is written.  `compact`: launch only over the super-tiles this rank's frames can
+    see (F3D_FUSE_COMPACT: one stream synchronisation inside the call, same results)."""
     frame_end = table.F if frame_end is None else frame_end
     N = points4.shape[0]
     ws = workspace(N, points4.device)
@@ -267,7 +268,7 @@ def fuse_project_vote_exchange(points4, table: FrameTable, depth, mask, nclasses
         ptr(points4), N, ptr(table.table), frame_begin, frame_end, dptr, fmt, mptr, table.H, table.W,
         ptr(table.K), float(radius), float(zmin), float(zmax), int(nclasses1), int(nranks), int(points_per_shard), ptr(arrs[0]),
         ptr(arrs[1]), ptr(arrs[2]), int(sub_rows), int(sub_cap), ptr(cursors), ptr(overflow), ptr(ws), ws.numel(), ptr(stats),
-        0, stream_ptr()), "f3d_fuse_project_vote_exchange")
+        2 if compact else 0, stream_ptr()), "f3d_fuse_project_vote_exchange")
 
 
 def exchange_publish(cursors, peer_count_ptrs, rank, sub_cap):

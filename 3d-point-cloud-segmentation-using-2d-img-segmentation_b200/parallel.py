@@ -154,7 +154,7 @@ class VoteExchange:
         int32 shard row and the label -> apply the queue entries -> all-gather the labels.
     Nothing dense crosses the fabric and the sweep never writes a vote tensor; the owner writes its shard once."""
 
-    def __init__(self, npoints: int, c1: int, device, group=None, rows_per_block=64, sub_cap=None):
+    def __init__(self, npoints: int, c1: int, device, group=None, rows_per_block=64, sub_cap=None, compact=None):
         import numpy as np
         import torch.distributed._symmetric_memory as symm
         from . import engine
@@ -164,6 +164,9 @@ class VoteExchange:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.npoints, self.c1 = npoints, c1
         G = self.world
+        # compacted launches pay one stream synchronisation per step to skip the super-tiles this rank's frames cannot see:
+        # worth it once the cloud is large (measured at 2 ranks, 20 M points, 100 frames each: sweep 0.54 -> 0.44 ms)
+        self.compact = (G >= 2 and npoints >= (1 << 22)) if compact is None else bool(compact)
         self.nreg, self.nsub, self.nsub_fix, self.nlevel = engine.exchange_constants()
         self.per = shard_points(npoints, G)
         self.rows = max(0, min(self.per, npoints - self.rank * self.per))
@@ -209,7 +212,7 @@ class VoteExchange:
         """Keyword arguments of engine.fuse_project_vote_exchange that describe this exchange."""
         return dict(nranks=self.world, points_per_shard=self.per, peer_slot_ptrs=self.peer_slot_ptrs,
                     peer_dir_ptrs=self.peer_dir_ptrs, peer_queue_ptrs=self.peer_queue_ptrs, sub_rows=self.sub_rows,
-                    sub_cap=self.sub_cap, cursors=self.cursors, overflow=self.overflow)
+                    sub_cap=self.sub_cap, cursors=self.cursors, overflow=self.overflow, compact=self.compact)
 
     def run(self, fuse, nclasses_id, threshold=0.5, filter_classes=None, check=True, gather=True) -> torch.Tensor:
         """`fuse(**self.fuse_args())` enqueues the exchange-mode fused kernel over this rank's frames.  Returns labels

@@ -639,7 +639,7 @@ def run_multi(args, torch, mods, rank, world, local_rank):
     dist.broadcast(p4, 0)
     torch.cuda.synchronize()
 
-    xchg = parallel.VoteExchange(N, C1, torch.device("cuda", local_rank))
+    xchg = parallel.VoteExchange(N, C1, torch.device("cuda", local_rank), compact={"auto": None, "on": True, "off": False}[args.compact])
     stats_total = {}
 
     def run_shard(mode, steps, warmup):
@@ -941,7 +941,7 @@ def run_multi(args, torch, mods, rank, world, local_rank):
             "dtype": "f32+f64", "data": "synthetic",
             "config": workload_config(desc, N, F_total, W, H, world, args.shard),
             "roofline": roof, "cpu_baseline": parity.get("cpu_baseline"), "e2e": e2e, "gpu_launches": 7 * args.steps, "clocks": primary["clocks"],
-            "per_step_counts_rank0": primary["stats"], "parity": parity, "other_shard": other, "point_sharded": point_sharded, "numa": numa,
+            "compacted_launch": bool(xchg.compact), "per_step_counts_rank0": primary["stats"], "parity": parity, "other_shard": other, "point_sharded": point_sharded, "numa": numa,
             "bench_seconds": time.time() - T_START,
         }
         print(json.dumps(line))
@@ -958,6 +958,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="default: C2 on one GPU, C3 on several")
     ap.add_argument("--configs", default="micro,C1,C5,C4,C3", help="N = 1: other BASELINE configs / kernels nested in the line")
     ap.add_argument("--budget-s", type=float, default=420.0, help="nested configs are skipped once the run is this old")
+    ap.add_argument("--compact", default="auto", choices=["auto", "on", "off"],
+                    help="N > 1: launch the fused kernel only over the super-tiles a rank's frames can see (auto: 4+ ranks, large cloud)")
     ap.add_argument("--shard", default="contiguous", choices=["interleaved", "contiguous"],
                     help="how the frames of the N-GPU job are dealt to the ranks (same results either way; the other one is timed too)")
     ap.add_argument("--scaling", default=None, choices=["strong", "weak"], help="N > 1 with --workload C2: weak = N x 500 frames")

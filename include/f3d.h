@@ -140,6 +140,10 @@ int f3d_fuse_project_vote_u16(const void* points, int64_t N, const void* frame_t
  * The label all-gather can ride inside these two kernels: h_peer_labels16 (host array of nranks device pointers, one per
  * rank, each an int16 array of nranks * points_per_shard labels in peer-mapped memory; NULL = off) makes the owner store
  * every label it resolves at index first_point + row of all nranks arrays (labels must fit int16). */
+/* f3d_fuse_project_vote_exchange, flags bit 1: launch the fused kernel only over the 4096-point super-tiles that some frame
+ * of the call can see (a rank of a frame-sharded job sees a fraction of the cloud).  The call then SYNCHRONISES the stream
+ * once (it reads the number of such super-tiles) -- not capturable into a CUDA graph.  Results are identical. */
+#define F3D_FUSE_COMPACT 2
 int f3d_exchange_constants(int32_t* out4);
 int f3d_fuse_project_vote_exchange(const void* points, int64_t N, const void* frame_table, int32_t frame_begin,
                                    int32_t frame_end, const void* depth, int32_t depth_fmt, const uint8_t* mask,

@@ -381,7 +381,7 @@ def test_uint16_histogram_build_matches(engine, scenes, monkeypatch):
 # multi-GPU vote exchange, emulated on one device: every "rank" fuses its frame shard into the owners' receive buffers
 # ---------------------------------------------------------------------------------------------------------------------
 
-def _emulated_exchange(engine, s, world, nclasses_id=133, thr=0.5, fc=None, sub_rows=None, sub_cap=None):
+def _emulated_exchange(engine, s, world, nclasses_id=133, thr=0.5, fc=None, sub_rows=None, sub_cap=None, compact=False):
     parallel = importlib.import_module(PKG_NAME + ".parallel")
     N, C1, F = len(s["points"]), 134, len(s["t"])
     tab = engine.FrameTable(s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["zmax"])
@@ -465,3 +465,23 @@ def test_vote_exchange_spills_and_flushes(engine, scenes):
         votes, labels, _, nq, nrec = _emulated_exchange(engine, s, world, sub_rows=sub_rows, sub_cap=1 << 14)
         assert np.array_equal(votes, ov) and sum(nq) > 0
         assert np.array_equal(labels, orc.segment(ov, 133, 0.5, None))
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_vote_exchange_compacted_launch(engine, scenes, world):
+    """F3D_FUSE_COMPACT: the fused kernel runs only over the super-tiles a rank's frames can see; the directory entries of
+    the skipped ones (pre-filled with garbage here) are cleared by dead_directory_kernel.  > 32 frames per rank so that the
+    first cull level runs, unseen super-tiles before / between / after the scene, ragged last super-tile."""
+    s = dict(small_scene(scenes, orc, npoints=9000, nframes=40 * world, width=96, height=72, seed=13))
+    far = np.random.default_rng(0).uniform(-1, 1, (3 * 4096 + 777, 3)).astype(np.float32) + np.float32(500.0)
+    s["points"] = np.concatenate([far[:4096], s["points"][:5000], far[4096:8192], s["points"][5000:], far[8192:]])
+    ov = orc.fuse_project_vote(s["points"], s["K"], s["W"], s["H"], s["wxyz"], s["t"], s["depths"], s["masks"], 134, 0, 0.05,
+                               0.1, 4.0, 4.0)
+    assert ov[:4096].sum() == 0 and ov.sum() > 1000
+    plain = _emulated_exchange(engine, s, world)
+    comp = _emulated_exchange(engine, s, world, compact=True)
+    for votes, labels, st, nq, nrec in (plain, comp):
+        assert np.array_equal(votes, ov)
+        assert np.array_equal(labels, orc.segment(ov, 133, 0.5, None))
+        assert st["seen"] == int(ov.sum())
+    assert comp[2]["candidates"] == plain[2]["candidates"]

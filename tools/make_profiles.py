@@ -117,7 +117,7 @@ for name in ("gather_fetch_ncu_default.csv",):
                        f"{v['lts__t_sectors_srcunit_tex_op_read.sum']:>17s} {v['dram__sectors_read.sum']:>19s} {float(v['dram__sectors_read.sum']) / 8.0e7:10.2f}")
         (P / "r2_gather_fetch_granularity_ncu.txt").write_text("\n".join(out) + "\n")
 lines = []
-for n in ("bench_d.json", "bench_n2.json", "bench_n4.json", "bench_n8.json", "bench_ref.json"):
+for n in ("bench_d.json", "bench_n2.json", "bench_n2_compact.json", "bench_n4.json", "bench_n8.json", "bench_ref.json"):
     f = G / n
     if f.exists():
         ls = [l for l in f.read_text().splitlines() if l.startswith("{")]

@@ -14,7 +14,8 @@ Two contracts (SURVEY a-14 / a-15):
   hull-vertex covariance, so "parity unpinned" for the fit itself; the membership rule |(p-c).axis_k| <= extent_k/2 and
   the corner order are Open3D's, and the driver logic is pinned against the unmodified reference run on the same box
   models (tests/golden/make_golden_merge.py).
-* `cal_min_max`, `check_intersection`, `update_id_info`, `intersection_point_bb` -- the reference's helper signatures.
+* `cal_min_max`, `check_intersection`, `check_intersection_open3d`, `update_id_info`, `intersection_point_bb` -- the
+  reference's helper signatures.
 """
 from __future__ import annotations
 
@@ -132,6 +133,33 @@ def intersection_point_bb(lst1, lst2):
     reference's O(|A||B|) scan; same result)."""
     s2 = set(int(v) for v in lst2)
     return [value for value in lst1 if int(value) in s2]
+
+
+def check_intersection_open3d(id1, id_list, id_info_per_point, pcd_points, pcd, info_sem, box_model="pca"):
+    """Reference `check_intersection_open3d` (`merge_intersecting_bb.py:68-91`), same call and result: the list positions id2
+    whose oriented box shares at least one point of the cloud with the box of id1.  Kept as shipped: the loop index is the
+    instance id value (`:70,81`), the `< len(info_sem) - 1` guards (`:79`), the same-parent gate (`:80`), an empty result when
+    id1 has < 4 points (`:72-73`) and the early `return` of the partial list at the first id2 with < 4 points (`:83-84`).
+    Boxes are fitted on `pcd_points`, membership is tested on `pcd.points` (`:71,76`); all boxes come from one GPU pass."""
+    dev = require_cuda()
+    fit_pts = torch.as_tensor(np.ascontiguousarray(np.asarray(pcd_points, dtype=np.float64))).to(dev)
+    cloud = np.ascontiguousarray(np.asarray(pcd.points if hasattr(pcd, "points") else pcd, dtype=np.float64))
+    all_pts = torch.as_tensor(cloud).to(dev)
+    ids = torch.as_tensor(np.ascontiguousarray(np.asarray(id_info_per_point)).astype(np.int64)).to(dev)
+    intersecting_id = []
+    cand = [id2 for id2 in range(1, len(id_list))
+            if id1 != id2 and id2 < len(info_sem) - 1 and id1 < len(info_sem) - 1
+            and info_sem[id1]["parent_id"] == info_sem[id2]["parent_id"]]
+    boxes, counts = _instance_boxes(fit_pts, ids, [int(id1)] + cand, box_model)
+    if counts[0] < 4:
+        return intersecting_id
+    inside1 = engine.obb_contains(all_pts, boxes[0][None, :])[0]
+    for k, id2 in enumerate(cand, start=1):
+        if counts[k] < 4:
+            return intersecting_id
+        if bool((inside1 & engine.obb_contains(all_pts, boxes[k][None, :])[0]).any()):
+            intersecting_id.append(id2)
+    return intersecting_id
 
 
 def merge_bb(dir_name, info_sem, id_info_per_point, pcd, box_model="pca"):

@@ -92,7 +92,13 @@ def main():
                 if (ids == id_list[id1]).sum() >= 4 and all((ids == id_list[j]).sum() >= 4 or info[id1]["category_id"] != info[j]["category_id"]
                                                              for j in range(1, len(id_list)) if j != id1):
                     ci[str(id1)] = ref.check_intersection(id1, id_list, ids, pts, info)
-            case["models"][model] = {"final_info": fin_info, "final_ids": fin_ids.tolist(), "cal_min_max": mm, "check_intersection": ci}
+            # check_intersection_open3d (:68-91) called directly on the INITIAL state, every id1 (incl. the < 4 point instance
+            # and the early `return` an id2 with < 4 points causes)
+            pcd0 = o3d.geometry.PointCloud(pts)
+            cio = {str(id1): [int(v) for v in ref.check_intersection_open3d(id1, id_list, ids, pts, pcd0, info)]
+                   for id1 in range(1, len(id_list))}
+            case["models"][model] = {"final_info": fin_info, "final_ids": fin_ids.tolist(), "cal_min_max": mm, "check_intersection": ci,
+                                     "check_intersection_open3d": cio}
         out["cases"].append(case)
         print(kind, seed, {m: [d["id"] for d in case["models"][m]["final_info"]] for m in case["models"]},
               {m: [d["area"] for d in case["models"][m]["final_info"]] for m in case["models"]})

@@ -93,3 +93,64 @@ def test_gpu_cal_min_max_and_check_intersection(case, model):
     id_list = [d["id"] for d in info]
     for id1, ref in gold["check_intersection"].items():
         assert mbb.check_intersection(int(id1), id_list, ids, pts, info, box_model=model) == ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,model", list(_cases()))
+def test_gpu_check_intersection_open3d(case, model):
+    mbb = importlib.import_module(PKG + ".Fusion3DSeg.merge_intersecting_bb")
+    pts, ids, info = np.asarray(case["points"]), np.asarray(case["ids"], dtype=np.int64), case["info_sem"]
+    id_list = [d["id"] for d in info]
+    for id1, ref in case["models"][model]["check_intersection_open3d"].items():
+        assert mbb.check_intersection_open3d(int(id1), id_list, ids, pts, _Cloud(pts), info, box_model=model) == ref
+
+
+@pytest.mark.parametrize("case,model", list(_cases()))
+def test_oracle_check_intersection_open3d(case, model):
+    """The oracle's hit function is the geometric part of `check_intersection_open3d`; wrapped in the loop as shipped it must
+    give the rows the unmodified reference returned."""
+    pts, ids, info = np.asarray(case["points"]), np.asarray(case["ids"], dtype=np.int64), case["info_sem"]
+    hit = orc.merge_hit_fn(pts, model)
+    for id1s, ref in case["models"][model]["check_intersection_open3d"].items():
+        id1, got = int(id1s), []
+        if hit(id1, None, ids) is not False:
+            for id2 in range(1, len(info)):
+                if id1 != id2 and id2 < len(info) - 1 and id1 < len(info) - 1 and info[id1]["parent_id"] == info[id2]["parent_id"]:
+                    h = hit(id1, id2, ids)
+                    if h is None:
+                        break
+                    if h:
+                        got.append(id2)
+        assert got == ref
+
+
+@pytest.mark.parametrize("case,model", list(_cases()))
+def test_check_intersection_open3d_host_logic(case, model, monkeypatch):
+    """The mirror's HOST logic (guards, early return, candidate batching) with the two GPU operators it composes replaced by
+    numpy stand-ins of the same contract -- the operators themselves are checked on the GPU (test_gpu_* above,
+    tests/test_gpu_round2.py); this runs without a device."""
+    import torch
+    mbb = importlib.import_module(PKG + ".Fusion3DSeg.merge_intersecting_bb")
+
+    def fake_obb_fit(points64, ids, instance_ids, model_="pca"):
+        p, i = points64.numpy(), ids.numpy()
+        boxes, counts = np.zeros((len(instance_ids), 15)), np.zeros(len(instance_ids), dtype=np.int64)
+        for k, inst in enumerate(instance_ids):
+            sel = i == inst
+            counts[k] = sel.sum()
+            if counts[k] >= 1:
+                c, R, e = orc.fit_box(p[sel], model_)
+                boxes[k] = np.concatenate([c, R.reshape(-1), e])
+        return torch.as_tensor(boxes), torch.as_tensor(counts)
+
+    def fake_obb_contains(points64, boxes15):
+        p, b = points64.numpy(), boxes15.numpy().reshape(-1, 15)
+        return torch.as_tensor(np.stack([orc.obb_contains(r[:3], r[3:12].reshape(3, 3), r[12:], p) for r in b]).astype(np.uint8))
+
+    monkeypatch.setattr(mbb, "require_cuda", lambda: torch.device("cpu"))
+    monkeypatch.setattr(mbb.engine, "obb_fit", fake_obb_fit)
+    monkeypatch.setattr(mbb.engine, "obb_contains", fake_obb_contains)
+    pts, ids, info = np.asarray(case["points"]), np.asarray(case["ids"], dtype=np.int64), case["info_sem"]
+    id_list = [d["id"] for d in info]
+    for id1, ref in case["models"][model]["check_intersection_open3d"].items():
+        assert mbb.check_intersection_open3d(int(id1), id_list, ids, pts, _Cloud(pts), info, box_model=model) == ref

@@ -95,16 +95,6 @@ def test_gpu_cal_min_max_and_check_intersection(case, model):
         assert mbb.check_intersection(int(id1), id_list, ids, pts, info, box_model=model) == ref
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("case,model", list(_cases()))
-def test_gpu_check_intersection_open3d(case, model):
-    mbb = importlib.import_module(PKG + ".Fusion3DSeg.merge_intersecting_bb")
-    pts, ids, info = np.asarray(case["points"]), np.asarray(case["ids"], dtype=np.int64), case["info_sem"]
-    id_list = [d["id"] for d in info]
-    for id1, ref in case["models"][model]["check_intersection_open3d"].items():
-        assert mbb.check_intersection_open3d(int(id1), id_list, ids, pts, _Cloud(pts), info, box_model=model) == ref
-
-
 @pytest.mark.parametrize("case,model", list(_cases()))
 def test_oracle_check_intersection_open3d(case, model):
     """The oracle's hit function is the geometric part of `check_intersection_open3d`; wrapped in the loop as shipped it must

@@ -22,6 +22,41 @@ def test_oracle_split_matches_reference(tag):
     assert info == json.loads(str(g[f"info_{tag}"]))
 
 
+def _numpy_union_find(n, edges):
+    """Stand-in with `engine.union_find`'s contract: label = smallest index of the connected component."""
+    import torch
+    parent = np.arange(n)
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    for a, b in edges.numpy().astype(np.int64):
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+    return torch.as_tensor(np.array([find(i) for i in range(n)], dtype=np.int32))
+
+
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_split_host_logic_matches_reference(tag, monkeypatch):
+    """The mirror's HOST side (edge filtering, component table, the reference's id numbering and small-component fold) with the
+    GPU union-find replaced by a numpy stand-in of the same contract -- runs without a device; the kernel itself is
+    checked on the GPU below."""
+    import torch
+    cv = importlib.import_module(PKG_NAME + ".Fusion3DSeg.segUtils.cv")
+    monkeypatch.setattr(cv, "require_cuda", lambda: torch.device("cpu"))
+    monkeypatch.setattr(cv.engine, "union_find", _numpy_union_find)
+    g = load_golden("g5_instances")
+    ic, mp = CASES[tag]
+    adj = [g["indices"][g["indptr"][i]:g["indptr"][i + 1]] for i in range(len(g["classes"]))]
+    for a in (adj, (g["indptr"], g["indices"])):                    # the reference's list form and the CSR pair
+        insts, ids, info, cls = cv.split_into_instances(g["classes"], a, 133, ic, mp)
+        assert len(insts) == int(g[f"ninst_{tag}"]) and np.array_equal(ids, g[f"ids_{tag}"])
+        assert np.array_equal(cls, g[f"classes_{tag}"]) and info == json.loads(str(g[f"info_{tag}"]))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", sorted(CASES))
 def test_gpu_split_matches_reference(engine, tag):

@@ -114,11 +114,10 @@ def test_oracle_check_intersection_open3d(case, model):
         assert got == ref
 
 
-@pytest.mark.parametrize("case,model", list(_cases()))
-def test_check_intersection_open3d_host_logic(case, model, monkeypatch):
-    """The mirror's HOST logic (guards, early return, candidate batching) with the two GPU operators it composes replaced by
-    numpy stand-ins of the same contract -- the operators themselves are checked on the GPU (test_gpu_* above,
-    tests/test_gpu_round2.py); this runs without a device."""
+def _device_free(monkeypatch):
+    """The mirror module with the two GPU operators it composes (`engine.obb_fit`, `engine.obb_contains`) replaced by numpy
+    stand-ins of the same contract: what remains under test is the mirror's HOST logic.  The operators themselves are checked
+    on the GPU (test_gpu_* here, tests/test_gpu_round2.py)."""
     import torch
     mbb = importlib.import_module(PKG + ".Fusion3DSeg.merge_intersecting_bb")
 
@@ -140,7 +139,41 @@ def test_check_intersection_open3d_host_logic(case, model, monkeypatch):
     monkeypatch.setattr(mbb, "require_cuda", lambda: torch.device("cpu"))
     monkeypatch.setattr(mbb.engine, "obb_fit", fake_obb_fit)
     monkeypatch.setattr(mbb.engine, "obb_contains", fake_obb_contains)
+    return mbb
+
+
+@pytest.mark.parametrize("case,model", list(_cases()))
+def test_check_intersection_open3d_host_logic(case, model, monkeypatch):
+    """Guards, early return and candidate batching of the mirror, without a device."""
+    mbb = _device_free(monkeypatch)
     pts, ids, info = np.asarray(case["points"]), np.asarray(case["ids"], dtype=np.int64), case["info_sem"]
     id_list = [d["id"] for d in info]
     for id1, ref in case["models"][model]["check_intersection_open3d"].items():
         assert mbb.check_intersection_open3d(int(id1), id_list, ids, pts, _Cloud(pts), info, box_model=model) == ref
+
+
+@pytest.mark.parametrize("case,model", list(_cases()))
+def test_merge_bb_host_logic(case, model, monkeypatch, tmp_path):
+    """The sequential driver of the mirror `merge_bb` (membership cache, re-fit after a relabel, index-as-id and shrinking-list
+    quirks, the two output files) against the unmodified reference's result, without a device."""
+    mbb = _device_free(monkeypatch)
+    pts, ids, info = np.asarray(case["points"]), np.asarray(case["ids"], dtype=np.int64), copy.deepcopy(case["info_sem"])
+    gold = case["models"][model]
+    mbb.merge_bb(tmp_path, info, ids, _Cloud(pts), box_model=model)
+    assert np.array_equal(ids, np.asarray(gold["final_ids"]))
+    assert _strip(info) == _strip(gold["final_info"])
+    _same_boxes(info, gold["final_info"])
+    assert np.array_equal(np.load(tmp_path / "panoptic_segmentation" / "ids.npy"), ids)
+
+
+@pytest.mark.parametrize("case,model", list(_cases()))
+def test_cal_min_max_and_check_intersection_host_logic(case, model, monkeypatch):
+    mbb = _device_free(monkeypatch)
+    pts, ids, info = np.asarray(case["points"]), np.asarray(case["ids"], dtype=np.int64), case["info_sem"]
+    gold = case["models"][model]
+    for k, ref in gold["cal_min_max"].items():
+        for g, r in zip(mbb.cal_min_max(int(k), ids, pts, box_model=model), ref):
+            np.testing.assert_allclose(g, np.asarray(r), rtol=0, atol=1e-9)
+    id_list = [d["id"] for d in info]
+    for id1, ref in gold["check_intersection"].items():
+        assert mbb.check_intersection(int(id1), id_list, ids, pts, info, box_model=model) == ref

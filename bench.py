@@ -490,6 +490,8 @@ def run_single(args, torch, mods):
         roof["fp32_pipe_pct"] = prof.get("fp32_pipe_pct")
         roof["dram_frac"] = float(prof["dram_bytes_per_launch"]) / (kms * 1e-3) / 1e9 / peak
         roof["profile"] = prof.get("source")
+        if prof.get("note"):
+            roof["profile_note"] = prof["note"]
 
     # ---- the same step on the two-array inputs and with the re-pack inside the step
     alt = {}

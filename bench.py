@@ -942,7 +942,11 @@ def run_multi(args, torch, mods, rank, world, local_rank):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32+f64", "data": "synthetic",
             "config": workload_config(desc, N, F_total, W, H, world, args.shard),
-            "roofline": roof, "cpu_baseline": parity.get("cpu_baseline"), "e2e": e2e, "gpu_launches": 7 * args.steps, "clocks": primary["clocks"],
+            "roofline": roof, "cpu_baseline": parity.get("cpu_baseline"), "e2e": e2e, "gpu_launches": (9 if xchg.compact else 7) * args.steps,
+            "gpu_launches_per_step": "supertile_cull(_group), [supertile_compact, dead_directory], fuse_kernel, fixup_apply(_table), exchange_publish, "
+                                     "slot_merge, queue_accumulate, queue_relabel (own kernels per rank; torch fills, symmetric-memory barriers and the "
+                                     "4-byte NCCL flag reduce not counted)",
+            "clocks": primary["clocks"],
             "compacted_launch": bool(xchg.compact), "per_step_counts_rank0": primary["stats"], "parity": parity, "other_shard": other, "point_sharded": point_sharded, "numa": numa,
             "bench_seconds": time.time() - T_START,
         }

@@ -14,10 +14,11 @@ pinned HOST buffers through the public API, the CPU port of the reference on the
 lines for the other BASELINE configs (C1 compared cell for cell with the CPU port, C4, C5) and the other kernels.
 
 N > 1 (default workload C3, configs[2]: 100 M points x 5000 frames = a FIXED problem split over the ranks, strong scaling):
-frames sharded over the ranks (interleaved and contiguous are both timed), the vote exchange fused into the kernel
-(slot records written straight into the owner rank's memory over NVLink), owner-side merge + label resolve, all-gather of the
-labels.  Rank 0 additionally runs the whole frame set on its single GPU and the CPU port on a sample, and the line says
-whether the N-rank result equals both.
+frames sharded over the ranks (contiguous = headline, interleaved and point-sharded also timed), the vote exchange fused into
+the kernel (slot records written straight into the owner rank's memory over NVLink; launched only over the super-tiles a rank's
+frames can see, `--compact`), owner-side merge + label resolve with the labels stored into every rank's copy from inside the
+merge.  Rank 0 additionally runs the whole frame set on its single GPU and the CPU port on a sample, and the line says whether
+the N-rank result equals both.
 
 A point-view is one (point, frame) pair of the nominal N_points x N_frames product.  Rank 0 prints ONE JSON line.
 """
